@@ -1,0 +1,306 @@
+// Special functions needed by the likelihood and the quantile map, written for the device
+// (CUDA has no regularised incomplete gamma / beta, their inverses, digamma or trigamma).
+// Every function is __host__ __device__ so that tests/hostmath can compile this header with g++
+// and compare it against scipy.special on the CPU (a unit test of the math, not a product path).
+//
+// What the reference calls for these (through scipy.stats, attrici/distributions.py:81-216 and
+// attrici/estimation/model_scipy.py:352,373,468,494):
+//   norm.cdf / ppf        -> ndtr, ndtri          -> ndtr(), ndtri()
+//   gamma.cdf / ppf       -> gammainc, gammaincinv-> gamma_p(), gamma_p_inv()
+//   beta.cdf / ppf        -> betainc, betaincinv  -> beta_i(), beta_i_inv()
+//   gamma/beta.logpdf     -> gammaln              -> lgam()   (+ digamma/trigamma for gradients)
+#pragma once
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define ATTRICI_HD __host__ __device__ __forceinline__
+#define ATTRICI_HD_NOINLINE __host__ __device__
+#else
+#define ATTRICI_HD inline
+#define ATTRICI_HD_NOINLINE inline
+#endif
+
+namespace attrici {
+
+template <typename R> ATTRICI_HD R lgam(R x);
+template <> ATTRICI_HD double lgam<double>(double x) { return lgamma(x); }
+template <> ATTRICI_HD float lgam<float>(float x) { return lgammaf(x); }
+
+// digamma for x > 0: upward recurrence to x >= X0, then the asymptotic series
+template <typename R> ATTRICI_HD R digamma(R x) {
+    const R X0 = (sizeof(R) == 8) ? R(10) : R(6);
+    R acc = 0;
+    while (x < X0) {
+        acc -= R(1) / x;
+        x += R(1);
+    }
+    R inv = R(1) / x, inv2 = inv * inv;
+    R s = inv2 * (R(1.0 / 12) - inv2 * (R(1.0 / 120) - inv2 * (R(1.0 / 252) - inv2 * (R(1.0 / 240) - inv2 * (R(1.0 / 132) - inv2 * R(691.0 / 32760))))));
+    return acc + log(x) - R(0.5) * inv - s;
+}
+
+template <typename R> ATTRICI_HD R trigamma(R x) {
+    const R X0 = (sizeof(R) == 8) ? R(10) : R(6);
+    R acc = 0;
+    while (x < X0) {
+        R i = R(1) / x;
+        acc += i * i;
+        x += R(1);
+    }
+    R inv = R(1) / x, inv2 = inv * inv;
+    R s = inv * (R(1) + inv * (R(0.5) + inv * (R(1.0 / 6) - inv2 * (R(1.0 / 30) - inv2 * (R(1.0 / 42) - inv2 * (R(1.0 / 30) - inv2 * (R(5.0 / 66) - inv2 * R(691.0 / 2730))))))));
+    return acc + s;
+}
+
+// ---------------------------------------------------------------------------------------
+// normal distribution
+// ---------------------------------------------------------------------------------------
+// same branch structure as cephes ndtr (what scipy.special.ndtr evaluates)
+ATTRICI_HD double ndtr(double a) {
+    if (isnan(a)) return a;
+    double x = a * 0.70710678118654752440;
+    double z = fabs(x);
+    if (z < 0.70710678118654752440) return 0.5 + 0.5 * erf(x);
+    double y = 0.5 * erfc(z);
+    return x > 0 ? 1.0 - y : y;
+}
+
+// inverse normal cdf: Wichura's AS 241 (PPND16), relative error ~1e-16
+ATTRICI_HD_NOINLINE double ndtri(double p) {
+    if (isnan(p) || p < 0.0 || p > 1.0) return NAN;
+    if (p == 0.0) return -INFINITY;
+    if (p == 1.0) return INFINITY;
+    double q = p - 0.5, r, val;
+    if (fabs(q) <= 0.425) {
+        r = 0.180625 - q * q;
+        val = q * (((((((2.5090809287301226727e3 * r + 3.3430575583588128105e4) * r + 6.7265770927008700853e4) * r + 4.5921953931549871457e4) * r + 1.3731693765509461125e4) * r + 1.9715909503065514427e3) * r + 1.3314166789178437745e2) * r + 3.3871328727963666080e0) /
+              (((((((5.2264952788528545610e3 * r + 2.8729085735721942674e4) * r + 3.9307895800092710610e4) * r + 2.1213794301586595867e4) * r + 5.3941960214247511077e3) * r + 6.8718700749205790830e2) * r + 4.2313330701600911252e1) * r + 1.0);
+        return val;
+    }
+    r = q < 0 ? p : 1.0 - p;
+    r = sqrt(-log(r));
+    if (r <= 5.0) {
+        r -= 1.6;
+        val = (((((((7.74545014278341407640e-4 * r + 2.27238449892691845833e-2) * r + 2.41780725177450611770e-1) * r + 1.27045825245236838258e0) * r + 3.64784832476320460504e0) * r + 5.76949722146069140550e0) * r + 4.63033784615654529590e0) * r + 1.42343711074968357734e0) /
+              (((((((1.05075007164441684324e-9 * r + 5.47593808499534494600e-4) * r + 1.51986665636164571966e-2) * r + 1.48103976427480074590e-1) * r + 6.89767334985100004550e-1) * r + 1.67638483018380384940e0) * r + 2.05319162663775882187e0) * r + 1.0);
+    } else {
+        r -= 5.0;
+        val = (((((((2.01033439929228813265e-7 * r + 2.71155556874348757815e-5) * r + 1.24266094738807843860e-3) * r + 2.65321895265761230930e-2) * r + 2.96560571828504891230e-1) * r + 1.78482653991729133580e0) * r + 5.46378491116411436990e0) * r + 6.65790464350110377720e0) /
+              (((((((2.04426310338993978564e-15 * r + 1.42151175831644588870e-7) * r + 1.84631831751005468180e-5) * r + 7.86869131145613259100e-4) * r + 1.48753612908506148525e-2) * r + 1.36929880922735805310e-1) * r + 5.99832206555887937690e-1) * r + 1.0);
+    }
+    return q < 0 ? -val : val;
+}
+
+// ---------------------------------------------------------------------------------------
+// regularised incomplete gamma P(a, x), Q(a, x) and the inverse of P
+// ---------------------------------------------------------------------------------------
+// x^a e^-x / Gamma(a)
+ATTRICI_HD double gamma_prefactor(double a, double x) { return exp(a * log(x) - x - lgamma(a)); }
+
+// series for P, converges quickly for x < a + 1
+ATTRICI_HD_NOINLINE double gamma_p_series(double a, double x) {
+    double ap = a, del = 1.0 / a, sum = del;
+    for (int n = 0; n < 2000; ++n) {
+        ap += 1.0;
+        del *= x / ap;
+        sum += del;
+        if (fabs(del) < fabs(sum) * 1e-17) break;
+    }
+    return sum * gamma_prefactor(a, x);
+}
+
+// modified Lentz continued fraction for Q, converges quickly for x > a + 1
+ATTRICI_HD_NOINLINE double gamma_q_cf(double a, double x) {
+    const double tiny = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    for (int i = 1; i < 2000; ++i) {
+        double an = -i * (i - a);
+        b += 2.0;
+        d = an * d + b;
+        if (fabs(d) < tiny) d = tiny;
+        c = b + an / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return h * gamma_prefactor(a, x);
+}
+
+ATTRICI_HD double gamma_p(double a, double x) {
+    if (isnan(a) || isnan(x) || a <= 0.0 || x < 0.0) return NAN;
+    if (x == 0.0) return 0.0;
+    if (isinf(x)) return 1.0;
+    if (x < a + 1.0) return gamma_p_series(a, x);
+    return 1.0 - gamma_q_cf(a, x);
+}
+
+ATTRICI_HD double gamma_q(double a, double x) {
+    if (isnan(a) || isnan(x) || a <= 0.0 || x < 0.0) return NAN;
+    if (x == 0.0) return 1.0;
+    if (isinf(x)) return 0.0;
+    if (x < a + 1.0) return 1.0 - gamma_p_series(a, x);
+    return gamma_q_cf(a, x);
+}
+
+// x with P(a, x) = p   (scipy.special.gammaincinv); safeguarded Halley iteration
+ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p) {
+    if (isnan(a) || isnan(p) || a <= 0.0 || p < 0.0 || p > 1.0) return NAN;
+    if (p == 0.0) return 0.0;
+    if (p == 1.0) return INFINITY;
+    const double gln = lgamma(a);
+    const double a1 = a - 1.0;
+    double x;
+    // starting value (Abramowitz & Stegun 26.2.22 / 26.4.17, as in Numerical Recipes invgammp)
+    if (a > 1.0) {
+        double pp = p < 0.5 ? p : 1.0 - p;
+        double t = sqrt(-2.0 * log(pp));
+        x = (2.30753 + t * 0.27061) / (1.0 + t * (0.99229 + t * 0.04481)) - t;
+        if (p < 0.5) x = -x;
+        double w = 1.0 - 1.0 / (9.0 * a) - x / (3.0 * sqrt(a));
+        x = a * w * w * w;
+        if (x < 1e-3) x = 1e-3;
+    } else {
+        double t = 1.0 - a * (0.253 + a * 0.12);
+        if (p < t)
+            x = pow(p / t, 1.0 / a);
+        else
+            x = 1.0 - log(1.0 - (p - t) / (1.0 - t));
+    }
+    double lo = 0.0, hi = INFINITY;
+    const double lna1 = a > 1.0 ? log(a1) : 0.0;
+    const double afac = a > 1.0 ? exp(a1 * (lna1 - 1.0) - gln) : 0.0;
+    for (int it = 0; it < 60; ++it) {
+        if (x <= 0.0) x = 0.5 * (lo + (isinf(hi) ? lo + 1e-300 : hi));
+        // error in the better-conditioned tail
+        double err = (p < 0.5) ? gamma_p(a, x) - p : (1.0 - p) - gamma_q(a, x);
+        if (err > 0.0) hi = x; else lo = x;
+        double dens;  // dP/dx
+        if (a > 1.0)
+            dens = afac * exp(-(x - a1) + a1 * (log(x) - lna1));
+        else
+            dens = exp(-x + a1 * log(x) - gln);
+        if (!(dens > 0.0)) {
+            x = isinf(hi) ? 2.0 * x + 1.0 : 0.5 * (lo + hi);
+            continue;
+        }
+        double u = err / dens;
+        // Halley correction, limited as in Numerical Recipes
+        double corr = u * (a1 / x - 1.0);
+        if (corr > 1.0) corr = 1.0;
+        double dx = u / (1.0 - 0.5 * corr);
+        double xn = x - dx;
+        if (fabs(xn - x) <= 4e-16 * x) { x = xn; break; }
+        if (!(xn >= lo) || !(xn <= hi)) xn = isinf(hi) ? 2.0 * x : 0.5 * (lo + hi);
+        x = xn;
+    }
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------
+// regularised incomplete beta I_x(a, b) and its inverse
+// ---------------------------------------------------------------------------------------
+ATTRICI_HD_NOINLINE double beta_cf(double a, double b, double x) {
+    const double tiny = 1e-300;
+    double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m < 3000; ++m) {
+        int m2 = 2 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d;
+        if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c;
+        if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return h;
+}
+
+// returns I_x(a,b); if comp != nullptr also 1 - I_x(a,b) computed without cancellation
+ATTRICI_HD_NOINLINE double beta_i2(double a, double b, double x, double* comp) {
+    if (isnan(a) || isnan(b) || isnan(x) || a <= 0.0 || b <= 0.0 || x < 0.0 || x > 1.0) {
+        if (comp) *comp = NAN;
+        return NAN;
+    }
+    if (x == 0.0) { if (comp) *comp = 1.0; return 0.0; }
+    if (x == 1.0) { if (comp) *comp = 0.0; return 1.0; }
+    double bt = exp(lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log1p(-x));
+    double p, q;
+    if (x < (a + 1.0) / (a + b + 2.0)) {
+        p = bt * beta_cf(a, b, x) / a;
+        q = 1.0 - p;
+    } else {
+        q = bt * beta_cf(b, a, 1.0 - x) / b;
+        p = 1.0 - q;
+    }
+    if (comp) *comp = q;
+    return p;
+}
+
+ATTRICI_HD double beta_i(double a, double b, double x) { return beta_i2(a, b, x, nullptr); }
+
+// x with I_x(a, b) = p   (scipy.special.betaincinv); safeguarded Halley iteration
+ATTRICI_HD_NOINLINE double beta_i_inv(double a, double b, double p) {
+    if (isnan(a) || isnan(b) || isnan(p) || a <= 0.0 || b <= 0.0 || p < 0.0 || p > 1.0) return NAN;
+    if (p == 0.0) return 0.0;
+    if (p == 1.0) return 1.0;
+    const double a1 = a - 1.0, b1 = b - 1.0;
+    double x;
+    if (a >= 1.0 && b >= 1.0) {
+        double pp = p < 0.5 ? p : 1.0 - p;
+        double t = sqrt(-2.0 * log(pp));
+        x = (2.30753 + t * 0.27061) / (1.0 + t * (0.99229 + t * 0.04481)) - t;
+        if (p < 0.5) x = -x;
+        double al = (x * x - 3.0) / 6.0;
+        double h = 2.0 / (1.0 / (2.0 * a - 1.0) + 1.0 / (2.0 * b - 1.0));
+        double w = x * sqrt(al + h) / h - (1.0 / (2.0 * b - 1.0) - 1.0 / (2.0 * a - 1.0)) * (al + 5.0 / 6.0 - 2.0 / (3.0 * h));
+        x = a / (a + b * exp(2.0 * w));
+    } else {
+        double lna = log(a / (a + b)), lnb = log(b / (a + b));
+        double t = exp(a * lna) / a, u = exp(b * lnb) / b, w = t + u;
+        if (p < t / w)
+            x = pow(a * w * p, 1.0 / a);
+        else
+            x = 1.0 - pow(b * w * (1.0 - p), 1.0 / b);
+    }
+    const double afac = -lgamma(a) - lgamma(b) + lgamma(a + b);
+    double lo = 0.0, hi = 1.0;
+    for (int it = 0; it < 80; ++it) {
+        if (!(x > 0.0) || !(x < 1.0)) x = 0.5 * (lo + hi);
+        double q;
+        double pv = beta_i2(a, b, x, &q);
+        double err = (p < 0.5) ? pv - p : (1.0 - p) - q;
+        if (err > 0.0) hi = x; else lo = x;
+        double dens = exp(a1 * log(x) + b1 * log1p(-x) + afac);
+        double xn;
+        if (!(dens > 0.0) || isinf(dens)) {
+            xn = 0.5 * (lo + hi);
+        } else {
+            double u = err / dens;
+            double corr = u * (a1 / x - b1 / (1.0 - x));
+            if (corr > 1.0) corr = 1.0;
+            xn = x - u / (1.0 - 0.5 * corr);
+            if (fabs(xn - x) <= 4e-16 * x) { x = xn; break; }
+            if (!(xn >= lo) || !(xn <= hi)) xn = 0.5 * (lo + hi);
+        }
+        x = xn;
+    }
+    return x;
+}
+
+}  // namespace attrici

@@ -1,0 +1,185 @@
+/*
+ * attrici_b200 -- C ABI of the B200-native batched solver for ATTRICI's per-gridcell
+ * detrending path (scale -> MAP fit -> factual/counterfactual parameters -> quantile map).
+ *
+ * This is the drop-in boundary.  The reference has no FFI (it is pure Python); each entry
+ * point below names the reference code it replaces (paths relative to the reference repo).
+ * The Python binding a maintainer adds is the ctypes stub in INTEGRATION.md
+ * (attrici_b200/_lib.py is that stub, shipped).
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer unless the parameter name ends in _host;
+ *     the caller (torch / cudaMalloc) owns every buffer, the library never allocates device
+ *     memory except inside attrici_detrend_host (streams/events only, see there);
+ *   - cell series are TIME-MAJOR: element (day t, cell c) of a [T x C] array lives at
+ *     t*ld + c, ld >= C (the layout a (time, lat, lon) NetCDF variable already has after
+ *     the reference's obs_data.stack(latlon=("lat","lon")), attrici/detrend.py:672);
+ *   - per-cell vectors are [C]; per-cell parameter vectors are row-major [C x P] in the
+ *     reference's theta layout (attrici/estimation/model_scipy.py:410-421, 104-113, 225-234);
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), return 0 on
+ *     success, a negative ATTRICI_E* code for invalid arguments, or a positive cudaError_t;
+ *     attrici_last_error() gives a thread-local message;  numerical trouble in one cell is
+ *     reported in status[c], never as a call failure;
+ *   - the library is re-entrant per stream and keeps no global mutable state.
+ */
+#ifndef ATTRICI_B200_H
+#define ATTRICI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATTRICI_ABI_VERSION 1
+#define ATTRICI_MAX_MODES 4
+
+/* distributions (attrici/distributions.py:64-216; attrici/variables.py model table) */
+enum {
+    ATTRICI_NORMAL = 0,          /* tas ps rlds rsds tasskew : mu (identity, GMT-dep), sigma (exp)      */
+    ATTRICI_GAMMA = 1,           /* tasrange                 : mu (exp, dep), nu (exp)                   */
+    ATTRICI_BETA = 2,            /* hurs                     : mu (invlogit, dep), phi (exp)             */
+    ATTRICI_WEIBULL = 3,         /* sfcWind / wind           : alpha (exp), beta (exp, dep); theta=[alpha|beta] */
+    ATTRICI_BERNOULLI_GAMMA = 4  /* pr                       : p (invlogit, dep), mu (exp, dep), nu (exp) */
+};
+
+/* scaling rules (attrici/variables.py:92-111, 363-403, 574-591, 619-623, 722-732, 770-780) */
+enum {
+    ATTRICI_SCALE_UNITY = 0,   /* (y - min) / (max - min)                       tas ps rlds rsds     */
+    ATTRICI_SCALE_NONE = 1,    /* mask a copy with thresholds, no scaling        tasskew              */
+    ATTRICI_SCALE_PERCENT = 2, /* mask in place, y / 100                         hurs                 */
+    ATTRICI_SCALE_RANGE = 3,   /* mask in place, y / (max - min)                 tasrange sfcWind     */
+    ATTRICI_SCALE_PR = 4       /* y - THRESHOLD, <=0 -> dry (NaN), / gamma-fit scale   pr             */
+};
+
+/* post rule of the quantile map (attrici/variables.py:645-653, 691-698) */
+enum { ATTRICI_POST_NONE = 0, ATTRICI_POST_LE0_NAN = 1, ATTRICI_POST_OUTSIDE01_NAN = 2 };
+
+/* per-cell fit status */
+enum {
+    ATTRICI_STATUS_CONVERGED = 0,
+    ATTRICI_STATUS_RUNNING = 1,   /* only seen if max_pass was hit */
+    ATTRICI_STATUS_STALLED = 2,   /* damping exceeded its bound without an acceptable step */
+    ATTRICI_STATUS_NONFINITE = 3, /* objective not finite at the starting point */
+    ATTRICI_STATUS_NO_DATA = 4    /* no valid day in the fit window (reference skips: detrend.py:315-317) */
+};
+
+/* `replaced` codes (the reference stores NaN / +Inf / -Inf as float64, detrend.py:397-411) */
+enum { ATTRICI_REPLACED_NONE = 0, ATTRICI_REPLACED_NAN = 1, ATTRICI_REPLACED_PINF = 2, ATTRICI_REPLACED_NINF = 3 };
+
+enum {
+    ATTRICI_EINVAL = -1,     /* bad argument */
+    ATTRICI_EWORKSPACE = -2, /* workspace too small */
+    ATTRICI_EUNSUPPORTED = -3
+};
+
+/* what create_variable() + Variable.create_model() decide for one variable name
+ * (attrici/variables.py:801-834 and the create_model overrides) */
+typedef struct attrici_variable {
+    int32_t family;     /* ATTRICI_NORMAL ... */
+    int32_t scaling;    /* ATTRICI_SCALE_* */
+    int32_t post_rule;  /* ATTRICI_POST_* */
+    int32_t modes;      /* 1..ATTRICI_MAX_MODES (Config.modes, attrici/detrend.py:66) */
+    float lower_threshold; /* values <= this are masked; NaN = none (mask_thresholded, variables.py:40-68) */
+    float upper_threshold; /* values >= this are masked; NaN = none */
+} attrici_variable_t;
+
+typedef struct attrici_fit_options {
+    int32_t max_pass;     /* cap on likelihood passes per cell (default 60) */
+    int32_t use_fp64;     /* 0: FP32 per-day arithmetic, FP64 reductions (production); 1: all FP64 */
+    double tol_pred;      /* stop when the predicted decrease <= tol_pred * max(|f|,1) (default 1e-11) */
+    double lambda0;       /* initial Levenberg-Marquardt damping (default 1e-3) */
+    int32_t zero_init;    /* 1: start from theta = 0 like model_scipy.py:113,234; 0: moment-based start */
+    int32_t reserved;
+} attrici_fit_options_t;
+
+const char* attrici_last_error(void);
+int attrici_abi_version(void);
+
+/* number of fitted coefficients of a family (model_scipy.py:113, 234, 410-421) */
+int attrici_num_params(int family, int modes);
+
+/* bytes of device scratch needed by the calls below for a [T x C] batch */
+int attrici_workspace_bytes(int T, int C, size_t* bytes);
+
+/* Fourier / GMT basis shared by all cells.
+ * replaces attrici/util.py:85-104 (calc_oscillations) and the covariate construction of
+ * attrici/estimation/model_scipy.py:180-197, 280-289.
+ *   days[T]  int32 day offsets of the time axis (days since its first day; integers from the host)
+ *   gmt[T]   float64 scaled predictor (attrici/detrend.py:698-707) */
+int attrici_build_basis(void* workspace, size_t workspace_bytes, const int32_t* days, const double* gmt,
+                        int T, void* stream);
+
+/* scaling + validity / wet-dry masks.
+ * replaces create_variable -> <Variable>.__init__ (attrici/variables.py:92-111, 354-403, 565-591,
+ * 619-623, 712-732, 760-780) and the Inf -> NaN step of attrici/detrend.py:311.
+ *   y[T x ld]         float32 observations
+ *   y_scaled[T x ld]  float32 out; NaN = masked / dry / missing (bit-exact float32 arithmetic)
+ *   scaling[C x 2]    float64 out: {datamin, scale} (datamin = 0 where the reference has none)
+ * Also gathers the per-cell start values / phase origins of the fit window [i0, i1) into the workspace. */
+int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                            const float* y, float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
+                            double* scaling, void* stream);
+
+/* log-posterior, gradient and Fisher information at given coefficients (known-answer entry).
+ * replaces DistributionScipy.log_likelihood (model_scipy.py:311-331) summed as in :520; the
+ * reference has no gradient (finite differences inside scipy's L-BFGS-B).
+ *   theta[C x P] in ; nll[C] out (= -log posterior) ; grad[C x P] out ; fisher[C x P x P] out (nullable)
+ * needs attrici_build_basis + attrici_prep_scale_mask on the same workspace first. */
+int attrici_nll_grad(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                     const float* y_scaled, int64_t ld, int T, int C, int i0, int i1, int use_fp64,
+                     const double* theta, double* nll, double* grad, double* fisher, void* stream);
+
+/* batched MAP fit: Fisher-scoring Levenberg-Marquardt with per-cell convergence masks.
+ * replaces ModelScipy.fit (model_scipy.py:505-527: scipy L-BFGS-B with finite differences).
+ *   params[C x P] out, logp[C] out (log posterior, FP64 evaluation at the returned point),
+ *   status[C] out, n_pass[C] out (nullable).  Synchronises `stream` internally between passes. */
+int attrici_fit_batch(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                      const float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
+                      const attrici_fit_options_t* opts, double* params, double* logp, int32_t* status,
+                      int32_t* n_pass, void* stream);
+
+/* factual / counterfactual distribution parameters, quantile map, rescale, replacement.
+ * replaces ModelScipy.estimate_distribution x2 (model_scipy.py:547-570; attrici/detrend.py:362-370),
+ * Variable.quantile_mapping and overrides (attrici/variables.py:287-303, 422-480, 645-653, 691-698),
+ * attrici/distributions.py:81-216, rescale (variables.py:71-89, 114-131, 483-486) and the NaN/Inf
+ * replacement of attrici/detrend.py:392-411.
+ *   y, y_scaled [T x ld]   ; params[C x P] ; scaling[C x 2]
+ *   seeds[C] uint32  (pr only; attrici/detrend.py:285, consumed by np.random.rand in variables.py:458)
+ *   cfact[T x ld_out] float64 out ; replaced[T x ld_out] uint8 out (nullable) ;
+ *   cfact_scaled[T x ld_out] float64 out (nullable) */
+int attrici_quantile_map(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                         const float* y, const float* y_scaled, int64_t ld, int T, int C,
+                         const double* params, const double* scaling, const uint32_t* seeds,
+                         double* cfact, uint8_t* replaced, double* cfact_scaled, int64_t ld_out,
+                         void* stream);
+
+/* per-day distribution parameters for report_variables (attrici/detrend.py:462-467):
+ *   which = index of the parameter in the family's order, counterfactual != 0 -> predictor = 0 */
+int attrici_eval_parameter(void* workspace, size_t workspace_bytes, const attrici_variable_t* var, int T,
+                           int C, const double* params, int which, int counterfactual, double* out,
+                           int64_t ld_out, void* stream);
+
+/* NumPy-legacy MT19937 doubles, one stream per cell (np.random.seed(s); np.random.rand(n)).
+ *   out[n x ld] float64, cell-minor like every other series */
+int attrici_mt19937_uniform(const uint32_t* seeds, int C, int n, double* out, int64_t ld, void* stream);
+
+/* whole path for one batch with HOST buffers (pinned recommended): H2D of y, scale, fit,
+ * quantile map, D2H of cfact / params / logp / status, cells processed in slabs of
+ * `slab_cells` with copies and kernels overlapped on internal streams.
+ * replaces the cell loop attrici/detrend.py:760-788 around fit_and_detrend_cell (:258-416, I/O excluded).
+ *   device_scratch: device buffer of attrici_detrend_host_scratch_bytes() bytes */
+int attrici_detrend_host_scratch_bytes(int T, int slab_cells, size_t* bytes);
+int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_options_t* opts,
+                         const float* y_host, int64_t ld_host, int T, int C, int i0, int i1,
+                         const int32_t* days_host, const double* gmt_host, const uint32_t* seeds_host,
+                         double* cfact_host, int64_t ld_out_host, uint8_t* replaced_host,
+                         double* params_host, double* logp_host, double* scaling_host,
+                         int32_t* status_host, int32_t* n_pass_host,
+                         void* device_scratch, size_t device_scratch_bytes, int slab_cells);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATTRICI_B200_H */
