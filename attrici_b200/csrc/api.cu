@@ -1,0 +1,453 @@
+// C ABI of libattrici_b200.so (declared in include/attrici_b200.h): argument checking, workspace
+// carving, the batched fit loop and the host-buffer pipeline.  No torch types, no global mutable
+// state; every call is asynchronous on the caller's stream except where stated.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <atomic>
+#include <vector>
+#include "common.cuh"
+
+namespace attrici {
+
+static thread_local char g_error[512] = "";
+
+// diagnostics: kernels launched by this process, and the pass-kernel timing of the last profiled fit
+std::atomic<long long> g_launches{0};
+struct FitProfile {
+    double pass_ms;        // summed device time of the moment passes
+    long long launches;    // number of moment-pass launches
+    double cell_days;      // sum over launches of (cells still iterating) x (days in the fit window)
+};
+static thread_local FitProfile g_profile = {0.0, 0, 0.0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+bool valid_family(int f) { return f >= ATTRICI_NORMAL && f <= ATTRICI_BERNOULLI_GAMMA; }
+
+int check_var(const attrici_variable_t* var) {
+    if (!var) { set_error("variable descriptor is null"); return ATTRICI_EINVAL; }
+    if (!valid_family(var->family)) { set_error("unknown family %d", var->family); return ATTRICI_EINVAL; }
+    if (var->scaling < ATTRICI_SCALE_UNITY || var->scaling > ATTRICI_SCALE_PR) {
+        set_error("unknown scaling %d", var->scaling);
+        return ATTRICI_EINVAL;
+    }
+    if (var->post_rule < ATTRICI_POST_NONE || var->post_rule > ATTRICI_POST_OUTSIDE01_NAN) {
+        set_error("unknown post rule %d", var->post_rule);
+        return ATTRICI_EINVAL;
+    }
+    if (var->modes < 1 || var->modes > ATTRICI_MAX_MODES) {
+        set_error("modes must be in 1..%d, got %d", ATTRICI_MAX_MODES, var->modes);
+        return ATTRICI_EINVAL;
+    }
+    if (var->scaling == ATTRICI_SCALE_PR && var->family != ATTRICI_BERNOULLI_GAMMA) {
+        set_error("the pr scaling belongs to the Bernoulli-Gamma family (variables.py:341-486)");
+        return ATTRICI_EINVAL;
+    }
+    return 0;
+}
+
+int check_shape(int T, int C, int64_t ld) {
+    if (T < 2 || C < 1) { set_error("need T >= 2 and C >= 1, got T=%d C=%d", T, C); return ATTRICI_EINVAL; }
+    if (ld < C) { set_error("leading dimension %lld < C=%d", (long long)ld, C); return ATTRICI_EINVAL; }
+    return 0;
+}
+
+int check_window(int T, int i0, int i1) {
+    if (i0 < 0 || i1 > T || i1 <= i0) {
+        set_error("fit window [%d, %d) outside [0, %d)", i0, i1, T);
+        return ATTRICI_EINVAL;
+    }
+    return 0;
+}
+
+int bind_workspace(Workspace& ws, void* workspace, size_t workspace_bytes, int T, int C, int family) {
+    if (!workspace) { set_error("workspace is null"); return ATTRICI_EINVAL; }
+    if (((uintptr_t)workspace & 255) != 0) { set_error("workspace must be 256-byte aligned"); return ATTRICI_EINVAL; }
+    size_t need = ws.layout(T, C, family, workspace);
+    if (need > workspace_bytes) {
+        set_error("workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
+        return ATTRICI_EWORKSPACE;
+    }
+    return 0;
+}
+
+attrici_fit_options_t default_options() {
+    attrici_fit_options_t o;
+    o.max_pass = 60;
+    o.use_fp64 = 0;
+    o.tol_pred = 1e-11;
+    o.lambda0 = 1e-3;
+    o.zero_init = 0;
+    o.profile = 0;
+    return o;
+}
+
+StepParams step_params(const attrici_variable_t& var, const attrici_fit_options_t& o, int slot) {
+    StepParams sp;
+    sp.term = family_term(var.family, slot);
+    sp.modes = var.modes;
+    sp.slot = slot;
+    sp.fp64 = o.use_fp64;
+    sp.max_pass = o.max_pass;
+    sp.tol_pred = o.tol_pred;
+    sp.lambda0 = o.lambda0;
+    sp.zero_init = o.zero_init;
+    return sp;
+}
+
+// Fisher-scoring iteration of one likelihood term over the whole batch
+int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_options_t& o, int slot,
+             const float* y_scaled, int64_t ld, int i0, int i1, cudaStream_t s) {
+    StepParams sp = step_params(var, o, slot);
+    ATTRICI_TRY(launch_fit_init(ws, sp, s));
+    int running = 0;
+    ATTRICI_CUDA_CHECK(cudaMemcpyAsync(&running, ws.n_running, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ATTRICI_CUDA_CHECK(cudaStreamSynchronize(s));
+    const bool profile = o.profile != 0;
+    std::vector<cudaEvent_t> ev;
+    // a cell may spend passes on rejected trial points: the cap counts passes, not accepted steps
+    for (int it = 0; running > 0 && it < o.max_pass; ++it) {
+        if (profile) {
+            cudaEvent_t e0, e1;
+            ATTRICI_CUDA_CHECK(cudaEventCreate(&e0));
+            ATTRICI_CUDA_CHECK(cudaEventCreate(&e1));
+            ev.push_back(e0);
+            ev.push_back(e1);
+            g_profile.cell_days += (double)running * (double)(i1 - i0);
+            ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
+        }
+        ATTRICI_TRY(launch_pass(ws, sp.term, o.use_fp64 != 0, true, y_scaled, ld, i0, i1, ws.status, s));
+        if (profile) ATTRICI_CUDA_CHECK(cudaEventRecord(ev.back(), s));
+        ATTRICI_TRY(launch_fit_step(ws, sp, s));
+        ATTRICI_CUDA_CHECK(cudaMemcpyAsync(&running, ws.n_running, sizeof(int), cudaMemcpyDeviceToHost, s));
+        ATTRICI_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    for (size_t k = 0; k + 1 < ev.size(); k += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) {
+            g_profile.pass_ms += ms;
+            g_profile.launches += 1;
+        }
+        cudaEventDestroy(ev[k]);
+        cudaEventDestroy(ev[k + 1]);
+    }
+    // log posterior of the accepted point in FP64 (model_scipy.py:525: trace["logp"] = -res.fun)
+    ATTRICI_TRY(launch_fit_final_point(ws, sp, s));
+    ATTRICI_TRY(launch_pass(ws, sp.term, true, false, y_scaled, ld, i0, i1, nullptr, s));
+    sp.fp64 = 1;
+    ATTRICI_TRY(launch_fit_store(ws, sp, s));
+    return 0;
+}
+
+}  // namespace
+}  // namespace attrici
+
+using namespace attrici;
+
+extern "C" {
+
+const char* attrici_last_error(void) { return g_error; }
+
+int attrici_abi_version(void) { return ATTRICI_ABI_VERSION; }
+
+int attrici_num_params(int family, int modes) {
+    if (!valid_family(family) || modes < 1 || modes > ATTRICI_MAX_MODES) {
+        set_error("bad family %d / modes %d", family, modes);
+        return ATTRICI_EINVAL;
+    }
+    return family_num_params(family, modes);
+}
+
+long long attrici_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int attrici_fit_profile(int reset, double* pass_ms, long long* pass_launches, double* cell_days) {
+    if (pass_ms) *pass_ms = g_profile.pass_ms;
+    if (pass_launches) *pass_launches = g_profile.launches;
+    if (cell_days) *cell_days = g_profile.cell_days;
+    if (reset) g_profile = FitProfile{0.0, 0, 0.0};
+    return 0;
+}
+
+int attrici_default_fit_options(attrici_fit_options_t* opts) {
+    if (!opts) { set_error("opts is null"); return ATTRICI_EINVAL; }
+    *opts = default_options();
+    return 0;
+}
+
+int attrici_workspace_bytes(int family, int T, int C, size_t* bytes) {
+    if (!bytes) { set_error("bytes is null"); return ATTRICI_EINVAL; }
+    if (!valid_family(family)) { set_error("unknown family %d", family); return ATTRICI_EINVAL; }
+    ATTRICI_TRY(check_shape(T, C, C));
+    Workspace ws;
+    *bytes = ws.layout(T, C, family, nullptr);
+    return 0;
+}
+
+int attrici_build_basis(void* workspace, size_t workspace_bytes, int family, const int32_t* days,
+                        const double* gmt, int T, int C, void* stream) {
+    if (!days || !gmt) { set_error("days / gmt is null"); return ATTRICI_EINVAL; }
+    ATTRICI_TRY(check_shape(T, C, C));
+    Workspace ws;
+    ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, family));
+    return launch_build_basis(ws, days, gmt, (cudaStream_t)stream);
+}
+
+int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                            const float* y, float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
+                            double* scaling, void* stream) {
+    ATTRICI_TRY(check_var(var));
+    ATTRICI_TRY(check_shape(T, C, ld));
+    ATTRICI_TRY(check_window(T, i0, i1));
+    if (!y || !y_scaled || !scaling) { set_error("y / y_scaled / scaling is null"); return ATTRICI_EINVAL; }
+    Workspace ws;
+    ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, var->family));
+    return launch_prep(ws, *var, y, y_scaled, ld, i0, i1, scaling, (cudaStream_t)stream);
+}
+
+int attrici_nll_grad(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                     const float* y_scaled, int64_t ld, int T, int C, int i0, int i1, int use_fp64,
+                     const double* theta, double* nll, double* grad, double* fisher, void* stream) {
+    ATTRICI_TRY(check_var(var));
+    ATTRICI_TRY(check_shape(T, C, ld));
+    ATTRICI_TRY(check_window(T, i0, i1));
+    if (!y_scaled || !theta || !nll) { set_error("y_scaled / theta / nll is null"); return ATTRICI_EINVAL; }
+    Workspace ws;
+    ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, var->family));
+    cudaStream_t s = (cudaStream_t)stream;
+    attrici_fit_options_t o = default_options();
+    o.use_fp64 = use_fp64;
+    const int nt = family_terms_count(var->family);
+    for (int slot = 0; slot < nt; ++slot) {
+        StepParams sp = step_params(*var, o, slot);
+        ATTRICI_TRY(launch_phase_only(ws, sp, s));
+        ATTRICI_TRY(launch_load_theta(ws, var->family, var->modes, slot, theta, s));
+        ATTRICI_TRY(launch_rotate(ws, sp, s));
+        ATTRICI_TRY(launch_pass(ws, sp.term, use_fp64 != 0, true, y_scaled, ld, i0, i1, nullptr, s));
+        // canonical results go through idle fit-state buffers: f_acc, g_acc, h_acc
+        ATTRICI_TRY(launch_assemble(ws, sp, ws.f_acc, ws.g_acc, fisher ? ws.h_acc : nullptr, s));
+        ATTRICI_TRY(launch_scatter_kat(ws, var->family, var->modes, slot, ws.f_acc, ws.g_acc,
+                                       fisher ? ws.h_acc : nullptr, nll, grad, fisher, slot > 0, s));
+    }
+    return 0;
+}
+
+int attrici_fit_batch(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                      const float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
+                      const attrici_fit_options_t* opts, double* params, double* logp, int32_t* status,
+                      int32_t* n_pass, void* stream) {
+    ATTRICI_TRY(check_var(var));
+    ATTRICI_TRY(check_shape(T, C, ld));
+    ATTRICI_TRY(check_window(T, i0, i1));
+    if (!y_scaled || !params) { set_error("y_scaled / params is null"); return ATTRICI_EINVAL; }
+    attrici_fit_options_t o = opts ? *opts : default_options();
+    if (o.max_pass < 1 || !(o.tol_pred >= 0.0) || !(o.lambda0 >= 0.0)) {
+        set_error("bad fit options (max_pass=%d tol_pred=%g lambda0=%g)", o.max_pass, o.tol_pred, o.lambda0);
+        return ATTRICI_EINVAL;
+    }
+    Workspace ws;
+    ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, var->family));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nt = family_terms_count(var->family);
+    for (int slot = 0; slot < nt; ++slot) ATTRICI_TRY(fit_term(ws, *var, o, slot, y_scaled, ld, i0, i1, s));
+    return launch_store_params(ws, var->family, var->modes, params, logp, status, n_pass, s);
+}
+
+int attrici_quantile_map(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                         const float* y, const float* y_scaled, int64_t ld, int T, int C,
+                         const double* params, const double* scaling, const uint32_t* seeds,
+                         double* cfact, uint8_t* replaced, double* cfact_scaled, int64_t ld_out,
+                         void* stream) {
+    ATTRICI_TRY(check_var(var));
+    ATTRICI_TRY(check_shape(T, C, ld));
+    if (ld_out < C) { set_error("ld_out %lld < C=%d", (long long)ld_out, C); return ATTRICI_EINVAL; }
+    if (!y || !y_scaled || !params || !scaling || !cfact) {
+        set_error("y / y_scaled / params / scaling / cfact is null");
+        return ATTRICI_EINVAL;
+    }
+    Workspace ws;
+    ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, var->family));
+    return launch_qmap(ws, *var, y, y_scaled, ld, params, scaling, seeds, cfact, replaced, cfact_scaled, ld_out,
+                       (cudaStream_t)stream);
+}
+
+int attrici_eval_parameter(void* workspace, size_t workspace_bytes, const attrici_variable_t* var, int T,
+                           int C, const double* params, int which, int counterfactual, double* out,
+                           int64_t ld_out, void* stream) {
+    ATTRICI_TRY(check_var(var));
+    ATTRICI_TRY(check_shape(T, C, ld_out));
+    const int n_par = var->family == ATTRICI_BERNOULLI_GAMMA ? 3 : 2;
+    if (which < 0 || which >= n_par) { set_error("parameter index %d outside 0..%d", which, n_par - 1); return ATTRICI_EINVAL; }
+    if (!params || !out) { set_error("params / out is null"); return ATTRICI_EINVAL; }
+    Workspace ws;
+    ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, var->family));
+    return launch_eval_parameter(ws, *var, params, which, counterfactual, out, ld_out, (cudaStream_t)stream);
+}
+
+int attrici_mt19937_uniform(const uint32_t* seeds, int C, int n, double* out, int64_t ld, void* stream) {
+    if (!seeds || !out) { set_error("seeds / out is null"); return ATTRICI_EINVAL; }
+    if (C < 1 || n < 1 || ld < C) { set_error("bad shape C=%d n=%d ld=%lld", C, n, (long long)ld); return ATTRICI_EINVAL; }
+    return launch_mt19937(seeds, C, n, out, ld, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// whole path with HOST buffers: slabs of cells, copies and kernels overlapped on two streams
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct SlabBuffers {
+    float* y; float* ys; double* cfact; uint8_t* replaced; double* params; double* logp; double* scaling;
+    int32_t* status; int32_t* npass; uint32_t* seeds; void* ws; size_t ws_bytes;
+};
+
+size_t slab_layout(int family, int T, int slab, int P, char* base, SlabBuffers* b) {
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        size_t o = off;
+        off = Workspace::align(off + n);
+        return base ? (void*)(base + o) : (void*)nullptr;
+    };
+    size_t ts = (size_t)T * slab;
+    SlabBuffers tmp;
+    tmp.y = (float*)take(4 * ts);
+    tmp.ys = (float*)take(4 * ts);
+    tmp.cfact = (double*)take(8 * ts);
+    tmp.replaced = (uint8_t*)take(ts);
+    tmp.params = (double*)take(8 * (size_t)slab * P);
+    tmp.logp = (double*)take(8 * (size_t)slab);
+    tmp.scaling = (double*)take(16 * (size_t)slab);
+    tmp.status = (int32_t*)take(4 * (size_t)slab);
+    tmp.npass = (int32_t*)take(4 * (size_t)slab);
+    tmp.seeds = (uint32_t*)take(4 * (size_t)slab);
+    Workspace w;
+    tmp.ws_bytes = w.layout(T, slab, family, nullptr);
+    tmp.ws = take(tmp.ws_bytes);
+    if (b) *b = tmp;
+    return off;
+}
+}  // namespace
+
+int attrici_detrend_host_scratch_bytes(int family, int T, int slab_cells, size_t* bytes) {
+    if (!bytes) { set_error("bytes is null"); return ATTRICI_EINVAL; }
+    if (!valid_family(family)) { set_error("unknown family %d", family); return ATTRICI_EINVAL; }
+    ATTRICI_TRY(check_shape(T, slab_cells, slab_cells));
+    const int P = family_num_params(family, ATTRICI_MAX_MODES);
+    // two slab buffer sets (double buffering) + the day / gmt vectors
+    *bytes = 2 * slab_layout(family, T, slab_cells, P, nullptr, nullptr) + Workspace::align(4 * (size_t)T) +
+             Workspace::align(8 * (size_t)T);
+    return 0;
+}
+
+int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_options_t* opts,
+                         const float* y_host, int64_t ld_host, int T, int C, int i0, int i1,
+                         const int32_t* days_host, const double* gmt_host, const uint32_t* seeds_host,
+                         double* cfact_host, int64_t ld_out_host, uint8_t* replaced_host,
+                         double* params_host, double* logp_host, double* scaling_host,
+                         int32_t* status_host, int32_t* n_pass_host,
+                         void* device_scratch, size_t device_scratch_bytes, int slab_cells) {
+    ATTRICI_TRY(check_var(var));
+    ATTRICI_TRY(check_shape(T, C, ld_host));
+    ATTRICI_TRY(check_window(T, i0, i1));
+    if (slab_cells < 1) { set_error("slab_cells must be >= 1"); return ATTRICI_EINVAL; }
+    if (!y_host || !days_host || !gmt_host || !cfact_host || !params_host) {
+        set_error("y / days / gmt / cfact / params host pointer is null");
+        return ATTRICI_EINVAL;
+    }
+    if (ld_out_host < C) { set_error("ld_out_host %lld < C=%d", (long long)ld_out_host, C); return ATTRICI_EINVAL; }
+    if (var->family == ATTRICI_BERNOULLI_GAMMA && !seeds_host) {
+        set_error("pr needs per-cell seeds (detrend.py:285)");
+        return ATTRICI_EINVAL;
+    }
+    if (slab_cells > C) slab_cells = C;
+    size_t need = 0;
+    ATTRICI_TRY(attrici_detrend_host_scratch_bytes(var->family, T, slab_cells, &need));
+    if (!device_scratch || device_scratch_bytes < need) {
+        set_error("device scratch too small: %zu given, %zu needed", device_scratch_bytes, need);
+        return ATTRICI_EWORKSPACE;
+    }
+    if (((uintptr_t)device_scratch & 255) != 0) { set_error("device scratch must be 256-byte aligned"); return ATTRICI_EINVAL; }
+    const int P = family_num_params(var->family, var->modes);
+    const int Pmax = family_num_params(var->family, ATTRICI_MAX_MODES);
+    char* base = (char*)device_scratch;
+    SlabBuffers buf[2];
+    size_t one = slab_layout(var->family, T, slab_cells, Pmax, base, &buf[0]);
+    slab_layout(var->family, T, slab_cells, Pmax, base + one, &buf[1]);
+    int32_t* d_days = (int32_t*)(base + 2 * one);
+    double* d_gmt = (double*)(base + 2 * one + Workspace::align(4 * (size_t)T));
+
+    cudaStream_t st[2];
+    ATTRICI_CUDA_CHECK(cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking));
+    ATTRICI_CUDA_CHECK(cudaStreamCreateWithFlags(&st[1], cudaStreamNonBlocking));
+    int rc = 0;
+    auto run = [&]() -> int {
+        ATTRICI_CUDA_CHECK(cudaMemcpyAsync(d_days, days_host, 4 * (size_t)T, cudaMemcpyHostToDevice, st[0]));
+        ATTRICI_CUDA_CHECK(cudaMemcpyAsync(d_gmt, gmt_host, 8 * (size_t)T, cudaMemcpyHostToDevice, st[0]));
+        ATTRICI_CUDA_CHECK(cudaStreamSynchronize(st[0]));
+        int n_slabs = (C + slab_cells - 1) / slab_cells;
+        // upload of slab k is issued before the (host-synchronising) fit of slab k-1 starts, on the
+        // stream that owns its buffer set: stream order serialises the reuse of that set, and the copy
+        // overlaps the other stream's kernels and downloads
+        auto upload = [&](int k) -> int {
+            const int bb = k & 1;
+            const int cc0 = k * slab_cells;
+            const int ncc = (C - cc0 < slab_cells) ? C - cc0 : slab_cells;
+            ATTRICI_CUDA_CHECK(cudaMemcpy2DAsync(buf[bb].y, 4 * (size_t)ncc, y_host + cc0, 4 * (size_t)ld_host,
+                                                 4 * (size_t)ncc, T, cudaMemcpyHostToDevice, st[bb]));
+            if (seeds_host)
+                ATTRICI_CUDA_CHECK(cudaMemcpyAsync(buf[bb].seeds, seeds_host + cc0, 4 * (size_t)ncc,
+                                                   cudaMemcpyHostToDevice, st[bb]));
+            return 0;
+        };
+        ATTRICI_TRY(upload(0));
+        for (int is = 0; is < n_slabs; ++is) {
+            const int b = is & 1;
+            cudaStream_t s = st[b];
+            SlabBuffers& B = buf[b];
+            const int c0 = is * slab_cells;
+            const int nc = (C - c0 < slab_cells) ? C - c0 : slab_cells;
+            if (is + 1 < n_slabs) ATTRICI_TRY(upload(is + 1));
+            ATTRICI_TRY(attrici_build_basis(B.ws, B.ws_bytes, var->family, d_days, d_gmt, T, nc, s));
+            ATTRICI_TRY(attrici_prep_scale_mask(B.ws, B.ws_bytes, var, B.y, B.ys, nc, T, nc, i0, i1, B.scaling, s));
+            ATTRICI_TRY(attrici_fit_batch(B.ws, B.ws_bytes, var, B.ys, nc, T, nc, i0, i1, opts, B.params, B.logp,
+                                          B.status, B.npass, s));
+            ATTRICI_TRY(attrici_quantile_map(B.ws, B.ws_bytes, var, B.y, B.ys, nc, T, nc, B.params, B.scaling,
+                                             seeds_host ? B.seeds : nullptr, B.cfact, replaced_host ? B.replaced : nullptr,
+                                             nullptr, nc, s));
+            ATTRICI_CUDA_CHECK(cudaMemcpy2DAsync(cfact_host + c0, 8 * (size_t)ld_out_host, B.cfact, 8 * (size_t)nc,
+                                                 8 * (size_t)nc, T, cudaMemcpyDeviceToHost, s));
+            if (replaced_host)
+                ATTRICI_CUDA_CHECK(cudaMemcpy2DAsync(replaced_host + c0, (size_t)ld_out_host, B.replaced, (size_t)nc,
+                                                     (size_t)nc, T, cudaMemcpyDeviceToHost, s));
+            ATTRICI_CUDA_CHECK(cudaMemcpyAsync(params_host + (size_t)c0 * P, B.params, 8 * (size_t)nc * P,
+                                               cudaMemcpyDeviceToHost, s));
+            if (logp_host)
+                ATTRICI_CUDA_CHECK(cudaMemcpyAsync(logp_host + c0, B.logp, 8 * (size_t)nc, cudaMemcpyDeviceToHost, s));
+            if (scaling_host)
+                ATTRICI_CUDA_CHECK(cudaMemcpyAsync(scaling_host + 2 * (size_t)c0, B.scaling, 16 * (size_t)nc,
+                                                   cudaMemcpyDeviceToHost, s));
+            if (status_host)
+                ATTRICI_CUDA_CHECK(cudaMemcpyAsync(status_host + c0, B.status, 4 * (size_t)nc, cudaMemcpyDeviceToHost, s));
+            if (n_pass_host)
+                ATTRICI_CUDA_CHECK(cudaMemcpyAsync(n_pass_host + c0, B.npass, 4 * (size_t)nc, cudaMemcpyDeviceToHost, s));
+        }
+        ATTRICI_CUDA_CHECK(cudaStreamSynchronize(st[0]));
+        ATTRICI_CUDA_CHECK(cudaStreamSynchronize(st[1]));
+        return 0;
+    };
+    rc = run();
+    if (rc != 0) { cudaStreamSynchronize(st[0]); cudaStreamSynchronize(st[1]); }
+    cudaStreamDestroy(st[0]);
+    cudaStreamDestroy(st[1]);
+    return rc;
+}
+
+}  // extern "C"

@@ -4,19 +4,20 @@
 
 namespace attrici {
 
-// one thread per day; columns {gmt, cos(k w t) k=1..8, sin(k w t) k=1..8, 0, 0, 0}
+// one thread per day; columns {gmt, cos(k w t) k=1..8, sin(k w t) k=1..8, tau, 0, 0}
 __global__ void build_basis_kernel(const int32_t* __restrict__ days, const double* __restrict__ gmt, int T,
                                    int T_pad, float* __restrict__ b32, double* __restrict__ b64) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T_pad) return;
-    double row[B64_STRIDE];
+    double row[B_STRIDE];
 #pragma unroll
-    for (int i = 0; i < B64_STRIDE; ++i) row[i] = 0.0;
+    for (int i = 0; i < B_STRIDE; ++i) row[i] = 0.0;
     if (t < T) {
         // util.py:102: (t - t.min()) / (365 d + 6 h); the phase origin of the shared basis is the
         // first day of the series, per-cell origins are handled by rotating coefficients (step.cu)
         double tau = (double)(days[t] - days[0]) / 365.25;
         row[0] = gmt[t];
+        row[B_TAU] = tau;
         const double two_pi = 6.283185307179586;  // 2 * np.pi
 #pragma unroll
         for (int k = 1; k <= NH; ++k) {
@@ -29,9 +30,9 @@ __global__ void build_basis_kernel(const int32_t* __restrict__ days, const doubl
         }
     }
 #pragma unroll
-    for (int i = 0; i < B64_STRIDE; ++i) {
-        b64[(size_t)t * B64_STRIDE + i] = row[i];
-        b32[(size_t)t * B32_STRIDE + i] = (float)row[i];
+    for (int i = 0; i < B_STRIDE; ++i) {
+        b64[(size_t)t * B_STRIDE + i] = row[i];
+        b32[(size_t)t * B_STRIDE + i] = (float)row[i];
     }
 }
 

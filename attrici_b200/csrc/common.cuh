@@ -3,44 +3,18 @@
 // Layout vocabulary
 //   series   : [T x ld] time-major, cell-minor (a warp reads 32 neighbouring cells of one day
 //              = one 128-byte line)
-//   basis32  : [T][20] float  {gmt, cos(k w t) k=1..8, sin(k w t) k=1..8, pad x3}  - moments need
+//   basis32  : [T][20] float  {gmt, cos(k w t) k=1..8, sin(k w t) k=1..8, tau, pad x2}  - moments need
 //              harmonics up to 2*modes because products of two Fourier columns are Fourier columns
-//   basis64  : [T][20] double, same columns                                        - parameter evaluation, FP64 passes
-//   per-cell state arrays are [field][C] so that thread = cell accesses coalesce.
+//   basis64  : [T][20] double, same columns                                  - parameter evaluation, FP64 passes
+//   per-cell state arrays are [field][Cp] so that thread = cell accesses coalesce.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
 #include "../../include/attrici_b200.h"
+#include "layout.cuh"
 
 namespace attrici {
-
-constexpr int MAXM = ATTRICI_MAX_MODES;      // 4 Fourier modes
-constexpr int NA = 2 + 4 * MAXM;             // 18 coefficients of a GMT-dependent parameter
-constexpr int NB = 1 + 2 * MAXM;             // 9 coefficients of an independent parameter
-constexpr int NP = NA + NB;                  // 27 coefficients of one likelihood term (canonical layout)
-constexpr int NTRI = NP * (NP + 1) / 2;      // 378 packed lower-triangular entries
-constexpr int NH = 2 * MAXM;                 // 8 harmonics carried for the moments
-constexpr int NTRIG = 1 + 2 * NH;            // 17 trig columns {1, cos 1..8, sin 1..8}
-constexpr int B32_STRIDE = 20;               // floats per day in basis32
-constexpr int B64_STRIDE = 20;               // doubles per day in basis64 (same layout as basis32)
-
-// accumulator layout of one likelihood pass (per cell)
-constexpr int ACC_AA = 0;                    // 3 powers of gmt x 17 trig
-constexpr int ACC_AB = ACC_AA + 3 * NTRIG;   // 2 x 17
-constexpr int ACC_BB = ACC_AB + 2 * NTRIG;   // 17
-constexpr int ACC_GA = ACC_BB + NTRIG;       // 2 powers x {1, cos 1..4, sin 1..4}
-constexpr int ACC_GB = ACC_GA + 2 * NB;      // 9
-constexpr int NACC = ACC_GB + NB;            // 129
-
-constexpr int PASS_WARPS = 4;                // warps per CTA of the pass kernel
-constexpr int PASS_CELLS = 32 * PASS_WARPS;  // cells per CTA
-constexpr int PASS_TILE = 64;                // days per shared-memory basis tile
-constexpr int MAX_CHUNKS = 32;
-
-// likelihood term kinds (a Bernoulli-Gamma fit is a Bernoulli term plus a Gamma term that share
-// no coefficient: model_scipy.py:433-446)
-enum Term : int { T_NORMAL = 0, T_GAMMA = 1, T_BETA = 2, T_WEIBULL = 3, T_BERNOULLI = 4 };
 
 struct Chunking {
     int n_chunks;
@@ -70,48 +44,50 @@ struct Workspace {
     Chunking ck;
     char* base;
     size_t bytes;
-    // offsets
     float* basis32;
     double* basis64;
     // prep results
-    float* cmin;       // [C]
-    float* cmax;       // [C]
-    double* psum;      // [2][C] pr: sum x, sum ln x over wet days
-    int* pcnt;         // [C]    pr: wet days
+    float* cmin;       // [Cp]
+    float* cscale;     // [Cp]
     // start values / phase origins of the fit window, per term slot (0: main or bernoulli, 1: gamma of pr)
-    double* st_cnt;    // [2][C]
-    double* st_sum;    // [2][C]
-    double* st_sq;     // [2][C]
-    double* st_ln;     // [2][C]  sum of ln y (gamma / weibull start)
-    int* st_first;     // [2][C]  first used day index of the fit window (-1 = none)
+    double* st_cnt;    // [2][Cp]
+    double* st_sum;    // [2][Cp]
+    double* st_sq;     // [2][Cp]
+    double* st_ln;     // [2][Cp]  sum of ln y (gamma / weibull start)
+    int* st_first;     // [2][Cp]  first used day index of the fit window (-1 = none)
     // fit state
-    double* th_acc;    // [NP][C]
-    double* th_trial;  // [NP][C] cell frame
-    double* th_pass;   // [NP][C] shared frame (what the pass kernel reads)
-    double* g_acc;     // [NP][C]
-    double* h_acc;     // [NTRI][C]
-    double* h_wrk;     // [NTRI][C]
-    double* f_acc;     // [C]
-    double* pred;      // [C]
-    double* lam;       // [C]
-    double* rot;       // [2*NH][C] cos/sin of the per-cell phase offset, harmonics 1..8
-    int* status;       // [C]
-    int* npass;        // [C]
+    double* th_acc;    // [NP][Cp] accepted point, cell frame
+    double* th_trial;  // [NP][Cp] trial point, cell frame
+    double* th_pass;   // [NP][Cp] trial point, shared frame (what the pass kernel reads)
+    double* g_acc;     // [NP][Cp]
+    double* h_acc;     // [NTRI][Cp]
+    double* h_wrk;     // [NTRI][Cp]
+    double* f_acc;     // [Cp]
+    double* pred;      // [Cp]
+    double* lam;       // [Cp]
+    double* rot;       // [2*NH][Cp] cos/sin of the per-cell phase offset, harmonics 1..8
+    int* status;       // [Cp]
+    int* npass;        // [Cp]
     int* n_running;    // [1] (+pad)
-    double* part_nll;  // [MAX_CHUNKS][C]
-    void* part_acc;    // [n_chunks][NACC][C] float or double
-    // params staging for two-term fits: canonical per-term coefficients
-    double* th_out;    // [2][NP][C]
-    double* logp_part; // [2][C]
+    double* part_nll;  // [MAX_CHUNKS][Cp]
+    void* part_acc;    // [n_chunks][NACC][Cp] float or double
+    // results of the (up to) two likelihood terms, canonical layout, cell frame
+    double* th_out;    // [2][NP][Cp]
+    double* logp_part; // [2][Cp]
+    int* status_part;  // [2][Cp]
+    int* npass_part;   // [2][Cp]
+    double* uniforms;  // [T][Cp] MT19937 doubles (pr only, else nullptr)
+    int used_chunks;   // chunks written by the last pass
 
     static size_t align(size_t x) { return (x + 255) & ~size_t(255); }
 
-    // returns total bytes; if base != nullptr also sets the pointers
-    size_t layout(int T_, int C_, void* base_) {
+    // returns total bytes; if base_ != nullptr also sets the pointers
+    size_t layout(int T_, int C_, int family, void* base_) {
         T = T_;
         C = C_;
         Cp = round_up(C_, 32);
         ck = choose_chunks(T_, C_);
+        used_chunks = ck.n_chunks;
         base = (char*)base_;
         size_t off = 0;
         auto take = [&](size_t n) {
@@ -120,12 +96,10 @@ struct Workspace {
             return base ? (void*)(base + o) : (void*)nullptr;
         };
         size_t c = (size_t)Cp;
-        basis32 = (float*)take(sizeof(float) * B32_STRIDE * (size_t)(T + 2 * PASS_TILE));
-        basis64 = (double*)take(sizeof(double) * B64_STRIDE * (size_t)(T + 2 * PASS_TILE));
+        basis32 = (float*)take(sizeof(float) * B_STRIDE * (size_t)(T + 2 * PASS_TILE));
+        basis64 = (double*)take(sizeof(double) * B_STRIDE * (size_t)(T + 2 * PASS_TILE));
         cmin = (float*)take(4 * c);
-        cmax = (float*)take(4 * c);
-        psum = (double*)take(8 * 2 * c);
-        pcnt = (int*)take(4 * c);
+        cscale = (float*)take(4 * c);
         st_cnt = (double*)take(8 * 2 * c);
         st_sum = (double*)take(8 * 2 * c);
         st_sq = (double*)take(8 * 2 * c);
@@ -148,12 +122,16 @@ struct Workspace {
         part_acc = take(8 * (size_t)ck.n_chunks * NACC * c);
         th_out = (double*)take(8 * 2 * NP * c);
         logp_part = (double*)take(8 * 2 * c);
+        status_part = (int*)take(4 * 2 * c);
+        npass_part = (int*)take(4 * 2 * c);
+        uniforms = (family == ATTRICI_BERNOULLI_GAMMA) ? (double*)take(8 * (size_t)T * c) : nullptr;
         bytes = off;
         return off;
     }
 };
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define ATTRICI_CUDA_CHECK(expr)                                                             \
     do {                                                                                     \
@@ -167,6 +145,7 @@ void set_error(const char* fmt, ...);
 
 #define ATTRICI_LAUNCH_CHECK()                                                               \
     do {                                                                                     \
+        ::attrici::count_launch();                                                           \
         cudaError_t _e = cudaGetLastError();                                                 \
         if (_e != cudaSuccess) {                                                             \
             ::attrici::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
@@ -175,21 +154,28 @@ void set_error(const char* fmt, ...);
         }                                                                                    \
     } while (0)
 
+#define ATTRICI_TRY(expr)             \
+    do {                              \
+        int _rc = (expr);             \
+        if (_rc != 0) return _rc;     \
+    } while (0)
+
 // ---- kernel launchers (one per .cu file) -------------------------------------------------
 int launch_build_basis(Workspace& ws, const int32_t* days, const double* gmt, cudaStream_t s);
 
 int launch_prep(Workspace& ws, const attrici_variable_t& var, const float* y, float* y_scaled, int64_t ld,
                 int i0, int i1, double* scaling, cudaStream_t s);
 
-// one likelihood pass over the fit window at ws.th_pass; fills ws.part_nll / ws.part_acc
+// one likelihood pass over the fit window [i0, i1) at ws.th_pass; fills ws.part_nll / ws.part_acc.
+// status != nullptr: only cells whose status is RUNNING are evaluated.
 int launch_pass(Workspace& ws, int term, bool fp64, bool with_moments, const float* y_scaled, int64_t ld,
-                int i0, int i1, cudaStream_t s);
+                int i0, int i1, const int* status, cudaStream_t s);
 
 struct StepParams {
     int term;
     int modes;
     int slot;        // which start-value / phase-origin slot of the workspace
-    int fp64;
+    int fp64;        // partial moments of the last pass are double
     int max_pass;
     double tol_pred;
     double lambda0;
@@ -197,10 +183,24 @@ struct StepParams {
 };
 int launch_fit_init(Workspace& ws, const StepParams& sp, cudaStream_t s);
 int launch_fit_step(Workspace& ws, const StepParams& sp, cudaStream_t s);
-// reduce partials of a pass at th_pass into nll/grad/fisher in the cell frame (KAT entry, final logp)
-int launch_assemble(Workspace& ws, const StepParams& sp, double* nll, double* grad, double* fisher,
-                    int p_stride, cudaStream_t s);
-int launch_load_theta(Workspace& ws, const StepParams& sp, const double* theta_canon, cudaStream_t s);
+// th_trial := th_acc, rotated into th_pass (before the final FP64 evaluation)
+int launch_fit_final_point(Workspace& ws, const StepParams& sp, cudaStream_t s);
+// after an FP64 pass without moments at th_acc: store coefficients / logp / status of this term slot
+int launch_fit_store(Workspace& ws, const StepParams& sp, cudaStream_t s);
+// reduce the partials of a pass at th_trial into nll / grad / fisher in the cell frame (KAT entry)
+int launch_assemble(Workspace& ws, const StepParams& sp, double* nll, double* grad, double* fisher, cudaStream_t s);
+// phase offsets only (KAT entry: no fit_init)
+int launch_phase_only(Workspace& ws, const StepParams& sp, cudaStream_t s);
+int launch_rotate(Workspace& ws, const StepParams& sp, cudaStream_t s);
+
+// reference theta layout <-> canonical per-term layout
+int launch_load_theta(Workspace& ws, int family, int modes, int slot, const double* theta, cudaStream_t s);
+int launch_store_params(Workspace& ws, int family, int modes, double* params, double* logp, int32_t* status,
+                        int32_t* n_pass, cudaStream_t s);
+// scatter canonical grad / packed fisher of one term slot into the reference layout
+int launch_scatter_kat(Workspace& ws, int family, int modes, int slot, const double* nll_c, const double* grad_c,
+                       const double* fisher_c, double* nll, double* grad, double* fisher, int accumulate,
+                       cudaStream_t s);
 
 int launch_qmap(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled,
                 int64_t ld, const double* params, const double* scaling, const uint32_t* seeds, double* cfact,

@@ -17,7 +17,7 @@
 // 27 x 27 information matrix needs only 17 trig moments per (weight, power of gmt) instead of all
 // 378 column products: 102 + 27 accumulators per cell.
 #include "common.cuh"
-#include "families.cuh"
+#include "pass_impl.cuh"
 
 namespace attrici {
 
@@ -42,12 +42,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
-
-template <typename R> struct Row {
-    R g;        // gmt
-    R c[NH];    // cos k
-    R s[NH];    // sin k
-};
 
 template <typename R> __device__ __forceinline__ Row<R> load_row(const R* p);
 template <> __device__ __forceinline__ Row<float> load_row<float>(const float* p) {
@@ -77,21 +71,11 @@ template <> __device__ __forceinline__ Row<double> load_row<double>(const double
     return r;
 }
 
-// acc[0] += w, acc[k] += w cos_k, acc[NH+k] += w sin_k  for k = 1..K
-template <int K, typename R> __device__ __forceinline__ void accumulate(R* acc, R w, const Row<R>& b) {
-    acc[0] += w;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        acc[1 + k] = fma(w, b.c[k], acc[1 + k]);
-        acc[1 + K + k] = fma(w, b.s[k], acc[1 + K + k]);
-    }
-}
-
 template <int KIND, typename R, bool MOMENTS>
 __global__ void __launch_bounds__(PASS_CELLS, 2) pass_kernel(PassArgs a) {
     constexpr bool HAS_B = (KIND != K_BERNOULLI);
     constexpr bool HAS_AB = (KIND == K_WEIBULL || KIND == K_BETA);
-    __shared__ __align__(16) R tile[2][PASS_TILE * B32_STRIDE];
+    __shared__ __align__(16) R tile[2][PASS_TILE * B_STRIDE];
 
     const int cell = blockIdx.x * PASS_CELLS + threadIdx.x;
     const int chunk = blockIdx.y;
@@ -109,33 +93,24 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) pass_kernel(PassArgs a) {
 #pragma unroll
     for (int i = 0; i < NB; ++i) thB[i] = (active && HAS_B) ? (R)a.th_pass[(size_t)(NA + i) * a.Cp + cell] : R(0);
 
-    R accAA[3 * NTRIG], accAB[2 * NTRIG], accBB[NTRIG], accGA[2 * NB], accGB[NB];
-    if (MOMENTS) {
-#pragma unroll
-        for (int i = 0; i < 3 * NTRIG; ++i) accAA[i] = R(0);
-#pragma unroll
-        for (int i = 0; i < 2 * NTRIG; ++i) accAB[i] = R(0);
-#pragma unroll
-        for (int i = 0; i < NTRIG; ++i) accBB[i] = R(0);
-#pragma unroll
-        for (int i = 0; i < 2 * NB; ++i) accGA[i] = R(0);
-#pragma unroll
-        for (int i = 0; i < NB; ++i) accGB[i] = R(0);
-    }
+    PassAcc<R> acc;
+    acc.clear();
     double nll = 0.0;
 
     const R* basis = reinterpret_cast<const R*>(a.basis);
     const int n_tiles = (t_end - t_begin + PASS_TILE - 1) / PASS_TILE;
-    constexpr int VEC_PER_TILE = PASS_TILE * B32_STRIDE * (int)sizeof(R) / 16;
+    constexpr int VEC_PER_TILE = PASS_TILE * B_STRIDE * (int)sizeof(R) / 16;
     auto issue_tile = [&](int it) {
-        const char* src = reinterpret_cast<const char*>(basis + (size_t)(t_begin + it * PASS_TILE) * B32_STRIDE);
+        const char* src = reinterpret_cast<const char*>(basis + (size_t)(t_begin + it * PASS_TILE) * B_STRIDE);
         char* dst = reinterpret_cast<char*>(tile[it & 1]);
         for (int v = threadIdx.x; v < VEC_PER_TILE; v += PASS_CELLS) cp_async16(dst + 16 * v, src + 16 * v);
         cp_async_commit();
     };
     issue_tile(0);
 
-    const float* yp = a.ys + (size_t)t_begin * a.ld + cell;
+    // cells beyond C read a clamped (valid) column and are masked by `active`
+    const int col = min(cell, a.C - 1);
+    const float* yp = a.ys + (size_t)t_begin * a.ld + col;
     const float qnan = __int_as_float(0x7fc00000);
     constexpr int G = 4;  // days per prefetch group
     float ycur[G], ynext[G];
@@ -164,53 +139,9 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) pass_kernel(PassArgs a) {
 #pragma unroll
                 for (int j = 0; j < G; ++j) {
                     if (d0 + j < n_days) {
-                        const Row<R> b = load_row<R>(tb + (d0 + j) * B32_STRIDE);
-                        const float yf = ycur[j];
-                        bool valid;
-                        R y;
-                        if (KIND == K_BERNOULLI) {
-                            // every day of the window counts; NaN (dry) is the event (model_scipy.py:444)
-                            valid = active;
-                            y = isnan(yf) ? R(1) : R(0);
-                        } else {
-                            valid = active && !isnan(yf);
-                            y = valid ? (R)yf : R(0.5);
-                        }
-                        R etaA = fma(thA[1], b.g, thA[0]);
-                        R etaB = thB[0];
-#pragma unroll
-                        for (int k = 0; k < MAXM; ++k) {
-                            R ck = fma(b.g, thA[2 + 2 * MAXM + k], thA[2 + k]);
-                            R sk = fma(b.g, thA[2 + 3 * MAXM + k], thA[2 + MAXM + k]);
-                            etaA = fma(ck, b.c[k], etaA);
-                            etaA = fma(sk, b.s[k], etaA);
-                            if (HAS_B) {
-                                etaB = fma(thB[1 + k], b.c[k], etaB);
-                                etaB = fma(thB[1 + MAXM + k], b.s[k], etaB);
-                            }
-                        }
-                        DayTerms<R> dt = family_day_t<KIND, R>(y, etaA, etaB);
-                        if (!valid) { dt.nll = R(0); dt.rA = R(0); dt.rB = R(0); dt.wAA = R(0); dt.wAB = R(0); dt.wBB = R(0); }
-                        nll += (double)dt.nll;
-                        if (MOMENTS) {
-                            R w = dt.wAA;
-                            accumulate<NH, R>(accAA, w, b);
-                            w *= b.g;
-                            accumulate<NH, R>(accAA + NTRIG, w, b);
-                            w *= b.g;
-                            accumulate<NH, R>(accAA + 2 * NTRIG, w, b);
-                            if (HAS_AB) {
-                                w = dt.wAB;
-                                accumulate<NH, R>(accAB, w, b);
-                                accumulate<NH, R>(accAB + NTRIG, w * b.g, b);
-                            }
-                            if (HAS_B) {
-                                accumulate<NH, R>(accBB, dt.wBB, b);
-                                accumulate<MAXM, R>(accGB, dt.rB, b);
-                            }
-                            accumulate<MAXM, R>(accGA, dt.rA, b);
-                            accumulate<MAXM, R>(accGA + NB, dt.rA * b.g, b);
-                        }
+                        const Row<R> b = load_row<R>(tb + (d0 + j) * B_STRIDE);
+                        R d = pass_day<KIND, R, MOMENTS>(ycur[j], active, thA, thB, b, acc);
+                        nll += (double)d;
                     }
                 }
 #pragma unroll
@@ -225,15 +156,15 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) pass_kernel(PassArgs a) {
         if (MOMENTS) {
             R* out = reinterpret_cast<R*>(a.part_acc) + (size_t)chunk * NACC * a.Cp + cell;
 #pragma unroll
-            for (int i = 0; i < 3 * NTRIG; ++i) out[(size_t)(ACC_AA + i) * a.Cp] = accAA[i];
+            for (int i = 0; i < 3 * NTRIG; ++i) out[(size_t)(ACC_AA + i) * a.Cp] = acc.AA[i];
 #pragma unroll
-            for (int i = 0; i < 2 * NTRIG; ++i) out[(size_t)(ACC_AB + i) * a.Cp] = HAS_AB ? accAB[i] : R(0);
+            for (int i = 0; i < 2 * NTRIG; ++i) out[(size_t)(ACC_AB + i) * a.Cp] = HAS_AB ? acc.AB[i] : R(0);
 #pragma unroll
-            for (int i = 0; i < NTRIG; ++i) out[(size_t)(ACC_BB + i) * a.Cp] = HAS_B ? accBB[i] : R(0);
+            for (int i = 0; i < NTRIG; ++i) out[(size_t)(ACC_BB + i) * a.Cp] = HAS_B ? acc.BB[i] : R(0);
 #pragma unroll
-            for (int i = 0; i < 2 * NB; ++i) out[(size_t)(ACC_GA + i) * a.Cp] = accGA[i];
+            for (int i = 0; i < 2 * NB; ++i) out[(size_t)(ACC_GA + i) * a.Cp] = acc.GA[i];
 #pragma unroll
-            for (int i = 0; i < NB; ++i) out[(size_t)(ACC_GB + i) * a.Cp] = HAS_B ? accGB[i] : R(0);
+            for (int i = 0; i < NB; ++i) out[(size_t)(ACC_GB + i) * a.Cp] = HAS_B ? acc.GB[i] : R(0);
         }
     }
 }
@@ -252,6 +183,7 @@ template <int KIND> static int launch_kind(const PassArgs& a, dim3 grid, bool fp
 
 int launch_pass(Workspace& ws, int term, bool fp64, bool with_moments, const float* y_scaled, int64_t ld,
                 int i0, int i1, const int* status, cudaStream_t s) {
+    if (i1 <= i0) { set_error("empty fit window [%d, %d)", i0, i1); return ATTRICI_EINVAL; }
     PassArgs a;
     a.ys = y_scaled;
     a.ld = ld;
@@ -263,15 +195,13 @@ int launch_pass(Workspace& ws, int term, bool fp64, bool with_moments, const flo
     int len = round_up((i1 - i0 + ws.ck.n_chunks - 1) / ws.ck.n_chunks, PASS_TILE);
     if (len < PASS_TILE) len = PASS_TILE;
     a.chunk_len = len;
+    ws.used_chunks = (i1 - i0 + len - 1) / len;
     a.basis = fp64 ? (const void*)ws.basis64 : (const void*)ws.basis32;
     a.th_pass = ws.th_pass;
     a.status = status;
     a.part_nll = ws.part_nll;
     a.part_acc = ws.part_acc;
-    dim3 grid((ws.C + PASS_CELLS - 1) / PASS_CELLS, ws.ck.n_chunks);
-    // chunks beyond the window return immediately but must leave zeros: clear partial nll first
-    cudaError_t e = cudaMemsetAsync(ws.part_nll, 0, sizeof(double) * (size_t)MAX_CHUNKS * ws.Cp, s);
-    if (e != cudaSuccess) { set_error("memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    dim3 grid((ws.C + PASS_CELLS - 1) / PASS_CELLS, ws.used_chunks);
     switch (term) {
         case T_NORMAL: return launch_kind<K_NORMAL>(a, grid, fp64, with_moments, s);
         case T_GAMMA: return launch_kind<K_GAMMA>(a, grid, fp64, with_moments, s);

@@ -1,0 +1,220 @@
+// Per-day quantile map: factual / counterfactual distribution parameters, cdf -> inverse cdf,
+// rescale and NaN/Inf replacement, all in FP64 like the reference.
+// Replaces ModelScipy.estimate_distribution x2 (attrici/estimation/model_scipy.py:547-570 with the real
+// predictor and with predictor * 0, attrici/detrend.py:362-370), attrici/distributions.py:81-216,
+// Variable.quantile_mapping and its overrides (attrici/variables.py:287-303, 422-480, 645-653, 691-698),
+// rescale (variables.py:71-89, 114-131, 483-486) and the replacement of attrici/detrend.py:397-411.
+// __host__ __device__: tests/hostmath runs the identical code on the CPU against scipy.
+#pragma once
+#include "layout.cuh"
+
+namespace attrici {
+
+// coefficients of one cell in the canonical layout, per term slot (cell frame = what the reference
+// stores in trace["params"]; evaluation uses the series origin)
+struct CellCoef {
+    double a[2][NA];
+    double b[NB];      // the independent parameter (sigma / nu / phi / alpha)
+};
+
+struct DayParams {
+    double a_ref[2], a_cf[2];   // linear predictors of the dependent parameters, factual / counterfactual
+    double b;                   // linear predictor of the independent parameter
+};
+
+// row: basis64 row {gmt, cos 1..8, sin 1..8, ...}
+ATTRICI_HD void day_predictors(const CellCoef& c, const double* row, int n_dep, DayParams& d) {
+    const double g = row[0];
+    for (int s = 0; s < n_dep; ++s) {
+        double base = c.a[s][0], trend = c.a[s][1];
+#pragma unroll
+        for (int k = 0; k < MAXM; ++k) {
+            double ck = row[1 + k], sk = row[1 + NH + k];
+            base = fma(c.a[s][2 + k], ck, base);
+            base = fma(c.a[s][2 + MAXM + k], sk, base);
+            trend = fma(c.a[s][2 + 2 * MAXM + k], ck, trend);
+            trend = fma(c.a[s][2 + 3 * MAXM + k], sk, trend);
+        }
+        d.a_cf[s] = base;                 // predictor == 0 (detrend.py:366-370)
+        d.a_ref[s] = fma(g, trend, base);
+    }
+    double eb = c.b[0];
+#pragma unroll
+    for (int k = 0; k < MAXM; ++k) {
+        eb = fma(c.b[1 + k], row[1 + k], eb);
+        eb = fma(c.b[1 + MAXM + k], row[1 + NH + k], eb);
+    }
+    d.b = eb;
+}
+
+ATTRICI_HD double invlogit(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// scipy.stats.gamma.cdf(y, a, scale) / ppf(q, a, scale)
+ATTRICI_HD double gamma_cdf(double y, double a, double scale) {
+    if (isnan(y) || isnan(a) || isnan(scale) || !(a > 0.0) || !(scale > 0.0)) return NAN;
+    double x = y / scale;
+    if (x <= 0.0) return 0.0;
+    return gamma_p(a, x);
+}
+ATTRICI_HD double gamma_ppf(double q, double a, double scale) {
+    if (isnan(q) || isnan(a) || isnan(scale) || !(a > 0.0) || !(scale > 0.0) || q < 0.0 || q > 1.0) return NAN;
+    return gamma_p_inv(a, q) * scale;
+}
+
+// distribution parameters of the family (the values `report_variables` would store)
+struct DistPar {
+    double p0, p1, p2;        // in the family's own order (distributions.py dataclass fields)
+};
+
+// family parameters from the linear predictors: links of attrici/variables.py create_model tables
+ATTRICI_HD void family_params(int family, const DayParams& d, DistPar& ref, DistPar& cf) {
+    switch (family) {
+        case ATTRICI_NORMAL: {  // mu (identity), sigma (exp)
+            double sg = exp(d.b);
+            ref.p0 = d.a_ref[0]; cf.p0 = d.a_cf[0]; ref.p1 = cf.p1 = sg; ref.p2 = cf.p2 = 0.0;
+        } break;
+        case ATTRICI_GAMMA: {  // mu (exp), nu (exp)
+            double nu = exp(d.b);
+            ref.p0 = exp(d.a_ref[0]); cf.p0 = exp(d.a_cf[0]); ref.p1 = cf.p1 = nu; ref.p2 = cf.p2 = 0.0;
+        } break;
+        case ATTRICI_BETA: {  // mu (invlogit), phi (exp)
+            double phi = exp(d.b);
+            ref.p0 = invlogit(d.a_ref[0]); cf.p0 = invlogit(d.a_cf[0]); ref.p1 = cf.p1 = phi; ref.p2 = cf.p2 = 0.0;
+        } break;
+        case ATTRICI_WEIBULL: {  // alpha (exp, independent), beta (exp, dependent)
+            double al = exp(d.b);
+            ref.p0 = cf.p0 = al; ref.p1 = exp(d.a_ref[0]); cf.p1 = exp(d.a_cf[0]); ref.p2 = cf.p2 = 0.0;
+        } break;
+        default: {  // bernoulli-gamma: p (invlogit), mu (exp), nu (exp)
+            double nu = exp(d.b);
+            ref.p0 = invlogit(d.a_ref[0]); cf.p0 = invlogit(d.a_cf[0]);
+            ref.p1 = exp(d.a_ref[1]); cf.p1 = exp(d.a_cf[1]);
+            ref.p2 = cf.p2 = nu;
+        } break;
+    }
+}
+
+// cdf under the factual parameters, inverse cdf under the counterfactual ones (distributions.py:81-216)
+ATTRICI_HD double dist_cdf(int family, const DistPar& p, double y) {
+    switch (family) {
+        case ATTRICI_NORMAL: return ndtr((y - p.p0) / p.p1);
+        case ATTRICI_GAMMA: { double a = p.p1 * p.p1; return gamma_cdf(y, a, p.p0 / a); }
+        case ATTRICI_BETA: {
+            if (isnan(y)) return NAN;
+            double A = p.p0 * p.p1, B = (1.0 - p.p0) * p.p1;
+            if (y <= 0.0) return 0.0;
+            if (y >= 1.0) return 1.0;
+            return beta_i(A, B, y);
+        }
+        case ATTRICI_WEIBULL: {
+            if (isnan(y)) return NAN;
+            if (y <= 0.0) return 0.0;
+            return -expm1(-pow(y / p.p1, p.p0));
+        }
+        default: { double a = p.p2 * p.p2; return p.p0 + (1.0 - p.p0) * gamma_cdf(y, a, p.p1 / a); }
+    }
+}
+
+ATTRICI_HD double dist_invcdf(int family, const DistPar& p, double q) {
+    switch (family) {
+        case ATTRICI_NORMAL: return ndtri(q) * p.p1 + p.p0;
+        case ATTRICI_GAMMA: { double a = p.p1 * p.p1; return gamma_ppf(q, a, p.p0 / a); }
+        case ATTRICI_BETA: {
+            double A = p.p0 * p.p1, B = (1.0 - p.p0) * p.p1;
+            return beta_i_inv(A, B, q);
+        }
+        case ATTRICI_WEIBULL: {
+            if (isnan(q) || q < 0.0 || q > 1.0) return NAN;
+            return pow(-log1p(-q), 1.0 / p.p0) * p.p1;
+        }
+        default: { double a = p.p2 * p.p2; return gamma_ppf((q - p.p0) / (1.0 - p.p0), a, p.p1 / a); }
+    }
+}
+
+struct QmapOut {
+    double cfact_scaled, cfact;
+    int replaced;
+};
+
+// one day of one cell.  y: original observation (after the in-place masks of hurs / tasrange / sfcWind),
+// ys: scaled observation, u: the day's MT19937 uniform (pr only)
+ATTRICI_HD QmapOut qmap_day(int family, int scaling, int post_rule, float y, float ys, const DistPar& ref,
+                            const DistPar& cf, double datamin, double scale, double u) {
+    QmapOut o;
+    double cs;
+    if (family != ATTRICI_BERNOULLI_GAMMA) {
+        // variables.py:303: invcdf_cf(cdf_ref(y_scaled)); NaN in -> NaN out
+        double q = dist_cdf(family, ref, (double)ys);
+        cs = dist_invcdf(family, cf, q);
+        if (post_rule == ATTRICI_POST_LE0_NAN) { if (cs <= 0.0) cs = NAN; }               // Rsds, :697
+        else if (post_rule == ATTRICI_POST_OUTSIDE01_NAN) { if (cs >= 1.0 || cs <= 0.0) cs = NAN; }  // Tasskew
+    } else {
+        // Pr.quantile_mapping, variables.py:422-480
+        const bool dry = (ys != ys);
+        const double y0 = dry ? 0.0 : (double)ys;
+        const double q = dist_cdf(family, ref, y0);
+        const bool drier_cf = cf.p0 > ref.p0;
+        const bool qm0 = drier_cf && (q > cf.p0);
+        const bool qm1 = !drier_cf && !dry;
+        const bool to_wet = !qm1 && (u * ref.p0 > cf.p0);
+        cs = 0.0;
+        if (qm0 || qm1 || to_wet) cs = dist_invcdf(family, cf, q);
+    }
+    o.cfact_scaled = cs;
+    double c;
+    switch (scaling) {
+        case ATTRICI_SCALE_UNITY: c = cs * scale + datamin; break;      // variables.py:131
+        case ATTRICI_SCALE_NONE: c = cs * 1.0; break;                    // :657
+        case ATTRICI_SCALE_PR:                                           // :483-486
+            c = cs * scale + 0.0000011574;
+            if (cs <= 0.0) c = 0.0;
+            break;
+        default: c = cs * scale; break;                                  // :89
+    }
+    // detrend.py:397-411
+    o.replaced = ATTRICI_REPLACED_NONE;
+    if (c != c) { c = (double)y; o.replaced = ATTRICI_REPLACED_NAN; }
+    else if (c == INFINITY) { c = (double)y; o.replaced = ATTRICI_REPLACED_PINF; }
+    else if (c == -INFINITY) { c = (double)y; o.replaced = ATTRICI_REPLACED_NINF; }
+    o.cfact = c;
+    return o;
+}
+
+// NumPy legacy MT19937 (np.random.seed(int) = init_genrand; np.random.rand -> random_sample):
+// state mt[624] with stride `st` between consecutive words
+struct Mt19937 {
+    static constexpr int N = 624, M = 397;
+    template <typename Acc> ATTRICI_HD static void seed(Acc mt, uint32_t s) {
+        mt(0) = s;
+        for (int i = 1; i < N; ++i) {
+            uint32_t p = mt(i - 1);
+            mt(i) = 1812433253u * (p ^ (p >> 30)) + (uint32_t)i;
+        }
+    }
+    template <typename Acc> ATTRICI_HD static void twist(Acc mt) {
+        int kk;
+        for (kk = 0; kk < N - M; ++kk) {
+            uint32_t y = (mt(kk) & 0x80000000u) | (mt(kk + 1) & 0x7fffffffu);
+            mt(kk) = mt(kk + M) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        for (; kk < N - 1; ++kk) {
+            uint32_t y = (mt(kk) & 0x80000000u) | (mt(kk + 1) & 0x7fffffffu);
+            mt(kk) = mt(kk + (M - N)) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        uint32_t y = (mt(N - 1) & 0x80000000u) | (mt(0) & 0x7fffffffu);
+        mt(N - 1) = mt(M - 1) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    ATTRICI_HD static uint32_t temper(uint32_t y) {
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    // random_sample: (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53
+    ATTRICI_HD static double to_double(uint32_t a, uint32_t b) {
+        return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+    }
+};
+
+}  // namespace attrici

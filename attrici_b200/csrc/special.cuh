@@ -15,7 +15,7 @@
 
 #if defined(__CUDACC__)
 #define ATTRICI_HD __host__ __device__ __forceinline__
-#define ATTRICI_HD_NOINLINE __host__ __device__
+#define ATTRICI_HD_NOINLINE inline __host__ __device__
 #else
 #define ATTRICI_HD inline
 #define ATTRICI_HD_NOINLINE inline

@@ -1,391 +1,39 @@
-// Per-cell optimiser: Fisher-scoring Levenberg-Marquardt with per-cell convergence masks.
-// Replaces scipy.optimize.minimize(method="L-BFGS-B") of ModelScipy.fit
-// (attrici/estimation/model_scipy.py:519-523; finite differences, ~900-2400 objective calls per cell)
-// by ~5-12 likelihood passes per cell.  One thread = one cell; all per-cell state is laid out
-// [field][cell] so the 27 x 27 factorisations of 32 neighbouring cells coalesce.
-//
-// Frames: the reference builds each cell's Fourier columns with phase origin = first day the
-// cell's likelihood term uses (attrici/util.py:102 via model_scipy.py:189, 289 and the wet-day
-// selection :424-431), while all cells here share ONE basis with origin = first day of the series.
-// Coefficients are therefore optimised in the cell's own frame (where the priors of
-// model_scipy.py:142-171, 256-270 apply) and rotated harmonic by harmonic into the shared frame
-// for the likelihood pass; moments come back through the transposed rotation.
+// Kernels around the per-cell optimiser mathematics of step_impl.cuh (one thread = one cell) and the
+// conversions between the reference's theta layout and the canonical per-term layout.
 #include "common.cuh"
-#include "special.cuh"
+#include "step_impl.cuh"
 
 namespace attrici {
 
 namespace {
 
-struct StepArgs {
-    int C, Cp;
-    int n_chunks;        // chunks actually written by the last pass
-    int fp64;            // partial moments are double
-    int term, modes, slot;
-    int max_pass;
-    double tol_pred, lambda0;
-    int zero_init;
-    // workspace
-    const double* basis64;
-    const double* st_cnt; const double* st_sum; const double* st_sq; const double* st_ln; const int* st_first;
-    double* th_acc; double* th_trial; double* th_pass; double* g_acc; double* h_acc; double* h_wrk;
-    double* f_acc; double* pred; double* lam; double* rot;
-    int* status; int* npass; int* n_running;
-    const double* part_nll; const void* part_acc;
-};
-
-__device__ __forceinline__ bool term_has_b(int term) { return term != T_BERNOULLI; }
-__device__ __forceinline__ bool term_has_ab(int term) { return term == T_WEIBULL || term == T_BETA; }
-
-// canonical coefficient index -> (block, power of gmt, trig type 0 = cos / 1 = sin, harmonic)
-struct Col { int blk, pw, sn, k; };
-__device__ __forceinline__ Col col_of(int i) {
-    Col c;
-    if (i < NA) {
-        c.blk = 0;
-        if (i < 2) { c.pw = i; c.sn = 0; c.k = 0; }
-        else {
-            int j = i - 2;                  // 0..15: cos, sin, g*cos, g*sin blocks of MAXM
-            c.pw = j / (2 * MAXM);
-            c.sn = (j / MAXM) & 1;
-            c.k = j % MAXM + 1;
-        }
-    } else {
-        int j = i - NA;
-        c.blk = 1; c.pw = 0;
-        if (j == 0) { c.sn = 0; c.k = 0; }
-        else { c.sn = (j - 1) / MAXM; c.k = (j - 1) % MAXM + 1; }
-    }
-    return c;
-}
-
-__device__ __forceinline__ bool col_active(const Col& c, int term, int modes) {
-    if (c.blk == 1 && !term_has_b(term)) return false;
-    return c.k <= modes;
-}
-
-// prior precision 1/s^2 in the cell frame (model_scipy.py:142-171, 256-270): only the cos
-// coefficients of each Fourier block carry a prior
-__device__ __forceinline__ double prior_prec(const Col& c) {
-    if (c.k == 0) return c.pw == 0 ? 1.0 : 100.0;
-    if (c.sn) return 0.0;
-    if (c.pw) return 100.0;
-    double s = 2.0 * (c.k - 1) + 1.0;
-    return s * s;
-}
-
-// sum over prior terms of (-ln s - ln sqrt(2 pi)): part of the reference's logp
-__device__ __forceinline__ double prior_const(int term, int modes) {
-    const double lsq = 0.91893853320467274178, ln10 = 2.30258509299404568402;
-    double sl = 0.0;
-    for (int i = 0; i < modes; ++i) sl += log(2.0 * i + 1.0);
-    double a = ln10 * (1 + modes) + sl - (2 + 2 * modes) * lsq;
-    double b = sl - (1 + modes) * lsq;
-    return term_has_b(term) ? a + b : a;
-}
-
-__device__ __forceinline__ int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
-
-// cell frame -> shared frame: cos/sin pair of harmonic k rotated by the cell's phase offset
-__device__ void rotate_to_shared(const StepArgs& a, int cell, const double* th_cell /*local [NP]*/) {
-    const size_t cp = a.Cp;
-    double out[NP];
-    for (int i = 0; i < NP; ++i) out[i] = th_cell[i];
-    for (int k = 1; k <= MAXM; ++k) {
-        double c = a.rot[(size_t)(k - 1) * cp + cell], s = a.rot[(size_t)(NH + k - 1) * cp + cell];
-        // A block: plain and gmt-multiplied pairs; B block
-        const int ci[3] = {2 + (k - 1), 2 + 2 * MAXM + (k - 1), NA + 1 + (k - 1)};
-        const int si[3] = {2 + MAXM + (k - 1), 2 + 3 * MAXM + (k - 1), NA + 1 + MAXM + (k - 1)};
-        for (int q = 0; q < 3; ++q) {
-            double cc = th_cell[ci[q]], ss = th_cell[si[q]];
-            out[ci[q]] = cc * c - ss * s;
-            out[si[q]] = cc * s + ss * c;
-        }
-    }
-    for (int i = 0; i < NP; ++i) a.th_pass[(size_t)i * cp + cell] = out[i];
-}
-
-// reduce the chunk partials of one cell and rotate every trig moment into the cell frame
-// mom layout = accumulator layout of pass.cu
-__device__ double reduce_moments(const StepArgs& a, int cell, double* mom /*[NACC]*/) {
-    const size_t cp = a.Cp;
-    double nll = 0.0;
-    for (int ch = 0; ch < a.n_chunks; ++ch) nll += a.part_nll[(size_t)ch * cp + cell];
-    for (int i = 0; i < NACC; ++i) {
-        double s = 0.0;
-        if (a.fp64) {
-            const double* p = reinterpret_cast<const double*>(a.part_acc) + (size_t)i * cp + cell;
-            for (int ch = 0; ch < a.n_chunks; ++ch) s += p[(size_t)ch * NACC * cp];
-        } else {
-            const float* p = reinterpret_cast<const float*>(a.part_acc) + (size_t)i * cp + cell;
-            for (int ch = 0; ch < a.n_chunks; ++ch) s += (double)p[(size_t)ch * NACC * cp];
-        }
-        mom[i] = s;
-    }
-    // rotation: C'_k = c C_k + s S_k ; S'_k = c S_k - s C_k
-    for (int k = 1; k <= NH; ++k) {
-        double c = a.rot[(size_t)(k - 1) * cp + cell], s = a.rot[(size_t)(NH + k - 1) * cp + cell];
-        for (int blk = 0; blk < 6; ++blk) {  // AA p0..2, AB p0..1, BB
-            double* m = mom + blk * NTRIG;
-            double C_ = m[k], S_ = m[NH + k];
-            m[k] = c * C_ + s * S_;
-            m[NH + k] = c * S_ - s * C_;
-        }
-        if (k <= MAXM) {
-            for (int blk = 0; blk < 3; ++blk) {  // GA p0, GA p1, GB
-                double* m = mom + ACC_GA + blk * NB;
-                double C_ = m[k], S_ = m[MAXM + k];
-                m[k] = c * C_ + s * S_;
-                m[MAXM + k] = c * S_ - s * C_;
-            }
-        }
-    }
-    return nll;
-}
-
-// moment of (column i) x (column j) under weight stream `m` (17 trig moments at the right power)
-__device__ __forceinline__ double trig_product(const double* m, const Col& a, const Col& b) {
-    const double* Cm = m;           // Cm[0] const, Cm[k] cos k
-    const double* Sm = m + NH;      // Sm[k] sin k (Sm[0] aliases cos 8 and is never read)
-    int sum = a.k + b.k, dif = a.k - b.k;
-    int ad = dif < 0 ? -dif : dif;
-    if (!a.sn && !b.sn) return 0.5 * (Cm[ad] + Cm[sum]);
-    if (a.sn && b.sn) return 0.5 * (Cm[ad] - Cm[sum]);
-    // sin(x) cos(y) = 0.5 (sin(x + y) + sin(x - y))
-    int sgn = a.sn ? dif : -dif;    // (sin harmonic) - (cos harmonic)
-    double lo = ad == 0 ? 0.0 : (sgn > 0 ? Sm[ad] : -Sm[ad]);
-    return 0.5 * (Sm[sum] + lo);
-}
-
-// gradient and Fisher information (+ prior) of one cell, cell frame, canonical layout.
-// g: local [NP]; H: global packed [NTRI][Cp] column of this cell
-__device__ double assemble(const StepArgs& a, int cell, const double* th /*local [NP], cell frame*/, double* g,
-                           double* Hglob) {
-    const size_t cp = a.Cp;
-    double mom[NACC];
-    double f = reduce_moments(a, cell, mom);
-    for (int i = 0; i < NP; ++i) {
-        Col ci = col_of(i);
-        bool act_i = col_active(ci, a.term, a.modes);
-        double gi = 0.0;
-        if (act_i) {
-            const double* gm = (ci.blk == 0) ? mom + ACC_GA + ci.pw * NB : mom + ACC_GB;
-            gi = ci.k == 0 ? gm[0] : (ci.sn ? gm[MAXM + ci.k] : gm[ci.k]);
-            double pr = prior_prec(ci);
-            gi += pr * th[i];
-            f += 0.5 * pr * th[i] * th[i];
-        }
-        g[i] = gi;
-        for (int j = 0; j <= i; ++j) {
-            Col cj = col_of(j);
-            bool act_j = col_active(cj, a.term, a.modes);
-            double h;
-            if (!act_i || !act_j) {
-                h = (i == j) ? 1.0 : 0.0;
-            } else {
-                int pw = ci.pw + cj.pw;
-                const double* m;
-                if (ci.blk == 0 && cj.blk == 0) m = mom + ACC_AA + pw * NTRIG;
-                else if (ci.blk == 1 && cj.blk == 1) m = mom + ACC_BB;
-                else m = mom + ACC_AB + pw * NTRIG;
-                h = trig_product(m, ci, cj);
-                if (i == j) h += prior_prec(ci);
-            }
-            Hglob[(size_t)tri(i, j) * cp + cell] = h;
-        }
-    }
-    return f - prior_const(a.term, a.modes);
-}
-
-// solve (H + lam D) delta = -g by Cholesky in the global work column; returns false if not SPD
-__device__ bool lm_solve(const StepArgs& a, int cell, const double* g, double lam, double* delta) {
-    const size_t cp = a.Cp;
-    const double* H = a.h_acc + cell;
-    double* L = a.h_wrk + cell;
-    for (int j = 0; j < NP; ++j) {
-        double hjj = H[(size_t)tri(j, j) * cp];
-        double dj = fmax(fabs(hjj), 1e-12);
-        double s = hjj + lam * dj;
-        for (int k = 0; k < j; ++k) {
-            double l = L[(size_t)tri(j, k) * cp];
-            s -= l * l;
-        }
-        if (!(s > 0.0) || !isfinite(s)) return false;
-        double ljj = sqrt(s);
-        L[(size_t)tri(j, j) * cp] = ljj;
-        double inv = 1.0 / ljj;
-        for (int i = j + 1; i < NP; ++i) {
-            double t = H[(size_t)tri(i, j) * cp];
-            for (int k = 0; k < j; ++k) t -= L[(size_t)tri(i, k) * cp] * L[(size_t)tri(j, k) * cp];
-            L[(size_t)tri(i, j) * cp] = t * inv;
-        }
-    }
-    double y[NP];
-    for (int i = 0; i < NP; ++i) {
-        double t = -g[i];
-        for (int k = 0; k < i; ++k) t -= L[(size_t)tri(i, k) * cp] * y[k];
-        y[i] = t / L[(size_t)tri(i, i) * cp];
-    }
-    for (int i = NP - 1; i >= 0; --i) {
-        double t = y[i];
-        for (int k = i + 1; k < NP; ++k) t -= L[(size_t)tri(k, i) * cp] * delta[k];
-        delta[i] = t / L[(size_t)tri(i, i) * cp];
-    }
-    return true;
-}
-
-// from the accepted state (th_acc, f_acc, g_acc, h_acc, lam): next trial point, or termination
-__device__ void propose(const StepArgs& a, int cell) {
-    const size_t cp = a.Cp;
-    double g[NP], th[NP], delta[NP];
-    for (int i = 0; i < NP; ++i) {
-        g[i] = a.g_acc[(size_t)i * cp + cell];
-        th[i] = a.th_acc[(size_t)i * cp + cell];
-    }
-    double lam = a.lam[cell];
-    bool ok = false;
-    for (int tries = 0; tries < 40 && !ok; ++tries) {
-        ok = lm_solve(a, cell, g, lam, delta);
-        if (ok) for (int i = 0; i < NP; ++i) ok = ok && isfinite(delta[i]);
-        if (!ok) lam = fmax(lam * 10.0, 1e-6);
-    }
-    a.lam[cell] = lam;
-    if (!ok) { a.status[cell] = ATTRICI_STATUS_STALLED; return; }
-    // predicted decrease of the quadratic model: -g.d - 0.5 d.H.d
-    double gd = 0.0, dhd = 0.0;
-    const double* H = a.h_acc + cell;
-    for (int i = 0; i < NP; ++i) {
-        gd += g[i] * delta[i];
-        double hi = 0.0;
-        for (int j = 0; j < NP; ++j) hi += H[(size_t)tri(i, j) * cp] * delta[j];
-        dhd += delta[i] * hi;
-    }
-    double pred = -gd - 0.5 * dhd;
-    a.pred[cell] = pred;
-    double f = a.f_acc[cell];
-    if (pred <= a.tol_pred * fmax(fabs(f), 1.0)) { a.status[cell] = ATTRICI_STATUS_CONVERGED; return; }
-    if (a.npass[cell] >= a.max_pass) return;  // stays RUNNING: reported as not converged
-    for (int i = 0; i < NP; ++i) {
-        th[i] += delta[i];
-        a.th_trial[(size_t)i * cp + cell] = th[i];
-    }
-    rotate_to_shared(a, cell, th);
-}
+constexpr int STEP_THREADS = 64;
 
 __global__ void fit_init_kernel(StepArgs a) {
     int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= a.C) return;
-    const size_t cp = a.Cp;
-    const size_t so = (size_t)a.slot * cp + cell;
-    double th[NP];
-    for (int i = 0; i < NP; ++i) th[i] = 0.0;
-    double n = a.st_cnt[so];
-    int first = a.st_first[so];
-    int status = ATTRICI_STATUS_RUNNING;
-    if (!(n > 0.0) || first < 0) status = ATTRICI_STATUS_NO_DATA;
-    // phase offset of the cell frame: tau of the first used day (basis64 column 17)
-    double tau0 = (first >= 0) ? a.basis64[(size_t)first * B64_STRIDE + 17] : 0.0;
-    for (int k = 1; k <= NH; ++k) {
-        double s, c;
-        sincos((6.283185307179586 * (double)k) * tau0, &s, &c);
-        a.rot[(size_t)(k - 1) * cp + cell] = c;
-        a.rot[(size_t)(NH + k - 1) * cp + cell] = s;
-    }
-    if (status == ATTRICI_STATUS_RUNNING && !a.zero_init) {
-        // moment-matched intercepts (the reference starts from zero, model_scipy.py:113,234; the MAP
-        // estimate does not depend on the start, the number of passes does)
-        double mean = a.st_sum[so] / n;
-        double var = fmax(a.st_sq[so] / n - mean * mean, 1e-12);
-        switch (a.term) {
-            case T_NORMAL: th[0] = mean; th[NA] = 0.5 * log(var); break;
-            case T_GAMMA:
-                if (mean > 0.0) { th[0] = log(mean); th[NA] = 0.5 * log(fmax(mean * mean / var, 1e-3)); }
-                break;
-            case T_WEIBULL:
-                if (mean > 0.0) {
-                    double c = pow(sqrt(var) / mean, -1.086);
-                    c = fmin(fmax(c, 0.05), 50.0);
-                    th[NA] = log(c);
-                    th[0] = log(mean) - lgamma(1.0 + 1.0 / c);
-                }
-                break;
-            case T_BETA:
-                if (mean > 0.0 && mean < 1.0) {
-                    double phi = mean * (1.0 - mean) / var - 1.0;
-                    if (!(phi > 1e-3)) phi = 1.0;
-                    th[0] = log(mean / (1.0 - mean));
-                    th[NA] = log(phi);
-                }
-                break;
-            case T_BERNOULLI: {
-                double p = fmin(fmax(mean, 1e-6), 1.0 - 1e-6);
-                th[0] = log(p / (1.0 - p));
-            } break;
-        }
-        for (int i = 0; i < NP; ++i) if (!isfinite(th[i])) th[i] = 0.0;
-    }
-    for (int i = 0; i < NP; ++i) {
-        a.th_trial[(size_t)i * cp + cell] = th[i];
-        a.th_acc[(size_t)i * cp + cell] = th[i];
-    }
-    rotate_to_shared(a, cell, th);
-    a.lam[cell] = a.lambda0;
-    a.f_acc[cell] = INFINITY;
-    a.pred[cell] = 0.0;
-    a.status[cell] = status;
-    a.npass[cell] = 0;
-    if (status == ATTRICI_STATUS_RUNNING) atomicAdd(a.n_running, 1);
+    if (cell_init(a, cell)) atomicAdd(a.n_running, 1);
 }
 
-// after a pass at th_trial: accept / reject, update damping, propose the next trial
 __global__ void fit_step_kernel(StepArgs a) {
     int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= a.C) return;
-    if (a.status[cell] != ATTRICI_STATUS_RUNNING) return;
-    const size_t cp = a.Cp;
-    double th[NP], g[NP];
-    for (int i = 0; i < NP; ++i) th[i] = a.th_trial[(size_t)i * cp + cell];
-    // Fisher information of the trial goes to the work column first; promoted on acceptance
-    double f_t = assemble(a, cell, th, g, a.h_wrk + cell);
-    bool finite = isfinite(f_t);
-    for (int i = 0; i < NP; ++i) finite = finite && isfinite(g[i]);
-    int np = a.npass[cell];
-    a.npass[cell] = np + 1;
-    double f = a.f_acc[cell];
-    double lam = a.lam[cell];
-    bool accept;
-    if (np == 0) {
-        if (!finite) { a.status[cell] = ATTRICI_STATUS_NONFINITE; return; }
-        accept = true;
-    } else {
-        // float32 day arithmetic leaves ~1e-8 relative noise in f: tolerate it, the predicted-decrease
-        // test in propose() is what ends the iteration
-        double slack = 1e-9 * fabs(f);
-        double pred = a.pred[cell];
-        accept = finite && (f_t <= f + slack) && (f - f_t >= 1e-4 * pred - slack);
-        if (accept) {
-            double rho = (f - f_t) / pred;
-            if (rho > 0.75) lam = fmax(lam * 0.2, 1e-9);
-            else if (rho < 0.25) lam = lam * 2.0;
-        } else {
-            lam = fmax(lam * 8.0, 1e-4);
-            if (lam > 1e12) { a.status[cell] = ATTRICI_STATUS_STALLED; return; }
-        }
-    }
-    a.lam[cell] = lam;
-    if (accept) {
-        a.f_acc[cell] = f_t;
-        for (int i = 0; i < NP; ++i) {
-            a.th_acc[(size_t)i * cp + cell] = th[i];
-            a.g_acc[(size_t)i * cp + cell] = g[i];
-        }
-        for (int i = 0; i < NTRI; ++i) a.h_acc[(size_t)i * cp + cell] = a.h_wrk[(size_t)i * cp + cell];
-    }
-    propose(a, cell);
-    if (a.status[cell] == ATTRICI_STATUS_RUNNING && a.npass[cell] < a.max_pass) atomicAdd(a.n_running, 1);
+    if (cell_step(a, cell)) atomicAdd(a.n_running, 1);
 }
 
-// known-answer / final evaluation: objective, gradient, Fisher information at th_trial
+__global__ void fit_final_point_kernel(StepArgs a) {
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= a.C) return;
+    cell_final_point(a, cell);
+}
+
+__global__ void fit_store_kernel(StepArgs a) {
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= a.C) return;
+    cell_store(a, cell);
+}
+
+// known-answer evaluation: objective, gradient, Fisher information at th_trial
 __global__ void assemble_kernel(StepArgs a, double* nll, double* grad /*[NP][Cp] canonical*/,
                                 double* fisher /*[NTRI][Cp] canonical packed, nullable*/) {
     int cell = blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,10 +41,15 @@ __global__ void assemble_kernel(StepArgs a, double* nll, double* grad /*[NP][Cp]
     const size_t cp = a.Cp;
     double th[NP], g[NP];
     for (int i = 0; i < NP; ++i) th[i] = a.th_trial[(size_t)i * cp + cell];
-    double f = assemble(a, cell, th, g, a.h_wrk + cell);
+    double f = assemble(a, cell, th, g, fisher ? fisher + cell : nullptr);
     nll[cell] = f;
     if (grad) for (int i = 0; i < NP; ++i) grad[(size_t)i * cp + cell] = g[i];
-    if (fisher) for (int i = 0; i < NTRI; ++i) fisher[(size_t)i * cp + cell] = a.h_wrk[(size_t)i * cp + cell];
+}
+
+__global__ void phase_kernel(StepArgs a) {
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= a.C) return;
+    cell_phase(a, cell);
 }
 
 // th_trial (cell frame) -> th_pass (shared frame)
@@ -406,6 +59,82 @@ __global__ void rotate_kernel(StepArgs a) {
     double th[NP];
     for (int i = 0; i < NP; ++i) th[i] = a.th_trial[(size_t)i * a.Cp + cell];
     rotate_to_shared(a, cell, th);
+}
+
+// reference layout theta[C x P] -> th_trial of one term slot (inactive entries zero)
+__global__ void load_theta_kernel(int C, int Cp, int family, int modes, int slot, const double* __restrict__ theta,
+                                  double* __restrict__ th_trial) {
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= C) return;
+    const int P = family_num_params(family, modes);
+    for (int i = 0; i < NP; ++i) th_trial[(size_t)i * Cp + cell] = 0.0;
+    for (int j = 0; j < P; ++j) {
+        int sl, cn;
+        ref_to_canon(family, modes, j, &sl, &cn);
+        if (sl == slot) th_trial[(size_t)cn * Cp + cell] = theta[(size_t)cell * P + j];
+    }
+}
+
+// canonical per-term results -> reference layout params[C x P], logp, status, n_pass
+__global__ void store_params_kernel(int C, int Cp, int family, int modes, const double* __restrict__ th_out,
+                                    const double* __restrict__ logp_part, const int* __restrict__ status_part,
+                                    const int* __restrict__ npass_part, double* __restrict__ params,
+                                    double* __restrict__ logp, int32_t* __restrict__ status,
+                                    int32_t* __restrict__ n_pass) {
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= C) return;
+    const int P = family_num_params(family, modes);
+    const int nt = family_terms_count(family);
+    for (int j = 0; j < P; ++j) {
+        int sl, cn;
+        ref_to_canon(family, modes, j, &sl, &cn);
+        params[(size_t)cell * P + j] = th_out[((size_t)sl * NP + cn) * Cp + cell];
+    }
+    double lp = 0.0;
+    int st = 0, np = 0;
+    for (int s = 0; s < nt; ++s) {
+        lp += logp_part[(size_t)s * Cp + cell];
+        int ss = status_part[(size_t)s * Cp + cell];
+        st = ss > st ? ss : st;
+        np += npass_part[(size_t)s * Cp + cell];
+    }
+    if (st == ATTRICI_STATUS_NO_DATA || st == ATTRICI_STATUS_NONFINITE) {
+        // a cell without data in any of its terms has no model at all (detrend.py:315-317 skips it)
+        for (int j = 0; j < P; ++j) params[(size_t)cell * P + j] = NAN;
+        lp = NAN;
+    }
+    if (logp) logp[cell] = lp;
+    if (status) status[cell] = st;
+    if (n_pass) n_pass[cell] = np;
+}
+
+// canonical nll / grad / packed fisher of one term slot -> reference layout (accumulating over slots)
+__global__ void scatter_kat_kernel(int C, int Cp, int family, int modes, int slot, const double* __restrict__ nll_c,
+                                   const double* __restrict__ grad_c, const double* __restrict__ fisher_c,
+                                   double* __restrict__ nll, double* __restrict__ grad, double* __restrict__ fisher,
+                                   int accumulate) {
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= C) return;
+    const int P = family_num_params(family, modes);
+    if (nll) nll[cell] = (accumulate ? nll[cell] : 0.0) + nll_c[cell];
+    for (int j = 0; j < P; ++j) {
+        int sl, cn;
+        ref_to_canon(family, modes, j, &sl, &cn);
+        if (sl != slot) {
+            if (!accumulate && fisher)
+                for (int k = 0; k < P; ++k) fisher[((size_t)cell * P + j) * P + k] = 0.0;
+            continue;
+        }
+        if (grad) grad[(size_t)cell * P + j] = grad_c[(size_t)cn * Cp + cell];
+        if (fisher) {
+            for (int k = 0; k < P; ++k) {
+                int sl2, cn2;
+                ref_to_canon(family, modes, k, &sl2, &cn2);
+                fisher[((size_t)cell * P + j) * P + k] =
+                    (sl2 == slot) ? fisher_c[(size_t)tri(cn, cn2) * Cp + cell] : 0.0;
+            }
+        }
+    }
 }
 
 StepArgs make_args(Workspace& ws, const StepParams& sp) {
@@ -421,34 +150,78 @@ StepArgs make_args(Workspace& ws, const StepParams& sp) {
     a.h_acc = ws.h_acc; a.h_wrk = ws.h_wrk; a.f_acc = ws.f_acc; a.pred = ws.pred; a.lam = ws.lam; a.rot = ws.rot;
     a.status = ws.status; a.npass = ws.npass; a.n_running = ws.n_running;
     a.part_nll = ws.part_nll; a.part_acc = ws.part_acc;
+    a.th_out = ws.th_out; a.logp_part = ws.logp_part; a.status_part = ws.status_part; a.npass_part = ws.npass_part;
     return a;
 }
+
+inline int blocks(int C) { return (C + STEP_THREADS - 1) / STEP_THREADS; }
 
 }  // namespace
 
 int launch_fit_init(Workspace& ws, const StepParams& sp, cudaStream_t s) {
     ATTRICI_CUDA_CHECK(cudaMemsetAsync(ws.n_running, 0, sizeof(int), s));
-    fit_init_kernel<<<(ws.C + 63) / 64, 64, 0, s>>>(make_args(ws, sp));
+    fit_init_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_fit_step(Workspace& ws, const StepParams& sp, cudaStream_t s) {
     ATTRICI_CUDA_CHECK(cudaMemsetAsync(ws.n_running, 0, sizeof(int), s));
-    fit_step_kernel<<<(ws.C + 63) / 64, 64, 0, s>>>(make_args(ws, sp));
+    fit_step_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
-int launch_assemble(Workspace& ws, const StepParams& sp, double* nll, double* grad, double* fisher,
-                    cudaStream_t s) {
-    assemble_kernel<<<(ws.C + 63) / 64, 64, 0, s>>>(make_args(ws, sp), nll, grad, fisher);
+int launch_fit_final_point(Workspace& ws, const StepParams& sp, cudaStream_t s) {
+    fit_final_point_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    ATTRICI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_fit_store(Workspace& ws, const StepParams& sp, cudaStream_t s) {
+    fit_store_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    ATTRICI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_assemble(Workspace& ws, const StepParams& sp, double* nll, double* grad, double* fisher, cudaStream_t s) {
+    assemble_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp), nll, grad, fisher);
+    ATTRICI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_phase_only(Workspace& ws, const StepParams& sp, cudaStream_t s) {
+    phase_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_rotate(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    rotate_kernel<<<(ws.C + 63) / 64, 64, 0, s>>>(make_args(ws, sp));
+    rotate_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    ATTRICI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_load_theta(Workspace& ws, int family, int modes, int slot, const double* theta, cudaStream_t s) {
+    load_theta_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(ws.C, ws.Cp, family, modes, slot, theta, ws.th_trial);
+    ATTRICI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_store_params(Workspace& ws, int family, int modes, double* params, double* logp, int32_t* status,
+                        int32_t* n_pass, cudaStream_t s) {
+    store_params_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(ws.C, ws.Cp, family, modes, ws.th_out, ws.logp_part,
+                                                            ws.status_part, ws.npass_part, params, logp, status,
+                                                            n_pass);
+    ATTRICI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_scatter_kat(Workspace& ws, int family, int modes, int slot, const double* nll_c, const double* grad_c,
+                       const double* fisher_c, double* nll, double* grad, double* fisher, int accumulate,
+                       cudaStream_t s) {
+    scatter_kat_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(ws.C, ws.Cp, family, modes, slot, nll_c, grad_c, fisher_c,
+                                                           nll, grad, fisher, accumulate);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }

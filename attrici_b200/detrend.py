@@ -1,0 +1,163 @@
+"""Batched driver: what replaces the per-cell loop of ``attrici.detrend.detrend`` for ``solver="cuda"``.
+
+The reference walks over grid cells one at a time (attrici/detrend.py:760-788) and lets independent OS
+processes take contiguous index ranges (``get_task_indices``, :119-169; USAGE.md:128-137).  Here the
+cells of a rank's range are processed as one batch on its GPU, and ranks (one process per GPU) take the
+ranges the same partition function assigns.  Nothing is exchanged during the fit; the only collective is
+a final gather of per-cell results.
+"""
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .variables import create_variable
+
+
+@dataclass
+class Config:
+    """The fields of ``attrici.detrend.Config`` (attrici/detrend.py:46-116) the hot path reads, with the
+    reference's names and defaults, plus the knobs of the batched solver."""
+
+    variable: str
+    modes: int = 4
+    seed: int = 0
+    task_id: int = 0
+    task_count: int = 1
+    solver: str = "cuda"
+    slab_cells: int = 4096       # cells per device slab of the host pipeline
+    use_fp64: bool = False       # FP64 day arithmetic in the likelihood passes
+    device: str = None           # default: cuda:<LOCAL_RANK>
+
+
+def get_task_indices(indices_len, task_id, task_count):
+    """Cell indices of one task: same rule as attrici/detrend.py:119-169 (every task gets
+    ``indices_len // task_count + 1`` cells until they run out, the first task that would overshoot gets
+    the remainder, later tasks are empty; an exact division is split evenly)."""
+    if task_id < 0 or task_id >= task_count:
+        raise ValueError("Task ID must be between 0 and task count")
+    if indices_len % task_count == 0:
+        calls = np.full(task_count, indices_len // task_count, dtype=np.int64)
+    else:
+        calls = np.full(task_count, indices_len // task_count + 1, dtype=np.int64)
+        over = np.flatnonzero(np.cumsum(calls) > indices_len)
+        calls[over] = 0
+        calls[over[0]] = indices_len - calls.sum()
+    cum = np.cumsum(calls)
+    start = 0 if task_id == 0 else int(cum[task_id - 1])
+    end = int(cum[task_id]) - 1
+    return np.arange(start, end + 1)
+
+
+def scale_predictor(gmt, n_time):
+    """Predictor on the observation axis, attrici/detrend.py:698-707 (default branch): stretch the GMT
+    series over the normalised time index of a gap-free daily axis and min-max scale it to [0, 1]."""
+    t_scaled = np.arange(n_time, dtype=np.float64) / np.float64(n_time - 1)
+    g = np.interp(t_scaled, np.linspace(0, 1, len(gmt)), np.asarray(gmt, dtype=np.float64))
+    return (g - g.min()) / (g.max() - g.min())
+
+
+def validate_bounds(spec, values):
+    """``Variable.validate`` -> ``check_bounds`` (attrici/variables.py:17-37): same ValueError."""
+    if spec.lower_bound is not None:
+        m = np.nanmin(values)
+        if m < spec.lower_bound:
+            raise ValueError(m, "is smaller than lower bound", spec.lower_bound, ".")
+    if spec.upper_bound is not None:
+        m = np.nanmax(values)
+        if m > spec.upper_bound:
+            raise ValueError(m, "is bigger than upper bound", spec.upper_bound, ".")
+
+
+def _dist_info():
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_rank(), dist.get_world_size()
+    except ImportError:  # pragma: no cover
+        pass
+    return None, 0, 1
+
+
+def gather_cells(local, counts, dist=None, device=None):
+    """Final gather of per-cell arrays to every rank: the one collective of the path.
+
+    ``local``: dict name -> array whose LAST axis... no: whose FIRST axis is this rank's cells;
+    ``counts``: cells per rank.  Uses ``all_gather`` on tensors padded to the largest shard (shards are
+    uneven under the reference's partition rule)."""
+    import torch
+
+    if dist is None:
+        dist, _, world = _dist_info()
+    if dist is None:
+        return {k: np.asarray(v) for k, v in local.items()}
+    world = dist.get_world_size()
+    on_gpu = dist.get_backend() == "nccl"
+    dev = torch.device(device) if (on_gpu and device) else torch.device("cuda" if on_gpu else "cpu")
+    cmax = int(max(counts))
+    out = {}
+    for name, arr in local.items():
+        a = np.ascontiguousarray(arr)
+        pad = np.zeros((cmax,) + a.shape[1:], dtype=a.dtype)
+        pad[: a.shape[0]] = a
+        t = torch.from_numpy(pad).to(dev)
+        bucket = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(bucket, t)
+        out[name] = np.concatenate([b.cpu().numpy()[: int(n)] for b, n in zip(bucket, counts)], axis=0)
+    return out
+
+
+def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather=True, out=None):
+    """Detrend the cells of ``y`` ([T, C] float32 host array, time-major, cells stacked lat-major as
+    attrici/detrend.py:672 does) that the reference's partition assigns to this rank.
+
+    Returns a dict: ``indices`` (this rank's cell indices), ``cfact`` [T, n_local] float64 and
+    ``replaced`` [T, n_local] uint8 for those cells, and per-cell ``params`` [C', P], ``logp``, ``status``,
+    ``n_pass``, ``scaling`` — gathered over all ranks when ``gather`` and torch.distributed is
+    initialised (then C' = C), else local.
+    """
+    import os
+
+    import torch
+
+    from .solver import CellBatchSolver, cell_seeds
+
+    if config.solver != "cuda":
+        raise ValueError(f"attrici_b200 only provides solver='cuda', got {config.solver!r}")
+    spec = create_variable(config.variable)
+    y = np.asarray(y) if not isinstance(y, torch.Tensor) else y
+    if y.ndim != 2:
+        raise ValueError("y must be [T, C]")
+    T, C = y.shape
+    lat, lon = np.asarray(lat), np.asarray(lon)
+    if lat.shape != (C,) or lon.shape != (C,):
+        raise ValueError("lat / lon must have one entry per cell")
+    dist, rank, world = _dist_info()
+    task_id, task_count = (rank, world) if world > 1 else (config.task_id, config.task_count)
+    idx = get_task_indices(C, task_id, task_count)
+    device = config.device or f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+    n_local = len(idx)
+    P = spec.n_params(config.modes)
+    res = {"indices": idx}
+    if n_local:
+        solver = CellBatchSolver(spec, modes=config.modes, device=device, use_fp64=config.use_fp64)
+        sl = slice(int(idx[0]), int(idx[-1]) + 1)  # contiguous by construction
+        seeds = cell_seeds(config.seed, lat[sl], lon[sl]) if spec.family == _lib.BERNOULLI_GAMMA else None
+        y_local = y[:, sl]
+        if isinstance(y_local, np.ndarray):
+            y_local = torch.from_numpy(y_local)
+        o = solver.detrend_host(y_local, days, gmt_scaled, fit_window, seeds, config.slab_cells, out=out)
+        local = {k: (o[k].numpy() if o[k] is not None else None) for k in o}
+    else:
+        local = {"cfact": np.empty((T, 0)), "replaced": np.empty((T, 0), dtype=np.uint8),
+                 "params": np.empty((0, P)), "logp": np.empty(0), "scaling": np.empty((0, 2)),
+                 "status": np.empty(0, dtype=np.int32), "n_pass": np.empty(0, dtype=np.int32)}
+    res["cfact"], res["replaced"] = local["cfact"], local["replaced"]
+    per_cell = {k: local[k] for k in ("params", "logp", "scaling", "status", "n_pass")}
+    if gather and world > 1:
+        counts = [len(get_task_indices(C, r, world)) for r in range(world)]
+        per_cell = gather_cells(per_cell, counts, dist, device)
+    res.update(per_cell)
+    return res

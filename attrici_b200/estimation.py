@@ -1,0 +1,122 @@
+"""``ModelCuda``: the CUDA solver behind the reference's solver plugin interface.
+
+Mirrors ``attrici.estimation.model.Model`` (attrici/estimation/model.py:51-116) and the constructor
+keywords / trace schema of ``ModelScipy`` (attrici/estimation/model_scipy.py:379-570), so that
+``Variable.create_model(ModelCuda, predictor, modes=...)`` works in the reference's per-cell loop
+(attrici/detrend.py:326-416) and ``write_trace`` / ``--trace-file`` keep their format.  One cell per
+instance is the reference's interface; production runs use ``attrici_b200.detrend.detrend_cells``,
+which batches cells (the per-cell loop of attrici/detrend.py:760-788 is what this package replaces).
+
+There is no CPU fallback: constructing a model without the CUDA library or a GPU raises.
+"""
+
+import numpy as np
+import torch
+
+from . import _lib
+from .solver import CellBatchSolver
+from .variables import FAMILY_PARAMETERS, VariableSpec
+
+_FAMILY_OF_DISTRIBUTION = {
+    "Normal": _lib.NORMAL,
+    "Gamma": _lib.GAMMA,
+    "Beta": _lib.BETA,
+    "Weibull": _lib.WEIBULL,
+    "BernoulliGamma": _lib.BERNOULLI_GAMMA,
+}
+# which parameters depend on the predictor (attrici/variables.py create_model tables)
+_DEPENDENT = {
+    _lib.NORMAL: (True, False),
+    _lib.GAMMA: (True, False),
+    _lib.BETA: (True, False),
+    _lib.WEIBULL: (False, True),
+    _lib.BERNOULLI_GAMMA: (True, True, False),
+}
+
+
+def _values(x):
+    return np.asarray(getattr(x, "values", x))
+
+
+def _day_offsets(time):
+    """Integer day offsets of a datetime64 (or already integer) time vector."""
+    t = _values(getattr(time, "time", time))
+    if np.issubdtype(t.dtype, np.datetime64):
+        d = (t - t.min()) / np.timedelta64(1, "D")
+        days = np.rint(d).astype(np.int64)
+        if not np.array_equal(days.astype(np.float64), d):
+            raise ValueError("time axis must be at whole-day spacing")
+    elif np.issubdtype(t.dtype, np.integer):
+        days = t.astype(np.int64) - int(t.min())
+    else:
+        raise TypeError("time coordinate must be datetime64 or integer days")
+    if days.max(initial=0) >= 2**31:
+        raise ValueError("time axis too long")
+    return days.astype(np.int32)
+
+
+class ModelCuda:
+    """Single-cell view of the batched CUDA solver (``solver="cuda"``)."""
+
+    def __init__(self, distribution, parameters, observed, predictor, modes=None, window_size=None,
+                 device="cuda:0", use_fp64=False, zero_init=False):
+        if window_size is not None:
+            # same restriction and exception as ModelScipy (model_scipy.py:58-59)
+            raise NotImplementedError("Rolling window not implemented for the CUDA solver")
+        if modes is None:
+            raise ValueError("modes must be given")
+        name = getattr(distribution, "__name__", str(distribution))
+        if name not in _FAMILY_OF_DISTRIBUTION:
+            raise ValueError(f"Distribution {distribution} not supported")
+        family = _FAMILY_OF_DISTRIBUTION[name]
+        expect = FAMILY_PARAMETERS[family]
+        if tuple(parameters) != expect:
+            raise ValueError(f"{name} expects parameters {expect} in this order, got {tuple(parameters)}")
+        for (pname, par), dep in zip(parameters.items(), _DEPENDENT[family]):
+            if bool(getattr(par, "dependent", dep)) != dep:
+                raise ValueError(f"parameter {pname} of {name}: dependent={not dep} is not a model of the reference")
+        self._distribution_class = distribution
+        self._family = family
+        self._modes = int(modes)
+        y = _values(observed).astype(np.float32)
+        gmt = _values(predictor).astype(np.float64)
+        if y.shape != gmt.shape or y.ndim != 1:
+            raise ValueError("observed and predictor must be 1-D and aligned")
+        self._days = _day_offsets(predictor)
+        self._y = y
+        self._gmt = gmt
+        # the series handed over is already scaled and masked by the Variable class: identity scaling
+        spec = VariableSpec("cell", family, _lib.SCALE_NONE)
+        self._solver = CellBatchSolver(spec, modes=self._modes, device=device, use_fp64=use_fp64, zero_init=zero_init)
+
+    def fit(self, **kwargs):
+        """Returns the SciPy trace schema ``{"logp": float, "params": ndarray[P]}`` (model_scipy.py:524-527)."""
+        s = self._solver
+        s.set_predictor(self._days, self._gmt, 1)
+        y = torch.as_tensor(self._y[:, None]).to(s.device)
+        ys, _ = s.scale(y)
+        fit = s.fit(ys)
+        self._status = int(fit.status.item())
+        self._n_pass = int(fit.n_pass.item())
+        return {"logp": float(fit.logp.item()), "params": fit.params[0].cpu().numpy()}
+
+    def estimate_logp(self, trace, **kwargs):
+        return trace["logp"]
+
+    def estimate_distribution(self, trace, predictor, **kwargs):
+        """Per-day distribution parameters on ``predictor``'s time axis (phase origin = its first day, as
+        model_scipy.py:565-567 re-sets the predictor data) wrapped in the distribution class given to the
+        constructor."""
+        s = self._solver
+        gmt = _values(predictor).astype(np.float64)
+        s.set_predictor(_day_offsets(predictor), gmt, 1)
+        params = torch.as_tensor(np.asarray(trace["params"], dtype=np.float64)[None, :]).to(s.device)
+        out = {}
+        for i, pname in enumerate(FAMILY_PARAMETERS[self._family]):
+            out[pname] = s.eval_parameter(params, i)[:, 0].cpu().numpy()
+        return self._distribution_class(**out)
+
+    def fit_cached(self, defining_data_inputs=None, cache_dir=None, timeout=None, **kwargs):
+        """The reference wraps ``fit`` in a joblib cache and a wall-clock timeout (model.py:118-188); a
+        fit takes milliseconds here, so this simply fits."""
+        return self.fit(**kwargs)

@@ -1,0 +1,88 @@
+"""Variable -> model table: what ``attrici.variables.create_variable`` (attrici/variables.py:801-834)
+and each class's ``__init__`` / ``scale`` / ``create_model`` / ``quantile_mapping`` / ``rescale`` decide,
+flattened into the descriptor the CUDA library takes (``attrici_variable_t``).
+
+The reference keeps these as classes (``Tas``, ``Pr``, ...: attrici/variables.py:306-798); their
+arithmetic runs on the device here (``csrc/prep.cu``, ``csrc/qmap_impl.cuh``), so only the table is
+left on the host.
+"""
+
+from dataclasses import dataclass
+
+from . import _lib
+
+# distribution parameter names in the field order of attrici/distributions.py dataclasses
+# (Normal :64-90, Gamma :132-158, Beta :161-187, Weibull :190-216, BernoulliGamma :93-129)
+FAMILY_PARAMETERS = {
+    _lib.NORMAL: ("mu", "sigma"),
+    _lib.GAMMA: ("mu", "nu"),
+    _lib.BETA: ("mu", "phi"),
+    _lib.WEIBULL: ("alpha", "beta"),
+    _lib.BERNOULLI_GAMMA: ("p", "mu", "nu"),
+}
+
+FAMILY_NAMES = {
+    _lib.NORMAL: "Normal",
+    _lib.GAMMA: "Gamma",
+    _lib.BETA: "Beta",
+    _lib.WEIBULL: "Weibull",
+    _lib.BERNOULLI_GAMMA: "BernoulliGamma",
+}
+
+
+@dataclass(frozen=True)
+class VariableSpec:
+    name: str
+    family: int
+    scaling: int
+    post_rule: int = _lib.POST_NONE
+    lower_threshold: float = float("nan")  # values <= this are masked (mask_thresholded, variables.py:40-68)
+    upper_threshold: float = float("nan")  # values >= this are masked
+    lower_bound: float = None  # Variable.validate / check_bounds (variables.py:17-37)
+    upper_bound: float = None
+    scaling_keys: tuple = ()  # keys of Variable.scaling, i.e. the scaling_<k> variables of the trace file
+
+    def descriptor(self, modes):
+        if not 1 <= modes <= _lib.MAX_MODES:
+            raise ValueError(f"modes must be in 1..{_lib.MAX_MODES}, got {modes}")
+        return _lib.Variable(self.family, self.scaling, self.post_rule, modes, self.lower_threshold,
+                             self.upper_threshold)
+
+    @property
+    def parameters(self):
+        return FAMILY_PARAMETERS[self.family]
+
+    def n_params(self, modes):
+        return _lib.num_params(self.family, modes)
+
+
+# attrici/variables.py: Tas :306-338, Pr :341-486, Rlds :489-521, Ps :524-555, Hurs :558-609,
+# Tasskew :612-657, Rsds :660-702, Tasrange :705-750, Wind :753-798
+VARIABLES = {
+    "tas": VariableSpec("tas", _lib.NORMAL, _lib.SCALE_UNITY, lower_bound=0.0, scaling_keys=("datamin", "scale")),
+    "ps": VariableSpec("ps", _lib.NORMAL, _lib.SCALE_UNITY, lower_bound=0.0, scaling_keys=("datamin", "scale")),
+    "rlds": VariableSpec("rlds", _lib.NORMAL, _lib.SCALE_UNITY, lower_bound=0.0, scaling_keys=("datamin", "scale")),
+    "rsds": VariableSpec("rsds", _lib.NORMAL, _lib.SCALE_UNITY, _lib.POST_LE0_NAN, lower_bound=0.0,
+                         scaling_keys=("datamin", "scale")),
+    "tasskew": VariableSpec("tasskew", _lib.NORMAL, _lib.SCALE_NONE, _lib.POST_OUTSIDE01_NAN, 0.0001, 0.9999,
+                            lower_bound=0.0, upper_bound=1.0),
+    "pr": VariableSpec("pr", _lib.BERNOULLI_GAMMA, _lib.SCALE_PR, lower_bound=0.0, scaling_keys=("scale",)),
+    "tasrange": VariableSpec("tasrange", _lib.GAMMA, _lib.SCALE_RANGE, lower_threshold=0.01, lower_bound=0.0,
+                             scaling_keys=("scale",)),
+    "hurs": VariableSpec("hurs", _lib.BETA, _lib.SCALE_PERCENT, lower_threshold=0.01, upper_threshold=99.99,
+                         lower_bound=0.0, upper_bound=100.0, scaling_keys=("scale",)),
+    "sfcWind": VariableSpec("sfcWind", _lib.WEIBULL, _lib.SCALE_RANGE, lower_threshold=0.01, lower_bound=0.0,
+                            scaling_keys=("scale",)),
+}
+VARIABLES["wind"] = VariableSpec("wind", *[getattr(VARIABLES["sfcWind"], f) for f in
+                                           ("family", "scaling", "post_rule", "lower_threshold", "upper_threshold",
+                                            "lower_bound", "upper_bound", "scaling_keys")])
+
+
+def create_variable(name):
+    """Counterpart of ``attrici.variables.create_variable`` (variables.py:801-834): same names, same
+    ``ValueError`` for an unknown variable."""
+    try:
+        return VARIABLES[name]
+    except KeyError:
+        raise ValueError(f"Variable {name} not supported") from None

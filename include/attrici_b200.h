@@ -33,6 +33,11 @@ extern "C" {
 #endif
 
 #define ATTRICI_ABI_VERSION 1
+#if defined(__GNUC__)
+#define ATTRICI_API __attribute__((visibility("default")))
+#else
+#define ATTRICI_API
+#endif
 #define ATTRICI_MAX_MODES 4
 
 /* distributions (attrici/distributions.py:64-216; attrici/variables.py model table) */
@@ -91,25 +96,35 @@ typedef struct attrici_fit_options {
     double tol_pred;      /* stop when the predicted decrease <= tol_pred * max(|f|,1) (default 1e-11) */
     double lambda0;       /* initial Levenberg-Marquardt damping (default 1e-3) */
     int32_t zero_init;    /* 1: start from theta = 0 like model_scipy.py:113,234; 0: moment-based start */
-    int32_t reserved;
+    int32_t profile;      /* 1: time every likelihood pass with CUDA events (see attrici_fit_profile) */
 } attrici_fit_options_t;
 
-const char* attrici_last_error(void);
-int attrici_abi_version(void);
+ATTRICI_API const char* attrici_last_error(void);
+ATTRICI_API int attrici_abi_version(void);
+
+/* diagnostics (bench.py): kernels launched by this process so far; device time of the likelihood
+ * passes of the profiled fits of this thread (options.profile = 1) with the work they covered
+ * (cell_days = sum over launches of cells still iterating x days in the fit window) */
+ATTRICI_API long long attrici_launch_count(void);
+ATTRICI_API int attrici_fit_profile(int reset, double* pass_ms, long long* pass_launches, double* cell_days);
 
 /* number of fitted coefficients of a family (model_scipy.py:113, 234, 410-421) */
-int attrici_num_params(int family, int modes);
+ATTRICI_API int attrici_num_params(int family, int modes);
 
-/* bytes of device scratch needed by the calls below for a [T x C] batch */
-int attrici_workspace_bytes(int T, int C, size_t* bytes);
+/* defaults of the fit options (max_pass 60, FP32 day arithmetic, tol_pred 1e-11, lambda0 1e-3) */
+ATTRICI_API int attrici_default_fit_options(attrici_fit_options_t* opts);
+
+/* bytes of device scratch needed by the calls below for a [T x C] batch of one family
+ * (the Bernoulli-Gamma family also holds the [T x C] MT19937 uniforms of variables.py:458) */
+ATTRICI_API int attrici_workspace_bytes(int family, int T, int C, size_t* bytes);
 
 /* Fourier / GMT basis shared by all cells.
  * replaces attrici/util.py:85-104 (calc_oscillations) and the covariate construction of
  * attrici/estimation/model_scipy.py:180-197, 280-289.
  *   days[T]  int32 day offsets of the time axis (days since its first day; integers from the host)
  *   gmt[T]   float64 scaled predictor (attrici/detrend.py:698-707) */
-int attrici_build_basis(void* workspace, size_t workspace_bytes, const int32_t* days, const double* gmt,
-                        int T, void* stream);
+ATTRICI_API int attrici_build_basis(void* workspace, size_t workspace_bytes, int family, const int32_t* days,
+                        const double* gmt, int T, int C, void* stream);
 
 /* scaling + validity / wet-dry masks.
  * replaces create_variable -> <Variable>.__init__ (attrici/variables.py:92-111, 354-403, 565-591,
@@ -118,7 +133,7 @@ int attrici_build_basis(void* workspace, size_t workspace_bytes, const int32_t* 
  *   y_scaled[T x ld]  float32 out; NaN = masked / dry / missing (bit-exact float32 arithmetic)
  *   scaling[C x 2]    float64 out: {datamin, scale} (datamin = 0 where the reference has none)
  * Also gathers the per-cell start values / phase origins of the fit window [i0, i1) into the workspace. */
-int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+ATTRICI_API int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
                             const float* y, float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
                             double* scaling, void* stream);
 
@@ -127,7 +142,7 @@ int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes, const attri
  * reference has no gradient (finite differences inside scipy's L-BFGS-B).
  *   theta[C x P] in ; nll[C] out (= -log posterior) ; grad[C x P] out ; fisher[C x P x P] out (nullable)
  * needs attrici_build_basis + attrici_prep_scale_mask on the same workspace first. */
-int attrici_nll_grad(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+ATTRICI_API int attrici_nll_grad(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
                      const float* y_scaled, int64_t ld, int T, int C, int i0, int i1, int use_fp64,
                      const double* theta, double* nll, double* grad, double* fisher, void* stream);
 
@@ -135,7 +150,7 @@ int attrici_nll_grad(void* workspace, size_t workspace_bytes, const attrici_vari
  * replaces ModelScipy.fit (model_scipy.py:505-527: scipy L-BFGS-B with finite differences).
  *   params[C x P] out, logp[C] out (log posterior, FP64 evaluation at the returned point),
  *   status[C] out, n_pass[C] out (nullable).  Synchronises `stream` internally between passes. */
-int attrici_fit_batch(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+ATTRICI_API int attrici_fit_batch(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
                       const float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
                       const attrici_fit_options_t* opts, double* params, double* logp, int32_t* status,
                       int32_t* n_pass, void* stream);
@@ -149,7 +164,7 @@ int attrici_fit_batch(void* workspace, size_t workspace_bytes, const attrici_var
  *   seeds[C] uint32  (pr only; attrici/detrend.py:285, consumed by np.random.rand in variables.py:458)
  *   cfact[T x ld_out] float64 out ; replaced[T x ld_out] uint8 out (nullable) ;
  *   cfact_scaled[T x ld_out] float64 out (nullable) */
-int attrici_quantile_map(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+ATTRICI_API int attrici_quantile_map(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
                          const float* y, const float* y_scaled, int64_t ld, int T, int C,
                          const double* params, const double* scaling, const uint32_t* seeds,
                          double* cfact, uint8_t* replaced, double* cfact_scaled, int64_t ld_out,
@@ -157,21 +172,21 @@ int attrici_quantile_map(void* workspace, size_t workspace_bytes, const attrici_
 
 /* per-day distribution parameters for report_variables (attrici/detrend.py:462-467):
  *   which = index of the parameter in the family's order, counterfactual != 0 -> predictor = 0 */
-int attrici_eval_parameter(void* workspace, size_t workspace_bytes, const attrici_variable_t* var, int T,
+ATTRICI_API int attrici_eval_parameter(void* workspace, size_t workspace_bytes, const attrici_variable_t* var, int T,
                            int C, const double* params, int which, int counterfactual, double* out,
                            int64_t ld_out, void* stream);
 
 /* NumPy-legacy MT19937 doubles, one stream per cell (np.random.seed(s); np.random.rand(n)).
  *   out[n x ld] float64, cell-minor like every other series */
-int attrici_mt19937_uniform(const uint32_t* seeds, int C, int n, double* out, int64_t ld, void* stream);
+ATTRICI_API int attrici_mt19937_uniform(const uint32_t* seeds, int C, int n, double* out, int64_t ld, void* stream);
 
 /* whole path for one batch with HOST buffers (pinned recommended): H2D of y, scale, fit,
  * quantile map, D2H of cfact / params / logp / status, cells processed in slabs of
  * `slab_cells` with copies and kernels overlapped on internal streams.
  * replaces the cell loop attrici/detrend.py:760-788 around fit_and_detrend_cell (:258-416, I/O excluded).
  *   device_scratch: device buffer of attrici_detrend_host_scratch_bytes() bytes */
-int attrici_detrend_host_scratch_bytes(int T, int slab_cells, size_t* bytes);
-int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_options_t* opts,
+ATTRICI_API int attrici_detrend_host_scratch_bytes(int family, int T, int slab_cells, size_t* bytes);
+ATTRICI_API int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_options_t* opts,
                          const float* y_host, int64_t ld_host, int T, int C, int i0, int i1,
                          const int32_t* days_host, const double* gmt_host, const uint32_t* seeds_host,
                          double* cfact_host, int64_t ld_out_host, uint8_t* replaced_host,

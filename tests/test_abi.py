@@ -1,0 +1,86 @@
+"""The C-ABI library loads and exports every symbol include/attrici_b200.h declares; argument errors are
+reported as ATTRICI_E* codes with a message (no compute call here: no GPU needed)."""
+
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from attrici_b200 import _lib
+from attrici_b200.variables import VARIABLES, create_variable
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "attrici_b200.h")).read()
+    return sorted(set(re.findall(r"ATTRICI_API\s+[\w\s\*]+?\b(attrici_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert sorted(_lib.EXPORTS) == syms  # the ctypes stub binds exactly the header
+
+
+def test_abi_version_and_param_counts():
+    lib = _lib.load()
+    assert lib.attrici_abi_version() == _lib.ABI_VERSION
+    # P = 3 + 6m (27 at m = 4), Bernoulli-Gamma 5 + 10m (45)
+    for m in (1, 2, 3, 4):
+        for fam in (_lib.NORMAL, _lib.GAMMA, _lib.BETA, _lib.WEIBULL):
+            assert _lib.num_params(fam, m) == 3 + 6 * m
+        assert _lib.num_params(_lib.BERNOULLI_GAMMA, m) == 5 + 10 * m
+    assert lib.attrici_num_params(9, 4) == -1
+    assert lib.attrici_num_params(0, 5) == -1
+    assert b"bad family" in lib.attrici_last_error()
+
+
+def test_workspace_query_and_argument_errors():
+    lib = _lib.load()
+    n = _lib.workspace_bytes(_lib.NORMAL, 43464, 10000)
+    assert 50e6 < n < 1e9
+    assert _lib.workspace_bytes(_lib.BERNOULLI_GAMMA, 43464, 10000) > n + 8 * 43464 * 10000 - 1
+    with pytest.raises(_lib.AttriciCudaError, match="T >= 2"):
+        _lib.workspace_bytes(_lib.NORMAL, 1, 10)
+    var = create_variable("tas").descriptor(4)
+    # null pointers and bad shapes are rejected before any CUDA call
+    rc = lib.attrici_fit_batch(None, 0, C.byref(var), None, 10, 100, 10, 0, 100, None, None, None, None, None, None)
+    assert rc == -1 and b"null" in lib.attrici_last_error()
+    rc = lib.attrici_prep_scale_mask(None, 0, C.byref(var), None, None, 5, 100, 10, 0, 100, None, None)
+    assert rc == -1 and b"leading dimension" in lib.attrici_last_error()
+    rc = lib.attrici_quantile_map(None, 0, None, None, None, 10, 100, 10, None, None, None, None, None, None, 10, None)
+    assert rc == -1 and b"descriptor" in lib.attrici_last_error()
+    bad = create_variable("tas").descriptor(4)
+    bad.modes = 7
+    rc = lib.attrici_nll_grad(None, 0, C.byref(bad), None, 10, 100, 10, 0, 100, 1, None, None, None, None, None)
+    assert rc == -1 and b"modes" in lib.attrici_last_error()
+
+
+def test_variable_table_matches_reference_model_table():
+    # attrici/variables.py create_variable (:801-834) and SURVEY.md section 8a
+    fam = {"tas": _lib.NORMAL, "ps": _lib.NORMAL, "rlds": _lib.NORMAL, "rsds": _lib.NORMAL, "tasskew": _lib.NORMAL,
+           "pr": _lib.BERNOULLI_GAMMA, "tasrange": _lib.GAMMA, "hurs": _lib.BETA, "sfcWind": _lib.WEIBULL,
+           "wind": _lib.WEIBULL}
+    assert set(VARIABLES) == set(fam)
+    for k, f in fam.items():
+        assert VARIABLES[k].family == f
+    with pytest.raises(ValueError, match="not supported"):
+        create_variable("huss")
+    assert create_variable("pr").parameters == ("p", "mu", "nu")
+    assert create_variable("sfcWind").parameters == ("alpha", "beta")
+
+
+def test_solver_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from attrici_b200.solver import CellBatchSolver
+
+    with pytest.raises(_lib.AttriciCudaError, match="no CPU fallback"):
+        CellBatchSolver("tas")

@@ -1,0 +1,344 @@
+"""Parity of the CUDA path (through the C ABI / ctypes) with the oracle and the reference's golden vectors.
+
+Tolerances (north_star): masks, wet/dry patterns, replacement flags and float32 y_scaled bit-exact;
+log posterior no worse than the reference's + 1e-6 relative (we require 1e-9 of the oracle's exact MAP);
+coefficients within 2e-5 of the exact MAP; counterfactual values within 1e-5 relative of the oracle run at
+the same optimum and within 2e-4 of the reference's own (L-BFGS-B, ftol 2.2e-9) result.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from attrici_b200 import _lib, synthetic
+from attrici_b200.detrend import Config, detrend_cells
+from attrici_b200.solver import CellBatchSolver, cell_seeds
+from oracle import attrici_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(DEV)
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def golden_batch(name, extra=0):
+    """[T, 1 + extra] batch: the fixture cell plus perturbed copies (scaled / shifted noise-free variants)."""
+    c = helpers.Cell(name)
+    cols = [c.d["y"]]
+    rng = np.random.default_rng(5)
+    for i in range(extra):
+        y = c.d["y"].copy()
+        k = rng.integers(10, 400)
+        y[:k] = np.nan  # leading gap: phase origin moves
+        cols.append(y)
+    return c, np.stack(cols, axis=1).astype(np.float32)
+
+
+def solver_for(c, n_cells, **kw):
+    s = CellBatchSolver(c.variable, modes=helpers.MODES, device=DEV, **kw)
+    s.set_predictor(c.days, c.gmt, n_cells)
+    return s
+
+
+@pytest.mark.parametrize("name", helpers.ONE_PER_VARIABLE)
+def test_scale_and_masks_bit_exact(name):
+    c, y = golden_batch(name, extra=2)
+    y[100, 1] = np.inf  # detrend.py:311
+    y[200, 2] = -np.inf
+    s = solver_for(c, y.shape[1])
+    ys, scaling = s.scale(dev(y), (0, c.n_fit))
+    ys, scaling = host(ys), host(scaling)
+    for j in range(y.shape[1]):
+        want, sc, _ = oracle.scale_variable(c.variable, y[:, j])
+        assert np.array_equal(np.isnan(ys[:, j]), np.isnan(want))
+        if c.variable == "pr":
+            m = ~np.isnan(want)
+            np.testing.assert_allclose(ys[m, j], want[m], rtol=1e-5)
+            np.testing.assert_allclose(scaling[j, 1], sc["scale"], rtol=1e-5)
+        else:
+            assert np.array_equal(ys[:, j], want, equal_nan=True)
+            assert scaling[j, 1] == sc.get("scale", 1.0)
+            assert scaling[j, 0] == sc.get("datamin", 0.0)
+    if c.variable != "pr":
+        assert np.array_equal(ys[:, 0], c.d["y_scaled"], equal_nan=True)  # the reference's own y_scaled
+
+
+@pytest.mark.parametrize("name", helpers.ONE_PER_VARIABLE)
+@pytest.mark.parametrize("fp64", [True, False])
+def test_nll_grad_known_answers(name, fp64):
+    c, y = golden_batch(name, extra=1)
+    s = solver_for(c, 2)
+    ys, _ = s.scale(dev(y), (0, c.n_fit))
+    th = np.stack([c.d["theta_probe"], 0.5 * c.d["theta_probe"]])
+    nll, grad, fisher = s.nll_grad(ys, th, use_fp64=fp64, want_fisher=True)
+    nll, grad, fisher = host(nll), host(grad), host(fisher)
+    ys_h = host(ys)
+    for j in range(2):
+        prob = oracle.build_problem(c.family, ys_h[:, j], c.gmt, c.days, helpers.MODES, slice(0, c.n_fit))
+        f, g = prob.nll(th[j], 1)
+        if fp64:
+            np.testing.assert_allclose(nll[j], f, rtol=1e-11)
+            np.testing.assert_allclose(grad[j], g, rtol=1e-8, atol=1e-6)
+        else:
+            np.testing.assert_allclose(nll[j], f, rtol=3e-7)
+            assert np.abs(grad[j] - g).max() <= 3e-5 * np.abs(g).max() + 1e-2
+        assert np.allclose(fisher[j], fisher[j].T)
+        assert np.all(np.linalg.eigvalsh(fisher[j]) > 0)
+    if fp64 and c.variable != "pr":
+        np.testing.assert_allclose(nll[0], c.d["ref_f_probe"], rtol=1e-11)  # the unmodified reference's value
+
+
+@pytest.mark.parametrize("name", helpers.FIXTURES)
+def test_fit_reaches_exact_map(name):
+    c, y = golden_batch(name, extra=1)
+    s = solver_for(c, 2)
+    ys, _ = s.scale(dev(y), (0, c.n_fit))
+    fit = s.fit(ys)
+    params, logp, status, n_pass = host(fit.params), host(fit.logp), host(fit.status), host(fit.n_pass)
+    ys_h = host(ys)
+    assert (status == _lib.STATUS_CONVERGED).all()
+    assert (n_pass <= 30).all()
+    for j in range(2):
+        prob = oracle.build_problem(c.family, ys_h[:, j], c.gmt, c.days, helpers.MODES, slice(0, c.n_fit))
+        ref = oracle.fit_newton(prob)
+        np.testing.assert_allclose(logp[j], ref["logp"], rtol=1e-9)
+        assert np.abs(params[j] - ref["params"]).max() < 2e-5
+    ref_nll = -float(c.d["ref_logp"])
+    assert -logp[0] <= ref_nll + 1e-6 * abs(ref_nll)  # north_star: no worse than the reference
+    assert np.abs(params[0] - c.d["ref_params"]).max() < 5e-3
+
+
+@pytest.mark.parametrize("name", helpers.ONE_PER_VARIABLE)
+def test_quantile_map_at_reference_coefficients(name):
+    """estimate_distribution x2 + quantile map + rescale + replacement at the reference's own trace."""
+    c, y = golden_batch(name)
+    s = solver_for(c, 1)
+    ys, scaling = s.scale(dev(y), (0, c.n_fit))
+    seeds = cell_seeds(0, [c.d["lat"]], [c.d["lon"]]) if c.variable == "pr" else None
+    cfact, replaced, cs = s.quantile_map(dev(y), ys, dev(c.d["ref_params"][None, :]), scaling, seeds, want_scaled=True)
+    idx = c.d["sample_idx"]
+    got = host(cfact)[idx, 0]
+    np.testing.assert_allclose(got, c.d["ref_cfact"], rtol=1e-5 if c.variable == "pr" else 1e-10, equal_nan=True)
+    assert np.array_equal(host(replaced)[idx, 0], helpers.replaced_codes(c.d["ref_replaced"]))
+    if c.variable == "pr":
+        assert np.array_equal(got == 0, c.d["ref_cfact"] == 0)  # same days dry / made wet (MT19937 stream)
+    for i, pname in enumerate(s.spec.parameters):
+        p = host(s.eval_parameter(dev(c.d["ref_params"][None, :]), pname))[idx, 0]
+        pc = host(s.eval_parameter(dev(c.d["ref_params"][None, :]), i, counterfactual=True))[idx, 0]
+        np.testing.assert_allclose(p, c.d[f"ref_{pname}"], rtol=1e-12)
+        np.testing.assert_allclose(pc, c.d[f"ref_{pname}_cfact"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", helpers.ONE_PER_VARIABLE)
+def test_detrend_end_to_end(name):
+    c, y = golden_batch(name, extra=1)
+    s = CellBatchSolver(c.variable, modes=helpers.MODES, device=DEV)
+    seeds = cell_seeds(0, [c.d["lat"]] * 2, [c.d["lon"]] * 2) if c.variable == "pr" else None
+    s.set_predictor(c.days, c.gmt, 2)
+    out = s.detrend_device(dev(y), c.days, c.gmt, (0, c.n_fit), seeds)
+    cfact, replaced = host(out["cfact"]), host(out["replaced"])
+    for j in range(2):
+        ref = oracle.detrend_cell(c.variable, y[:, j], c.gmt, c.days, helpers.MODES, fit_stop=c.n_fit,
+                                  lat=c.d["lat"], lon=c.d["lon"])
+        if c.variable == "pr":
+            # dry -> wet decisions compare u * p_ref with p_cf: identical unless a day sits within the
+            # fit tolerance of the boundary
+            differ = (cfact[:, j] == 0) != (ref["cfact"] == 0)
+            assert differ.sum() <= 2
+            m = ~differ & (ref["cfact"] > 0)
+            np.testing.assert_allclose(cfact[m, j], ref["cfact"][m], rtol=2e-4)
+        else:
+            np.testing.assert_allclose(cfact[:, j], ref["cfact"], rtol=1e-5, equal_nan=True)
+            assert np.array_equal(replaced[:, j], helpers.replaced_codes(ref["replaced"]))
+    idx = c.d["sample_idx"]
+    if c.variable != "pr":
+        # the reference's own result (optimum only converged to ~1e-4)
+        np.testing.assert_allclose(cfact[idx, 0], c.d["ref_cfact"], rtol=3e-4, equal_nan=True)
+
+
+def test_mt19937_stream_is_numpys():
+    s = CellBatchSolver("pr", device=DEV)
+    seeds = np.array([0, 1, 12345, 2**32 - 1, oracle.cell_seed(0, 50.75, 9.25)], dtype=np.uint32)
+    u = host(s.mt19937_uniform(seeds, 2000))
+    for j, sd in enumerate(seeds):
+        np.random.seed(int(sd))
+        assert np.array_equal(u[:, j], np.random.rand(2000))
+
+
+@pytest.mark.parametrize("n_cells", [1, 33, 130])
+def test_ragged_batches_and_empty_cells(n_cells):
+    """cell counts that do not fill a warp / CTA, a cell without any valid day, a cell with a NaN block."""
+    T = 2500
+    y = synthetic.tas_cells(n_cells, T, seed=7)
+    if n_cells > 2:
+        y[:, 1] = np.nan                      # no data: reference skips the cell (detrend.py:315-317)
+        y[300:900, 2] = np.nan
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    s = CellBatchSolver("tas", device=DEV)
+    out = s.detrend_device(dev(y), days, gmt)
+    status, logp, params = host(out["fit"].status), host(out["fit"].logp), host(out["fit"].params)
+    cfact = host(out["cfact"])
+    for j in sorted({0, min(2, n_cells - 1), n_cells - 1}):
+        ref = oracle.detrend_cell("tas", y[:, j], gmt, days, helpers.MODES)
+        assert status[j] == 0
+        np.testing.assert_allclose(logp[j], ref["logp"], rtol=1e-9)
+        assert np.abs(params[j] - ref["trace"]["params"]).max() < 5e-5
+        np.testing.assert_allclose(cfact[:, j], ref["cfact"], rtol=1e-5, equal_nan=True)
+    if n_cells > 2:
+        assert status[1] == _lib.STATUS_NO_DATA and np.isnan(logp[1]) and np.isnan(params[1]).all()
+        assert np.isnan(cfact[:, 1]).all()
+
+
+@pytest.mark.parametrize("variable,modes", [("sfcWind", 1), ("sfcWind", 3), ("hurs", 2), ("tasrange", 4), ("rsds", 4),
+                                            ("tas", 2)])
+def test_synthetic_families_and_modes_sweep(variable, modes):
+    """Config 4: other distributions on synthetic series, modes 1-4, per-cell convergence masks."""
+    T, C = 4000, 6
+    y = synthetic.GENERATORS[variable](C, T)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    s = CellBatchSolver(variable, modes=modes, device=DEV)
+    out = s.detrend_device(dev(y), days, gmt)
+    status, logp, cfact = host(out["fit"].status), host(out["fit"].logp), host(out["cfact"])
+    replaced = host(out["replaced"])
+    assert (status == 0).all()
+    for j in (0, C - 1):
+        ref = oracle.detrend_cell(variable, y[:, j], gmt, days, modes)
+        np.testing.assert_allclose(logp[j], ref["logp"], rtol=1e-9)
+        np.testing.assert_allclose(cfact[:, j], ref["cfact"], rtol=2e-5, atol=1e-9, equal_nan=True)
+        assert np.array_equal(replaced[:, j], helpers.replaced_codes(ref["replaced"]))
+
+
+def test_pr_synthetic_wet_dry_exact():
+    """Config 3: dry/wet mask bit-exact, counterfactual dry days exactly 0, same days made wet."""
+    T, C = 6000, 4
+    y = synthetic.pr_cells(C, T)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    lat, lon = synthetic.tile_coordinates(2, 2)
+    seeds = cell_seeds(0, lat, lon)
+    s = CellBatchSolver("pr", device=DEV)
+    out = s.detrend_device(dev(y), days, gmt, seeds=seeds)
+    ys, cfact, status = host(out["y_scaled"]), host(out["cfact"]), host(out["fit"].status)
+    assert (status == 0).all()
+    for j in range(C):
+        ref = oracle.detrend_cell("pr", y[:, j], gmt, days, helpers.MODES, lat=lat[j], lon=lon[j])
+        assert np.array_equal(np.isnan(ys[:, j]), np.isnan(ref["y_scaled"]))
+        differ = (cfact[:, j] == 0) != (ref["cfact"] == 0)
+        assert differ.sum() <= 2
+        m = ~differ & (ref["cfact"] > 0)
+        np.testing.assert_allclose(cfact[m, j], ref["cfact"][m], rtol=2e-4)
+        np.testing.assert_allclose(host(out["fit"].logp)[j], ref["logp"], rtol=1e-8)
+
+
+def test_host_pipeline_matches_device_path():
+    """attrici_detrend_host (slabs, pinned host buffers, two streams) == the device-resident calls."""
+    T, C = 3000, 300
+    y = synthetic.tas_cells(C, T, seed=11, nan_fraction=0.05)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    s = CellBatchSolver("tas", device=DEV)
+    a = s.detrend_device(dev(y), days, gmt)
+    s2 = CellBatchSolver("tas", device=DEV)
+    b = s2.detrend_host(torch.from_numpy(y).pin_memory(), days, gmt, slab_cells=128)  # 128 + 128 + 44
+    assert np.array_equal(host(a["cfact"]), b["cfact"].numpy(), equal_nan=True)
+    assert np.array_equal(host(a["replaced"]), b["replaced"].numpy())
+    assert np.array_equal(host(a["fit"].params), b["params"].numpy())
+    assert np.array_equal(host(a["fit"].logp), b["logp"].numpy())
+    assert np.array_equal(host(a["fit"].status), b["status"].numpy())
+    assert np.array_equal(host(a["scaling"]), b["scaling"].numpy())
+
+
+def test_batched_driver_single_rank():
+    T, n_lat, n_lon = 2500, 3, 5
+    lat, lon = synthetic.tile_coordinates(n_lat, n_lon)
+    y = synthetic.tas_cells(n_lat * n_lon, T, seed=21)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    res = detrend_cells(Config("tas", slab_cells=8), y, gmt, days, lat, lon)
+    assert res["indices"].tolist() == list(range(15)) and res["params"].shape == (15, 27)
+    part = detrend_cells(Config("tas", task_id=1, task_count=4), y, gmt, days, lat, lon)
+    assert part["indices"].tolist() == [4, 5, 6, 7]
+    np.testing.assert_array_equal(part["cfact"], res["cfact"][:, 4:8])
+    ref = oracle.detrend_cell("tas", y[:, 9], gmt, days, helpers.MODES)
+    np.testing.assert_allclose(res["cfact"][:, 9], ref["cfact"], rtol=1e-5)
+
+
+def test_full_length_series_properties():
+    """BASELINE size in time (43 464 days), 1 024 cells: size-independent properties of the map."""
+    T, C = synthetic.DAYS_1901_2019, 1024
+    y = synthetic.tas_tile_torch(C, T, device=DEV, nan_fraction=0.01)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    s = CellBatchSolver("tas", device=DEV)
+    s.set_predictor(days, gmt, C)
+    ys, scaling = s.scale(y)
+    fit = s.fit(ys)
+    assert (fit.status == 0).all()
+    cfact, replaced, cs = s.quantile_map(y, ys, fit.params, scaling, want_scaled=True)
+    mu = s.eval_parameter(fit.params, "mu")
+    mu_cf = s.eval_parameter(fit.params, "mu", counterfactual=True)
+    sigma = s.eval_parameter(fit.params, "sigma")
+    ok = ~torch.isnan(ys) & (replaced == 0)
+    # Normal with GMT-independent sigma: cfact_scaled - y_scaled == mu_cf - mu_ref day by day (SURVEY 8d iv)
+    z = (ys.double() - mu) / sigma
+    inner = ok & (z.abs() < 5)
+    err = ((cs - ys.double()) - (mu_cf - mu)).abs()[inner]
+    assert err.max().item() < 1e-9
+    # NaN days stay NaN and are flagged; everything else is finite
+    assert torch.equal(torch.isnan(cfact), torch.isnan(y))
+    assert torch.equal(replaced == 1, torch.isnan(y))
+    # rank preservation: F_cf(cfact_scaled) == F_ref(y_scaled)
+    q_ref = torch.special.ndtr(z)
+    q_cf = torch.special.ndtr((cs - mu_cf) / sigma)
+    assert (q_ref - q_cf).abs()[inner].max().item() < 1e-12
+    # one cell against the oracle at full length
+    yh = y[:, 5].cpu().numpy()
+    ref = oracle.detrend_cell("tas", yh, gmt, days, helpers.MODES)
+    np.testing.assert_allclose(fit.logp[5].item(), ref["logp"], rtol=1e-9)
+    np.testing.assert_allclose(cfact[:, 5].cpu().numpy(), ref["cfact"], rtol=1e-5, equal_nan=True)
+
+
+def test_model_cuda_plugin_interface():
+    """ModelCuda behind the reference's Model interface: fit / estimate_logp / estimate_distribution."""
+    from dataclasses import dataclass
+
+    from attrici_b200.estimation import ModelCuda
+
+    @dataclass
+    class Normal:  # stands for attrici.distributions.Normal (a dataclass with these fields, :64-90)
+        mu: np.ndarray
+        sigma: np.ndarray
+
+    @dataclass
+    class Par:
+        link: object
+        dependent: bool
+
+    c = helpers.Cell("tas_lat50.75_lon9.25")
+    t = np.datetime64("1901-01-01") + np.arange(c.n).astype("timedelta64[D]")
+
+    class Arr:
+        def __init__(self, values, time):
+            self.values = values
+            self.time = type("T", (), {"values": time})()
+
+    valid = ~np.isnan(c.ys[: c.n_fit])
+    obs = Arr(c.ys[: c.n_fit][valid], t[: c.n_fit][valid])
+    pred = Arr(c.gmt[: c.n_fit][valid], t[: c.n_fit][valid])
+    m = ModelCuda(Normal, {"mu": Par(None, True), "sigma": Par(np.exp, False)}, obs, pred, modes=4)
+    trace = m.fit()
+    ref = oracle.fit_newton(c.problem)
+    np.testing.assert_allclose(m.estimate_logp(trace), ref["logp"], rtol=1e-9)
+    assert np.abs(trace["params"] - ref["params"]).max() < 2e-5
+    d = m.estimate_distribution(trace, Arr(c.gmt, t))
+    want = oracle.estimate_params("normal", trace["params"], c.gmt, c.days, 4)
+    np.testing.assert_allclose(d.mu, want["mu"], rtol=1e-12)
+    np.testing.assert_allclose(d.sigma, want["sigma"], rtol=1e-12)
+    with pytest.raises(NotImplementedError):
+        ModelCuda(Normal, {"mu": Par(None, True), "sigma": Par(np.exp, False)}, obs, pred, modes=4, window_size=31)
+    with pytest.raises(ValueError):
+        ModelCuda(dict, {"mu": Par(None, True)}, obs, pred, modes=4)

@@ -1,0 +1,93 @@
+"""Host logic of the multi-GPU path on CPU: the reference's cell partition rule and the final gather
+over a world_size-2 gloo group."""
+
+import os
+
+import numpy as np
+import pytest
+
+from attrici_b200.detrend import gather_cells, get_task_indices, scale_predictor
+from attrici_b200.solver import cell_seeds
+from oracle import attrici_oracle as oracle
+
+
+def reference_rule(n, k):
+    """attrici/detrend.py:138-153 restated with plain integers."""
+    if n % k == 0:
+        return [n // k] * k
+    calls = [n // k + 1] * k
+    out, tot = [], 0
+    for c in calls:
+        if tot + c > n:
+            out.append(n - tot)
+            out.extend([0] * (k - len(out)))
+            break
+        out.append(c)
+        tot += c
+    return out
+
+
+@pytest.mark.parametrize("n,k", [(67420, 8), (10000, 8), (10000, 3), (7, 4), (5, 8), (16, 4), (1, 1), (100, 7)])
+def test_partition_rule(n, k):
+    counts = reference_rule(n, k)
+    seen = []
+    for r in range(k):
+        idx = get_task_indices(n, r, k)
+        assert len(idx) == counts[r]
+        seen.extend(idx.tolist())
+    assert seen == list(range(n))  # contiguous, disjoint, complete
+    if (n, k) == (67420, 8):
+        assert counts == [8428] * 7 + [8424]
+
+
+def test_partition_errors():
+    with pytest.raises(ValueError):
+        get_task_indices(10, 4, 4)
+    with pytest.raises(ValueError):
+        get_task_indices(10, -1, 4)
+
+
+def test_predictor_and_seeds_match_oracle():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ssa_gmt.npz"))["tas"]
+    assert np.array_equal(scale_predictor(g, 44925), oracle.gmt_on_time_axis(g, 44925))
+    lat, lon = np.array([50.75, -33.25, 0.25]), np.array([9.25, -70.75, 179.75])
+    want = [oracle.cell_seed(3, a, b) for a, b in zip(lat, lon)]
+    assert cell_seeds(3, lat, lon).tolist() == want
+
+
+def _worker(rank, world, port, n_cells, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        counts = [len(get_task_indices(n_cells, r, world)) for r in range(world)]
+        idx = get_task_indices(n_cells, rank, world)
+        local = {"params": np.stack([np.full(27, float(i)) for i in idx]) if len(idx) else np.empty((0, 27)),
+                 "logp": idx.astype(np.float64) * 2.0,
+                 "status": (idx % 3).astype(np.int32)}
+        out = gather_cells(local, counts, dist)
+        ok = (out["params"].shape == (n_cells, 27) and np.array_equal(out["params"][:, 0], np.arange(n_cells))
+              and np.array_equal(out["logp"], 2.0 * np.arange(n_cells))
+              and np.array_equal(out["status"], (np.arange(n_cells) % 3).astype(np.int32)))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_cells", [11, 8])
+def test_gather_world_size_2_gloo(n_cells):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n_cells) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_cells, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(2))
+    assert got == [(0, True), (1, True)]
