@@ -93,7 +93,7 @@ class ModelCuda:
         """Returns the SciPy trace schema ``{"logp": float, "params": ndarray[P]}`` (model_scipy.py:524-527)."""
         s = self._solver
         s.set_predictor(self._days, self._gmt, 1)
-        y = torch.as_tensor(self._y[:, None]).to(s.device)
+        y = torch.from_numpy(np.ascontiguousarray(self._y.reshape(-1, 1))).to(s.device)
         ys, _ = s.scale(y)
         fit = s.fit(ys)
         self._status = int(fit.status.item())

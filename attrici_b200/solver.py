@@ -84,7 +84,7 @@ class CellBatchSolver:
     def _check_series(self, y, name):
         if not (isinstance(y, torch.Tensor) and y.is_cuda and y.dtype == torch.float32 and y.dim() == 2):
             raise TypeError(f"{name} must be a 2-D float32 CUDA tensor [T, C]")
-        if y.stride(1) != 1:
+        if y.shape[1] > 1 and y.stride(1) != 1:
             raise ValueError(f"{name} must be time-major with unit stride along cells")
         return y.shape[0], y.shape[1], y.stride(0)
 

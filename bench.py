@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Headline benchmark: gridcell-fits/sec (43 464-day series, modes=4) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # the CUDA path (this repo)
+    python bench.py --impl reference [...]                       # the reference's CPU algorithm
+
+A "step" is one pass of the hot path (scale -> MAP fit -> factual/counterfactual parameters -> quantile
+map -> rescale/replacement) over one batch: the 100x100-cell tas tile of BASELINE.json configs[1]
+(C = 10 000 cells, T = 43 464 days, synthetic, float32).  With N > 1 every rank (one process per GPU, torchrun)
+detrends its own tile of the same size - weak scaling - and the step ends with the path's one collective,
+an all-gather of the per-cell coefficients.
+
+``value``  : cells / second with the tile resident in HBM (device-timed with CUDA events, max over ranks).
+``e2e``    : the same through the reference-facing host API (``CellBatchSolver.detrend_host`` ->
+             ``attrici_detrend_host``): float32 series in pinned host memory, float64 counterfactuals and
+             flags back in pinned host memory, copies inside the timed region.
+``roofline``: the likelihood-pass kernel (dominant), achieved = algorithmic bytes (4 B per cell-day still
+             iterating) / its CUDA-event time summed over the timed steps.
+``cpu_baseline`` / ``--impl reference``: the oracle's port of the reference algorithm (SciPy L-BFGS-B with
+             finite-difference gradients on the reference objective, scipy.stats quantile map) on the
+             host cores, one cell per process, on a bounded sample of the same tile.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+T_DAYS = 43464
+TILE_CELLS = 10000
+MODES = 4
+METRIC = "gridcell-fits/sec (43k-day series, modes=4)"
+UNIT = "cells/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [x for x in sm if x > 0.5 * max(smax)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port), one cell per process
+# ------------------------------------------------------------------------------------------------
+def _cpu_cell(args):
+    cell, n_days = args
+    from attrici_b200 import synthetic
+    from oracle import attrici_oracle as oracle
+
+    y = synthetic.tas_cells(1, n_days, seed=1234, first_cell=cell)[:, 0]
+    gmt, days = synthetic.smoothed_gmt(n_days), synthetic.time_axis(n_days)
+    t0 = time.perf_counter()
+    out = oracle.detrend_cell("tas", y, gmt, days, MODES, solver="lbfgsb")
+    return time.perf_counter() - t0, int(out["trace"]["nfev"])
+
+
+def _cpu_init():
+    from attrici_b200 import synthetic  # noqa: F401
+    from oracle import attrici_oracle  # noqa: F401
+
+
+def cpu_pool(cores):
+    """Worker pool with one BLAS thread per process, as in the reference's HPC recipe (USAGE.md:128-174);
+    the variables must be in the environment the workers are spawned with."""
+    import multiprocessing as mp
+
+    saved = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    for k in saved:
+        os.environ[k] = "1"
+    try:
+        pool = mp.get_context("spawn").Pool(cores, initializer=_cpu_init)
+        pool.map(abs, range(cores))  # workers up and imported before anything is timed
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return pool
+
+
+def cpu_sample(pool, n_cells, first_cell=0):
+    """Detrend ``n_cells`` synthetic tas cells with the reference algorithm; returns (wall s, per-cell results)."""
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_cell, [(first_cell + i, T_DAYS) for i in range(n_cells)], chunksize=1)
+    return time.perf_counter() - t0, res
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = min(host_cores(), 64)
+    n_cells = cores  # one cell per core and step: ~11 s of CPU per step
+    times = []
+    with cpu_pool(cores) as pool:  # worker start-up and imports are the warm-up; the CPU path has no other
+        for k in range(args.steps):
+            wall, _ = cpu_sample(pool, n_cells, first_cell=k * n_cells)
+            times.append(wall)
+    total = sum(times)
+    value = n_cells * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "tas Gaussian 100x100-cell tile, T=43464, modes=4 (BASELINE configs[1])",
+                   "cells_per_step": n_cells},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_cells} cells of the tile per step, one process per core, "
+                                   "SciPy L-BFGS-B + finite differences on the reference objective, scipy.stats quantile map"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    from attrici_b200 import _lib, synthetic
+    from attrici_b200.solver import CellBatchSolver
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    C, T = args.cells, T_DAYS
+    y = synthetic.tas_tile_torch(C, T, seed=1234 + rank, device=device, nan_fraction=0.001)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    solver = CellBatchSolver("tas", modes=MODES, device=device, profile=True)
+    solver.set_predictor(days, gmt, C)
+    P = solver.n_params
+    gathered = torch.empty((world * C, P), dtype=torch.float64, device=device) if world > 1 else None
+
+    def step():
+        out = solver.detrend_device(y, days, gmt)
+        if world > 1:  # the path's one collective: final gather of the per-cell coefficients
+            dist.all_gather_into_tensor(gathered, out["fit"].params)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    barrier()
+    n_pass = out["fit"].n_pass.cpu().numpy()
+    status = out["fit"].status.cpu().numpy()
+    _lib.fit_profile(reset=True)
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - launches0
+    pass_ms, pass_launches, cell_days = _lib.fit_profile(reset=True)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * C * args.steps / (ms / 1e3)
+
+    # end to end through the host API: pinned host buffers, copies inside the timed region
+    del out
+    y_host = torch.empty((T, C), dtype=torch.float32, pin_memory=True)
+    y_host.copy_(y)
+    del y
+    torch.cuda.empty_cache()
+    solver_h = CellBatchSolver("tas", modes=MODES, device=device)
+    res = solver_h.detrend_host(y_host, days, gmt, slab_cells=args.slab)  # warm-up, allocates pinned outputs
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = solver_h.detrend_host(y_host, days, gmt, slab_cells=args.slab, out=res)
+        _ = float(res["logp"][0])  # result read on the host
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * C * e2e_steps / e2e_s
+    h2d = y_host.numel() * 4 + T * 12
+    d2h = sum(int(v.numel() * v.element_size()) for v in res.values() if v is not None)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = (4.0 * cell_days / 1e9) / (pass_ms / 1e3) if pass_ms > 0 else None
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = min(host_cores(), 64)
+            with cpu_pool(cores) as pool:
+                wall, r = cpu_sample(pool, cores)
+            cpu = {"value": cores / wall, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{cores} cells of the same tile, one process per core (SciPy L-BFGS-B with finite "
+                             f"differences, {int(np.mean([x[1] for x in r]))} objective evaluations per cell on average)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 day arithmetic, f64 reductions/solve/quantile map",
+            "data": "synthetic",
+            "config": {"workload": "tas Gaussian 100x100-cell tile, T=43464, modes=4 (BASELINE configs[1])",
+                       "cells_per_gpu": C, "days": T, "modes": MODES,
+                       "l2": "inputs larger than L2 (1.74 GB float32 series per tile per pass)",
+                       "passes_per_cell_mean": float(n_pass.mean()), "passes_per_cell_max": int(n_pass.max()),
+                       "converged_fraction": float((status == 0).mean())},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "slab_cells": args.slab},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "pass_kernel<normal, float, moments>", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": None, "peak_source": peak_src,
+                         "launches": int(pass_launches), "avg_launch_ms": pass_ms / max(pass_launches, 1),
+                         "share_of_step": pass_ms / ms},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--cells", type=int, default=TILE_CELLS, help="cells per GPU (default: the 100x100 tile)")
+    ap.add_argument("--slab", type=int, default=2048, help="cells per device slab of the host pipeline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()
