@@ -98,7 +98,6 @@ StepParams step_params(const attrici_variable_t& var, const attrici_fit_options_
     sp.term = family_term(var.family, slot);
     sp.modes = var.modes;
     sp.slot = slot;
-    sp.fp64 = o.use_fp64;
     sp.max_pass = o.max_pass;
     sp.tol_pred = o.tol_pred;
     sp.lambda0 = o.lambda0;
@@ -106,18 +105,29 @@ StepParams step_params(const attrici_variable_t& var, const attrici_fit_options_
     return sp;
 }
 
-// Fisher-scoring iteration of one likelihood term over the whole batch
+int read_counter(const int* dev, int* host, cudaStream_t s) {
+    ATTRICI_CUDA_CHECK(cudaMemcpyAsync(host, dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ATTRICI_CUDA_CHECK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Fisher-scoring iteration of one likelihood term over the whole batch.  Cells still iterating are kept in
+// a compact list (ping-pong); once fewer than half of the batch is left the likelihood pass runs over the
+// list (gathered columns, more time chunks per cell) instead of over all cells with a status mask.
 int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_options_t& o, int slot,
              const float* y_scaled, int64_t ld, int i0, int i1, cudaStream_t s) {
     StepParams sp = step_params(var, o, slot);
-    ATTRICI_TRY(launch_fit_init(ws, sp, s));
-    int running = 0;
-    ATTRICI_CUDA_CHECK(cudaMemcpyAsync(&running, ws.n_running, sizeof(int), cudaMemcpyDeviceToHost, s));
-    ATTRICI_CUDA_CHECK(cudaStreamSynchronize(s));
+    const bool fp64 = o.use_fp64 != 0;
+    int cur = 0, running = 0;
+    ATTRICI_TRY(launch_fit_init(ws, sp, ws.list[cur], ws.counters + cur, s));
+    ATTRICI_TRY(read_counter(ws.counters + cur, &running, s));
     const bool profile = o.profile != 0;
     std::vector<cudaEvent_t> ev;
     // a cell may spend passes on rejected trial points: the cap counts passes, not accepted steps
     for (int it = 0; running > 0 && it < o.max_pass; ++it) {
+        const bool use_list = 2 * running < ws.C;
+        PassShape ps = use_list ? plan_pass(ws, ws.list[cur], running, i0, i1, fp64)
+                                : plan_pass(ws, nullptr, ws.C, i0, i1, fp64);
         if (profile) {
             cudaEvent_t e0, e1;
             ATTRICI_CUDA_CHECK(cudaEventCreate(&e0));
@@ -127,11 +137,12 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
             g_profile.cell_days += (double)running * (double)(i1 - i0);
             ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
         }
-        ATTRICI_TRY(launch_pass(ws, sp.term, o.use_fp64 != 0, true, y_scaled, ld, i0, i1, ws.status, s));
+        ATTRICI_TRY(launch_pass(ws, ps, sp.term, fp64, true, y_scaled, ld, i0, i1, use_list ? nullptr : ws.status, s));
         if (profile) ATTRICI_CUDA_CHECK(cudaEventRecord(ev.back(), s));
-        ATTRICI_TRY(launch_fit_step(ws, sp, s));
-        ATTRICI_CUDA_CHECK(cudaMemcpyAsync(&running, ws.n_running, sizeof(int), cudaMemcpyDeviceToHost, s));
-        ATTRICI_CUDA_CHECK(cudaStreamSynchronize(s));
+        ATTRICI_TRY(launch_reduce(ws, ps, fp64, true, s));
+        ATTRICI_TRY(launch_fit_step(ws, sp, ws.list[cur], running, ws.list[cur ^ 1], ws.counters + (cur ^ 1), s));
+        cur ^= 1;
+        ATTRICI_TRY(read_counter(ws.counters + cur, &running, s));
     }
     for (size_t k = 0; k + 1 < ev.size(); k += 2) {
         float ms = 0.f;
@@ -144,8 +155,9 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
     }
     // log posterior of the accepted point in FP64 (model_scipy.py:525: trace["logp"] = -res.fun)
     ATTRICI_TRY(launch_fit_final_point(ws, sp, s));
-    ATTRICI_TRY(launch_pass(ws, sp.term, true, false, y_scaled, ld, i0, i1, nullptr, s));
-    sp.fp64 = 1;
+    PassShape all = plan_pass(ws, nullptr, ws.C, i0, i1, true);
+    ATTRICI_TRY(launch_pass(ws, all, sp.term, true, false, y_scaled, ld, i0, i1, nullptr, s));
+    ATTRICI_TRY(launch_reduce(ws, all, true, false, s));
     ATTRICI_TRY(launch_fit_store(ws, sp, s));
     return 0;
 }
@@ -233,8 +245,10 @@ int attrici_nll_grad(void* workspace, size_t workspace_bytes, const attrici_vari
         ATTRICI_TRY(launch_phase_only(ws, sp, s));
         ATTRICI_TRY(launch_load_theta(ws, var->family, var->modes, slot, theta, s));
         ATTRICI_TRY(launch_rotate(ws, sp, s));
-        ATTRICI_TRY(launch_pass(ws, sp.term, use_fp64 != 0, true, y_scaled, ld, i0, i1, nullptr, s));
-        // canonical results go through idle fit-state buffers: f_acc, g_acc, h_acc
+        PassShape all = plan_pass(ws, nullptr, ws.C, i0, i1, use_fp64 != 0);
+        ATTRICI_TRY(launch_pass(ws, all, sp.term, use_fp64 != 0, true, y_scaled, ld, i0, i1, nullptr, s));
+        ATTRICI_TRY(launch_reduce(ws, all, use_fp64 != 0, true, s));
+        // canonical results go through idle fit-state buffers: f_acc, g_acc [Cp][NP], h_acc [Cp][NTRI]
         ATTRICI_TRY(launch_assemble(ws, sp, ws.f_acc, ws.g_acc, fisher ? ws.h_acc : nullptr, s));
         ATTRICI_TRY(launch_scatter_kat(ws, var->family, var->modes, slot, ws.f_acc, ws.g_acc,
                                        fisher ? ws.h_acc : nullptr, nll, grad, fisher, slot > 0, s));

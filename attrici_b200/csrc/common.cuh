@@ -55,29 +55,31 @@ struct Workspace {
     double* st_sq;     // [2][Cp]
     double* st_ln;     // [2][Cp]  sum of ln y (gamma / weibull start)
     int* st_first;     // [2][Cp]  first used day index of the fit window (-1 = none)
-    // fit state
-    double* th_acc;    // [NP][Cp] accepted point, cell frame
-    double* th_trial;  // [NP][Cp] trial point, cell frame
-    double* th_pass;   // [NP][Cp] trial point, shared frame (what the pass kernel reads)
-    double* g_acc;     // [NP][Cp]
-    double* h_acc;     // [NTRI][Cp]
-    double* h_wrk;     // [NTRI][Cp]
+    // fit state ("cell-major" = [Cp][n], read by one warp per cell)
+    double* th_acc;    // [Cp][NP] accepted point, cell frame
+    double* th_trial;  // [Cp][NP] trial point, cell frame
+    double* th_pass;   // [NP][Cp] trial point, shared frame (what the pass kernel reads, thread = cell)
+    double* g_acc;     // [Cp][NP]
+    double* h_acc;     // [Cp][NTRI] (also the canonical Fisher output of the known-answer entry)
     double* f_acc;     // [Cp]
     double* pred;      // [Cp]
     double* lam;       // [Cp]
-    double* rot;       // [2*NH][Cp] cos/sin of the per-cell phase offset, harmonics 1..8
+    double* rot;       // [Cp][2*NH] cos/sin of the per-cell phase offset, harmonics 1..8
     int* status;       // [Cp]
     int* npass;        // [Cp]
-    int* n_running;    // [1] (+pad)
-    double* part_nll;  // [MAX_CHUNKS][Cp]
-    void* part_acc;    // [n_chunks][NACC][Cp] float or double
+    int* list[2];      // [Cp] each: cells still iterating (ping-pong)
+    int* counters;     // [2] lengths of the two lists (+pad)
+    double* momd;      // [NACC + 1][Cp] chunk-reduced moments, row NACC = sum of the day terms of the nll
+    double* part_nll;  // [chunk][Pp]
+    size_t part_nll_cap;   // doubles
+    void* part_acc;    // [chunk][NACC][Pp] float or double
+    size_t part_acc_cap;   // 8-byte units
     // results of the (up to) two likelihood terms, canonical layout, cell frame
     double* th_out;    // [2][NP][Cp]
     double* logp_part; // [2][Cp]
     int* status_part;  // [2][Cp]
     int* npass_part;   // [2][Cp]
     double* uniforms;  // [T][Cp] MT19937 doubles (pr only, else nullptr)
-    int used_chunks;   // chunks written by the last pass
 
     static size_t align(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -87,7 +89,6 @@ struct Workspace {
         C = C_;
         Cp = round_up(C_, 32);
         ck = choose_chunks(T_, C_);
-        used_chunks = ck.n_chunks;
         base = (char*)base_;
         size_t off = 0;
         auto take = [&](size_t n) {
@@ -110,16 +111,20 @@ struct Workspace {
         th_pass = (double*)take(8 * NP * c);
         g_acc = (double*)take(8 * NP * c);
         h_acc = (double*)take(8 * NTRI * c);
-        h_wrk = (double*)take(8 * NTRI * c);
         f_acc = (double*)take(8 * c);
         pred = (double*)take(8 * c);
         lam = (double*)take(8 * c);
         rot = (double*)take(8 * 2 * NH * c);
         status = (int*)take(4 * c);
         npass = (int*)take(4 * c);
-        n_running = (int*)take(256);
-        part_nll = (double*)take(8 * (size_t)MAX_CHUNKS * c);
-        part_acc = take(8 * (size_t)ck.n_chunks * NACC * c);
+        list[0] = (int*)take(4 * c);
+        list[1] = (int*)take(4 * c);
+        counters = (int*)take(256);
+        momd = (double*)take(8 * (size_t)(NACC + 1) * c);
+        part_nll_cap = (size_t)MAX_CHUNKS * c;
+        part_nll = (double*)take(8 * part_nll_cap);
+        part_acc_cap = (size_t)ck.n_chunks * NACC * c;
+        part_acc = take(8 * part_acc_cap);
         th_out = (double*)take(8 * 2 * NP * c);
         logp_part = (double*)take(8 * 2 * c);
         status_part = (int*)take(4 * 2 * c);
@@ -129,6 +134,16 @@ struct Workspace {
         return off;
     }
 };
+
+// shape of one likelihood pass: which cells (list of still-iterating cells or all), how the fit window is
+// cut into time chunks, and the stride of the partial buffers (indexed by list position)
+struct PassShape {
+    const int* list;   // nullptr: cell = position
+    int n_active;
+    int Pp;            // stride of the partials = round_up(n_active, 32)
+    int n_chunks, chunk_len;
+};
+PassShape plan_pass(const Workspace& ws, const int* list, int n_active, int i0, int i1, bool fp64);
 
 void set_error(const char* fmt, ...);
 void count_launch();
@@ -166,28 +181,32 @@ int launch_build_basis(Workspace& ws, const int32_t* days, const double* gmt, cu
 int launch_prep(Workspace& ws, const attrici_variable_t& var, const float* y, float* y_scaled, int64_t ld,
                 int i0, int i1, double* scaling, cudaStream_t s);
 
-// one likelihood pass over the fit window [i0, i1) at ws.th_pass; fills ws.part_nll / ws.part_acc.
-// status != nullptr: only cells whose status is RUNNING are evaluated.
-int launch_pass(Workspace& ws, int term, bool fp64, bool with_moments, const float* y_scaled, int64_t ld,
-                int i0, int i1, const int* status, cudaStream_t s);
+// one likelihood pass over the fit window [i0, i1) at ws.th_pass for the cells of `ps`; fills ws.part_nll /
+// ws.part_acc.  status != nullptr (only without a list): only cells whose status is RUNNING are evaluated.
+int launch_pass(Workspace& ws, const PassShape& ps, int term, bool fp64, bool with_moments, const float* y_scaled,
+                int64_t ld, int i0, int i1, const int* status, cudaStream_t s);
+// cross-chunk reduction of the partials of the last pass into ws.momd
+int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_moments, cudaStream_t s);
 
 struct StepParams {
     int term;
     int modes;
     int slot;        // which start-value / phase-origin slot of the workspace
-    int fp64;        // partial moments of the last pass are double
     int max_pass;
     double tol_pred;
     double lambda0;
     int zero_init;
 };
-int launch_fit_init(Workspace& ws, const StepParams& sp, cudaStream_t s);
-int launch_fit_step(Workspace& ws, const StepParams& sp, cudaStream_t s);
+// start values and phase origins; list_out / counter receive the cells that iterate
+int launch_fit_init(Workspace& ws, const StepParams& sp, int* list_out, int* counter, cudaStream_t s);
+// accept / reject / propose for the cells of list_in; list_out / counter receive those that go on
+int launch_fit_step(Workspace& ws, const StepParams& sp, const int* list_in, int n_in, int* list_out, int* counter,
+                    cudaStream_t s);
 // th_trial := th_acc, rotated into th_pass (before the final FP64 evaluation)
 int launch_fit_final_point(Workspace& ws, const StepParams& sp, cudaStream_t s);
-// after an FP64 pass without moments at th_acc: store coefficients / logp / status of this term slot
+// after an FP64 pass without moments at th_acc (+ reduce): store coefficients / logp / status of this term slot
 int launch_fit_store(Workspace& ws, const StepParams& sp, cudaStream_t s);
-// reduce the partials of a pass at th_trial into nll / grad / fisher in the cell frame (KAT entry)
+// after a pass at th_trial (+ reduce): nll [Cp], grad [Cp][NP], fisher [Cp][NTRI] in the cell frame (KAT entry)
 int launch_assemble(Workspace& ws, const StepParams& sp, double* nll, double* grad, double* fisher, cudaStream_t s);
 // phase offsets only (KAT entry: no fit_init)
 int launch_phase_only(Workspace& ws, const StepParams& sp, cudaStream_t s);

@@ -24,14 +24,17 @@ namespace attrici {
 struct PassArgs {
     const float* ys;
     int64_t ld;
-    int C, Cp;
+    int Cp;
+    const int* list;         // nullable: cells still iterating (cell = list[position]); else cell = position
+    int n_active;            // positions
+    int Pp;                  // stride of the partials (indexed by position)
     int i0, i1;
     int chunk_len;
     const void* basis;       // float or double [.][20]
     const double* th_pass;   // [NP][Cp]
     const int* status;       // nullable: only cells with RUNNING status are evaluated
-    double* part_nll;        // [n_chunks][Cp]
-    void* part_acc;          // [n_chunks][NACC][Cp]
+    double* part_nll;        // [n_chunks][Pp]
+    void* part_acc;          // [n_chunks][NACC][Pp]
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -77,11 +80,14 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) pass_kernel(PassArgs a) {
     constexpr bool HAS_AB = (KIND == K_WEIBULL || KIND == K_BETA);
     __shared__ __align__(16) R tile[2][PASS_TILE * B_STRIDE];
 
-    const int cell = blockIdx.x * PASS_CELLS + threadIdx.x;
+    const int pos = blockIdx.x * PASS_CELLS + threadIdx.x;
     const int chunk = blockIdx.y;
     const int t_begin = a.i0 + chunk * a.chunk_len;
     const int t_end = min(a.i1, t_begin + a.chunk_len);
-    bool active = cell < a.C;
+    const bool in_range = pos < a.n_active;
+    // positions beyond the batch read a clamped (valid) column and are masked by `active`
+    const int cell = a.list ? a.list[in_range ? pos : 0] : (in_range ? pos : a.n_active - 1);
+    bool active = in_range;
     if (active && a.status) active = (a.status[cell] == ATTRICI_STATUS_RUNNING);
     if (__syncthreads_or(active) == 0 || t_begin >= t_end) return;  // uniform per CTA
     const bool warp_active = __any_sync(0xffffffffu, active);
@@ -108,9 +114,7 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) pass_kernel(PassArgs a) {
     };
     issue_tile(0);
 
-    // cells beyond C read a clamped (valid) column and are masked by `active`
-    const int col = min(cell, a.C - 1);
-    const float* yp = a.ys + (size_t)t_begin * a.ld + col;
+    const float* yp = a.ys + (size_t)t_begin * a.ld + cell;
     const float qnan = __int_as_float(0x7fc00000);
     constexpr int G = 4;  // days per prefetch group
     float ycur[G], ynext[G];
@@ -151,20 +155,20 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) pass_kernel(PassArgs a) {
         __syncthreads();
     }
 
-    if (cell < a.C) {
-        a.part_nll[(size_t)chunk * a.Cp + cell] = nll;
+    if (in_range) {
+        a.part_nll[(size_t)chunk * a.Pp + pos] = nll;
         if (MOMENTS) {
-            R* out = reinterpret_cast<R*>(a.part_acc) + (size_t)chunk * NACC * a.Cp + cell;
+            R* out = reinterpret_cast<R*>(a.part_acc) + (size_t)chunk * NACC * a.Pp + pos;
 #pragma unroll
-            for (int i = 0; i < 3 * NTRIG; ++i) out[(size_t)(ACC_AA + i) * a.Cp] = acc.AA[i];
+            for (int i = 0; i < 3 * NTRIG; ++i) out[(size_t)(ACC_AA + i) * a.Pp] = acc.AA[i];
 #pragma unroll
-            for (int i = 0; i < 2 * NTRIG; ++i) out[(size_t)(ACC_AB + i) * a.Cp] = HAS_AB ? acc.AB[i] : R(0);
+            for (int i = 0; i < 2 * NTRIG; ++i) out[(size_t)(ACC_AB + i) * a.Pp] = HAS_AB ? acc.AB[i] : R(0);
 #pragma unroll
-            for (int i = 0; i < NTRIG; ++i) out[(size_t)(ACC_BB + i) * a.Cp] = HAS_B ? acc.BB[i] : R(0);
+            for (int i = 0; i < NTRIG; ++i) out[(size_t)(ACC_BB + i) * a.Pp] = HAS_B ? acc.BB[i] : R(0);
 #pragma unroll
-            for (int i = 0; i < 2 * NB; ++i) out[(size_t)(ACC_GA + i) * a.Cp] = acc.GA[i];
+            for (int i = 0; i < 2 * NB; ++i) out[(size_t)(ACC_GA + i) * a.Pp] = acc.GA[i];
 #pragma unroll
-            for (int i = 0; i < NB; ++i) out[(size_t)(ACC_GB + i) * a.Cp] = HAS_B ? acc.GB[i] : R(0);
+            for (int i = 0; i < NB; ++i) out[(size_t)(ACC_GB + i) * a.Pp] = HAS_B ? acc.GB[i] : R(0);
         }
     }
 }
@@ -181,27 +185,49 @@ template <int KIND> static int launch_kind(const PassArgs& a, dim3 grid, bool fp
     return 0;
 }
 
-int launch_pass(Workspace& ws, int term, bool fp64, bool with_moments, const float* y_scaled, int64_t ld,
-                int i0, int i1, const int* status, cudaStream_t s) {
+// time chunks for the cells of one pass: enough CTAs for ~3 waves of 2 CTAs/SM on 148 SMs, bounded by
+// the partial buffers (indexed by position, so fewer cells leave room for more chunks)
+PassShape plan_pass(const Workspace& ws, const int* list, int n_active, int i0, int i1, bool fp64) {
+    PassShape ps;
+    ps.list = list;
+    ps.n_active = n_active;
+    ps.Pp = round_up(n_active > 0 ? n_active : 1, 32);
+    const int window = i1 - i0;
+    const int n_cb = (n_active + PASS_CELLS - 1) / PASS_CELLS;
+    int want = (148 * 2 * 3 + n_cb - 1) / (n_cb > 0 ? n_cb : 1);
+    size_t cap_nll = ws.part_nll_cap / (size_t)ps.Pp;
+    size_t cap_acc = (fp64 ? ws.part_acc_cap : 2 * ws.part_acc_cap) / ((size_t)NACC * ps.Pp);
+    size_t cap = cap_nll < cap_acc ? cap_nll : cap_acc;
+    if (cap > 256) cap = 256;
+    if (want > (int)cap) want = (int)cap;
+    if (want < 1) want = 1;
+    int len = round_up((window + want - 1) / want, PASS_TILE);
+    if (len < PASS_TILE) len = PASS_TILE;
+    ps.chunk_len = len;
+    ps.n_chunks = (window + len - 1) / len;
+    return ps;
+}
+
+int launch_pass(Workspace& ws, const PassShape& ps, int term, bool fp64, bool with_moments, const float* y_scaled,
+                int64_t ld, int i0, int i1, const int* status, cudaStream_t s) {
     if (i1 <= i0) { set_error("empty fit window [%d, %d)", i0, i1); return ATTRICI_EINVAL; }
+    if (ps.n_active <= 0) return 0;
     PassArgs a;
     a.ys = y_scaled;
     a.ld = ld;
-    a.C = ws.C;
     a.Cp = ws.Cp;
+    a.list = ps.list;
+    a.n_active = ps.n_active;
+    a.Pp = ps.Pp;
     a.i0 = i0;
     a.i1 = i1;
-    // chunks cover the fit window; the chunk count chosen for T bounds the partial buffers
-    int len = round_up((i1 - i0 + ws.ck.n_chunks - 1) / ws.ck.n_chunks, PASS_TILE);
-    if (len < PASS_TILE) len = PASS_TILE;
-    a.chunk_len = len;
-    ws.used_chunks = (i1 - i0 + len - 1) / len;
+    a.chunk_len = ps.chunk_len;
     a.basis = fp64 ? (const void*)ws.basis64 : (const void*)ws.basis32;
     a.th_pass = ws.th_pass;
     a.status = status;
     a.part_nll = ws.part_nll;
     a.part_acc = ws.part_acc;
-    dim3 grid((ws.C + PASS_CELLS - 1) / PASS_CELLS, ws.used_chunks);
+    dim3 grid((ps.n_active + PASS_CELLS - 1) / PASS_CELLS, ps.n_chunks);
     switch (term) {
         case T_NORMAL: return launch_kind<K_NORMAL>(a, grid, fp64, with_moments, s);
         case T_GAMMA: return launch_kind<K_GAMMA>(a, grid, fp64, with_moments, s);

@@ -1,5 +1,6 @@
-// Kernels around the per-cell optimiser mathematics of step_impl.cuh (one thread = one cell) and the
-// conversions between the reference's theta layout and the canonical per-term layout.
+// Kernels around the per-cell optimiser mathematics of step_impl.cuh (one warp = one cell, the cell's
+// 27 x 27 system in shared memory), the cross-chunk reduction of the pass partials, and the conversions
+// between the reference's theta layout and the canonical per-term layout.
 #include "common.cuh"
 #include "step_impl.cuh"
 
@@ -7,71 +8,135 @@ namespace attrici {
 
 namespace {
 
-constexpr int STEP_THREADS = 64;
+constexpr int STEP_WARPS = 4;
+constexpr int STEP_THREADS = 32 * STEP_WARPS;
+constexpr int RED_THREADS = 128;
+constexpr int RED_GROUP = 10;   // accumulators per thread of the reduction kernel (13 groups cover 130)
 
-__global__ void fit_init_kernel(StepArgs a) {
-    int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= a.C) return;
-    if (cell_init(a, cell)) atomicAdd(a.n_running, 1);
+struct WarpCtx {
+    static constexpr int W = 32;
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ double sum(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
+};
+
+// cell handled by this warp: position in the active list (or the identity), -1 if none
+__device__ __forceinline__ int warp_cell(const int* list, int n) {
+    int pos = blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
+    if (pos >= n) return -1;
+    return list ? list[pos] : pos;
 }
 
-__global__ void fit_step_kernel(StepArgs a) {
-    int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= a.C) return;
-    if (cell_step(a, cell)) atomicAdd(a.n_running, 1);
+__global__ void __launch_bounds__(STEP_THREADS) fit_init_kernel(StepArgs a, int* list_out, int* counter) {
+    __shared__ CellScratch S[STEP_WARPS];
+    int cell = warp_cell(nullptr, a.C);
+    if (cell < 0) return;
+    WarpCtx ctx;
+    bool run = cell_init(a, cell, S[threadIdx.x >> 5], ctx);
+    if (run && ctx.lane() == 0) list_out[atomicAdd(counter, 1)] = cell;
 }
 
-__global__ void fit_final_point_kernel(StepArgs a) {
-    int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= a.C) return;
-    cell_final_point(a, cell);
+__global__ void __launch_bounds__(STEP_THREADS) fit_step_kernel(StepArgs a, const int* list_in, int n_in,
+                                                                int* list_out, int* counter) {
+    __shared__ CellScratch S[STEP_WARPS];
+    int cell = warp_cell(list_in, n_in);
+    if (cell < 0) return;
+    WarpCtx ctx;
+    bool run = cell_step(a, cell, S[threadIdx.x >> 5], ctx);
+    if (run && ctx.lane() == 0) list_out[atomicAdd(counter, 1)] = cell;
 }
 
-__global__ void fit_store_kernel(StepArgs a) {
-    int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= a.C) return;
-    cell_store(a, cell);
+__global__ void __launch_bounds__(STEP_THREADS) fit_final_point_kernel(StepArgs a) {
+    __shared__ CellScratch S[STEP_WARPS];
+    int cell = warp_cell(nullptr, a.C);
+    if (cell < 0) return;
+    WarpCtx ctx;
+    cell_final_point(a, cell, S[threadIdx.x >> 5], ctx);
+}
+
+__global__ void __launch_bounds__(STEP_THREADS) fit_store_kernel(StepArgs a) {
+    __shared__ CellScratch S[STEP_WARPS];
+    int cell = warp_cell(nullptr, a.C);
+    if (cell < 0) return;
+    WarpCtx ctx;
+    cell_store(a, cell, S[threadIdx.x >> 5], ctx);
 }
 
 // known-answer evaluation: objective, gradient, Fisher information at th_trial
-__global__ void assemble_kernel(StepArgs a, double* nll, double* grad /*[NP][Cp] canonical*/,
-                                double* fisher /*[NTRI][Cp] canonical packed, nullable*/) {
-    int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= a.C) return;
-    const size_t cp = a.Cp;
-    double th[NP], g[NP];
-    for (int i = 0; i < NP; ++i) th[i] = a.th_trial[(size_t)i * cp + cell];
-    double f = assemble(a, cell, th, g, fisher ? fisher + cell : nullptr);
-    nll[cell] = f;
-    if (grad) for (int i = 0; i < NP; ++i) grad[(size_t)i * cp + cell] = g[i];
+__global__ void __launch_bounds__(STEP_THREADS) assemble_kernel(StepArgs a, double* nll, double* grad /*[Cp][NP]*/,
+                                                                double* fisher /*[Cp][NTRI], nullable*/) {
+    __shared__ CellScratch Ss[STEP_WARPS];
+    int cell = warp_cell(nullptr, a.C);
+    if (cell < 0) return;
+    WarpCtx ctx;
+    CellScratch& S = Ss[threadIdx.x >> 5];
+    for (int i = ctx.lane(); i < NP; i += 32) S.th[i] = a.th_trial[(size_t)cell * NP + i];
+    load_moments(a, cell, S, ctx);
+    double f = assemble(a, S, fisher != nullptr, ctx);
+    if (ctx.lane() == 0) nll[cell] = f;
+    if (grad) for (int i = ctx.lane(); i < NP; i += 32) grad[(size_t)cell * NP + i] = S.g[i];
+    if (fisher) for (int i = ctx.lane(); i < NTRI; i += 32) fisher[(size_t)cell * NTRI + i] = S.H[i];
 }
 
-__global__ void phase_kernel(StepArgs a) {
-    int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= a.C) return;
-    cell_phase(a, cell);
+__global__ void __launch_bounds__(STEP_THREADS) phase_kernel(StepArgs a) {
+    int cell = warp_cell(nullptr, a.C);
+    if (cell < 0) return;
+    WarpCtx ctx;
+    cell_phase(a, cell, ctx);
 }
 
 // th_trial (cell frame) -> th_pass (shared frame)
-__global__ void rotate_kernel(StepArgs a) {
-    int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= a.C) return;
-    double th[NP];
-    for (int i = 0; i < NP; ++i) th[i] = a.th_trial[(size_t)i * a.Cp + cell];
-    rotate_to_shared(a, cell, th);
+__global__ void __launch_bounds__(STEP_THREADS) rotate_kernel(StepArgs a) {
+    __shared__ double th[STEP_WARPS][NP];
+    int cell = warp_cell(nullptr, a.C);
+    if (cell < 0) return;
+    WarpCtx ctx;
+    double* t = th[threadIdx.x >> 5];
+    for (int i = ctx.lane(); i < NP; i += 32) t[i] = a.th_trial[(size_t)cell * NP + i];
+    ctx.sync();
+    rotate_to_shared(a, cell, t, ctx);
 }
 
-// reference layout theta[C x P] -> th_trial of one term slot (inactive entries zero)
-__global__ void load_theta_kernel(int C, int Cp, int family, int modes, int slot, const double* __restrict__ theta,
+// cross-chunk reduction of the pass partials: thread = active cell (coalesced), blockIdx.y = group of
+// accumulators.  partials are indexed by list position when a list is given (stride Pp), results by cell.
+template <typename R>
+__global__ void __launch_bounds__(RED_THREADS) reduce_partials_kernel(const int* __restrict__ list, int n, int Pp, int Cp,
+                                                                      int n_chunks, int row0,
+                                                                      const double* __restrict__ part_nll,
+                                                                      const R* __restrict__ part_acc,
+                                                                      double* __restrict__ momd) {
+    int pos = blockIdx.x * RED_THREADS + threadIdx.x;
+    if (pos >= n) return;
+    int cell = list ? list[pos] : pos;
+    int i0 = row0 + blockIdx.y * RED_GROUP;
+    for (int i = i0; i < i0 + RED_GROUP && i <= NACC; ++i) {
+        double s = 0.0;
+        if (i == NACC) {
+            for (int ch = 0; ch < n_chunks; ++ch) s += part_nll[(size_t)ch * Pp + pos];
+        } else {
+            const R* p = part_acc + (size_t)i * Pp + pos;
+            for (int ch = 0; ch < n_chunks; ++ch) s += (double)p[(size_t)ch * NACC * Pp];
+        }
+        momd[(size_t)i * Cp + cell] = s;
+    }
+}
+
+// reference layout theta[C x P] -> th_trial [Cp][NP] of one term slot (inactive entries zero)
+__global__ void load_theta_kernel(int C, int family, int modes, int slot, const double* __restrict__ theta,
                                   double* __restrict__ th_trial) {
     int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= C) return;
     const int P = family_num_params(family, modes);
-    for (int i = 0; i < NP; ++i) th_trial[(size_t)i * Cp + cell] = 0.0;
+    for (int i = 0; i < NP; ++i) th_trial[(size_t)cell * NP + i] = 0.0;
     for (int j = 0; j < P; ++j) {
         int sl, cn;
         ref_to_canon(family, modes, j, &sl, &cn);
-        if (sl == slot) th_trial[(size_t)cn * Cp + cell] = theta[(size_t)cell * P + j];
+        if (sl == slot) th_trial[(size_t)cell * NP + cn] = theta[(size_t)cell * P + j];
     }
 }
 
@@ -108,8 +173,9 @@ __global__ void store_params_kernel(int C, int Cp, int family, int modes, const 
     if (n_pass) n_pass[cell] = np;
 }
 
-// canonical nll / grad / packed fisher of one term slot -> reference layout (accumulating over slots)
-__global__ void scatter_kat_kernel(int C, int Cp, int family, int modes, int slot, const double* __restrict__ nll_c,
+// canonical nll / grad [Cp][NP] / packed fisher [Cp][NTRI] of one term slot -> reference layout
+// (accumulating over slots)
+__global__ void scatter_kat_kernel(int C, int family, int modes, int slot, const double* __restrict__ nll_c,
                                    const double* __restrict__ grad_c, const double* __restrict__ fisher_c,
                                    double* __restrict__ nll, double* __restrict__ grad, double* __restrict__ fisher,
                                    int accumulate) {
@@ -125,13 +191,13 @@ __global__ void scatter_kat_kernel(int C, int Cp, int family, int modes, int slo
                 for (int k = 0; k < P; ++k) fisher[((size_t)cell * P + j) * P + k] = 0.0;
             continue;
         }
-        if (grad) grad[(size_t)cell * P + j] = grad_c[(size_t)cn * Cp + cell];
+        if (grad) grad[(size_t)cell * P + j] = grad_c[(size_t)cell * NP + cn];
         if (fisher) {
             for (int k = 0; k < P; ++k) {
                 int sl2, cn2;
                 ref_to_canon(family, modes, k, &sl2, &cn2);
                 fisher[((size_t)cell * P + j) * P + k] =
-                    (sl2 == slot) ? fisher_c[(size_t)tri(cn, cn2) * Cp + cell] : 0.0;
+                    (sl2 == slot) ? fisher_c[(size_t)cell * NTRI + tri(cn, cn2)] : 0.0;
             }
         }
     }
@@ -140,79 +206,97 @@ __global__ void scatter_kat_kernel(int C, int Cp, int family, int modes, int slo
 StepArgs make_args(Workspace& ws, const StepParams& sp) {
     StepArgs a;
     a.C = ws.C; a.Cp = ws.Cp;
-    a.n_chunks = ws.used_chunks;
-    a.fp64 = sp.fp64;
     a.term = sp.term; a.modes = sp.modes; a.slot = sp.slot;
     a.max_pass = sp.max_pass; a.tol_pred = sp.tol_pred; a.lambda0 = sp.lambda0; a.zero_init = sp.zero_init;
     a.basis64 = ws.basis64;
     a.st_cnt = ws.st_cnt; a.st_sum = ws.st_sum; a.st_sq = ws.st_sq; a.st_ln = ws.st_ln; a.st_first = ws.st_first;
+    a.momd = ws.momd;
     a.th_acc = ws.th_acc; a.th_trial = ws.th_trial; a.th_pass = ws.th_pass; a.g_acc = ws.g_acc;
-    a.h_acc = ws.h_acc; a.h_wrk = ws.h_wrk; a.f_acc = ws.f_acc; a.pred = ws.pred; a.lam = ws.lam; a.rot = ws.rot;
-    a.status = ws.status; a.npass = ws.npass; a.n_running = ws.n_running;
-    a.part_nll = ws.part_nll; a.part_acc = ws.part_acc;
+    a.h_acc = ws.h_acc; a.f_acc = ws.f_acc; a.pred = ws.pred; a.lam = ws.lam; a.rot = ws.rot;
+    a.status = ws.status; a.npass = ws.npass;
     a.th_out = ws.th_out; a.logp_part = ws.logp_part; a.status_part = ws.status_part; a.npass_part = ws.npass_part;
     return a;
 }
 
-inline int blocks(int C) { return (C + STEP_THREADS - 1) / STEP_THREADS; }
+inline int warp_blocks(int n) { return (n + STEP_WARPS - 1) / STEP_WARPS; }
+inline int thread_blocks(int n) { return (n + 127) / 128; }
 
 }  // namespace
 
-int launch_fit_init(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    ATTRICI_CUDA_CHECK(cudaMemsetAsync(ws.n_running, 0, sizeof(int), s));
-    fit_init_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+int launch_fit_init(Workspace& ws, const StepParams& sp, int* list_out, int* counter, cudaStream_t s) {
+    ATTRICI_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), s));
+    fit_init_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp), list_out, counter);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
-int launch_fit_step(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    ATTRICI_CUDA_CHECK(cudaMemsetAsync(ws.n_running, 0, sizeof(int), s));
-    fit_step_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+int launch_fit_step(Workspace& ws, const StepParams& sp, const int* list_in, int n_in, int* list_out, int* counter,
+                    cudaStream_t s) {
+    ATTRICI_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), s));
+    if (n_in <= 0) return 0;
+    fit_step_kernel<<<warp_blocks(n_in), STEP_THREADS, 0, s>>>(make_args(ws, sp), list_in, n_in, list_out, counter);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_fit_final_point(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    fit_final_point_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    fit_final_point_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_fit_store(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    fit_store_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    fit_store_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    ATTRICI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_moments, cudaStream_t s) {
+    if (ps.n_active <= 0) return 0;
+    dim3 grid((ps.n_active + RED_THREADS - 1) / RED_THREADS, (NACC + 1 + RED_GROUP - 1) / RED_GROUP);
+    // without moments only row NACC (the sum of the day terms of the nll) is reduced
+    const int row0 = with_moments ? 0 : NACC;
+    if (!with_moments) grid.y = 1;
+    if (fp64)
+        reduce_partials_kernel<double><<<grid, RED_THREADS, 0, s>>>(ps.list, ps.n_active, ps.Pp, ws.Cp, ps.n_chunks,
+                                                                   row0, ws.part_nll,
+                                                                   (const double*)ws.part_acc, ws.momd);
+    else
+        reduce_partials_kernel<float><<<grid, RED_THREADS, 0, s>>>(ps.list, ps.n_active, ps.Pp, ws.Cp, ps.n_chunks,
+                                                                  row0, ws.part_nll,
+                                                                  (const float*)ws.part_acc, ws.momd);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_assemble(Workspace& ws, const StepParams& sp, double* nll, double* grad, double* fisher, cudaStream_t s) {
-    assemble_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp), nll, grad, fisher);
+    assemble_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp), nll, grad, fisher);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_phase_only(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    phase_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    phase_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_rotate(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    rotate_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    rotate_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_load_theta(Workspace& ws, int family, int modes, int slot, const double* theta, cudaStream_t s) {
-    load_theta_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(ws.C, ws.Cp, family, modes, slot, theta, ws.th_trial);
+    load_theta_kernel<<<thread_blocks(ws.C), 128, 0, s>>>(ws.C, family, modes, slot, theta, ws.th_trial);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_store_params(Workspace& ws, int family, int modes, double* params, double* logp, int32_t* status,
                         int32_t* n_pass, cudaStream_t s) {
-    store_params_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(ws.C, ws.Cp, family, modes, ws.th_out, ws.logp_part,
-                                                            ws.status_part, ws.npass_part, params, logp, status,
-                                                            n_pass);
+    store_params_kernel<<<thread_blocks(ws.C), 128, 0, s>>>(ws.C, ws.Cp, family, modes, ws.th_out, ws.logp_part,
+                                                          ws.status_part, ws.npass_part, params, logp, status, n_pass);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
@@ -220,8 +304,8 @@ int launch_store_params(Workspace& ws, int family, int modes, double* params, do
 int launch_scatter_kat(Workspace& ws, int family, int modes, int slot, const double* nll_c, const double* grad_c,
                        const double* fisher_c, double* nll, double* grad, double* fisher, int accumulate,
                        cudaStream_t s) {
-    scatter_kat_kernel<<<blocks(ws.C), STEP_THREADS, 0, s>>>(ws.C, ws.Cp, family, modes, slot, nll_c, grad_c, fisher_c,
-                                                           nll, grad, fisher, accumulate);
+    scatter_kat_kernel<<<thread_blocks(ws.C), 128, 0, s>>>(ws.C, family, modes, slot, nll_c, grad_c, fisher_c, nll, grad,
+                                                         fisher, accumulate);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }

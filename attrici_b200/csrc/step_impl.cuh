@@ -1,8 +1,10 @@
 // Per-cell optimiser mathematics: Fisher-scoring Levenberg-Marquardt with per-cell convergence.
 // Replaces scipy.optimize.minimize(method="L-BFGS-B") of ModelScipy.fit
 // (attrici/estimation/model_scipy.py:519-523; finite differences, ~900-2400 objective calls per cell)
-// by ~5-15 likelihood passes per cell.  One thread = one cell; all per-cell state is laid out
-// [field][cell] so that the 27 x 27 factorisations of 32 neighbouring cells coalesce.
+// by ~5-15 likelihood passes per cell.
+//
+// Execution model: one cooperative group of W lanes per cell (a warp on the device, W = 1 in the CPU
+// unit tests), the cell's 27 x 27 system in shared memory, Cholesky / substitutions parallel over rows.
 //
 // Frames: the reference builds each cell's Fourier columns with phase origin = first day the
 // cell's likelihood term uses (attrici/util.py:102 via model_scipy.py:189, 289 and the wet-day
@@ -18,21 +20,43 @@
 
 namespace attrici {
 
+// Layouts: "cell-major" arrays are [Cp][n] (a group's lanes read consecutive entries of one cell);
+// th_pass and momd are [n][Cp] (the pass / reduce kernels run thread = cell).
 struct StepArgs {
     int C, Cp;
-    int n_chunks;        // chunks written by the last pass
-    int fp64;            // partial moments are double
     int term, modes, slot;
     int max_pass;
     double tol_pred, lambda0;
     int zero_init;
     const double* basis64;
     const double* st_cnt; const double* st_sum; const double* st_sq; const double* st_ln; const int* st_first;
-    double* th_acc; double* th_trial; double* th_pass; double* g_acc; double* h_acc; double* h_wrk;
-    double* f_acc; double* pred; double* lam; double* rot;
-    int* status; int* npass; int* n_running;
-    const double* part_nll; const void* part_acc;
-    double* th_out; double* logp_part; int* status_part; int* npass_part;
+    const double* momd;      // [NACC + 1][Cp] chunk-reduced moments; row NACC = sum of the day terms of the nll
+    double* th_acc;          // [Cp][NP]
+    double* th_trial;        // [Cp][NP]
+    double* th_pass;         // [NP][Cp]
+    double* g_acc;           // [Cp][NP]
+    double* h_acc;           // [Cp][NTRI]
+    double* f_acc; double* pred; double* lam;
+    double* rot;             // [Cp][2 NH]
+    int* status; int* npass;
+    double* th_out; double* logp_part; int* status_part; int* npass_part;   // [2][NP][Cp], [2][Cp] ...
+};
+
+// per-cell scratch (shared memory on the device)
+struct CellScratch {
+    double mom[NACC + 1];
+    double H[NTRI];
+    double L[NTRI];
+    double g[NP], th[NP], delta[NP], y[NP];
+};
+
+// serial "group" of one lane (CPU unit tests)
+struct SerialCtx {
+    static constexpr int W = 1;
+    ATTRICI_HD int lane() const { return 0; }
+    ATTRICI_HD void sync() const {}
+    ATTRICI_HD double sum(double v) const { return v; }
+    ATTRICI_HD bool all(bool p) const { return p; }
 };
 
 // prior precision 1/s^2 in the cell frame (model_scipy.py:142-171, 256-270): only the cos
@@ -55,72 +79,47 @@ ATTRICI_HD double prior_const(int term, int modes) {
     return term_has_b(term) ? a + b : a;
 }
 
-// 0.5 sum prec theta^2 over the active coefficients
-ATTRICI_HD_NOINLINE double prior_energy(const double* th, int term, int modes) {
-    double e = 0.0;
-    for (int i = 0; i < NP; ++i) {
-        Col c = col_of(i);
-        if (col_active(c, term, modes)) e += 0.5 * prior_prec(c) * th[i] * th[i];
-    }
-    return e;
-}
-
 // cell frame -> shared frame: cos/sin pair of harmonic k rotated by the cell's phase offset.
 // With x = w (t - t_cell) = X - phi (X the shared-frame phase): a cos kx + b sin kx =
 // (a ck - b sk) cos kX + (a sk + b ck) sin kX, ck = cos k phi, sk = sin k phi.
-ATTRICI_HD_NOINLINE void rotate_to_shared(const StepArgs& a, int cell, const double* th_cell /*local [NP]*/) {
+// th_cell: [NP] readable by every lane; writes th_pass[.][cell]
+template <class Ctx>
+ATTRICI_HD void rotate_to_shared(const StepArgs& a, int cell, const double* th_cell, const Ctx& ctx) {
     const size_t cp = a.Cp;
-    double out[NP];
-    for (int i = 0; i < NP; ++i) out[i] = th_cell[i];
-    for (int k = 1; k <= MAXM; ++k) {
-        double c = a.rot[(size_t)(k - 1) * cp + cell], s = a.rot[(size_t)(NH + k - 1) * cp + cell];
-        // A block: plain and gmt-multiplied pairs; B block
-        const int ci[3] = {2 + (k - 1), 2 + 2 * MAXM + (k - 1), NA + 1 + (k - 1)};
-        const int si[3] = {2 + MAXM + (k - 1), 2 + 3 * MAXM + (k - 1), NA + 1 + MAXM + (k - 1)};
-        for (int q = 0; q < 3; ++q) {
-            double cc = th_cell[ci[q]], ss = th_cell[si[q]];
-            out[ci[q]] = cc * c - ss * s;
-            out[si[q]] = cc * s + ss * c;
+    const double* rot = a.rot + (size_t)cell * 2 * NH;
+    for (int i = ctx.lane(); i < NP; i += Ctx::W) {
+        Col c = col_of(i);
+        double v = th_cell[i];
+        if (c.k > 0 && c.k <= MAXM) {
+            // partner coefficient of the same (block, power) pair
+            int partner = c.sn ? i - MAXM : i + MAXM;
+            double ck = rot[c.k - 1], sk = rot[NH + c.k - 1];
+            double other = th_cell[partner];
+            v = c.sn ? (other * sk + v * ck) : (v * ck - other * sk);
         }
+        a.th_pass[(size_t)i * cp + cell] = v;
     }
-    for (int i = 0; i < NP; ++i) a.th_pass[(size_t)i * cp + cell] = out[i];
 }
 
-// reduce the chunk partials of one cell and rotate every trig moment into the cell frame
+// chunk-reduced moments of one cell -> S.mom, every trig moment rotated into the cell frame
 // (cos kx = ck cos kX + sk sin kX ; sin kx = ck sin kX - sk cos kX).  mom layout = pass.cu's.
-ATTRICI_HD_NOINLINE double reduce_moments(const StepArgs& a, int cell, double* mom /*[NACC]*/) {
+template <class Ctx> ATTRICI_HD void load_moments(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
     const size_t cp = a.Cp;
-    double nll = 0.0;
-    for (int ch = 0; ch < a.n_chunks; ++ch) nll += a.part_nll[(size_t)ch * cp + cell];
-    for (int i = 0; i < NACC; ++i) {
-        double s = 0.0;
-        if (a.fp64) {
-            const double* p = reinterpret_cast<const double*>(a.part_acc) + (size_t)i * cp + cell;
-            for (int ch = 0; ch < a.n_chunks; ++ch) s += p[(size_t)ch * NACC * cp];
-        } else {
-            const float* p = reinterpret_cast<const float*>(a.part_acc) + (size_t)i * cp + cell;
-            for (int ch = 0; ch < a.n_chunks; ++ch) s += (double)p[(size_t)ch * NACC * cp];
-        }
-        mom[i] = s;
+    for (int i = ctx.lane(); i <= NACC; i += Ctx::W) S.mom[i] = a.momd[(size_t)i * cp + cell];
+    ctx.sync();
+    const double* rot = a.rot + (size_t)cell * 2 * NH;
+    // 9 (block, harmonic) families: AA p0..2, AB p0..1, BB carry 8 harmonics; GA p0, GA p1, GB carry 4
+    for (int w = ctx.lane(); w < 6 * NH + 3 * MAXM; w += Ctx::W) {
+        double* m;
+        int k, half;
+        if (w < 6 * NH) { m = S.mom + (w / NH) * NTRIG; k = w % NH + 1; half = NH; }
+        else { int q = w - 6 * NH; m = S.mom + ACC_GA + (q / MAXM) * NB; k = q % MAXM + 1; half = MAXM; }
+        double c = rot[k - 1], s = rot[NH + k - 1];
+        double C_ = m[k], S_ = m[half + k];
+        m[k] = c * C_ + s * S_;
+        m[half + k] = c * S_ - s * C_;
     }
-    for (int k = 1; k <= NH; ++k) {
-        double c = a.rot[(size_t)(k - 1) * cp + cell], s = a.rot[(size_t)(NH + k - 1) * cp + cell];
-        for (int blk = 0; blk < 6; ++blk) {  // AA p0..2, AB p0..1, BB
-            double* m = mom + blk * NTRIG;
-            double C_ = m[k], S_ = m[NH + k];
-            m[k] = c * C_ + s * S_;
-            m[NH + k] = c * S_ - s * C_;
-        }
-        if (k <= MAXM) {
-            for (int blk = 0; blk < 3; ++blk) {  // GA p0, GA p1, GB
-                double* m = mom + ACC_GA + blk * NB;
-                double C_ = m[k], S_ = m[MAXM + k];
-                m[k] = c * C_ + s * S_;
-                m[MAXM + k] = c * S_ - s * C_;
-            }
-        }
-    }
-    return nll;
+    ctx.sync();
 }
 
 // moment of (column i) x (column j) under weight stream `m` (17 trig moments at the right power)
@@ -137,220 +136,237 @@ ATTRICI_HD double trig_product(const double* m, const Col& a, const Col& b) {
     return 0.5 * (Sm[sum] + lo);
 }
 
-// objective, gradient and Fisher information (+ prior) of one cell, cell frame, canonical layout.
-// g: local [NP]; Hglob: packed [NTRI] column of this cell with stride Cp (nullable)
-ATTRICI_HD_NOINLINE double assemble(const StepArgs& a, int cell, const double* th /*local [NP], cell frame*/,
-                                    double* g, double* Hglob) {
-    const size_t cp = a.Cp;
-    double mom[NACC];
-    double f = reduce_moments(a, cell, mom);
-    // cos(0) moment doubles as "cos k with k = 0": trig_product reads Cm[0] for equal harmonics
-    for (int i = 0; i < NP; ++i) {
+// objective, gradient (S.g) and Fisher information + prior (S.H, packed lower triangle) of one cell in
+// the cell frame, canonical layout, at S.th.  Needs S.mom (load_moments).  Returns the objective.
+template <class Ctx> ATTRICI_HD double assemble(const StepArgs& a, CellScratch& S, bool want_H, const Ctx& ctx) {
+    double fp = 0.0;
+    for (int i = ctx.lane(); i < NP; i += Ctx::W) {
         Col ci = col_of(i);
-        bool act_i = col_active(ci, a.term, a.modes);
         double gi = 0.0;
-        if (act_i) {
-            const double* gm = (ci.blk == 0) ? mom + ACC_GA + ci.pw * NB : mom + ACC_GB;
+        if (col_active(ci, a.term, a.modes)) {
+            const double* gm = (ci.blk == 0) ? S.mom + ACC_GA + ci.pw * NB : S.mom + ACC_GB;
             gi = ci.k == 0 ? gm[0] : (ci.sn ? gm[MAXM + ci.k] : gm[ci.k]);
             double pr = prior_prec(ci);
-            gi += pr * th[i];
-            f += 0.5 * pr * th[i] * th[i];
+            gi += pr * S.th[i];
+            fp += 0.5 * pr * S.th[i] * S.th[i];
         }
-        g[i] = gi;
-        if (!Hglob) continue;
-        for (int j = 0; j <= i; ++j) {
-            Col cj = col_of(j);
-            bool act_j = col_active(cj, a.term, a.modes);
-            double h;
-            if (!act_i || !act_j) {
-                h = (i == j) ? 1.0 : 0.0;
-            } else {
-                int pw = ci.pw + cj.pw;
-                const double* m;
-                if (ci.blk == 0 && cj.blk == 0) m = mom + ACC_AA + pw * NTRIG;
-                else if (ci.blk == 1 && cj.blk == 1) m = mom + ACC_BB;
-                else m = mom + ACC_AB + pw * NTRIG;
-                h = trig_product(m, ci, cj);
-                if (i == j) h += prior_prec(ci);
+        S.g[i] = gi;
+    }
+    if (want_H) {
+        for (int i = 0; i < NP; ++i) {
+            Col ci = col_of(i);
+            bool act_i = col_active(ci, a.term, a.modes);
+            for (int j = ctx.lane(); j <= i; j += Ctx::W) {
+                Col cj = col_of(j);
+                bool act_j = col_active(cj, a.term, a.modes);
+                double h;
+                if (!act_i || !act_j) {
+                    h = (i == j) ? 1.0 : 0.0;
+                } else {
+                    int pw = ci.pw + cj.pw;
+                    const double* m;
+                    if (ci.blk == 0 && cj.blk == 0) m = S.mom + ACC_AA + pw * NTRIG;
+                    else if (ci.blk == 1 && cj.blk == 1) m = S.mom + ACC_BB;
+                    else m = S.mom + ACC_AB + pw * NTRIG;
+                    h = trig_product(m, ci, cj);
+                    if (i == j) h += prior_prec(ci);
+                }
+                S.H[tri(i, j)] = h;
             }
-            Hglob[(size_t)tri(i, j) * cp] = h;
         }
     }
-    return f - prior_const(a.term, a.modes);
+    double f = S.mom[NACC] + ctx.sum(fp) - prior_const(a.term, a.modes);
+    ctx.sync();
+    return f;
 }
 
-// solve (H + lam D) delta = -g by Cholesky in the global work column; returns false if not SPD
-ATTRICI_HD_NOINLINE bool lm_solve(const StepArgs& a, int cell, const double* g, double lam, double* delta) {
-    const size_t cp = a.Cp;
-    const double* H = a.h_acc + cell;
-    double* L = a.h_wrk + cell;
+// solve (H + lam D) delta = -g by Cholesky (S.L), rows in parallel; returns false if not SPD
+template <class Ctx> ATTRICI_HD bool lm_solve(CellScratch& S, double lam, const Ctx& ctx) {
     for (int j = 0; j < NP; ++j) {
-        double hjj = H[(size_t)tri(j, j) * cp];
-        double dj = fmax(fabs(hjj), 1e-12);
-        double s = hjj + lam * dj;
-        for (int k = 0; k < j; ++k) {
-            double l = L[(size_t)tri(j, k) * cp];
-            s -= l * l;
-        }
-        if (!(s > 0.0) || !isfinite(s)) return false;
+        double part = 0.0;
+        for (int k = ctx.lane(); k < j; k += Ctx::W) { double l = S.L[tri(j, k)]; part += l * l; }
+        double hjj = S.H[tri(j, j)];
+        double s = hjj + lam * fmax(fabs(hjj), 1e-12) - ctx.sum(part);
+        if (!(s > 0.0) || !isfinite(s)) return false;   // uniform: s is the same in every lane
         double ljj = sqrt(s);
-        L[(size_t)tri(j, j) * cp] = ljj;
         double inv = 1.0 / ljj;
-        for (int i = j + 1; i < NP; ++i) {
-            double t = H[(size_t)tri(i, j) * cp];
-            for (int k = 0; k < j; ++k) t -= L[(size_t)tri(i, k) * cp] * L[(size_t)tri(j, k) * cp];
-            L[(size_t)tri(i, j) * cp] = t * inv;
+        for (int i = j + 1 + ctx.lane(); i < NP; i += Ctx::W) {
+            double t = S.H[tri(i, j)];
+            for (int k = 0; k < j; ++k) t -= S.L[tri(i, k)] * S.L[tri(j, k)];
+            S.L[tri(i, j)] = t * inv;
         }
+        if (ctx.lane() == 0) S.L[tri(j, j)] = ljj;
+        ctx.sync();
     }
-    double y[NP];
-    for (int i = 0; i < NP; ++i) {
-        double t = -g[i];
-        for (int k = 0; k < i; ++k) t -= L[(size_t)tri(i, k) * cp] * y[k];
-        y[i] = t / L[(size_t)tri(i, i) * cp];
+    for (int i = 0; i < NP; ++i) {   // L y = -g
+        double part = 0.0;
+        for (int k = ctx.lane(); k < i; k += Ctx::W) part += S.L[tri(i, k)] * S.y[k];
+        double t = (-S.g[i] - ctx.sum(part)) / S.L[tri(i, i)];
+        if (ctx.lane() == 0) S.y[i] = t;
+        ctx.sync();
     }
-    for (int i = NP - 1; i >= 0; --i) {
-        double t = y[i];
-        for (int k = i + 1; k < NP; ++k) t -= L[(size_t)tri(k, i) * cp] * delta[k];
-        delta[i] = t / L[(size_t)tri(i, i) * cp];
+    for (int i = NP - 1; i >= 0; --i) {   // L^T delta = y
+        double part = 0.0;
+        for (int k = i + 1 + ctx.lane(); k < NP; k += Ctx::W) part += S.L[tri(k, i)] * S.delta[k];
+        double t = (S.y[i] - ctx.sum(part)) / S.L[tri(i, i)];
+        if (ctx.lane() == 0) S.delta[i] = t;
+        ctx.sync();
     }
     return true;
 }
 
-// from the accepted state (th_acc, f_acc, g_acc, h_acc, lam): next trial point, or termination
-ATTRICI_HD_NOINLINE void propose(const StepArgs& a, int cell) {
-    const size_t cp = a.Cp;
-    double g[NP], th[NP], delta[NP];
-    for (int i = 0; i < NP; ++i) {
-        g[i] = a.g_acc[(size_t)i * cp + cell];
-        th[i] = a.th_acc[(size_t)i * cp + cell];
-    }
+// from the accepted state in S (th, g, H) and lam: next trial point, or termination.
+// Every lane returns the same status.
+template <class Ctx> ATTRICI_HD int propose(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
     double lam = a.lam[cell];
     bool ok = false;
     for (int tries = 0; tries < 40 && !ok; ++tries) {
-        ok = lm_solve(a, cell, g, lam, delta);
-        if (ok) for (int i = 0; i < NP; ++i) ok = ok && isfinite(delta[i]);
+        ok = lm_solve(S, lam, ctx);
+        if (ok) {
+            bool fin = true;
+            for (int i = ctx.lane(); i < NP; i += Ctx::W) fin = fin && isfinite(S.delta[i]);
+            ok = ctx.all(fin);
+        }
         if (!ok) lam = fmax(lam * 10.0, 1e-6);
     }
-    a.lam[cell] = lam;
-    if (!ok) { a.status[cell] = ATTRICI_STATUS_STALLED; return; }
-    // predicted decrease of the quadratic model: -g.d - 0.5 d.H.d
-    double gd = 0.0, dhd = 0.0;
-    const double* H = a.h_acc + cell;
-    for (int i = 0; i < NP; ++i) {
-        gd += g[i] * delta[i];
-        double hi = 0.0;
-        for (int j = 0; j < NP; ++j) hi += H[(size_t)tri(i, j) * cp] * delta[j];
-        dhd += delta[i] * hi;
+    int status = ATTRICI_STATUS_RUNNING;
+    double pred = 0.0;
+    if (!ok) {
+        status = ATTRICI_STATUS_STALLED;
+    } else {
+        // predicted decrease of the quadratic model: -g.d - 0.5 d.H.d
+        double part = 0.0;
+        for (int i = ctx.lane(); i < NP; i += Ctx::W) {
+            double hi = 0.0;
+            for (int j = 0; j < NP; ++j) hi += S.H[tri(i, j)] * S.delta[j];
+            part += -S.g[i] * S.delta[i] - 0.5 * S.delta[i] * hi;
+        }
+        pred = ctx.sum(part);
+        double f = a.f_acc[cell];
+        if (pred <= a.tol_pred * fmax(fabs(f), 1.0)) status = ATTRICI_STATUS_CONVERGED;
     }
-    double pred = -gd - 0.5 * dhd;
-    a.pred[cell] = pred;
-    double f = a.f_acc[cell];
-    if (pred <= a.tol_pred * fmax(fabs(f), 1.0)) { a.status[cell] = ATTRICI_STATUS_CONVERGED; return; }
-    if (a.npass[cell] >= a.max_pass) return;  // stays RUNNING: reported as not converged
-    for (int i = 0; i < NP; ++i) {
-        th[i] += delta[i];
-        a.th_trial[(size_t)i * cp + cell] = th[i];
+    const bool go_on = (status == ATTRICI_STATUS_RUNNING) && (a.npass[cell] < a.max_pass);
+    ctx.sync();
+    if (go_on) {
+        for (int i = ctx.lane(); i < NP; i += Ctx::W) {
+            double v = S.th[i] + S.delta[i];
+            S.y[i] = v;   // y is free after the solve: holds the trial point for the rotation
+            a.th_trial[(size_t)cell * NP + i] = v;
+        }
+        ctx.sync();
+        rotate_to_shared(a, cell, S.y, ctx);
     }
-    rotate_to_shared(a, cell, th);
+    if (ctx.lane() == 0) {
+        a.lam[cell] = lam;
+        a.pred[cell] = pred;
+        a.status[cell] = status;   // stays RUNNING if max_pass was hit: reported as not converged
+    }
+    ctx.sync();
+    return go_on ? ATTRICI_STATUS_RUNNING : (status == ATTRICI_STATUS_RUNNING ? -1 : status);
 }
 
 // phase offset of the cell frame: tau of the first day this term uses (basis64 column B_TAU)
-ATTRICI_HD_NOINLINE void cell_phase(const StepArgs& a, int cell) {
-    const size_t cp = a.Cp;
-    int first = a.st_first[(size_t)a.slot * cp + cell];
+template <class Ctx> ATTRICI_HD void cell_phase(const StepArgs& a, int cell, const Ctx& ctx) {
+    int first = a.st_first[(size_t)a.slot * a.Cp + cell];
     double tau0 = (first >= 0) ? a.basis64[(size_t)first * B_STRIDE + B_TAU] : 0.0;
-    for (int k = 1; k <= NH; ++k) {
+    double* rot = a.rot + (size_t)cell * 2 * NH;
+    for (int k = 1 + ctx.lane(); k <= NH; k += Ctx::W) {
         double x = (6.283185307179586 * (double)k) * tau0;
-        a.rot[(size_t)(k - 1) * cp + cell] = cos(x);
-        a.rot[(size_t)(NH + k - 1) * cp + cell] = sin(x);
+        rot[k - 1] = cos(x);
+        rot[NH + k - 1] = sin(x);
     }
+    ctx.sync();
 }
 
 // returns true if the cell takes part in the iteration
-ATTRICI_HD_NOINLINE bool cell_init(const StepArgs& a, int cell) {
-    const size_t cp = a.Cp;
-    const size_t so = (size_t)a.slot * cp + cell;
-    double th[NP];
-    for (int i = 0; i < NP; ++i) th[i] = 0.0;
+template <class Ctx> ATTRICI_HD bool cell_init(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
+    const size_t so = (size_t)a.slot * a.Cp + cell;
     double n = a.st_cnt[so];
     int first = a.st_first[so];
     int status = ATTRICI_STATUS_RUNNING;
     if (!(n > 0.0) || first < 0) status = ATTRICI_STATUS_NO_DATA;
-    cell_phase(a, cell);
+    cell_phase(a, cell, ctx);
+    double v0 = 0.0, vb = 0.0;   // start values of the two intercepts
     if (status == ATTRICI_STATUS_RUNNING && !a.zero_init) {
         // moment-matched intercepts (the reference starts from zero, model_scipy.py:113,234; the MAP
         // estimate does not depend on the start, the number of passes does)
         double mean = a.st_sum[so] / n;
         double var = fmax(a.st_sq[so] / n - mean * mean, 1e-12);
         switch (a.term) {
-            case T_NORMAL: th[0] = mean; th[NA] = 0.5 * log(var); break;
+            case T_NORMAL: v0 = mean; vb = 0.5 * log(var); break;
             case T_GAMMA:
-                if (mean > 0.0) { th[0] = log(mean); th[NA] = 0.5 * log(fmax(mean * mean / var, 1e-3)); }
+                if (mean > 0.0) { v0 = log(mean); vb = 0.5 * log(fmax(mean * mean / var, 1e-3)); }
                 break;
             case T_WEIBULL:
                 if (mean > 0.0) {
                     double c = pow(sqrt(var) / mean, -1.086);
                     c = fmin(fmax(c, 0.05), 50.0);
-                    th[NA] = log(c);
-                    th[0] = log(mean) - lgamma(1.0 + 1.0 / c);
+                    vb = log(c);
+                    v0 = log(mean) - lgamma(1.0 + 1.0 / c);
                 }
                 break;
             case T_BETA:
                 if (mean > 0.0 && mean < 1.0) {
                     double phi = mean * (1.0 - mean) / var - 1.0;
                     if (!(phi > 1e-3)) phi = 1.0;
-                    th[0] = log(mean / (1.0 - mean));
-                    th[NA] = log(phi);
+                    v0 = log(mean / (1.0 - mean));
+                    vb = log(phi);
                 }
                 break;
             case T_BERNOULLI: {
                 double p = fmin(fmax(mean, 1e-6), 1.0 - 1e-6);
-                th[0] = log(p / (1.0 - p));
+                v0 = log(p / (1.0 - p));
             } break;
         }
         // stay inside the bulk of the N(0,1) priors of the intercepts
-        for (int i = 0; i < NP; ++i) {
-            if (!isfinite(th[i])) th[i] = 0.0;
-            th[i] = fmin(fmax(th[i], -6.0), 6.0);
-        }
+        if (!isfinite(v0)) v0 = 0.0;
+        if (!isfinite(vb)) vb = 0.0;
+        v0 = fmin(fmax(v0, -6.0), 6.0);
+        vb = fmin(fmax(vb, -6.0), 6.0);
     }
-    for (int i = 0; i < NP; ++i) {
-        a.th_trial[(size_t)i * cp + cell] = th[i];
-        a.th_acc[(size_t)i * cp + cell] = th[i];
+    for (int i = ctx.lane(); i < NP; i += Ctx::W) {
+        double v = (i == 0) ? v0 : (i == NA ? vb : 0.0);
+        S.th[i] = v;
+        a.th_trial[(size_t)cell * NP + i] = v;
+        a.th_acc[(size_t)cell * NP + i] = v;
     }
-    rotate_to_shared(a, cell, th);
-    a.lam[cell] = a.lambda0;
-    a.f_acc[cell] = INFINITY;
-    a.pred[cell] = 0.0;
-    a.status[cell] = status;
-    a.npass[cell] = 0;
+    ctx.sync();
+    rotate_to_shared(a, cell, S.th, ctx);
+    if (ctx.lane() == 0) {
+        a.lam[cell] = a.lambda0;
+        a.f_acc[cell] = INFINITY;
+        a.pred[cell] = 0.0;
+        a.status[cell] = status;
+        a.npass[cell] = 0;
+    }
+    ctx.sync();
     return status == ATTRICI_STATUS_RUNNING;
 }
 
-// after a pass at th_trial: accept / reject, update damping, propose the next trial.
-// returns true if the cell needs another pass
-ATTRICI_HD_NOINLINE bool cell_step(const StepArgs& a, int cell) {
+// after a pass at th_trial (moments reduced into momd): accept / reject, update damping, propose the
+// next trial.  Returns true if the cell needs another pass.
+template <class Ctx> ATTRICI_HD bool cell_step(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
     if (a.status[cell] != ATTRICI_STATUS_RUNNING) return false;
-    const size_t cp = a.Cp;
-    double th[NP], g[NP];
-    for (int i = 0; i < NP; ++i) th[i] = a.th_trial[(size_t)i * cp + cell];
-    // Fisher information of the trial goes to the work column first; promoted on acceptance
-    double f_t = assemble(a, cell, th, g, a.h_wrk + cell);
-    bool finite = isfinite(f_t);
-    for (int i = 0; i < NP; ++i) finite = finite && isfinite(g[i]);
-    int np = a.npass[cell];
-    a.npass[cell] = np + 1;
-    double f = a.f_acc[cell];
+    for (int i = ctx.lane(); i < NP; i += Ctx::W) S.th[i] = a.th_trial[(size_t)cell * NP + i];
+    load_moments(a, cell, S, ctx);
+    double f_t = assemble(a, S, true, ctx);
+    bool fin = isfinite(f_t);
+    for (int i = ctx.lane(); i < NP; i += Ctx::W) fin = fin && isfinite(S.g[i]);
+    const bool finite = ctx.all(fin);
+    const int np = a.npass[cell];
+    const double f = a.f_acc[cell];
     double lam = a.lam[cell];
+    const double pred = a.pred[cell];
+    ctx.sync();
     bool accept;
+    int status = ATTRICI_STATUS_RUNNING;
     if (np == 0) {
-        if (!finite) { a.status[cell] = ATTRICI_STATUS_NONFINITE; return false; }
-        accept = true;
+        accept = finite;
+        if (!finite) status = ATTRICI_STATUS_NONFINITE;
     } else {
         // float32 day arithmetic leaves ~1e-9 relative noise in f: tolerate it, the predicted-decrease
         // test in propose() is what ends the iteration
         double slack = 4e-9 * fabs(f);
-        double pred = a.pred[cell];
         accept = finite && (f_t <= f + slack) && (f - f_t >= 1e-4 * pred - slack);
         if (accept) {
             double rho = (f - f_t) / pred;
@@ -358,48 +374,68 @@ ATTRICI_HD_NOINLINE bool cell_step(const StepArgs& a, int cell) {
             else if (rho < 0.25) lam = lam * 2.0;
         } else {
             lam = fmax(lam * 8.0, 1e-4);
-            if (lam > 1e12) { a.status[cell] = ATTRICI_STATUS_STALLED; return false; }
+            if (lam > 1e12) status = ATTRICI_STATUS_STALLED;
         }
     }
-    a.lam[cell] = lam;
+    if (ctx.lane() == 0) {
+        a.npass[cell] = np + 1;
+        a.lam[cell] = lam;
+        if (accept) a.f_acc[cell] = f_t;
+        if (status != ATTRICI_STATUS_RUNNING) a.status[cell] = status;
+    }
     if (accept) {
-        a.f_acc[cell] = f_t;
-        for (int i = 0; i < NP; ++i) {
-            a.th_acc[(size_t)i * cp + cell] = th[i];
-            a.g_acc[(size_t)i * cp + cell] = g[i];
+        for (int i = ctx.lane(); i < NP; i += Ctx::W) {
+            a.th_acc[(size_t)cell * NP + i] = S.th[i];
+            a.g_acc[(size_t)cell * NP + i] = S.g[i];
         }
-        for (int i = 0; i < NTRI; ++i) a.h_acc[(size_t)i * cp + cell] = a.h_wrk[(size_t)i * cp + cell];
+        for (int i = ctx.lane(); i < NTRI; i += Ctx::W) a.h_acc[(size_t)cell * NTRI + i] = S.H[i];
+    } else {
+        for (int i = ctx.lane(); i < NP; i += Ctx::W) {
+            S.th[i] = a.th_acc[(size_t)cell * NP + i];
+            S.g[i] = a.g_acc[(size_t)cell * NP + i];
+        }
+        for (int i = ctx.lane(); i < NTRI; i += Ctx::W) S.H[i] = a.h_acc[(size_t)cell * NTRI + i];
     }
-    propose(a, cell);
-    return a.status[cell] == ATTRICI_STATUS_RUNNING && a.npass[cell] < a.max_pass;
+    ctx.sync();
+    if (status != ATTRICI_STATUS_RUNNING) return false;
+    return propose(a, cell, S, ctx) == ATTRICI_STATUS_RUNNING;
 }
 
 // th_trial := th_acc and its shared-frame image (before the final FP64 evaluation)
-ATTRICI_HD_NOINLINE void cell_final_point(const StepArgs& a, int cell) {
-    const size_t cp = a.Cp;
-    double th[NP];
-    for (int i = 0; i < NP; ++i) {
-        th[i] = a.th_acc[(size_t)i * cp + cell];
-        a.th_trial[(size_t)i * cp + cell] = th[i];
+template <class Ctx> ATTRICI_HD void cell_final_point(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
+    for (int i = ctx.lane(); i < NP; i += Ctx::W) {
+        double v = a.th_acc[(size_t)cell * NP + i];
+        S.th[i] = v;
+        a.th_trial[(size_t)cell * NP + i] = v;
     }
-    rotate_to_shared(a, cell, th);
+    ctx.sync();
+    rotate_to_shared(a, cell, S.th, ctx);
+    ctx.sync();
 }
 
-// after the FP64 pass at th_acc: log posterior (model_scipy.py:525 "logp"), coefficients, status
-ATTRICI_HD_NOINLINE void cell_store(const StepArgs& a, int cell) {
+// after the FP64 pass at th_acc (day terms reduced into momd row NACC): log posterior
+// (model_scipy.py:525 "logp"), coefficients, status
+template <class Ctx> ATTRICI_HD void cell_store(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
     const size_t cp = a.Cp;
-    double th[NP];
-    for (int i = 0; i < NP; ++i) th[i] = a.th_acc[(size_t)i * cp + cell];
-    double nll = 0.0;
-    for (int ch = 0; ch < a.n_chunks; ++ch) nll += a.part_nll[(size_t)ch * cp + cell];
-    double f = nll + prior_energy(th, a.term, a.modes) - prior_const(a.term, a.modes);
+    double fp = 0.0;
+    for (int i = ctx.lane(); i < NP; i += Ctx::W) {
+        double v = a.th_acc[(size_t)cell * NP + i];
+        S.th[i] = v;
+        Col c = col_of(i);
+        if (col_active(c, a.term, a.modes)) fp += 0.5 * prior_prec(c) * v * v;
+    }
+    double f = a.momd[(size_t)NACC * cp + cell] + ctx.sum(fp) - prior_const(a.term, a.modes);
     int st = a.status[cell];
     bool bad = (st == ATTRICI_STATUS_NO_DATA || st == ATTRICI_STATUS_NONFINITE);
-    const size_t so = (size_t)a.slot * cp + cell;
-    for (int i = 0; i < NP; ++i) a.th_out[((size_t)a.slot * NP + i) * cp + cell] = bad ? NAN : th[i];
-    a.logp_part[so] = bad ? NAN : -f;
-    a.status_part[so] = st;
-    a.npass_part[so] = a.npass[cell];
+    ctx.sync();
+    for (int i = ctx.lane(); i < NP; i += Ctx::W) a.th_out[((size_t)a.slot * NP + i) * cp + cell] = bad ? NAN : S.th[i];
+    if (ctx.lane() == 0) {
+        const size_t so = (size_t)a.slot * cp + cell;
+        a.logp_part[so] = bad ? NAN : -f;
+        a.status_part[so] = st;
+        a.npass_part[so] = a.npass[cell];
+    }
+    ctx.sync();
 }
 
 }  // namespace attrici

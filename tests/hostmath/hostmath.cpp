@@ -78,28 +78,43 @@ struct HostCell {
     std::vector<float> b32;
     double st_cnt[2], st_sum[2], st_sq[2], st_ln[2];
     int st_first[2];
-    double th_acc[NP], th_trial[NP], th_pass[NP], g_acc[NP], h_acc[NTRI], h_wrk[NTRI];
+    double th_acc[NP], th_trial[NP], th_pass[NP], g_acc[NP], h_acc[NTRI], momd[NACC + 1];
     double f_acc, pred, lam, rot[2 * NH];
-    int status, npass, n_running;
+    int status, npass;
     double part_nll[MAX_CHUNKS];
     std::vector<double> part_acc;   // holds float or double partials
     double th_out[2 * NP], logp_part[2];
     int status_part[2], npass_part[2];
+    CellScratch S;
 
-    StepArgs args(int term, int modes, int slot, int fp64, int max_pass, double tol_pred, double lambda0, int zero_init,
-                  int n_chunks) {
+    StepArgs args(int term, int modes, int slot, int max_pass, double tol_pred, double lambda0, int zero_init) {
         StepArgs a;
-        a.C = 1; a.Cp = 1; a.n_chunks = n_chunks; a.fp64 = fp64;
+        a.C = 1; a.Cp = 1;
         a.term = term; a.modes = modes; a.slot = slot;
         a.max_pass = max_pass; a.tol_pred = tol_pred; a.lambda0 = lambda0; a.zero_init = zero_init;
         a.basis64 = b64.data();
         a.st_cnt = st_cnt; a.st_sum = st_sum; a.st_sq = st_sq; a.st_ln = st_ln; a.st_first = st_first;
-        a.th_acc = th_acc; a.th_trial = th_trial; a.th_pass = th_pass; a.g_acc = g_acc; a.h_acc = h_acc; a.h_wrk = h_wrk;
+        a.momd = momd;
+        a.th_acc = th_acc; a.th_trial = th_trial; a.th_pass = th_pass; a.g_acc = g_acc; a.h_acc = h_acc;
         a.f_acc = &f_acc; a.pred = &pred; a.lam = &lam; a.rot = rot;
-        a.status = &status; a.npass = &npass; a.n_running = &n_running;
-        a.part_nll = part_nll; a.part_acc = part_acc.data();
+        a.status = &status; a.npass = &npass;
         a.th_out = th_out; a.logp_part = logp_part; a.status_part = status_part; a.npass_part = npass_part;
         return a;
+    }
+
+    // reduce_partials_kernel
+    void reduce(bool fp64, bool moments, int n_chunks) {
+        double s = 0.0;
+        for (int ch = 0; ch < n_chunks; ++ch) s += part_nll[ch];
+        momd[NACC] = s;
+        if (!moments) return;
+        for (int i = 0; i < NACC; ++i) {
+            double t = 0.0;
+            for (int ch = 0; ch < n_chunks; ++ch)
+                t += fp64 ? part_acc[(size_t)ch * NACC + i]
+                          : (double)reinterpret_cast<const float*>(part_acc.data())[(size_t)ch * NACC + i];
+            momd[i] = t;
+        }
     }
 };
 
@@ -202,17 +217,19 @@ int hm_nll_grad_cell(int term, int modes, int T, int i0, int i1, const float* ys
     if (n_chunks > MAX_CHUNKS) n_chunks = MAX_CHUNKS;
     int chunk_len = (i1 - i0 + n_chunks - 1) / n_chunks;
     n_chunks = (i1 - i0 + chunk_len - 1) / chunk_len;
-    StepArgs a = hc.args(term, modes, 0, fp64, 60, 1e-11, 1e-3, 1, n_chunks);
-    cell_phase(a, 0);
-    for (int i = 0; i < NP; ++i) hc.th_trial[i] = theta[i];
-    rotate_to_shared(a, 0, hc.th_trial);
+    StepArgs a = hc.args(term, modes, 0, 60, 1e-11, 1e-3, 1);
+    SerialCtx ctx;
+    cell_phase(a, 0, ctx);
+    for (int i = 0; i < NP; ++i) { hc.th_trial[i] = theta[i]; hc.S.th[i] = theta[i]; }
+    rotate_to_shared(a, 0, hc.th_trial, ctx);
     run_pass(hc, term, fp64 != 0, true, ys, i0, i1, chunk_len, n_chunks);
-    double g[NP];
-    *nll = assemble(a, 0, hc.th_trial, g, hc.h_wrk);
-    for (int i = 0; i < NP; ++i) grad[i] = g[i];
+    hc.reduce(fp64 != 0, true, n_chunks);
+    load_moments(a, 0, hc.S, ctx);
+    *nll = assemble(a, hc.S, true, ctx);
+    for (int i = 0; i < NP; ++i) grad[i] = hc.S.g[i];
     if (fisher)
         for (int i = 0; i < NP; ++i)
-            for (int j = 0; j < NP; ++j) fisher[i * NP + j] = hc.h_wrk[tri(i, j)];
+            for (int j = 0; j < NP; ++j) fisher[i * NP + j] = hc.S.H[tri(i, j)];
     return 0;
 }
 
@@ -227,16 +244,18 @@ int hm_fit_cell(int term, int modes, int T, int i0, int i1, const float* ys, con
     if (n_chunks > MAX_CHUNKS) n_chunks = MAX_CHUNKS;
     int chunk_len = (i1 - i0 + n_chunks - 1) / n_chunks;
     n_chunks = (i1 - i0 + chunk_len - 1) / chunk_len;
-    StepArgs a = hc.args(term, modes, 0, fp64, max_pass, tol_pred, lambda0, zero_init, n_chunks);
-    bool running = cell_init(a, 0);
+    StepArgs a = hc.args(term, modes, 0, max_pass, tol_pred, lambda0, zero_init);
+    SerialCtx ctx;
+    bool running = cell_init(a, 0, hc.S, ctx);
     for (int it = 0; running && it < max_pass; ++it) {
         run_pass(hc, term, fp64 != 0, true, ys, i0, i1, chunk_len, n_chunks);
-        running = cell_step(a, 0);
+        hc.reduce(fp64 != 0, true, n_chunks);
+        running = cell_step(a, 0, hc.S, ctx);
     }
-    cell_final_point(a, 0);
+    cell_final_point(a, 0, hc.S, ctx);
     run_pass(hc, term, true, false, ys, i0, i1, chunk_len, n_chunks);
-    a.fp64 = 1;
-    cell_store(a, 0);
+    hc.reduce(true, false, n_chunks);
+    cell_store(a, 0, hc.S, ctx);
     for (int i = 0; i < NP; ++i) theta_out[i] = hc.th_out[i];
     *logp = hc.logp_part[0];
     *status = hc.status_part[0];
