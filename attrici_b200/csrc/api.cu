@@ -212,7 +212,8 @@ int attrici_build_basis(void* workspace, size_t workspace_bytes, int family, con
     ATTRICI_TRY(check_shape(T, C, C));
     Workspace ws;
     ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, family));
-    return launch_build_basis(ws, days, gmt, (cudaStream_t)stream);
+    ATTRICI_TRY(launch_build_basis(ws, days, gmt, (cudaStream_t)stream));
+    return launch_build_zmat(ws, (cudaStream_t)stream);
 }
 
 int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,

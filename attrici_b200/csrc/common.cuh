@@ -46,6 +46,7 @@ struct Workspace {
     size_t bytes;
     float* basis32;
     double* basis64;
+    float* zmat;       // [T + pad][ZM_STRIDE] TF32 hi / lo parts of the moment matrix (tensor-core pass)
     // prep results
     float* cmin;       // [Cp]
     float* cscale;     // [Cp]
@@ -99,6 +100,7 @@ struct Workspace {
         size_t c = (size_t)Cp;
         basis32 = (float*)take(sizeof(float) * B_STRIDE * (size_t)(T + 2 * PASS_TILE));
         basis64 = (double*)take(sizeof(double) * B_STRIDE * (size_t)(T + 2 * PASS_TILE));
+        zmat = (float*)take(sizeof(float) * ZM_STRIDE * (size_t)(T + 2 * PASS_TILE));
         cmin = (float*)take(4 * c);
         cscale = (float*)take(4 * c);
         st_cnt = (double*)take(8 * 2 * c);
@@ -185,6 +187,10 @@ int launch_prep(Workspace& ws, const attrici_variable_t& var, const float* y, fl
 // ws.part_acc.  status != nullptr (only without a list): only cells whose status is RUNNING are evaluated.
 int launch_pass(Workspace& ws, const PassShape& ps, int term, bool fp64, bool with_moments, const float* y_scaled,
                 int64_t ld, int i0, int i1, const int* status, cudaStream_t s);
+// tensor-core variant for the Normal family, FP32 path with moments (pass_mma.cu)
+int launch_build_zmat(Workspace& ws, cudaStream_t s);
+int launch_pass_mma(Workspace& ws, const PassShape& ps, const float* y_scaled, int64_t ld, int i0, int i1,
+                    const int* status, cudaStream_t s);
 // cross-chunk reduction of the partials of the last pass into ws.momd
 int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_moments, cudaStream_t s);
 

@@ -16,6 +16,7 @@
 // Products of two Fourier columns are Fourier columns of the sum / difference harmonic, so the
 // 27 x 27 information matrix needs only 17 trig moments per (weight, power of gmt) instead of all
 // 378 column products: 102 + 27 accumulators per cell.
+#include <stdlib.h>
 #include "common.cuh"
 #include "pass_impl.cuh"
 
@@ -185,6 +186,12 @@ template <int KIND> static int launch_kind(const PassArgs& a, dim3 grid, bool fp
     return 0;
 }
 
+// ATTRICI_NO_MMA=1 keeps the Normal family on the FMA kernel (A/B measurements only)
+static bool use_tensor_cores() {
+    static const bool on = [] { const char* e = getenv("ATTRICI_NO_MMA"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 // time chunks for the cells of one pass: enough CTAs for ~3 waves of 2 CTAs/SM on 148 SMs, bounded by
 // the partial buffers (indexed by position, so fewer cells leave room for more chunks)
 PassShape plan_pass(const Workspace& ws, const int* list, int n_active, int i0, int i1, bool fp64) {
@@ -212,6 +219,8 @@ int launch_pass(Workspace& ws, const PassShape& ps, int term, bool fp64, bool wi
                 int64_t ld, int i0, int i1, const int* status, cudaStream_t s) {
     if (i1 <= i0) { set_error("empty fit window [%d, %d)", i0, i1); return ATTRICI_EINVAL; }
     if (ps.n_active <= 0) return 0;
+    if (term == T_NORMAL && !fp64 && with_moments && use_tensor_cores())
+        return launch_pass_mma(ws, ps, y_scaled, ld, i0, i1, status, s);
     PassArgs a;
     a.ys = y_scaled;
     a.ld = ld;

@@ -1,0 +1,361 @@
+// Likelihood pass of the Normal family on the tensor cores (TF32 mma.sync m16n8k8, 3-term split products
+// that carry FP32-level accuracy), replacing the FMA chains of pass.cu's thread-per-cell kernel.
+//
+// Both contractions of a pass are GEMM-shaped because the basis is shared by all cells:
+//   stage 1   eta[cells x days]  = Theta[cells x K] . Z[days x K]^T          (linear predictors of mu, log sigma)
+//   (elementwise, registers)      e = exp(-eta_s), z = (y - eta_mu) e, nll += z^2/2 + eta_s,
+//                                 r_mu = z e, r_s = 1 - z^2, w = e^2, v = valid
+//   stage 3   M[cells x cols]   += Q[cells x days] . Z[days x cols]          Q in {r_mu, r_s, w, v}
+// Z holds the 51 products gmt^p x {1, cos k, sin k} (k <= 8) whose first 18 columns are also the design
+// columns of stage 1 (products of Fourier columns are Fourier columns: see pass.cu).  A warp owns 16 cells;
+// the accumulator fragment of stage 1 is reused as the A fragment of stage 3 by pairing MMA k-index t with
+// day 2t and t+4 with day 2t+1, so no shuffles are needed (the FlashAttention-2 register trick).
+//
+// Accuracy: every operand is split x = hi + lo with hi = tf32_rn(x), lo = tf32_rn(x - hi) and the product
+// is hi.hi + lo.hi + hi.lo (exact TF32 products, FP32 accumulation): relative error ~2^-22 per term, the
+// level of an FP32 FMA chain of this length.  Fisher moments (w, v) only steer the step: single TF32.
+//
+// Replaces the same reference code as pass.cu (DistributionScipy.log_likelihood,
+// attrici/estimation/model_scipy.py:311-331 with np.dot(covariates, weights) + scipy.stats.norm.logpdf).
+#include "common.cuh"
+#include "pass_impl.cuh"
+
+namespace attrici {
+
+namespace {
+
+constexpr int MMA_WARPS = 8;                    // warps per CTA
+constexpr int MMA_THREADS = 32 * MMA_WARPS;
+constexpr int MMA_CELLS = 16 * MMA_WARPS;       // cells per CTA
+constexpr int ZC_HI = 56;                       // 51 hi columns padded to 7 n-tiles
+constexpr int ZC_LO = 24;                       // lo parts of the first 18 columns, 3 n-tiles
+
+struct MmaArgs {
+    const float* ys;
+    int64_t ld;
+    int Cp;
+    const int* list;
+    int n_active, Pp;
+    int i0, i1, chunk_len;
+    const float* zmat;       // [T + pad][ZM_STRIDE]
+    const double* th_pass;   // [NP][Cp]
+    const int* status;
+    double* part_nll;        // [chunk][Pp]
+    float* part_acc;         // [chunk][NACC][Pp]
+};
+
+__device__ __forceinline__ uint32_t tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_rn(x);
+    lo = tf32_rn(x - __uint_as_float(hi));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Z column -> index in the accumulator layout of pass.cu (ACC_AA block) ; -1 = padding
+__device__ __forceinline__ int zcol_to_aa(int c) {
+    if (c >= ZM_COLS) return -1;
+    int p, t;   // power of gmt, trig17 index {0: 1, 1..8: cos k, 9..16: sin k}
+    if (c < 18) { p = c / 9; int j = c % 9; t = j == 0 ? 0 : (j <= 4 ? j : NH + (j - 4)); }
+    else if (c < 34) { p = (c - 18) / 8; int j = (c - 18) % 8; t = j < 4 ? 5 + j : NH + 5 + (j - 4); }
+    else { p = 2; t = c - 34; }
+    return ACC_AA + p * NTRIG + t;
+}
+
+__global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
+    extern __shared__ __align__(16) float smem[];   // [2][PASS_TILE][ZM_STRIDE]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, t4 = lane & 3;
+    const int chunk = blockIdx.y;
+    const int t_begin = a.i0 + chunk * a.chunk_len;
+    const int t_end = min(a.i1, t_begin + a.chunk_len);
+
+    // the two cells (rows gid, gid + 8 of the warp's 16) this thread holds fragments of
+    int pos[2], cell[2];
+    bool act[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        pos[h] = blockIdx.x * MMA_CELLS + warp * 16 + gid + 8 * h;
+        const bool in_range = pos[h] < a.n_active;
+        cell[h] = a.list ? a.list[in_range ? pos[h] : 0] : (in_range ? pos[h] : a.n_active - 1);
+        act[h] = in_range;
+        if (act[h] && a.status) act[h] = (a.status[cell[h]] == ATTRICI_STATUS_RUNNING);
+    }
+    if (__syncthreads_or(act[0] || act[1]) == 0 || t_begin >= t_end) return;   // uniform per CTA
+    const bool warp_active = __any_sync(0xffffffffu, act[0] || act[1]);
+
+    // coefficient fragments (A operands of stage 1): Z column k <-> canonical coefficient
+    //   mu block   : k < 9 -> {0, 2..5, 6..9}[k], 9 <= k < 18 -> {1, 10..13, 14..17}[k - 9]
+    //   sigma block: k < 9 -> NA + k
+    uint32_t thA_h[3][4], thA_l[3][4], thB_h[2][4], thB_l[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int h = r & 1;                       // a0,a2: row gid ; a1,a3: row gid + 8
+            const int k = 8 * ks + t4 + 4 * (r >> 1);
+            float va = 0.f, vb = 0.f;
+            if (act[h]) {
+                if (k < 18) {
+                    int j = k % 9;
+                    int ia = (k < 9) ? (j == 0 ? 0 : 1 + j) : (j == 0 ? 1 : 9 + j);
+                    va = (float)a.th_pass[(size_t)ia * a.Cp + cell[h]];
+                }
+                if (k < 9) vb = (float)a.th_pass[(size_t)(NA + k) * a.Cp + cell[h]];
+            }
+            split_tf32(va, thA_h[ks][r], thA_l[ks][r]);
+            if (ks < 2) split_tf32(vb, thB_h[ks][r], thB_l[ks][r]);
+        }
+    }
+
+    float accAA[7][4], accBB[4][4], accGA[3][4], accGB[2][4];
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) accAA[i][r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) accBB[i][r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) accGA[i][r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) accGB[i][r] = 0.f;
+    double nll[2] = {0.0, 0.0};
+
+    const int n_tiles = (t_end - t_begin + PASS_TILE - 1) / PASS_TILE;
+    constexpr int VEC_PER_TILE = PASS_TILE * ZM_STRIDE / 4;
+    auto issue_tile = [&](int it) {
+        const float4* src = reinterpret_cast<const float4*>(a.zmat + (size_t)(t_begin + it * PASS_TILE) * ZM_STRIDE);
+        float4* dst = reinterpret_cast<float4*>(smem + (size_t)(it & 1) * PASS_TILE * ZM_STRIDE);
+        for (int v = threadIdx.x; v < VEC_PER_TILE; v += MMA_THREADS) cp_async16(dst + v, src + v);
+        cp_async_commit();
+    };
+    issue_tile(0);
+
+    // observations of one 8-day step: y[row h][day 2 t4 + d], index h * 2 + d
+    const float qnan = __int_as_float(0x7fc00000);
+    auto load_y = [&](int t0, float (&y)[4]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const int t = t0 + 2 * t4 + d;
+                y[h * 2 + d] = (act[h] && t < t_end) ? a.ys[(size_t)t * a.ld + cell[h]] : qnan;
+            }
+    };
+    float ycur[4], ynext[4];
+    load_y(t_begin, ycur);
+
+    for (int it = 0; it < n_tiles; ++it) {
+        if (it + 1 < n_tiles) {
+            issue_tile(it + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (warp_active) {
+            const float* tile = smem + (size_t)(it & 1) * PASS_TILE * ZM_STRIDE;
+            const int t_tile = t_begin + it * PASS_TILE;
+#pragma unroll 1
+            for (int s8 = 0; s8 < PASS_TILE / 8; ++s8) {
+                const int t0 = t_tile + 8 * s8;
+                if (t0 >= t_end) break;
+                load_y(t0 + 8, ynext);
+                const float* zt = tile + (size_t)(8 * s8) * ZM_STRIDE;
+                // ---- stage 1: eta_mu, eta_sigma for 16 cells x 8 days (B operand: k = Z column, n = day)
+                float etaA[4] = {0.f, 0.f, 0.f, 0.f}, etaB[4] = {0.f, 0.f, 0.f, 0.f};
+                const float* zrow = zt + (size_t)gid * ZM_STRIDE;
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) {
+                    const uint32_t bh0 = __float_as_uint(zrow[8 * ks + t4]), bh1 = __float_as_uint(zrow[8 * ks + t4 + 4]);
+                    const uint32_t bl0 = __float_as_uint(zrow[ZC_HI + 8 * ks + t4]),
+                                   bl1 = __float_as_uint(zrow[ZC_HI + 8 * ks + t4 + 4]);
+                    mma_tf32(etaA, thA_h[ks], bh0, bh1);
+                    mma_tf32(etaA, thA_l[ks], bh0, bh1);
+                    mma_tf32(etaA, thA_h[ks], bl0, bl1);
+                    if (ks < 2) {
+                        mma_tf32(etaB, thB_h[ks], bh0, bh1);
+                        mma_tf32(etaB, thB_l[ks], bh0, bh1);
+                        mma_tf32(etaB, thB_h[ks], bl0, bl1);
+                    }
+                }
+                // ---- elementwise: accumulator fragment c{0,1,2,3} = (row gid | gid + 8) x (day 2 t4 | 2 t4 + 1)
+                // -> A fragment a{0,1,2,3} = (row gid, k t4), (row gid + 8, k t4), (row gid, k t4 + 4), (gid + 8, t4 + 4)
+                //    with k = t4 <-> day 2 t4 and k = t4 + 4 <-> day 2 t4 + 1
+                uint32_t qAh[4], qAl[4], qBh[4], qBl[4], qW[4], qV[4];
+                float nl[2] = {0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int h = c >> 1, d = c & 1;        // c0,c1: row gid ; c2,c3: row gid + 8
+                    const float yv = ycur[h * 2 + d];
+                    const bool valid = (yv == yv);
+                    const float e = __expf(-etaB[c]);
+                    const float z = ((valid ? yv : 0.f) - etaA[c]) * e;
+                    const float z2 = z * z;
+                    const float rA = valid ? -z * e : 0.f;
+                    const float rB = valid ? 1.f - z2 : 0.f;
+                    const float w = valid ? e * e : 0.f;
+                    nl[h] += valid ? fmaf(0.5f, z2, etaB[c]) + 0.91893853320467274178f : 0.f;
+                    const int ai = h + 2 * d;               // position in the A fragment
+                    split_tf32(rA, qAh[ai], qAl[ai]);
+                    split_tf32(rB, qBh[ai], qBl[ai]);
+                    qW[ai] = tf32_rn(w);
+                    qV[ai] = valid ? 0x3f800000u : 0u;
+                }
+                nll[0] += (double)nl[0];
+                nll[1] += (double)nl[1];
+                // ---- stage 3: moments (B operand: k = day, n = Z column)
+                const float* zd0 = zt + (size_t)(2 * t4) * ZM_STRIDE + gid;
+                const float* zd1 = zd0 + ZM_STRIDE;
+#pragma unroll
+                for (int nt = 0; nt < 7; ++nt) {
+                    const uint32_t bh0 = __float_as_uint(zd0[8 * nt]), bh1 = __float_as_uint(zd1[8 * nt]);
+                    mma_tf32(accAA[nt], qW, bh0, bh1);
+                    if (nt < 4) mma_tf32(accBB[nt], qV, bh0, bh1);
+                    if (nt < 3) {
+                        const uint32_t bl0 = __float_as_uint(zd0[ZC_HI + 8 * nt]), bl1 = __float_as_uint(zd1[ZC_HI + 8 * nt]);
+                        mma_tf32(accGA[nt], qAh, bh0, bh1);
+                        mma_tf32(accGA[nt], qAl, bh0, bh1);
+                        mma_tf32(accGA[nt], qAh, bl0, bl1);
+                        if (nt < 2) {
+                            mma_tf32(accGB[nt], qBh, bh0, bh1);
+                            mma_tf32(accGB[nt], qBl, bh0, bh1);
+                            mma_tf32(accGB[nt], qBh, bl0, bl1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ycur[j] = ynext[j];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- write the chunk's partial sums in the accumulator layout of pass.cu (indexed by position)
+    // accumulator fragment: c0,c1 -> row gid, columns 2 t4, 2 t4 + 1 ; c2,c3 -> row gid + 8
+    float* out = a.part_acc + (size_t)chunk * NACC * a.Pp;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        // per-cell nll: sum over the 4 threads sharing the row
+        double s = nll[h];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const bool in_range = pos[h] < a.n_active;
+        if (!in_range) continue;
+        const size_t p = pos[h];
+        if (t4 == 0) a.part_nll[(size_t)chunk * a.Pp + p] = s;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const int r = 2 * h + d;
+#pragma unroll
+            for (int nt = 0; nt < 7; ++nt) {
+                const int c = 8 * nt + 2 * t4 + d;
+                const int ia = zcol_to_aa(c);
+                if (ia >= 0) out[(size_t)ia * a.Pp + p] = accAA[nt][r];
+                if (nt < 4 && c < 26) {
+                    // sigma block: w_BB = 2 on valid days; columns of power 0 only (c < 9 or 18 <= c < 26)
+                    if (c < 9 || c >= 18) out[(size_t)(ACC_BB + (ia - ACC_AA)) * a.Pp + p] = 2.f * accBB[nt][r];
+                }
+                if (nt < 3 && c < 18) {
+                    // gradient of the mu block: [power][{1, cos 1..4, sin 1..4}]; r_mu was accumulated with sign
+                    out[(size_t)(ACC_GA + (c / 9) * NB + (c % 9)) * a.Pp + p] = accGA[nt][r];
+                }
+                if (nt < 2 && c < 9) out[(size_t)(ACC_GB + c) * a.Pp + p] = accGB[nt][r];
+            }
+        }
+    }
+    // the cross moments of the two blocks vanish in expectation for the Normal family
+    for (int i = threadIdx.x; i < 2 * NTRIG * MMA_CELLS; i += MMA_THREADS) {
+        const int row = i % MMA_CELLS, k = i / MMA_CELLS;
+        const int p = blockIdx.x * MMA_CELLS + row;
+        if (p < a.n_active) out[(size_t)(ACC_AB + k) * a.Pp + p] = 0.f;
+    }
+}
+
+// hi / lo TF32 parts of the moment matrix, from the FP64 basis: row t =
+//   [ hi of the 51 columns | pad to 56 | lo of the first 18 columns | pad to 24 | pad to ZM_STRIDE ]
+// column order: p0 x {1, cos 1..4, sin 1..4}, p1 x same, p0 x {cos 5..8, sin 5..8}, p1 x same, p2 x trig17
+__global__ void build_zmat_kernel(const double* __restrict__ b64, int T_pad, float* __restrict__ zmat) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T_pad) return;
+    const double* row = b64 + (size_t)t * B_STRIDE;
+    const double g = row[0];
+    float* z = zmat + (size_t)t * ZM_STRIDE;
+    for (int c = 0; c < ZM_STRIDE; ++c) z[c] = 0.f;
+    // rows beyond the series are all-zero in basis64 (cos columns included): keep them zero here
+    bool pad_row = true;
+    for (int i = 1; i <= NH; ++i) pad_row = pad_row && (row[i] == 0.0) && (row[NH + i] == 0.0);
+    if (pad_row) return;
+    for (int c = 0; c < ZM_COLS; ++c) {
+        int p, tr;
+        if (c < 18) { p = c / 9; int j = c % 9; tr = j == 0 ? 0 : (j <= 4 ? j : NH + (j - 4)); }
+        else if (c < 34) { p = (c - 18) / 8; int j = (c - 18) % 8; tr = j < 4 ? 5 + j : NH + 5 + (j - 4); }
+        else { p = 2; tr = c - 34; }
+        double v = (tr == 0) ? 1.0 : row[tr];
+        for (int q = 0; q < p; ++q) v *= g;
+        const float vf = (float)v;
+        uint32_t hi, lo;
+        split_tf32(vf, hi, lo);
+        z[c] = __uint_as_float(hi);
+        if (c < 18) z[ZC_HI + c] = __uint_as_float(lo);
+    }
+}
+
+}  // namespace
+
+int launch_build_zmat(Workspace& ws, cudaStream_t s) {
+    int T_pad = ws.T + 2 * PASS_TILE;
+    build_zmat_kernel<<<(T_pad + 127) / 128, 128, 0, s>>>(ws.basis64, T_pad, ws.zmat);
+    ATTRICI_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_pass_mma(Workspace& ws, const PassShape& ps, const float* y_scaled, int64_t ld, int i0, int i1,
+                    const int* status, cudaStream_t s) {
+    MmaArgs a;
+    a.ys = y_scaled;
+    a.ld = ld;
+    a.Cp = ws.Cp;
+    a.list = ps.list;
+    a.n_active = ps.n_active;
+    a.Pp = ps.Pp;
+    a.i0 = i0;
+    a.i1 = i1;
+    a.chunk_len = ps.chunk_len;
+    a.zmat = ws.zmat;
+    a.th_pass = ws.th_pass;
+    a.status = status;
+    a.part_nll = ws.part_nll;
+    a.part_acc = (float*)ws.part_acc;
+    const size_t smem = 2 * (size_t)PASS_TILE * ZM_STRIDE * sizeof(float);
+    ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(pass_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((ps.n_active + MMA_CELLS - 1) / MMA_CELLS, ps.n_chunks);
+    pass_mma_kernel<<<grid, MMA_THREADS, smem, s>>>(a);
+    ATTRICI_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace attrici

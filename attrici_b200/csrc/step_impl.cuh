@@ -215,9 +215,25 @@ template <class Ctx> ATTRICI_HD bool lm_solve(CellScratch& S, double lam, const 
     return true;
 }
 
+// Relative size of the predicted decrease below which a step is applied WITHOUT being evaluated: the
+// iteration is in its quadratic phase there (the next predicted decrease is orders of magnitude below
+// tol_pred), and the float32 noise of the objective (~1e-9 relative) could not confirm the step anyway.
+constexpr double TOL_FINAL_STEP = 1e-8;
+
+// Normal family, first step from the moment start: with sigma constant the objective is exactly quadratic in
+// the coefficients of mu, so the mu block is solved alone (ordinary least squares) and the intercept of
+// log sigma is set to the residual standard deviation that solution will have.  A joint scoring step
+// would fit log sigma to residuals that still contain the whole annual cycle and overshoot.
+struct FirstStep {
+    bool on;
+    double sum_z2;   // sum of squared standardised residuals at the start
+    double n;        // valid days
+};
+
 // from the accepted state in S (th, g, H) and lam: next trial point, or termination.
 // Every lane returns the same status.
-template <class Ctx> ATTRICI_HD int propose(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
+template <class Ctx>
+ATTRICI_HD int propose(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx, FirstStep first = FirstStep{false, 0.0, 0.0}) {
     double lam = a.lam[cell];
     bool ok = false;
     for (int tries = 0; tries < 40 && !ok; ++tries) {
@@ -243,7 +259,22 @@ template <class Ctx> ATTRICI_HD int propose(const StepArgs& a, int cell, CellScr
         }
         pred = ctx.sum(part);
         double f = a.f_acc[cell];
-        if (pred <= a.tol_pred * fmax(fabs(f), 1.0)) status = ATTRICI_STATUS_CONVERGED;
+        double fs = fmax(fabs(f), 1.0);
+        if (pred <= a.tol_pred * fs) {
+            status = ATTRICI_STATUS_CONVERGED;
+        } else if (!first.on && pred <= fmax(TOL_FINAL_STEP, a.tol_pred) * fs) {
+            // final step: applied to the accepted point, not evaluated by another moment pass
+            ctx.sync();
+            for (int i = ctx.lane(); i < NP; i += Ctx::W) a.th_acc[(size_t)cell * NP + i] = S.th[i] + S.delta[i];
+            status = ATTRICI_STATUS_CONVERGED;
+        }
+        if (first.on && status == ATTRICI_STATUS_RUNNING) {
+            double z2 = first.sum_z2 - 2.0 * pred;
+            if (z2 > 0.0 && first.n > 0.0) {
+                ctx.sync();
+                if (ctx.lane() == 0) S.delta[NA] = 0.5 * log(z2 / first.n);
+            }
+        }
     }
     const bool go_on = (status == ATTRICI_STATUS_RUNNING) && (a.npass[cell] < a.max_pass);
     ctx.sync();
@@ -398,7 +429,17 @@ template <class Ctx> ATTRICI_HD bool cell_step(const StepArgs& a, int cell, Cell
     }
     ctx.sync();
     if (status != ATTRICI_STATUS_RUNNING) return false;
-    return propose(a, cell, S, ctx) == ATTRICI_STATUS_RUNNING;
+    FirstStep first{false, 0.0, 0.0};
+    if (np == 0 && a.term == T_NORMAL && !a.zero_init) {
+        // start point has a constant sigma = exp(th[NA]): nll day terms = 0.5 z^2 + th[NA] + ln sqrt(2 pi)
+        first.on = true;
+        first.n = 0.5 * S.mom[ACC_BB];   // w_BB = 2 on every valid day
+        first.sum_z2 = 2.0 * (S.mom[NACC] - first.n * (S.th[NA] + 0.91893853320467274178));
+        ctx.sync();
+        for (int i = NA + ctx.lane(); i < NP; i += Ctx::W) S.g[i] = 0.0;   // mu block alone
+        ctx.sync();
+    }
+    return propose(a, cell, S, ctx, first) == ATTRICI_STATUS_RUNNING;
 }
 
 // th_trial := th_acc and its shared-frame image (before the final FP64 evaluation)

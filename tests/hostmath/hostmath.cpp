@@ -236,7 +236,7 @@ int hm_nll_grad_cell(int term, int modes, int T, int i0, int i1, const float* ys
 // the Fisher-scoring fit of one likelihood term for one cell, same control flow as api.cu fit_term
 int hm_fit_cell(int term, int modes, int T, int i0, int i1, const float* ys, const int32_t* days, const double* gmt,
                 int fp64, int zero_init, int max_pass, double tol_pred, double lambda0, int n_chunks,
-                double* theta_out, double* logp, int* status, int* npass) {
+                double* theta_out, double* logp, int* status, int* npass, double* trace /*[max_pass][4], nullable*/) {
     HostCell hc;
     host_basis(days, gmt, T, hc.b64, hc.b32);
     hc.part_acc.assign((size_t)MAX_CHUNKS * NACC, 0.0);
@@ -251,6 +251,7 @@ int hm_fit_cell(int term, int modes, int T, int i0, int i1, const float* ys, con
         run_pass(hc, term, fp64 != 0, true, ys, i0, i1, chunk_len, n_chunks);
         hc.reduce(fp64 != 0, true, n_chunks);
         running = cell_step(a, 0, hc.S, ctx);
+        if (trace) { trace[4 * it] = hc.momd[NACC]; trace[4 * it + 1] = hc.f_acc; trace[4 * it + 2] = hc.pred; trace[4 * it + 3] = hc.lam; }
     }
     cell_final_point(a, 0, hc.S, ctx);
     run_pass(hc, term, true, false, ys, i0, i1, chunk_len, n_chunks);

@@ -107,17 +107,22 @@ def nll_grad_cell(term, modes, ys, days, gmt, i0, i1, theta_canon, fp64=True, n_
 
 
 def fit_cell(term, modes, ys, days, gmt, i0, i1, fp64=False, zero_init=False, max_pass=60, tol_pred=1e-11,
-             lambda0=1e-3, n_chunks=8):
+             lambda0=1e-3, n_chunks=8, want_trace=False):
     ys = np.ascontiguousarray(ys, dtype=np.float32)
     days = np.ascontiguousarray(days, dtype=np.int32)
     gmt = np.ascontiguousarray(gmt, dtype=np.float64)
     th = np.empty(NP_CANON)
     logp, status, npass = C.c_double(), C.c_int(), C.c_int()
+    trace = np.zeros((max_pass, 4))
     lib().hm_fit_cell(C.c_int(TERMS[term]), C.c_int(modes), C.c_int(len(ys)), C.c_int(i0), C.c_int(i1),
                       _p(ys, C.c_float), _p(days, C.c_int32), _p(gmt, C.c_double), C.c_int(int(fp64)),
                       C.c_int(int(zero_init)), C.c_int(max_pass), C.c_double(tol_pred), C.c_double(lambda0),
-                      C.c_int(n_chunks), _p(th, C.c_double), C.byref(logp), C.byref(status), C.byref(npass))
-    return {"theta": th, "logp": logp.value, "status": status.value, "n_pass": npass.value}
+                      C.c_int(n_chunks), _p(th, C.c_double), C.byref(logp), C.byref(status), C.byref(npass),
+                      _p(trace, C.c_double) if want_trace else None)
+    out = {"theta": th, "logp": logp.value, "status": status.value, "n_pass": npass.value}
+    if want_trace:
+        out["trace"] = trace[: npass.value]  # per pass: day-term nll of the trial, accepted f, predicted decrease, lambda
+    return out
 
 
 def qmap_cell(family_name, scaling, post, modes, y, ys, days, gmt, params, datamin, scale, uniforms=None):
