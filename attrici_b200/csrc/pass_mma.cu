@@ -24,7 +24,7 @@ namespace attrici {
 
 namespace {
 
-constexpr int MMA_WARPS = 8;                    // warps per CTA
+constexpr int MMA_WARPS = 4;                    // warps per CTA (3 CTAs per SM)
 constexpr int MMA_THREADS = 32 * MMA_WARPS;
 constexpr int MMA_CELLS = 16 * MMA_WARPS;       // cells per CTA
 constexpr int ZC_HI = 56;                       // 51 hi columns padded to 7 n-tiles
@@ -79,8 +79,14 @@ __device__ __forceinline__ int zcol_to_aa(int c) {
     return ACC_AA + p * NTRIG + t;
 }
 
-__global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
+constexpr int BB_COLS = 17;                     // Z columns of power 0 (0..8 and 18..25): moments of the sigma block
+
+__global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
     extern __shared__ __align__(16) float smem[];   // [2][PASS_TILE][ZM_STRIDE]
+    // sigma block: w_BB = 2 on every valid day, so its moments are 2 (column sums of Z over the chunk
+    // - rows of Z on the cell's missing days): one shared column sum per CTA + a rare per-cell correction
+    __shared__ float bb_sum[32];
+    __shared__ float bb_corr[MMA_WARPS][16][BB_COLS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gid = lane >> 2, t4 = lane & 3;
     const int chunk = blockIdx.y;
@@ -125,15 +131,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
         }
     }
 
-    float accAA[7][4], accBB[4][4], accGA[3][4], accGB[2][4];
+    float accAA[7][4], accGA[3][4], accGB[2][4];
 #pragma unroll
     for (int i = 0; i < 7; ++i)
 #pragma unroll
         for (int r = 0; r < 4; ++r) accAA[i][r] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) accBB[i][r] = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -143,6 +145,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) accGB[i][r] = 0.f;
     double nll[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < MMA_WARPS * 16 * BB_COLS; i += MMA_THREADS) (&bb_corr[0][0][0])[i] = 0.f;
+    // Z column summed by this thread (threads 0..16): power-0 columns are 0..8 and 18..25
+    const int bb_col = threadIdx.x < 9 ? threadIdx.x : threadIdx.x + 9;
+    float bb_acc = 0.f;
 
     const int n_tiles = (t_end - t_begin + PASS_TILE - 1) / PASS_TILE;
     constexpr int VEC_PER_TILE = PASS_TILE * ZM_STRIDE / 4;
@@ -176,6 +182,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
             cp_async_wait<0>();
         }
         __syncthreads();
+        if (threadIdx.x < BB_COLS) {
+            const float* tl = smem + (size_t)(it & 1) * PASS_TILE * ZM_STRIDE + bb_col;
+            const int nd = min(PASS_TILE, t_end - (t_begin + it * PASS_TILE));
+            float s0 = 0.f, s1 = 0.f;
+            for (int d = 0; d + 1 < nd; d += 2) { s0 += tl[(size_t)d * ZM_STRIDE]; s1 += tl[(size_t)(d + 1) * ZM_STRIDE]; }
+            if (nd & 1) s0 += tl[(size_t)(nd - 1) * ZM_STRIDE];
+            bb_acc += s0 + s1;
+        }
         if (warp_active) {
             const float* tile = smem + (size_t)(it & 1) * PASS_TILE * ZM_STRIDE;
             const int t_tile = t_begin + it * PASS_TILE;
@@ -186,7 +200,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
                 load_y(t0 + 8, ynext);
                 const float* zt = tile + (size_t)(8 * s8) * ZM_STRIDE;
                 // ---- stage 1: eta_mu, eta_sigma for 16 cells x 8 days (B operand: k = Z column, n = day)
+                // three independent accumulation chains per predictor (hi.hi, lo.hi, hi.lo) keep the
+                // dependent-MMA depth at 3 instead of 9
                 float etaA[4] = {0.f, 0.f, 0.f, 0.f}, etaB[4] = {0.f, 0.f, 0.f, 0.f};
+                float eA1[4] = {0.f, 0.f, 0.f, 0.f}, eA2[4] = {0.f, 0.f, 0.f, 0.f};
+                float eB1[4] = {0.f, 0.f, 0.f, 0.f}, eB2[4] = {0.f, 0.f, 0.f, 0.f};
                 const float* zrow = zt + (size_t)gid * ZM_STRIDE;
 #pragma unroll
                 for (int ks = 0; ks < 3; ++ks) {
@@ -194,25 +212,30 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
                     const uint32_t bl0 = __float_as_uint(zrow[ZC_HI + 8 * ks + t4]),
                                    bl1 = __float_as_uint(zrow[ZC_HI + 8 * ks + t4 + 4]);
                     mma_tf32(etaA, thA_h[ks], bh0, bh1);
-                    mma_tf32(etaA, thA_l[ks], bh0, bh1);
-                    mma_tf32(etaA, thA_h[ks], bl0, bl1);
+                    mma_tf32(eA1, thA_l[ks], bh0, bh1);
+                    mma_tf32(eA2, thA_h[ks], bl0, bl1);
                     if (ks < 2) {
                         mma_tf32(etaB, thB_h[ks], bh0, bh1);
-                        mma_tf32(etaB, thB_l[ks], bh0, bh1);
-                        mma_tf32(etaB, thB_h[ks], bl0, bl1);
+                        mma_tf32(eB1, thB_l[ks], bh0, bh1);
+                        mma_tf32(eB2, thB_h[ks], bl0, bl1);
                     }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    etaA[c] += eA1[c] + eA2[c];
+                    etaB[c] += eB1[c] + eB2[c];
                 }
                 // ---- elementwise: accumulator fragment c{0,1,2,3} = (row gid | gid + 8) x (day 2 t4 | 2 t4 + 1)
                 // -> A fragment a{0,1,2,3} = (row gid, k t4), (row gid + 8, k t4), (row gid, k t4 + 4), (gid + 8, t4 + 4)
                 //    with k = t4 <-> day 2 t4 and k = t4 + 4 <-> day 2 t4 + 1
-                uint32_t qAh[4], qAl[4], qBh[4], qBl[4], qW[4], qV[4];
+                uint32_t qAh[4], qAl[4], qBh[4], qBl[4], qW[4];
                 float nl[2] = {0.f, 0.f};
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int h = c >> 1, d = c & 1;        // c0,c1: row gid ; c2,c3: row gid + 8
                     const float yv = ycur[h * 2 + d];
                     const bool valid = (yv == yv);
-                    const float e = __expf(-etaB[c]);
+                    const float e = expf(-etaB[c]);   // full precision: __expf's error grows with |x| and is not zero-mean
                     const float z = ((valid ? yv : 0.f) - etaA[c]) * e;
                     const float z2 = z * z;
                     const float rA = valid ? -z * e : 0.f;
@@ -223,7 +246,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
                     split_tf32(rA, qAh[ai], qAl[ai]);
                     split_tf32(rB, qBh[ai], qBl[ai]);
                     qW[ai] = tf32_rn(w);
-                    qV[ai] = valid ? 0x3f800000u : 0u;
+                    if (!valid && act[h] && t0 + 2 * t4 + d < t_end) {
+                        // a missing day inside the chunk: take its Z row out of this cell's sigma-block moments
+                        const float* zr = zt + (size_t)(2 * t4 + d) * ZM_STRIDE;
+                        float* corr = bb_corr[warp][gid + 8 * h];
+                        for (int j = 0; j < BB_COLS; ++j) atomicAdd(&corr[j], -zr[j < 9 ? j : j + 9]);
+                    }
                 }
                 nll[0] += (double)nl[0];
                 nll[1] += (double)nl[1];
@@ -234,7 +262,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
                 for (int nt = 0; nt < 7; ++nt) {
                     const uint32_t bh0 = __float_as_uint(zd0[8 * nt]), bh1 = __float_as_uint(zd1[8 * nt]);
                     mma_tf32(accAA[nt], qW, bh0, bh1);
-                    if (nt < 4) mma_tf32(accBB[nt], qV, bh0, bh1);
                     if (nt < 3) {
                         const uint32_t bl0 = __float_as_uint(zd0[ZC_HI + 8 * nt]), bl1 = __float_as_uint(zd1[ZC_HI + 8 * nt]);
                         mma_tf32(accGA[nt], qAh, bh0, bh1);
@@ -257,6 +284,17 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
     // ---- write the chunk's partial sums in the accumulator layout of pass.cu (indexed by position)
     // accumulator fragment: c0,c1 -> row gid, columns 2 t4, 2 t4 + 1 ; c2,c3 -> row gid + 8
     float* out = a.part_acc + (size_t)chunk * NACC * a.Pp;
+    if (threadIdx.x < BB_COLS) bb_sum[threadIdx.x] = bb_acc;
+    __syncthreads();
+    // sigma-block moments: rows of the CTA x 26 columns, written by all threads
+    for (int i = threadIdx.x; i < MMA_CELLS * BB_COLS; i += MMA_THREADS) {
+        const int row = i % MMA_CELLS, j = i / MMA_CELLS;
+        const int p = blockIdx.x * MMA_CELLS + row;
+        if (p < a.n_active) {
+            const int ia = zcol_to_aa(j < 9 ? j : j + 9);   // power 0: index = trig17 slot
+            out[(size_t)(ACC_BB + (ia - ACC_AA)) * a.Pp + p] = 2.f * (bb_sum[j] + bb_corr[row >> 4][row & 15][j]);
+        }
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         // per-cell nll: sum over the 4 threads sharing the row
@@ -275,10 +313,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1) pass_mma_kernel(MmaArgs a) {
                 const int c = 8 * nt + 2 * t4 + d;
                 const int ia = zcol_to_aa(c);
                 if (ia >= 0) out[(size_t)ia * a.Pp + p] = accAA[nt][r];
-                if (nt < 4 && c < 26) {
-                    // sigma block: w_BB = 2 on valid days; columns of power 0 only (c < 9 or 18 <= c < 26)
-                    if (c < 9 || c >= 18) out[(size_t)(ACC_BB + (ia - ACC_AA)) * a.Pp + p] = 2.f * accBB[nt][r];
-                }
                 if (nt < 3 && c < 18) {
                     // gradient of the mu block: [power][{1, cos 1..4, sin 1..4}]; r_mu was accumulated with sign
                     out[(size_t)(ACC_GA + (c / 9) * NB + (c % 9)) * a.Pp + p] = accGA[nt][r];

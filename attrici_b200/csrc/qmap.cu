@@ -17,6 +17,7 @@ struct QmapArgs {
     int chunk_len;
     int family, scaling, post_rule, modes;
     const double* basis64;
+    const float* basis32;
     const double* params;    // [C x P] reference layout
     const double* scaling_v; // [C x 2]
     const double* uniforms;  // [T][Cp] (pr only)
@@ -48,22 +49,34 @@ __global__ void __launch_bounds__(QMAP_THREADS) qmap_kernel(QmapArgs a) {
     const int n_dep = (a.family == ATTRICI_BERNOULLI_GAMMA) ? 2 : 1;
     const double datamin = a.scaling_v[2 * (size_t)cell], scale = a.scaling_v[2 * (size_t)cell + 1];
     const bool mask_in_place = (a.scaling == ATTRICI_SCALE_PERCENT || a.scaling == ATTRICI_SCALE_RANGE);
+    const bool normal = (a.family == ATTRICI_NORMAL);
+    float af[NA], bf[NB];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) af[i] = (float)coef.a[0][i];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) bf[i] = (float)coef.b[i];
     for (int t = t0; t < t1; ++t) {
         const double* row = a.basis64 + (size_t)t * B_STRIDE;
-        double r[1 + 2 * NH];
-#pragma unroll
-        for (int i = 0; i < 1 + 2 * NH; ++i) r[i] = __ldg(row + i);
-        DayParams d;
-        day_predictors(coef, r, n_dep, d);
-        DistPar ref, cf;
-        family_params(a.family, d, ref, cf);
         float yv = a.y[(size_t)t * a.ld + cell];
         const float sv = a.ys[(size_t)t * a.ld + cell];
         // the caller-visible series after Inf -> NaN (detrend.py:311) and the in-place masks of
         // hurs / tasrange / sfcWind (variables.py:583, 723, 771)
         if (isinf(yv) || (mask_in_place && isnan(sv))) yv = __int_as_float(0x7fc00000);
-        const double u = a.uniforms ? a.uniforms[(size_t)t * a.Cp + cell] : 0.0;
-        QmapOut o = qmap_day(a.family, a.scaling, a.post_rule, yv, sv, ref, cf, datamin, scale, u);
+        QmapOut o;
+        double cs_fast;
+        if (normal && normal_fast_path(coef, af, bf, a.basis32 + (size_t)t * B_STRIDE, row, sv, &cs_fast)) {
+            o = qmap_finish(a.scaling, a.post_rule, cs_fast, yv, datamin, scale);
+        } else {
+            double r[1 + 2 * NH];
+#pragma unroll
+            for (int i = 0; i < 1 + 2 * NH; ++i) r[i] = __ldg(row + i);
+            DayParams d;
+            day_predictors(coef, r, n_dep, d);
+            DistPar ref, cf;
+            family_params(a.family, d, ref, cf);
+            const double u = a.uniforms ? a.uniforms[(size_t)t * a.Cp + cell] : 0.0;
+            o = qmap_day(a.family, a.scaling, a.post_rule, yv, sv, ref, cf, datamin, scale, u);
+        }
         const size_t oi = (size_t)t * a.ld_out + cell;
         a.cfact[oi] = o.cfact;
         if (a.replaced) a.replaced[oi] = (uint8_t)o.replaced;
@@ -157,6 +170,7 @@ int launch_qmap(Workspace& ws, const attrici_variable_t& var, const float* y, co
     a.T = ws.T; a.C = ws.C; a.Cp = ws.Cp;
     a.family = var.family; a.scaling = var.scaling; a.post_rule = var.post_rule; a.modes = var.modes;
     a.basis64 = ws.basis64;
+    a.basis32 = ws.basis32;
     a.params = params; a.scaling_v = scaling;
     a.uniforms = nullptr;
     if (var.family == ATTRICI_BERNOULLI_GAMMA) {

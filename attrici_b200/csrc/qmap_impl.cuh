@@ -131,23 +131,76 @@ ATTRICI_HD double dist_invcdf(int family, const DistPar& p, double q) {
     }
 }
 
+// Normal family shortcut.  sigma does not depend on the predictor, so F_cf^-1(F_ref(y)) = mu_cf + sigma z
+// with z = (y - mu_ref) / sigma, i.e. y + (mu_cf - mu_ref): the reference's ndtri(ndtr(z)) round trip only
+// adds its own rounding, at most 1.1e-16 / pdf(z) in z (8e-13 at |z| = 4).  Days with |z| < 4 (float32
+// estimate) therefore take y - gmt * trend(t) in FP64; the tails keep the full cdf -> ppf evaluation, which
+// reproduces the reference's saturation to +-Inf (and hence its `replaced` flags) exactly.
+// af / bf: float copies of the mu / log sigma coefficients; row32 / row64: the day's basis rows.
+ATTRICI_HD bool normal_fast_path(const CellCoef& c, const float* af, const float* bf, const float* row32,
+                                 const double* row64, float ys, double* cs) {
+    if (ys != ys) return false;
+    const float g = row32[0];
+    float mu = fmaf(af[1], g, af[0]);
+    float es = bf[0];
+#pragma unroll
+    for (int k = 0; k < MAXM; ++k) {
+        const float ck = row32[1 + k], sk = row32[1 + NH + k];
+        mu = fmaf(fmaf(g, af[2 + 2 * MAXM + k], af[2 + k]), ck, mu);
+        mu = fmaf(fmaf(g, af[2 + 3 * MAXM + k], af[2 + MAXM + k]), sk, mu);
+        es = fmaf(bf[1 + k], ck, es);
+        es = fmaf(bf[1 + MAXM + k], sk, es);
+    }
+    const float z = (ys - mu) * expf(-es);
+    if (!(fabsf(z) < 4.0f)) return false;
+    double trend = c.a[0][1];
+#pragma unroll
+    for (int k = 0; k < MAXM; ++k) {
+        trend = fma(c.a[0][2 + 2 * MAXM + k], row64[1 + k], trend);
+        trend = fma(c.a[0][2 + 3 * MAXM + k], row64[1 + NH + k], trend);
+    }
+    *cs = (double)ys - row64[0] * trend;
+    return true;
+}
+
 struct QmapOut {
     double cfact_scaled, cfact;
     int replaced;
 };
 
+// rescale (variables.py:71-89, 114-131, 483-486, 657) and replacement (detrend.py:397-411) of a mapped value
+ATTRICI_HD QmapOut qmap_finish(int scaling, int post_rule, double cs, float y, double datamin, double scale) {
+    QmapOut o;
+    if (post_rule == ATTRICI_POST_LE0_NAN) { if (cs <= 0.0) cs = NAN; }               // Rsds, :697
+    else if (post_rule == ATTRICI_POST_OUTSIDE01_NAN) { if (cs >= 1.0 || cs <= 0.0) cs = NAN; }  // Tasskew
+    o.cfact_scaled = cs;
+    double c;
+    switch (scaling) {
+        case ATTRICI_SCALE_UNITY: c = cs * scale + datamin; break;      // variables.py:131
+        case ATTRICI_SCALE_NONE: c = cs * 1.0; break;                    // :657
+        case ATTRICI_SCALE_PR:                                           // :483-486
+            c = cs * scale + 0.0000011574;
+            if (cs <= 0.0) c = 0.0;
+            break;
+        default: c = cs * scale; break;                                  // :89
+    }
+    o.replaced = ATTRICI_REPLACED_NONE;
+    if (c != c) { c = (double)y; o.replaced = ATTRICI_REPLACED_NAN; }
+    else if (c == INFINITY) { c = (double)y; o.replaced = ATTRICI_REPLACED_PINF; }
+    else if (c == -INFINITY) { c = (double)y; o.replaced = ATTRICI_REPLACED_NINF; }
+    o.cfact = c;
+    return o;
+}
+
 // one day of one cell.  y: original observation (after the in-place masks of hurs / tasrange / sfcWind),
 // ys: scaled observation, u: the day's MT19937 uniform (pr only)
 ATTRICI_HD QmapOut qmap_day(int family, int scaling, int post_rule, float y, float ys, const DistPar& ref,
                             const DistPar& cf, double datamin, double scale, double u) {
-    QmapOut o;
     double cs;
     if (family != ATTRICI_BERNOULLI_GAMMA) {
         // variables.py:303: invcdf_cf(cdf_ref(y_scaled)); NaN in -> NaN out
         double q = dist_cdf(family, ref, (double)ys);
         cs = dist_invcdf(family, cf, q);
-        if (post_rule == ATTRICI_POST_LE0_NAN) { if (cs <= 0.0) cs = NAN; }               // Rsds, :697
-        else if (post_rule == ATTRICI_POST_OUTSIDE01_NAN) { if (cs >= 1.0 || cs <= 0.0) cs = NAN; }  // Tasskew
     } else {
         // Pr.quantile_mapping, variables.py:422-480
         const bool dry = (ys != ys);
@@ -160,24 +213,7 @@ ATTRICI_HD QmapOut qmap_day(int family, int scaling, int post_rule, float y, flo
         cs = 0.0;
         if (qm0 || qm1 || to_wet) cs = dist_invcdf(family, cf, q);
     }
-    o.cfact_scaled = cs;
-    double c;
-    switch (scaling) {
-        case ATTRICI_SCALE_UNITY: c = cs * scale + datamin; break;      // variables.py:131
-        case ATTRICI_SCALE_NONE: c = cs * 1.0; break;                    // :657
-        case ATTRICI_SCALE_PR:                                           // :483-486
-            c = cs * scale + 0.0000011574;
-            if (cs <= 0.0) c = 0.0;
-            break;
-        default: c = cs * scale; break;                                  // :89
-    }
-    // detrend.py:397-411
-    o.replaced = ATTRICI_REPLACED_NONE;
-    if (c != c) { c = (double)y; o.replaced = ATTRICI_REPLACED_NAN; }
-    else if (c == INFINITY) { c = (double)y; o.replaced = ATTRICI_REPLACED_PINF; }
-    else if (c == -INFINITY) { c = (double)y; o.replaced = ATTRICI_REPLACED_NINF; }
-    o.cfact = c;
-    return o;
+    return qmap_finish(scaling, post_rule, cs, y, datamin, scale);
 }
 
 // NumPy legacy MT19937 (np.random.seed(int) = init_genrand; np.random.rand -> random_sample):

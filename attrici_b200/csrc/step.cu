@@ -11,7 +11,7 @@ namespace {
 constexpr int STEP_WARPS = 4;
 constexpr int STEP_THREADS = 32 * STEP_WARPS;
 constexpr int RED_THREADS = 128;
-constexpr int RED_GROUP = 10;   // accumulators per thread of the reduction kernel (13 groups cover 130)
+constexpr int RED_GROUP = 2;    // accumulators per thread of the reduction kernel
 
 struct WarpCtx {
     static constexpr int W = 32;

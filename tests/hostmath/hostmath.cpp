@@ -283,6 +283,9 @@ int hm_qmap_cell(int family, int scaling, int post_rule, int modes, int T, const
     }
     const int n_dep = family == ATTRICI_BERNOULLI_GAMMA ? 2 : 1;
     const bool mask_in_place = (scaling == ATTRICI_SCALE_PERCENT || scaling == ATTRICI_SCALE_RANGE);
+    float af[NA], bf[NB];
+    for (int i = 0; i < NA; ++i) af[i] = (float)c.a[0][i];
+    for (int i = 0; i < NB; ++i) bf[i] = (float)c.b[i];
     for (int t = 0; t < T; ++t) {
         DayParams d;
         day_predictors(c, &b64[(size_t)t * B_STRIDE], n_dep, d);
@@ -290,7 +293,13 @@ int hm_qmap_cell(int family, int scaling, int post_rule, int modes, int T, const
         family_params(family, d, ref, cf);
         float yv = y[t];
         if (std::isinf(yv) || (mask_in_place && (ys[t] != ys[t]))) yv = NAN;
-        QmapOut o = qmap_day(family, scaling, post_rule, yv, ys[t], ref, cf, datamin, scale, uniforms ? uniforms[t] : 0.0);
+        QmapOut o;
+        double cs_fast;
+        // same dispatch as qmap_kernel: shortcut for the bulk of the Normal family, full map otherwise
+        if (family == ATTRICI_NORMAL && normal_fast_path(c, af, bf, &b32[(size_t)t * B_STRIDE], &b64[(size_t)t * B_STRIDE], ys[t], &cs_fast))
+            o = qmap_finish(scaling, post_rule, cs_fast, yv, datamin, scale);
+        else
+            o = qmap_day(family, scaling, post_rule, yv, ys[t], ref, cf, datamin, scale, uniforms ? uniforms[t] : 0.0);
         cfact[t] = o.cfact;
         if (cfact_scaled) cfact_scaled[t] = o.cfact_scaled;
         if (replaced) replaced[t] = o.replaced;
