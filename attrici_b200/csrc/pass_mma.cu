@@ -66,6 +66,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
@@ -80,13 +84,23 @@ __device__ __forceinline__ int zcol_to_aa(int c) {
 }
 
 constexpr int BB_COLS = 17;                     // Z columns of power 0 (0..8 and 18..25): moments of the sigma block
+constexpr int MT = 32;                          // days per shared-memory tile
+constexpr int NSTAGE = 3;                       // tiles in flight (cp.async ring)
+constexpr int Y_STRIDE = MMA_CELLS + 4;         // floats per day of the observation tile; 2 * 68 = 8 (mod 32)
+constexpr int STAGE_FLOATS = MT * ZM_STRIDE + MT * Y_STRIDE;
+
+// a missing day inside the chunk: take its Z row out of the cell's sigma-block moments (rare)
+__device__ __noinline__ void bb_correct(float* corr, const float* zr) {
+    for (int j = 0; j < BB_COLS; ++j) atomicAdd(&corr[j], -zr[j < 9 ? j : j + 9]);
+}
 
 __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
-    extern __shared__ __align__(16) float smem[];   // [2][PASS_TILE][ZM_STRIDE]
+    extern __shared__ __align__(16) float smem[];   // [NSTAGE]{ Z tile [MT][ZM_STRIDE], y tile [MT][Y_STRIDE] }
     // sigma block: w_BB = 2 on every valid day, so its moments are 2 (column sums of Z over the chunk
     // - rows of Z on the cell's missing days): one shared column sum per CTA + a rare per-cell correction
     __shared__ float bb_sum[32];
     __shared__ float bb_corr[MMA_WARPS][16][BB_COLS];
+    __shared__ int row_cell[MMA_CELLS];             // series column of each row of the CTA, -1 = not evaluated
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gid = lane >> 2, t4 = lane & 3;
     const int chunk = blockIdx.y;
@@ -103,6 +117,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
         cell[h] = a.list ? a.list[in_range ? pos[h] : 0] : (in_range ? pos[h] : a.n_active - 1);
         act[h] = in_range;
         if (act[h] && a.status) act[h] = (a.status[cell[h]] == ATTRICI_STATUS_RUNNING);
+        if (t4 == 0) row_cell[warp * 16 + gid + 8 * h] = act[h] ? cell[h] : -1;
     }
     if (__syncthreads_or(act[0] || act[1]) == 0 || t_begin >= t_end) return;   // uniform per CTA
     const bool warp_active = __any_sync(0xffffffffu, act[0] || act[1]);
@@ -150,55 +165,67 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
     const int bb_col = threadIdx.x < 9 ? threadIdx.x : threadIdx.x + 9;
     float bb_acc = 0.f;
 
-    const int n_tiles = (t_end - t_begin + PASS_TILE - 1) / PASS_TILE;
-    constexpr int VEC_PER_TILE = PASS_TILE * ZM_STRIDE / 4;
+    const int n_tiles = (t_end - t_begin + MT - 1) / MT;
+    // tile `it` -> ring slot it % NSTAGE: the Z rows (16-byte copies) and the observations of the CTA's 64
+    // cells (4-byte copies: columns are arbitrary when the cells come from the active list).  Days beyond the
+    // chunk and rows that are not evaluated are not copied; the consumer masks them.
     auto issue_tile = [&](int it) {
-        const float4* src = reinterpret_cast<const float4*>(a.zmat + (size_t)(t_begin + it * PASS_TILE) * ZM_STRIDE);
-        float4* dst = reinterpret_cast<float4*>(smem + (size_t)(it & 1) * PASS_TILE * ZM_STRIDE);
-        for (int v = threadIdx.x; v < VEC_PER_TILE; v += MMA_THREADS) cp_async16(dst + v, src + v);
-        cp_async_commit();
+        if (it < n_tiles) {
+            float* zdst = smem + (size_t)(it % NSTAGE) * STAGE_FLOATS;
+            float* ydst = zdst + MT * ZM_STRIDE;
+            const int t_tile = t_begin + it * MT;
+            const float4* src = reinterpret_cast<const float4*>(a.zmat + (size_t)t_tile * ZM_STRIDE);
+            for (int v = threadIdx.x; v < MT * ZM_STRIDE / 4; v += MMA_THREADS)
+                cp_async16(reinterpret_cast<float4*>(zdst) + v, src + v);
+            const int row = threadIdx.x % MMA_CELLS;
+            const int col = row_cell[row];
+            if (col >= 0) {
+                for (int d = threadIdx.x / MMA_CELLS; d < MT; d += MMA_THREADS / MMA_CELLS) {
+                    const int t = t_tile + d;
+                    if (t < t_end) cp_async4(ydst + d * Y_STRIDE + row, a.ys + (size_t)t * a.ld + col);
+                }
+            }
+        }
+        cp_async_commit();   // one group per call (possibly empty) keeps the wait counts uniform
     };
     issue_tile(0);
-
-    // observations of one 8-day step: y[row h][day 2 t4 + d], index h * 2 + d
-    const float qnan = __int_as_float(0x7fc00000);
-    auto load_y = [&](int t0, float (&y)[4]) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-                const int t = t0 + 2 * t4 + d;
-                y[h * 2 + d] = (act[h] && t < t_end) ? a.ys[(size_t)t * a.ld + cell[h]] : qnan;
-            }
-    };
-    float ycur[4], ynext[4];
-    load_y(t_begin, ycur);
+    issue_tile(1);
 
     for (int it = 0; it < n_tiles; ++it) {
-        if (it + 1 < n_tiles) {
-            issue_tile(it + 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        issue_tile(it + 2);
+        cp_async_wait<2>();
         __syncthreads();
+        const float* tile = smem + (size_t)(it % NSTAGE) * STAGE_FLOATS;
+        const float* ytile = tile + MT * ZM_STRIDE;
+        const int t_tile = t_begin + it * MT;
         if (threadIdx.x < BB_COLS) {
-            const float* tl = smem + (size_t)(it & 1) * PASS_TILE * ZM_STRIDE + bb_col;
-            const int nd = min(PASS_TILE, t_end - (t_begin + it * PASS_TILE));
+            const float* tl = tile + bb_col;
+            const int nd = min(MT, t_end - t_tile);
             float s0 = 0.f, s1 = 0.f;
             for (int d = 0; d + 1 < nd; d += 2) { s0 += tl[(size_t)d * ZM_STRIDE]; s1 += tl[(size_t)(d + 1) * ZM_STRIDE]; }
             if (nd & 1) s0 += tl[(size_t)(nd - 1) * ZM_STRIDE];
             bb_acc += s0 + s1;
         }
         if (warp_active) {
-            const float* tile = smem + (size_t)(it & 1) * PASS_TILE * ZM_STRIDE;
-            const int t_tile = t_begin + it * PASS_TILE;
 #pragma unroll 1
-            for (int s8 = 0; s8 < PASS_TILE / 8; ++s8) {
+            for (int s8 = 0; s8 < MT / 8; ++s8) {
                 const int t0 = t_tile + 8 * s8;
                 if (t0 >= t_end) break;
-                load_y(t0 + 8, ynext);
                 const float* zt = tile + (size_t)(8 * s8) * ZM_STRIDE;
+                // observations y[row h][day 2 t4 + d] of this step, index h * 2 + d
+                float yv4[4];
+                bool ok4[4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int d = 0; d < 2; ++d) {
+                        const int dd = 8 * s8 + 2 * t4 + d;
+                        const bool in = act[h] && (t_tile + dd < t_end);
+                        const float v = in ? ytile[dd * Y_STRIDE + warp * 16 + gid + 8 * h] : 0.f;
+                        ok4[h * 2 + d] = in && (v == v);
+                        yv4[h * 2 + d] = ok4[h * 2 + d] ? v : 0.f;
+                        if (in && !(v == v)) bb_correct(bb_corr[warp][gid + 8 * h], zt + (size_t)(2 * t4 + d) * ZM_STRIDE);
+                    }
                 // ---- stage 1: eta_mu, eta_sigma for 16 cells x 8 days (B operand: k = Z column, n = day)
                 // three independent accumulation chains per predictor (hi.hi, lo.hi, hi.lo) keep the
                 // dependent-MMA depth at 3 instead of 9
@@ -233,10 +260,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int h = c >> 1, d = c & 1;        // c0,c1: row gid ; c2,c3: row gid + 8
-                    const float yv = ycur[h * 2 + d];
-                    const bool valid = (yv == yv);
+                    const bool valid = ok4[h * 2 + d];
                     const float e = expf(-etaB[c]);   // full precision: __expf's error grows with |x| and is not zero-mean
-                    const float z = ((valid ? yv : 0.f) - etaA[c]) * e;
+                    const float z = (yv4[h * 2 + d] - etaA[c]) * e;
                     const float z2 = z * z;
                     const float rA = valid ? -z * e : 0.f;
                     const float rB = valid ? 1.f - z2 : 0.f;
@@ -246,12 +272,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
                     split_tf32(rA, qAh[ai], qAl[ai]);
                     split_tf32(rB, qBh[ai], qBl[ai]);
                     qW[ai] = tf32_rn(w);
-                    if (!valid && act[h] && t0 + 2 * t4 + d < t_end) {
-                        // a missing day inside the chunk: take its Z row out of this cell's sigma-block moments
-                        const float* zr = zt + (size_t)(2 * t4 + d) * ZM_STRIDE;
-                        float* corr = bb_corr[warp][gid + 8 * h];
-                        for (int j = 0; j < BB_COLS; ++j) atomicAdd(&corr[j], -zr[j < 9 ? j : j + 9]);
-                    }
                 }
                 nll[0] += (double)nl[0];
                 nll[1] += (double)nl[1];
@@ -274,8 +294,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
                         }
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ycur[j] = ynext[j];
             }
         }
         __syncthreads();
@@ -286,7 +304,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
     float* out = a.part_acc + (size_t)chunk * NACC * a.Pp;
     if (threadIdx.x < BB_COLS) bb_sum[threadIdx.x] = bb_acc;
     __syncthreads();
-    // sigma-block moments: rows of the CTA x 26 columns, written by all threads
+    // sigma-block moments: rows of the CTA x 17 columns, written by all threads
     for (int i = threadIdx.x; i < MMA_CELLS * BB_COLS; i += MMA_THREADS) {
         const int row = i % MMA_CELLS, j = i / MMA_CELLS;
         const int p = blockIdx.x * MMA_CELLS + row;
@@ -384,7 +402,7 @@ int launch_pass_mma(Workspace& ws, const PassShape& ps, const float* y_scaled, i
     a.status = status;
     a.part_nll = ws.part_nll;
     a.part_acc = (float*)ws.part_acc;
-    const size_t smem = 2 * (size_t)PASS_TILE * ZM_STRIDE * sizeof(float);
+    const size_t smem = (size_t)NSTAGE * STAGE_FLOATS * sizeof(float);
     ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(pass_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((ps.n_active + MMA_CELLS - 1) / MMA_CELLS, ps.n_chunks);
     pass_mma_kernel<<<grid, MMA_THREADS, smem, s>>>(a);
