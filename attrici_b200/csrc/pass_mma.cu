@@ -6,8 +6,9 @@
 //   (elementwise, registers)      e = exp(-eta_s), z = (y - eta_mu) e, nll += z^2/2 + eta_s,
 //                                 r_mu = z e, r_s = 1 - z^2, w = e^2, v = valid
 //   stage 3   M[cells x cols]   += Q[cells x days] . Z[days x cols]          Q in {r_mu, r_s, w, v}
-// Z holds the 51 products gmt^p x {1, cos k, sin k} (k <= 8) whose first 18 columns are also the design
-// columns of stage 1 (products of Fourier columns are Fourier columns: see pass.cu).  A warp owns 16 cells;
+// Z holds the 51 products gmt^p x {1, cos k, sin k} (k <= 8); its first 16 columns (cos / sin 1..4 and their
+// products with gmt) are the design columns stage 1 runs on the tensor cores, the intercept and gmt columns
+// (16, 17) are added in FP32 (products of Fourier columns are Fourier columns: see pass.cu).  A warp owns 16 cells;
 // the accumulator fragment of stage 1 is reused as the A fragment of stage 3 by pairing MMA k-index t with
 // day 2t and t+4 with day 2t+1, so no shuffles are needed (the FlashAttention-2 register trick).
 //
@@ -73,15 +74,26 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// Column order of Z (power of gmt p, trig17 slot t = {0: 1, 1..8: cos k, 9..16: sin k}):
+//   0..7   p0 x {cos 1..4, sin 1..4}      8..15  p1 x same          16, 17  p0 x 1, p1 x 1
+//   18..25 p0 x {cos 5..8, sin 5..8}      26..33 p1 x same          34..50  p2 x trig17
+__host__ __device__ __forceinline__ void zcol_decode(int c, int& p, int& t) {
+    if (c < 16) { p = c >> 3; int j = c & 7; t = j < 4 ? 1 + j : NH + 1 + (j - 4); }
+    else if (c < 18) { p = c - 16; t = 0; }
+    else if (c < 34) { p = (c - 18) >> 3; int j = (c - 18) & 7; t = j < 4 ? 5 + j : NH + 5 + (j - 4); }
+    else { p = 2; t = c - 34; }
+}
+
 // Z column -> index in the accumulator layout of pass.cu (ACC_AA block) ; -1 = padding
 __device__ __forceinline__ int zcol_to_aa(int c) {
     if (c >= ZM_COLS) return -1;
-    int p, t;   // power of gmt, trig17 index {0: 1, 1..8: cos k, 9..16: sin k}
-    if (c < 18) { p = c / 9; int j = c % 9; t = j == 0 ? 0 : (j <= 4 ? j : NH + (j - 4)); }
-    else if (c < 34) { p = (c - 18) / 8; int j = (c - 18) % 8; t = j < 4 ? 5 + j : NH + 5 + (j - 4); }
-    else { p = 2; t = c - 34; }
+    int p, t;
+    zcol_decode(c, p, t);
     return ACC_AA + p * NTRIG + t;
 }
+
+// the 17 power-0 columns (moments of the sigma block): 0..7, 16, 18..25
+__device__ __forceinline__ int bb_zcol(int j) { return j < 8 ? j : (j == 8 ? 16 : j + 9); }
 
 constexpr int BB_COLS = 17;                     // Z columns of power 0 (0..8 and 18..25): moments of the sigma block
 constexpr int MT = 32;                          // days per shared-memory tile
@@ -91,7 +103,7 @@ constexpr int STAGE_FLOATS = MT * ZM_STRIDE + MT * Y_STRIDE;
 
 // a missing day inside the chunk: take its Z row out of the cell's sigma-block moments (rare)
 __device__ __noinline__ void bb_correct(float* corr, const float* zr) {
-    for (int j = 0; j < BB_COLS; ++j) atomicAdd(&corr[j], -zr[j < 9 ? j : j + 9]);
+    for (int j = 0; j < BB_COLS; ++j) atomicAdd(&corr[j], -zr[bb_zcol(j)]);
 }
 
 __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
@@ -122,27 +134,29 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
     if (__syncthreads_or(act[0] || act[1]) == 0 || t_begin >= t_end) return;   // uniform per CTA
     const bool warp_active = __any_sync(0xffffffffu, act[0] || act[1]);
 
-    // coefficient fragments (A operands of stage 1): Z column k <-> canonical coefficient
-    //   mu block   : k < 9 -> {0, 2..5, 6..9}[k], 9 <= k < 18 -> {1, 10..13, 14..17}[k - 9]
-    //   sigma block: k < 9 -> NA + k
-    uint32_t thA_h[3][4], thA_l[3][4], thB_h[2][4], thB_l[2][4];
+    // coefficient fragments (A operands of stage 1): Z column k < 16 <-> canonical coefficient k + 2 of the
+    // mu block; k < 8 <-> NA + 1 + k of the sigma block.  Intercepts and the gmt slope stay in FP32.
+    uint32_t thA_h[2][4], thA_l[2][4], thB_h[4], thB_l[4];
+    float thA0[2], thA1[2], thB0[2];
 #pragma unroll
-    for (int ks = 0; ks < 3; ++ks) {
+    for (int h = 0; h < 2; ++h) {
+        thA0[h] = act[h] ? (float)a.th_pass[(size_t)0 * a.Cp + cell[h]] : 0.f;
+        thA1[h] = act[h] ? (float)a.th_pass[(size_t)1 * a.Cp + cell[h]] : 0.f;
+        thB0[h] = act[h] ? (float)a.th_pass[(size_t)NA * a.Cp + cell[h]] : 0.f;
+    }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int h = r & 1;                       // a0,a2: row gid ; a1,a3: row gid + 8
             const int k = 8 * ks + t4 + 4 * (r >> 1);
             float va = 0.f, vb = 0.f;
             if (act[h]) {
-                if (k < 18) {
-                    int j = k % 9;
-                    int ia = (k < 9) ? (j == 0 ? 0 : 1 + j) : (j == 0 ? 1 : 9 + j);
-                    va = (float)a.th_pass[(size_t)ia * a.Cp + cell[h]];
-                }
-                if (k < 9) vb = (float)a.th_pass[(size_t)(NA + k) * a.Cp + cell[h]];
+                va = (float)a.th_pass[(size_t)(k + 2) * a.Cp + cell[h]];
+                if (ks == 0) vb = (float)a.th_pass[(size_t)(NA + 1 + k) * a.Cp + cell[h]];
             }
             split_tf32(va, thA_h[ks][r], thA_l[ks][r]);
-            if (ks < 2) split_tf32(vb, thB_h[ks][r], thB_l[ks][r]);
+            if (ks == 0) split_tf32(vb, thB_h[r], thB_l[r]);
         }
     }
 
@@ -161,8 +175,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
         for (int r = 0; r < 4; ++r) accGB[i][r] = 0.f;
     double nll[2] = {0.0, 0.0};
     for (int i = threadIdx.x; i < MMA_WARPS * 16 * BB_COLS; i += MMA_THREADS) (&bb_corr[0][0][0])[i] = 0.f;
-    // Z column summed by this thread (threads 0..16): power-0 columns are 0..8 and 18..25
-    const int bb_col = threadIdx.x < 9 ? threadIdx.x : threadIdx.x + 9;
+    // Z column summed by this thread (threads 0..16)
+    const int bb_col = bb_zcol(threadIdx.x < BB_COLS ? threadIdx.x : 0);
     float bb_acc = 0.f;
 
     const int n_tiles = (t_end - t_begin + MT - 1) / MT;
@@ -234,23 +248,31 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
                 float eB1[4] = {0.f, 0.f, 0.f, 0.f}, eB2[4] = {0.f, 0.f, 0.f, 0.f};
                 const float* zrow = zt + (size_t)gid * ZM_STRIDE;
 #pragma unroll
-                for (int ks = 0; ks < 3; ++ks) {
+                for (int ks = 0; ks < 2; ++ks) {
                     const uint32_t bh0 = __float_as_uint(zrow[8 * ks + t4]), bh1 = __float_as_uint(zrow[8 * ks + t4 + 4]);
                     const uint32_t bl0 = __float_as_uint(zrow[ZC_HI + 8 * ks + t4]),
                                    bl1 = __float_as_uint(zrow[ZC_HI + 8 * ks + t4 + 4]);
                     mma_tf32(etaA, thA_h[ks], bh0, bh1);
                     mma_tf32(eA1, thA_l[ks], bh0, bh1);
                     mma_tf32(eA2, thA_h[ks], bl0, bl1);
-                    if (ks < 2) {
-                        mma_tf32(etaB, thB_h[ks], bh0, bh1);
-                        mma_tf32(eB1, thB_l[ks], bh0, bh1);
-                        mma_tf32(eB2, thB_h[ks], bl0, bl1);
+                    if (ks == 0) {
+                        mma_tf32(etaB, thB_h, bh0, bh1);
+                        mma_tf32(eB1, thB_l, bh0, bh1);
+                        mma_tf32(eB2, thB_h, bl0, bl1);
                     }
+                }
+                // intercepts and the gmt slope in FP32: gmt of the thread's two days = hi + lo of Z column 17
+                float gday[2];
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                    const float* zr = zt + (size_t)(2 * t4 + d) * ZM_STRIDE;
+                    gday[d] = zr[17] + zr[ZC_HI + 17];
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    etaA[c] += eA1[c] + eA2[c];
-                    etaB[c] += eB1[c] + eB2[c];
+                    const int h = c >> 1, d = c & 1;
+                    etaA[c] = (etaA[c] + (eA1[c] + eA2[c])) + fmaf(thA1[h], gday[d], thA0[h]);
+                    etaB[c] = (etaB[c] + (eB1[c] + eB2[c])) + thB0[h];
                 }
                 // ---- elementwise: accumulator fragment c{0,1,2,3} = (row gid | gid + 8) x (day 2 t4 | 2 t4 + 1)
                 // -> A fragment a{0,1,2,3} = (row gid, k t4), (row gid + 8, k t4), (row gid, k t4 + 4), (gid + 8, t4 + 4)
@@ -275,24 +297,33 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
                 }
                 nll[0] += (double)nl[0];
                 nll[1] += (double)nl[1];
-                // ---- stage 3: moments (B operand: k = day, n = Z column)
+                // ---- stage 3: moments (B operand: k = day, n = Z column).  Issue order: all hi.hi products
+                // first, then lo.hi, then hi.lo, so that the three updates of one accumulator are far apart.
                 const float* zd0 = zt + (size_t)(2 * t4) * ZM_STRIDE + gid;
                 const float* zd1 = zd0 + ZM_STRIDE;
+                uint32_t zh0[7], zh1[7];
 #pragma unroll
                 for (int nt = 0; nt < 7; ++nt) {
-                    const uint32_t bh0 = __float_as_uint(zd0[8 * nt]), bh1 = __float_as_uint(zd1[8 * nt]);
-                    mma_tf32(accAA[nt], qW, bh0, bh1);
-                    if (nt < 3) {
-                        const uint32_t bl0 = __float_as_uint(zd0[ZC_HI + 8 * nt]), bl1 = __float_as_uint(zd1[ZC_HI + 8 * nt]);
-                        mma_tf32(accGA[nt], qAh, bh0, bh1);
-                        mma_tf32(accGA[nt], qAl, bh0, bh1);
-                        mma_tf32(accGA[nt], qAh, bl0, bl1);
-                        if (nt < 2) {
-                            mma_tf32(accGB[nt], qBh, bh0, bh1);
-                            mma_tf32(accGB[nt], qBl, bh0, bh1);
-                            mma_tf32(accGB[nt], qBh, bl0, bl1);
-                        }
-                    }
+                    zh0[nt] = __float_as_uint(zd0[8 * nt]);
+                    zh1[nt] = __float_as_uint(zd1[8 * nt]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 7; ++nt) {
+                    mma_tf32(accAA[nt], qW, zh0[nt], zh1[nt]);
+                    if (nt < 3) mma_tf32(accGA[nt], qAh, zh0[nt], zh1[nt]);
+                    // sigma block: columns 0..7 (n-tile 0) and the intercept column 16 (n-tile 2)
+                    if (nt == 0 || nt == 2) mma_tf32(accGB[nt >> 1], qBh, zh0[nt], zh1[nt]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt) {
+                    mma_tf32(accGA[nt], qAl, zh0[nt], zh1[nt]);
+                    if (nt != 1) mma_tf32(accGB[nt >> 1], qBl, zh0[nt], zh1[nt]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt) {
+                    const uint32_t bl0 = __float_as_uint(zd0[ZC_HI + 8 * nt]), bl1 = __float_as_uint(zd1[ZC_HI + 8 * nt]);
+                    mma_tf32(accGA[nt], qAh, bl0, bl1);
+                    if (nt != 1) mma_tf32(accGB[nt >> 1], qBh, bl0, bl1);
                 }
             }
         }
@@ -309,7 +340,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
         const int row = i % MMA_CELLS, j = i / MMA_CELLS;
         const int p = blockIdx.x * MMA_CELLS + row;
         if (p < a.n_active) {
-            const int ia = zcol_to_aa(j < 9 ? j : j + 9);   // power 0: index = trig17 slot
+            const int ia = zcol_to_aa(bb_zcol(j));   // power 0: index = trig17 slot
             out[(size_t)(ACC_BB + (ia - ACC_AA)) * a.Pp + p] = 2.f * (bb_sum[j] + bb_corr[row >> 4][row & 15][j]);
         }
     }
@@ -332,10 +363,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
                 const int ia = zcol_to_aa(c);
                 if (ia >= 0) out[(size_t)ia * a.Pp + p] = accAA[nt][r];
                 if (nt < 3 && c < 18) {
-                    // gradient of the mu block: [power][{1, cos 1..4, sin 1..4}]; r_mu was accumulated with sign
-                    out[(size_t)(ACC_GA + (c / 9) * NB + (c % 9)) * a.Pp + p] = accGA[nt][r];
+                    // gradient slots [power][{1, cos 1..4, sin 1..4}]: Z columns 0..7 / 8..15 are the Fourier
+                    // columns of power 0 / 1, columns 16 / 17 the intercept and gmt columns
+                    const int pw = c < 16 ? (c >> 3) : c - 16;
+                    const int slot = c < 16 ? 1 + (c & 7) : 0;
+                    out[(size_t)(ACC_GA + pw * NB + slot) * a.Pp + p] = accGA[nt][r];
+                    if (pw == 0) out[(size_t)(ACC_GB + slot) * a.Pp + p] = accGB[nt >> 1][r];
                 }
-                if (nt < 2 && c < 9) out[(size_t)(ACC_GB + c) * a.Pp + p] = accGB[nt][r];
             }
         }
     }
@@ -349,7 +383,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 3) pass_mma_kernel(MmaArgs a) {
 
 // hi / lo TF32 parts of the moment matrix, from the FP64 basis: row t =
 //   [ hi of the 51 columns | pad to 56 | lo of the first 18 columns | pad to 24 | pad to ZM_STRIDE ]
-// column order: p0 x {1, cos 1..4, sin 1..4}, p1 x same, p0 x {cos 5..8, sin 5..8}, p1 x same, p2 x trig17
+// column order: see zcol_decode
 __global__ void build_zmat_kernel(const double* __restrict__ b64, int T_pad, float* __restrict__ zmat) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= T_pad) return;
@@ -363,9 +397,7 @@ __global__ void build_zmat_kernel(const double* __restrict__ b64, int T_pad, flo
     if (pad_row) return;
     for (int c = 0; c < ZM_COLS; ++c) {
         int p, tr;
-        if (c < 18) { p = c / 9; int j = c % 9; tr = j == 0 ? 0 : (j <= 4 ? j : NH + (j - 4)); }
-        else if (c < 34) { p = (c - 18) / 8; int j = (c - 18) % 8; tr = j < 4 ? 5 + j : NH + 5 + (j - 4); }
-        else { p = 2; tr = c - 34; }
+        zcol_decode(c, p, tr);
         double v = (tr == 0) ? 1.0 : row[tr];
         for (int q = 0; q < p; ++q) v *= g;
         const float vf = (float)v;

@@ -40,14 +40,28 @@ __device__ void load_coef(int family, int modes, const double* __restrict__ para
     }
 }
 
+constexpr int QT = 64;   // days per shared-memory tile of the basis rows
+
+__device__ __forceinline__ void qcp_async16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+
+// thread = cell, CTA = 128 cells x one time chunk.  The basis rows of the chunk (float row for the z
+// estimate of the Normal shortcut, double row for everything that reaches the output) are staged through
+// shared memory in double-buffered 64-day tiles and read back as warp-uniform broadcasts.
 __global__ void __launch_bounds__(QMAP_THREADS) qmap_kernel(QmapArgs a) {
+    __shared__ __align__(16) float tile32[2][QT * B_STRIDE];
+    __shared__ __align__(16) double tile64[2][QT * B_STRIDE];
     const int cell = blockIdx.x * QMAP_THREADS + threadIdx.x;
-    if (cell >= a.C) return;
+    const bool live = cell < a.C;
+    const int ccol = live ? cell : a.C - 1;
     const int t0 = blockIdx.y * a.chunk_len, t1 = min(a.T, t0 + a.chunk_len);
+    if (t0 >= t1) return;
     CellCoef coef;
-    load_coef(a.family, a.modes, a.params, cell, coef);
+    load_coef(a.family, a.modes, a.params, ccol, coef);
     const int n_dep = (a.family == ATTRICI_BERNOULLI_GAMMA) ? 2 : 1;
-    const double datamin = a.scaling_v[2 * (size_t)cell], scale = a.scaling_v[2 * (size_t)cell + 1];
+    const double datamin = a.scaling_v[2 * (size_t)ccol], scale = a.scaling_v[2 * (size_t)ccol + 1];
     const bool mask_in_place = (a.scaling == ATTRICI_SCALE_PERCENT || a.scaling == ATTRICI_SCALE_RANGE);
     const bool normal = (a.family == ATTRICI_NORMAL);
     float af[NA], bf[NB];
@@ -55,32 +69,63 @@ __global__ void __launch_bounds__(QMAP_THREADS) qmap_kernel(QmapArgs a) {
     for (int i = 0; i < NA; ++i) af[i] = (float)coef.a[0][i];
 #pragma unroll
     for (int i = 0; i < NB; ++i) bf[i] = (float)coef.b[i];
-    for (int t = t0; t < t1; ++t) {
-        const double* row = a.basis64 + (size_t)t * B_STRIDE;
-        float yv = a.y[(size_t)t * a.ld + cell];
-        const float sv = a.ys[(size_t)t * a.ld + cell];
-        // the caller-visible series after Inf -> NaN (detrend.py:311) and the in-place masks of
-        // hurs / tasrange / sfcWind (variables.py:583, 723, 771)
-        if (isinf(yv) || (mask_in_place && isnan(sv))) yv = __int_as_float(0x7fc00000);
-        QmapOut o;
-        double cs_fast;
-        if (normal && normal_fast_path(coef, af, bf, a.basis32 + (size_t)t * B_STRIDE, row, sv, &cs_fast)) {
-            o = qmap_finish(a.scaling, a.post_rule, cs_fast, yv, datamin, scale);
+
+    const int n_tiles = (t1 - t0 + QT - 1) / QT;
+    auto issue_tile = [&](int it) {
+        // rows beyond the series exist (the basis arrays are padded by two pass tiles of zeros)
+        const size_t r0 = (size_t)(t0 + it * QT) * B_STRIDE;
+        const float4* s32 = reinterpret_cast<const float4*>(a.basis32 + r0);
+        const double2* s64 = reinterpret_cast<const double2*>(a.basis64 + r0);
+        for (int v = threadIdx.x; v < QT * B_STRIDE / 4; v += QMAP_THREADS)
+            qcp_async16(reinterpret_cast<float4*>(tile32[it & 1]) + v, s32 + v);
+        for (int v = threadIdx.x; v < QT * B_STRIDE / 2; v += QMAP_THREADS)
+            qcp_async16(reinterpret_cast<double2*>(tile64[it & 1]) + v, s64 + v);
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    issue_tile(0);
+    for (int it = 0; it < n_tiles; ++it) {
+        if (it + 1 < n_tiles) {
+            issue_tile(it + 1);
+            asm volatile("cp.async.wait_group 1;\n" ::);
         } else {
-            double r[1 + 2 * NH];
-#pragma unroll
-            for (int i = 0; i < 1 + 2 * NH; ++i) r[i] = __ldg(row + i);
-            DayParams d;
-            day_predictors(coef, r, n_dep, d);
-            DistPar ref, cf;
-            family_params(a.family, d, ref, cf);
-            const double u = a.uniforms ? a.uniforms[(size_t)t * a.Cp + cell] : 0.0;
-            o = qmap_day(a.family, a.scaling, a.post_rule, yv, sv, ref, cf, datamin, scale, u);
+            asm volatile("cp.async.wait_group 0;\n" ::);
         }
-        const size_t oi = (size_t)t * a.ld_out + cell;
-        a.cfact[oi] = o.cfact;
-        if (a.replaced) a.replaced[oi] = (uint8_t)o.replaced;
-        if (a.cfact_scaled) a.cfact_scaled[oi] = o.cfact_scaled;
+        __syncthreads();
+        if (live) {
+            const int tt0 = t0 + it * QT;
+            const int nd = min(QT, t1 - tt0);
+            const float* r32 = tile32[it & 1];
+            const double* r64 = tile64[it & 1];
+            const float* yp = a.y + (size_t)tt0 * a.ld + cell;
+            const float* sp = a.ys + (size_t)tt0 * a.ld + cell;
+            float ynx = __ldg(yp), snx = __ldg(sp);
+            for (int d = 0; d < nd; ++d) {
+                float yv = ynx;
+                const float sv = snx;
+                if (d + 1 < nd) { ynx = __ldg(yp + (size_t)(d + 1) * a.ld); snx = __ldg(sp + (size_t)(d + 1) * a.ld); }
+                const double* row = r64 + d * B_STRIDE;
+                // the caller-visible series after Inf -> NaN (detrend.py:311) and the in-place masks of
+                // hurs / tasrange / sfcWind (variables.py:583, 723, 771)
+                if (isinf(yv) || (mask_in_place && isnan(sv))) yv = __int_as_float(0x7fc00000);
+                QmapOut o;
+                double cs_fast;
+                if (normal && normal_fast_path(coef, af, bf, r32 + d * B_STRIDE, row, sv, &cs_fast)) {
+                    o = qmap_finish(a.scaling, a.post_rule, cs_fast, yv, datamin, scale);
+                } else {
+                    DayParams dp;
+                    day_predictors(coef, row, n_dep, dp);
+                    DistPar ref, cf;
+                    family_params(a.family, dp, ref, cf);
+                    const double u = a.uniforms ? a.uniforms[(size_t)(tt0 + d) * a.Cp + cell] : 0.0;
+                    o = qmap_day(a.family, a.scaling, a.post_rule, yv, sv, ref, cf, datamin, scale, u);
+                }
+                const size_t oi = (size_t)(tt0 + d) * a.ld_out + cell;
+                a.cfact[oi] = o.cfact;
+                if (a.replaced) a.replaced[oi] = (uint8_t)o.replaced;
+                if (a.cfact_scaled) a.cfact_scaled[oi] = o.cfact_scaled;
+            }
+        }
+        __syncthreads();
     }
 }
 
