@@ -3,6 +3,7 @@
 // state; every call is asynchronous on the caller's stream except where stated.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <atomic>
@@ -111,6 +112,42 @@ int read_counter(const int* dev, int* host, cudaStream_t s) {
     return 0;
 }
 
+// ATTRICI_NO_FOLD=1 keeps every family on the day-by-day kernels (A/B measurements only)
+bool fold_enabled() {
+    static const bool on = [] { const char* e = getenv("ATTRICI_NO_FOLD"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
+// does the phase-folded pass apply?  Normal term on a gap-free daily axis (flag left by attrici_build_basis)
+// whose per-phase sums were gathered by attrici_prep_scale_mask on this workspace.  Synchronises `s`.
+int fold_applies(Workspace& ws, int term, int i0, int i1, cudaStream_t s, bool* fold) {
+    *fold = false;
+    if (term != T_NORMAL || !ws.ystat || !fold_enabled()) return 0;
+    int h[3] = {1, -1, -1};   // {days off the gap-free axis, fit window the sums were gathered for}
+    ATTRICI_CUDA_CHECK(cudaMemcpyAsync(h, ws.fold_bad, sizeof(h), cudaMemcpyDeviceToHost, s));
+    ATTRICI_CUDA_CHECK(cudaStreamSynchronize(s));
+    *fold = (h[0] == 0 && h[1] == i0 && h[2] == i1);
+    return 0;
+}
+
+// one likelihood pass + cross-chunk reduction at ws.th_pass, by whichever kernel applies
+int run_pass(Workspace& ws, bool fold, const int* list, int n_active, int term, bool fp64, bool with_moments,
+             bool exact, const float* y_scaled, int64_t ld, int i0, int i1, const int* status, cudaStream_t s,
+             cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr) {
+    if (fold) {
+        PassShape ps = plan_pass(ws, list, n_active, 0, fold_phases(ws), true);
+        if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
+        ATTRICI_TRY(launch_fold_pass(ws, ps, with_moments, exact, status, s));
+        if (e1) ATTRICI_CUDA_CHECK(cudaEventRecord(e1, s));
+        return launch_reduce(ws, ps, true, with_moments, s);
+    }
+    PassShape ps = plan_pass(ws, list, n_active, i0, i1, fp64);
+    if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
+    ATTRICI_TRY(launch_pass(ws, ps, term, fp64, with_moments, y_scaled, ld, i0, i1, status, s));
+    if (e1) ATTRICI_CUDA_CHECK(cudaEventRecord(e1, s));
+    return launch_reduce(ws, ps, fp64, with_moments, s);
+}
+
 // Fisher-scoring iteration of one likelihood term over the whole batch.  Cells still iterating are kept in
 // a compact list (ping-pong); once fewer than half of the batch is left the likelihood pass runs over the
 // list (gathered columns, more time chunks per cell) instead of over all cells with a status mask.
@@ -119,27 +156,26 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
     StepParams sp = step_params(var, o, slot);
     const bool fp64 = o.use_fp64 != 0;
     int cur = 0, running = 0;
+    bool fold = false;
     ATTRICI_TRY(launch_fit_init(ws, sp, ws.list[cur], ws.counters + cur, s));
+    ATTRICI_TRY(fold_applies(ws, sp.term, i0, i1, s, &fold));
+    if (!fold && !y_scaled) { set_error("y_scaled is needed: the phase-folded pass does not apply"); return ATTRICI_EINVAL; }
     ATTRICI_TRY(read_counter(ws.counters + cur, &running, s));
     const bool profile = o.profile != 0;
     std::vector<cudaEvent_t> ev;
     // a cell may spend passes on rejected trial points: the cap counts passes, not accepted steps
     for (int it = 0; running > 0 && it < o.max_pass; ++it) {
         const bool use_list = 2 * running < ws.C;
-        PassShape ps = use_list ? plan_pass(ws, ws.list[cur], running, i0, i1, fp64)
-                                : plan_pass(ws, nullptr, ws.C, i0, i1, fp64);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (profile) {
-            cudaEvent_t e0, e1;
             ATTRICI_CUDA_CHECK(cudaEventCreate(&e0));
             ATTRICI_CUDA_CHECK(cudaEventCreate(&e1));
             ev.push_back(e0);
             ev.push_back(e1);
             g_profile.cell_days += (double)running * (double)(i1 - i0);
-            ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
         }
-        ATTRICI_TRY(launch_pass(ws, ps, sp.term, fp64, true, y_scaled, ld, i0, i1, use_list ? nullptr : ws.status, s));
-        if (profile) ATTRICI_CUDA_CHECK(cudaEventRecord(ev.back(), s));
-        ATTRICI_TRY(launch_reduce(ws, ps, fp64, true, s));
+        ATTRICI_TRY(run_pass(ws, fold, use_list ? ws.list[cur] : nullptr, use_list ? running : ws.C, sp.term, fp64, true,
+                             false, y_scaled, ld, i0, i1, use_list ? nullptr : ws.status, s, e0, e1));
         ATTRICI_TRY(launch_fit_step(ws, sp, ws.list[cur], running, ws.list[cur ^ 1], ws.counters + (cur ^ 1), s));
         cur ^= 1;
         ATTRICI_TRY(read_counter(ws.counters + cur, &running, s));
@@ -155,9 +191,7 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
     }
     // log posterior of the accepted point in FP64 (model_scipy.py:525: trace["logp"] = -res.fun)
     ATTRICI_TRY(launch_fit_final_point(ws, sp, s));
-    PassShape all = plan_pass(ws, nullptr, ws.C, i0, i1, true);
-    ATTRICI_TRY(launch_pass(ws, all, sp.term, true, false, y_scaled, ld, i0, i1, nullptr, s));
-    ATTRICI_TRY(launch_reduce(ws, all, true, false, s));
+    ATTRICI_TRY(run_pass(ws, fold, nullptr, ws.C, sp.term, true, false, false, y_scaled, ld, i0, i1, nullptr, s));
     ATTRICI_TRY(launch_fit_store(ws, sp, s));
     return 0;
 }
@@ -222,7 +256,11 @@ int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes, const attri
     ATTRICI_TRY(check_var(var));
     ATTRICI_TRY(check_shape(T, C, ld));
     ATTRICI_TRY(check_window(T, i0, i1));
-    if (!y || !y_scaled || !scaling) { set_error("y / y_scaled / scaling is null"); return ATTRICI_EINVAL; }
+    if (!y || !scaling) { set_error("y / scaling is null"); return ATTRICI_EINVAL; }
+    if (!y_scaled && var->family != ATTRICI_NORMAL) {
+        set_error("y_scaled may only be omitted for the Normal family");
+        return ATTRICI_EINVAL;
+    }
     Workspace ws;
     ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, var->family));
     return launch_prep(ws, *var, y, y_scaled, ld, i0, i1, scaling, (cudaStream_t)stream);
@@ -246,9 +284,9 @@ int attrici_nll_grad(void* workspace, size_t workspace_bytes, const attrici_vari
         ATTRICI_TRY(launch_phase_only(ws, sp, s));
         ATTRICI_TRY(launch_load_theta(ws, var->family, var->modes, slot, theta, s));
         ATTRICI_TRY(launch_rotate(ws, sp, s));
-        PassShape all = plan_pass(ws, nullptr, ws.C, i0, i1, use_fp64 != 0);
-        ATTRICI_TRY(launch_pass(ws, all, sp.term, use_fp64 != 0, true, y_scaled, ld, i0, i1, nullptr, s));
-        ATTRICI_TRY(launch_reduce(ws, all, use_fp64 != 0, true, s));
+        bool fold = false;
+        ATTRICI_TRY(fold_applies(ws, sp.term, i0, i1, s, &fold));
+        ATTRICI_TRY(run_pass(ws, fold, nullptr, ws.C, sp.term, use_fp64 != 0, true, true, y_scaled, ld, i0, i1, nullptr, s));
         // canonical results go through idle fit-state buffers: f_acc, g_acc [Cp][NP], h_acc [Cp][NTRI]
         ATTRICI_TRY(launch_assemble(ws, sp, ws.f_acc, ws.g_acc, fisher ? ws.h_acc : nullptr, s));
         ATTRICI_TRY(launch_scatter_kat(ws, var->family, var->modes, slot, ws.f_acc, ws.g_acc,
@@ -264,7 +302,11 @@ int attrici_fit_batch(void* workspace, size_t workspace_bytes, const attrici_var
     ATTRICI_TRY(check_var(var));
     ATTRICI_TRY(check_shape(T, C, ld));
     ATTRICI_TRY(check_window(T, i0, i1));
-    if (!y_scaled || !params) { set_error("y_scaled / params is null"); return ATTRICI_EINVAL; }
+    if (!params) { set_error("params is null"); return ATTRICI_EINVAL; }
+    if (!y_scaled && var->family != ATTRICI_NORMAL) {
+        set_error("y_scaled may only be omitted for the Normal family");
+        return ATTRICI_EINVAL;
+    }
     attrici_fit_options_t o = opts ? *opts : default_options();
     if (o.max_pass < 1 || !(o.tol_pred >= 0.0) || !(o.lambda0 >= 0.0)) {
         set_error("bad fit options (max_pass=%d tol_pred=%g lambda0=%g)", o.max_pass, o.tol_pred, o.lambda0);
@@ -286,8 +328,12 @@ int attrici_quantile_map(void* workspace, size_t workspace_bytes, const attrici_
     ATTRICI_TRY(check_var(var));
     ATTRICI_TRY(check_shape(T, C, ld));
     if (ld_out < C) { set_error("ld_out %lld < C=%d", (long long)ld_out, C); return ATTRICI_EINVAL; }
-    if (!y || !y_scaled || !params || !scaling || !cfact) {
-        set_error("y / y_scaled / params / scaling / cfact is null");
+    if (!y || !params || !scaling || !cfact) {
+        set_error("y / params / scaling / cfact is null");
+        return ATTRICI_EINVAL;
+    }
+    if (!y_scaled && var->family != ATTRICI_NORMAL) {
+        set_error("y_scaled may only be omitted for the Normal family");
         return ATTRICI_EINVAL;
     }
     Workspace ws;
@@ -319,6 +365,12 @@ int attrici_mt19937_uniform(const uint32_t* seeds, int C, int n, double* out, in
 // whole path with HOST buffers: slabs of cells, copies and kernels overlapped on two streams
 // ---------------------------------------------------------------------------------------------
 namespace {
+bool contiguous_host(const int32_t* days, int T) {
+    for (int t = 0; t < T; ++t)
+        if (days[t] - days[0] != t) return false;
+    return true;
+}
+
 struct SlabBuffers {
     float* y; float* ys; double* cfact; uint8_t* replaced; double* params; double* logp; double* scaling;
     int32_t* status; int32_t* npass; uint32_t* seeds; void* ws; size_t ws_bytes;
@@ -423,6 +475,7 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
             return 0;
         };
         ATTRICI_TRY(upload(0));
+        const bool skip_scaled = var->family == ATTRICI_NORMAL && fold_enabled() && contiguous_host(days_host, T);
         for (int is = 0; is < n_slabs; ++is) {
             const int b = is & 1;
             cudaStream_t s = st[b];
@@ -431,10 +484,13 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
             const int nc = (C - c0 < slab_cells) ? C - c0 : slab_cells;
             if (is + 1 < n_slabs) ATTRICI_TRY(upload(is + 1));
             ATTRICI_TRY(attrici_build_basis(B.ws, B.ws_bytes, var->family, d_days, d_gmt, T, nc, s));
-            ATTRICI_TRY(attrici_prep_scale_mask(B.ws, B.ws_bytes, var, B.y, B.ys, nc, T, nc, i0, i1, B.scaling, s));
-            ATTRICI_TRY(attrici_fit_batch(B.ws, B.ws_bytes, var, B.ys, nc, T, nc, i0, i1, opts, B.params, B.logp,
+            // Normal family on a gap-free daily axis: the fit runs on the per-phase sums and the quantile map
+            // recomputes y_scaled from y, so the scaled series is never materialised
+            float* ys = skip_scaled ? nullptr : B.ys;
+            ATTRICI_TRY(attrici_prep_scale_mask(B.ws, B.ws_bytes, var, B.y, ys, nc, T, nc, i0, i1, B.scaling, s));
+            ATTRICI_TRY(attrici_fit_batch(B.ws, B.ws_bytes, var, ys, nc, T, nc, i0, i1, opts, B.params, B.logp,
                                           B.status, B.npass, s));
-            ATTRICI_TRY(attrici_quantile_map(B.ws, B.ws_bytes, var, B.y, B.ys, nc, T, nc, B.params, B.scaling,
+            ATTRICI_TRY(attrici_quantile_map(B.ws, B.ws_bytes, var, B.y, ys, nc, T, nc, B.params, B.scaling,
                                              seeds_host ? B.seeds : nullptr, B.cfact, replaced_host ? B.replaced : nullptr,
                                              nullptr, nc, s));
             ATTRICI_CUDA_CHECK(cudaMemcpy2DAsync(cfact_host + c0, 8 * (size_t)ld_out_host, B.cfact, 8 * (size_t)nc,

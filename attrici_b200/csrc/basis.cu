@@ -36,9 +36,21 @@ __global__ void build_basis_kernel(const int32_t* __restrict__ days, const doubl
     }
 }
 
+// counts the days that break days[t] = days[0] + t.  On a gap-free daily axis (count 0) every Fourier column
+// repeats after NPHASE = 1461 days, which is what the phase-folded kernels (fold.cu) build on; any other axis
+// keeps the day-by-day kernels.
+__global__ void fold_check_kernel(const int32_t* __restrict__ days, int T, int* __restrict__ bad) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool b = (t < T) && (days[t] - days[0] != t);
+    if (__syncthreads_or(b) && threadIdx.x == 0) atomicAdd(bad, 1);
+}
+
 int launch_build_basis(Workspace& ws, const int32_t* days, const double* gmt, cudaStream_t s) {
     int T_pad = ws.T + 2 * PASS_TILE;
     build_basis_kernel<<<(T_pad + 127) / 128, 128, 0, s>>>(days, gmt, ws.T, T_pad, ws.basis32, ws.basis64);
+    ATTRICI_LAUNCH_CHECK();
+    ATTRICI_CUDA_CHECK(cudaMemsetAsync(ws.fold_bad, 0, sizeof(int), s));
+    fold_check_kernel<<<(ws.T + 127) / 128, 128, 0, s>>>(days, ws.T, ws.fold_bad);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }

@@ -81,6 +81,12 @@ struct Workspace {
     int* status_part;  // [2][Cp]
     int* npass_part;   // [2][Cp]
     double* uniforms;  // [T][Cp] MT19937 doubles (pr only, else nullptr)
+    // phase-folded path (fold.cu): on a gap-free daily axis every Fourier column has period NPHASE days
+    int* fold_bad;     // [0] number of days that break days[t] = days[0] + t (0: the folded kernels apply); [1], [2] fit window of the per-phase sums
+    double* pb64;      // [NPHASE + pad][B_STRIDE] phase rows {n, cos 1..8, sin 1..8, sum gmt, sum gmt^2, 0} of the fit window
+    int* miss;         // [Cp] 1: the cell has missing days inside the fit window
+    double* ystat;     // [NPHASE][3][Cp] per-phase sums {y, y^2, y gmt} over the cell's valid window days (Normal only)
+    double* gstat;     // [NPHASE][3][Cp] per-phase {n, sum gmt, sum gmt^2} of cells with missing days (Normal only)
 
     static size_t align(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -132,6 +138,11 @@ struct Workspace {
         status_part = (int*)take(4 * 2 * c);
         npass_part = (int*)take(4 * 2 * c);
         uniforms = (family == ATTRICI_BERNOULLI_GAMMA) ? (double*)take(8 * (size_t)T * c) : nullptr;
+        fold_bad = (int*)take(256);
+        pb64 = (double*)take(sizeof(double) * B_STRIDE * (size_t)(NPHASE + 2 * PASS_TILE));
+        miss = (int*)take(4 * c);
+        ystat = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)NPHASE * c) : nullptr;
+        gstat = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)NPHASE * c) : nullptr;
         bytes = off;
         return off;
     }
@@ -191,6 +202,11 @@ int launch_pass(Workspace& ws, const PassShape& ps, int term, bool fp64, bool wi
 int launch_build_zmat(Workspace& ws, cudaStream_t s);
 int launch_pass_mma(Workspace& ws, const PassShape& ps, const float* y_scaled, int64_t ld, int i0, int i1,
                     const int* status, cudaStream_t s);
+// phase-folded pass of the Normal family over the per-phase sums of prep (fold.cu); `ps` is planned over
+// [0, fold_phases(ws)); partials are FP64
+int fold_phases(const Workspace& ws);
+int launch_fold_pass(Workspace& ws, const PassShape& ps, bool with_moments, bool exact, const int* status,
+                     cudaStream_t s);
 // cross-chunk reduction of the partials of the last pass into ws.momd
 int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_moments, cudaStream_t s);
 
@@ -230,6 +246,10 @@ int launch_scatter_kat(Workspace& ws, int family, int modes, int slot, const dou
 int launch_qmap(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled,
                 int64_t ld, const double* params, const double* scaling, const uint32_t* seeds, double* cfact,
                 uint8_t* replaced, double* cfact_scaled, int64_t ld_out, cudaStream_t s);
+// Normal family in phase order (qmap_fold.cu); runs only if ws.fold_bad[0] == 0 (checked on the device)
+int launch_qmap_fold(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled, int64_t ld,
+                     const double* params, const double* scaling, double* cfact, uint8_t* replaced,
+                     double* cfact_scaled, int64_t ld_out, cudaStream_t s);
 int launch_eval_parameter(Workspace& ws, const attrici_variable_t& var, const double* params, int which,
                           int counterfactual, double* out, int64_t ld_out, cudaStream_t s);
 int launch_mt19937(const uint32_t* seeds, int C, int n, double* out, int64_t ld, cudaStream_t s);

@@ -32,6 +32,7 @@ constexpr int PASS_CELLS = 32 * PASS_WARPS;  // cells per CTA
 constexpr int PASS_TILE = 64;                // days per shared-memory basis tile
 constexpr int MAX_CHUNKS = 32;
 constexpr int ZM_COLS = 51;                  // moment-matrix columns gmt^p x trig17 (tensor-core pass)
+constexpr int NPHASE = 1461;                // days after which every Fourier column repeats (4 x 365.25)
 constexpr int ZM_STRIDE = 100;               // floats per day of the moment matrix: 56 hi + 24 lo + pad; = 4 (mod 32)
 
 // likelihood term kinds (a Bernoulli-Gamma fit is a Bernoulli term plus a Gamma term that share

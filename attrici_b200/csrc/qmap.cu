@@ -1,6 +1,7 @@
 // Quantile-map kernels: thread = cell (coalesced 128-byte lines of the time-major series), CTA = 128
 // cells x one time chunk; FP64 throughout like the reference (scipy.stats cdf / ppf).
 // Mathematics in qmap_impl.cuh; reference lines cited there.
+#include <stdlib.h>
 #include "common.cuh"
 #include "qmap_impl.cuh"
 
@@ -23,6 +24,10 @@ struct QmapArgs {
     const double* uniforms;  // [T][Cp] (pr only)
     double* cfact; uint8_t* replaced; double* cfact_scaled;
     int64_t ld_out;
+    const int* fold_bad;     // device flag of attrici_build_basis: 0 = gap-free daily axis
+    int want_fold;           // this launch runs only if (fold_bad[0] == 0) == want_fold (-1: always)
+    int ph_len;              // phases per CTA of the folded kernel
+    float lo, hi; int has_lo, has_hi;   // thresholds, to recompute y_scaled when it is not given
 };
 
 __device__ void load_coef(int family, int modes, const double* __restrict__ params, int cell, CellCoef& c) {
@@ -40,6 +45,18 @@ __device__ void load_coef(int family, int modes, const double* __restrict__ para
     }
 }
 
+// y_scaled of one observation, recomputed with the float32 arithmetic of prep.cu (bit-identical), for callers
+// that do not keep the scaled series (Normal family: unity / none scaling)
+__device__ __forceinline__ float rescale_input(const QmapArgs& a, float v, float datamin, float scale) {
+    if (isinf(v)) v = __int_as_float(0x7fc00000);
+    if (a.scaling == ATTRICI_SCALE_UNITY) return __fdiv_rn(__fsub_rn(v, datamin), scale);
+    if (a.has_lo && v <= a.lo) v = __int_as_float(0x7fc00000);
+    if (a.has_hi && v >= a.hi) v = __int_as_float(0x7fc00000);
+    if (a.scaling == ATTRICI_SCALE_RANGE) return __fdiv_rn(v, scale);
+    if (a.scaling == ATTRICI_SCALE_PERCENT) return __fdiv_rn(v, 100.0f);
+    return v;
+}
+
 constexpr int QT = 64;   // days per shared-memory tile of the basis rows
 
 __device__ __forceinline__ void qcp_async16(void* smem, const void* gmem) {
@@ -53,6 +70,7 @@ __device__ __forceinline__ void qcp_async16(void* smem, const void* gmem) {
 __global__ void __launch_bounds__(QMAP_THREADS) qmap_kernel(QmapArgs a) {
     __shared__ __align__(16) float tile32[2][QT * B_STRIDE];
     __shared__ __align__(16) double tile64[2][QT * B_STRIDE];
+    if (a.want_fold >= 0 && (a.fold_bad[0] == 0) != (a.want_fold != 0)) return;   // uniform: the folded kernel runs instead
     const int cell = blockIdx.x * QMAP_THREADS + threadIdx.x;
     const bool live = cell < a.C;
     const int ccol = live ? cell : a.C - 1;
@@ -97,12 +115,15 @@ __global__ void __launch_bounds__(QMAP_THREADS) qmap_kernel(QmapArgs a) {
             const float* r32 = tile32[it & 1];
             const double* r64 = tile64[it & 1];
             const float* yp = a.y + (size_t)tt0 * a.ld + cell;
-            const float* sp = a.ys + (size_t)tt0 * a.ld + cell;
-            float ynx = __ldg(yp), snx = __ldg(sp);
+            const float* sp = a.ys ? a.ys + (size_t)tt0 * a.ld + cell : nullptr;
+            float ynx = __ldg(yp), snx = sp ? __ldg(sp) : 0.f;
             for (int d = 0; d < nd; ++d) {
                 float yv = ynx;
-                const float sv = snx;
-                if (d + 1 < nd) { ynx = __ldg(yp + (size_t)(d + 1) * a.ld); snx = __ldg(sp + (size_t)(d + 1) * a.ld); }
+                const float sv = sp ? snx : rescale_input(a, yv, (float)datamin, (float)scale);
+                if (d + 1 < nd) {
+                    ynx = __ldg(yp + (size_t)(d + 1) * a.ld);
+                    if (sp) snx = __ldg(sp + (size_t)(d + 1) * a.ld);
+                }
                 const double* row = r64 + d * B_STRIDE;
                 // the caller-visible series after Inf -> NaN (detrend.py:311) and the in-place masks of
                 // hurs / tasrange / sfcWind (variables.py:583, 723, 771)
@@ -225,8 +246,22 @@ int launch_qmap(Workspace& ws, const attrici_variable_t& var, const float* y, co
         a.uniforms = ws.uniforms;
     }
     a.cfact = cfact; a.replaced = replaced; a.cfact_scaled = cfact_scaled; a.ld_out = ld_out;
+    a.fold_bad = ws.fold_bad;
+    a.want_fold = -1;
+    a.ph_len = 1;
+    a.has_lo = !(var.lower_threshold != var.lower_threshold);
+    a.has_hi = !(var.upper_threshold != var.upper_threshold);
+    a.lo = var.lower_threshold; a.hi = var.upper_threshold;
+    const int n_cb = (ws.C + QMAP_THREADS - 1) / QMAP_THREADS;
+    static const bool fold_on = [] { const char* e = getenv("ATTRICI_NO_FOLD"); return !(e && e[0] == '1'); }();
+    if (fold_on && var.family == ATTRICI_NORMAL) {
+        // device-side dispatch on the axis flag keeps this call asynchronous: of the phase-ordered kernel
+        // (gap-free daily axis) and the day-ordered one below, the one that does not apply returns at once
+        ATTRICI_TRY(launch_qmap_fold(ws, var, y, y_scaled, ld, params, scaling, cfact, replaced, cfact_scaled, ld_out, s));
+        a.want_fold = 0;
+    }
     int n_chunks = qmap_chunks(ws.T, ws.C, &a.chunk_len);
-    dim3 grid((ws.C + QMAP_THREADS - 1) / QMAP_THREADS, n_chunks);
+    dim3 grid(n_cb, n_chunks);
     qmap_kernel<<<grid, QMAP_THREADS, 0, s>>>(a);
     ATTRICI_LAUNCH_CHECK();
     return 0;

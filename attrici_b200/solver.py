@@ -110,13 +110,17 @@ class CellBatchSolver:
         if not getattr(self, "_basis_ready", False) or (self.T, self.C) != (T, C_):
             raise RuntimeError("call set_predictor(days, gmt, n_cells) for this batch shape first")
 
-    def scale(self, y, fit_window=None):
+    def scale(self, y, fit_window=None, keep_scaled=True):
         """``create_variable`` arithmetic (variables.py:92-111, 363-403, 574-591, 619-623, 722-732, 770-780)
-        and Inf -> NaN (detrend.py:311).  Returns (y_scaled [T, C] float32, scaling [C, 2] float64)."""
+        and Inf -> NaN (detrend.py:311).  Returns (y_scaled [T, C] float32, scaling [C, 2] float64).
+
+        ``keep_scaled=False`` (Normal family only) does not materialise ``y_scaled`` (returned as None): on a
+        gap-free daily axis the fit runs on per-phase sums gathered here and the quantile map recomputes the
+        scaled values bit-identically from ``y``."""
         T, C_, ld = self._check_series(y, "y")
         self._need_basis(T, C_)
         i0, i1 = (0, T) if fit_window is None else fit_window
-        ys = torch.empty((T, C_), dtype=torch.float32, device=self.device)
+        ys = torch.empty((T, C_), dtype=torch.float32, device=self.device) if keep_scaled else None
         scaling = torch.empty((C_, 2), dtype=torch.float64, device=self.device)
         ws = self._ws
         with torch.cuda.device(self.device):
@@ -147,8 +151,12 @@ class CellBatchSolver:
         return nll, grad, fisher
 
     def fit(self, y_scaled, fit_window=None):
-        """Batched MAP fit (replaces ModelScipy.fit, model_scipy.py:505-527)."""
-        T, C_, ld = self._check_series(y_scaled, "y_scaled")
+        """Batched MAP fit (replaces ModelScipy.fit, model_scipy.py:505-527).  ``y_scaled=None``: fit from the
+        per-phase sums of the last ``scale`` call (Normal family, gap-free daily axis)."""
+        if y_scaled is None:
+            T, C_, ld = self.T, self.C, self.C
+        else:
+            T, C_, ld = self._check_series(y_scaled, "y_scaled")
         self._need_basis(T, C_)
         i0, i1 = self._fit_window if fit_window is None else fit_window
         params = torch.empty((C_, self.n_params), dtype=torch.float64, device=self.device)
@@ -168,9 +176,10 @@ class CellBatchSolver:
         (model_scipy.py:547-570, variables.py:287-303 / 422-480, detrend.py:392-411).
         Returns (cfact [T, C] float64, replaced [T, C] uint8 codes or None, cfact_scaled or None)."""
         T, C_, ld = self._check_series(y, "y")
-        T2, C2, ld2 = self._check_series(y_scaled, "y_scaled")
-        if (T2, C2, ld2) != (T, C_, ld):
-            raise ValueError("y and y_scaled must have the same shape and stride")
+        if y_scaled is not None:
+            T2, C2, ld2 = self._check_series(y_scaled, "y_scaled")
+            if (T2, C2, ld2) != (T, C_, ld):
+                raise ValueError("y and y_scaled must have the same shape and stride")
         self._need_basis(T, C_)
         cfact = out if out is not None else torch.empty((T, C_), dtype=torch.float64, device=self.device)
         replaced = torch.empty((T, C_), dtype=torch.uint8, device=self.device) if want_replaced else None
@@ -208,12 +217,17 @@ class CellBatchSolver:
         return out
 
     # -- whole path -----------------------------------------------------------------------------
-    def detrend_device(self, y, days, gmt, fit_window=None, seeds=None, want_replaced=True):
-        """Whole hot path with inputs and outputs resident in HBM."""
+    def detrend_device(self, y, days, gmt, fit_window=None, seeds=None, want_replaced=True, keep_scaled=True):
+        """Whole hot path with inputs and outputs resident in HBM.  ``keep_scaled=False`` (Normal family on a
+        gap-free daily axis) skips the ``y_scaled`` intermediate, see ``scale``."""
         T, C_, _ = self._check_series(y, "y")
         if not getattr(self, "_basis_ready", False) or (self.T, self.C) != (T, C_):
             self.set_predictor(days, gmt, C_)
-        ys, scaling = self.scale(y, fit_window)
+        if not keep_scaled:
+            d = np.asarray(days)
+            if self.spec.family != _lib.NORMAL or not np.array_equal(d - d[0], np.arange(len(d))):
+                keep_scaled = True
+        ys, scaling = self.scale(y, fit_window, keep_scaled)
         fit = self.fit(ys)
         cfact, replaced, _ = self.quantile_map(y, ys, fit.params, scaling, seeds, want_replaced)
         return {"y_scaled": ys, "scaling": scaling, "fit": fit, "cfact": cfact, "replaced": replaced}

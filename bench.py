@@ -14,8 +14,8 @@ an all-gather of the per-cell coefficients.
 ``e2e``    : the same through the reference-facing host API (``CellBatchSolver.detrend_host`` ->
              ``attrici_detrend_host``): float32 series in pinned host memory, float64 counterfactuals and
              flags back in pinned host memory, copies inside the timed region.
-``roofline``: the likelihood-pass kernel (dominant), achieved = algorithmic bytes (4 B per cell-day still
-             iterating) / its CUDA-event time summed over the timed steps.
+``roofline``: the dominant segment of the step (scaling / quantile map: HBM streaming kernels), achieved =
+             its algorithmic bytes / its CUDA-event time inside the timed steps; ``segments`` has all three.
 ``cpu_baseline`` / ``--impl reference``: the oracle's port of the reference algorithm (SciPy L-BFGS-B with
              finite-difference gradients on the reference objective, scipy.stats quantile map) on the
              host cores, one cell per process, on a bounded sample of the same tile.
@@ -209,11 +209,27 @@ def run_cuda(args):
     P = solver.n_params
     gathered = torch.empty((world * C, P), dtype=torch.float64, device=device) if world > 1 else None
 
-    def step():
-        out = solver.detrend_device(y, days, gmt)
+    # pre-allocated outputs: nothing but the library's kernels runs between the events of a step
+    cfact = torch.empty((T, C), dtype=torch.float64, device=device)
+    seg_names = ("scale", "fit", "quantile_map")
+
+    def step(ev=None):
+        """scale -> fit -> quantile map, outputs left in HBM.  The scaled series is an intermediate the
+        Normal family does not materialise (report_variables = cfact, replaced)."""
+        if ev:
+            ev[0].record()
+        ys, scaling = solver.scale(y, None, keep_scaled=False)
+        if ev:
+            ev[1].record()
+        fit = solver.fit(ys)
+        if ev:
+            ev[2].record()
+        _, replaced, _ = solver.quantile_map(y, ys, fit.params, scaling, out=cfact)
+        if ev:
+            ev[3].record()
         if world > 1:  # the path's one collective: final gather of the per-cell coefficients
-            dist.all_gather_into_tensor(gathered, out["fit"].params)
-        return out
+            dist.all_gather_into_tensor(gathered, fit.params)
+        return fit
 
     def barrier():
         if world > 1:
@@ -221,23 +237,25 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
-        out = step()
+        fit = step()
     barrier()
-    n_pass = out["fit"].n_pass.cpu().numpy()
-    status = out["fit"].status.cpu().numpy()
+    n_pass = fit.n_pass.cpu().numpy()
+    status = fit.status.cpu().numpy()
     _lib.fit_profile(reset=True)
     launches0 = _lib.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    seg_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
     ev0.record()
-    for _ in range(args.steps):
-        step()
+    for k in range(args.steps):
+        step(seg_ev[k])
     ev1.record()
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
+    seg_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in seg_ev) / args.steps for i in range(3)]
     launches = _lib.launch_count() - launches0
     pass_ms, pass_launches, cell_days = _lib.fit_profile(reset=True)
     if world > 1:
@@ -247,7 +265,7 @@ def run_cuda(args):
     value = world * C * args.steps / (ms / 1e3)
 
     # end to end through the host API: pinned host buffers, copies inside the timed region
-    del out
+    del cfact, fit
     y_host = torch.empty((T, C), dtype=torch.float32, pin_memory=True)
     y_host.copy_(y)
     del y
@@ -272,7 +290,19 @@ def run_cuda(args):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        achieved = (4.0 * cell_days / 1e9) / (pass_ms / 1e3) if pass_ms > 0 else None
+        # algorithmic bytes per cell-day of each segment (DESIGN.md "Kernels and rooflines"):
+        #   scale: the series is read twice (min/max, then scaling + per-phase sums)          8 B
+        #   quantile map: float32 observation in, float64 counterfactual + uint8 flag out     13 B
+        #   fit: per pass 3 float64 sums per phase instead of the series (1461 x 24 B per cell and pass)
+        seg_bytes = {"scale": 8.0 * T * C, "quantile_map": 13.0 * T * C,
+                     "fit": 24.0 * min(T, 1461) * C * float(n_pass.mean() + 1)}
+        segments = {n: {"ms": seg_ms[i], "share_of_step": seg_ms[i] / (ms / args.steps),
+                        "algorithmic_gbs": seg_bytes[n] / 1e9 / (seg_ms[i] / 1e3)}
+                    for i, n in enumerate(seg_names)}
+        dom = max(("scale", "quantile_map"), key=lambda n: segments[n]["ms"])
+        dom_kernel = {"scale": "prep_minmax_kernel + prep_scale_fold_kernel (2 launches)",
+                      "quantile_map": "qmap_fold_normal_kernel"}[dom]
+        achieved = segments[dom]["algorithmic_gbs"]
         cpu = None
         if not args.no_cpu_baseline:
             cores = min(host_cores(), 64)
@@ -284,21 +314,25 @@ def run_cuda(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 day arithmetic, f64 reductions/solve/quantile map",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 scaling (bit-exact), f64 sums/likelihood/solve/quantile map",
             "data": "synthetic",
             "config": {"workload": "tas Gaussian 100x100-cell tile, T=43464, modes=4 (BASELINE configs[1])",
                        "cells_per_gpu": C, "days": T, "modes": MODES,
-                       "l2": "inputs larger than L2 (1.74 GB float32 series per tile per pass)",
+                       "l2": "inputs larger than L2 (1.74 GB float32 series per tile, streamed three times per step)",
+                       "report_variables": ["cfact", "replaced"],
                        "passes_per_cell_mean": float(n_pass.mean()), "passes_per_cell_max": int(n_pass.max()),
                        "converged_fraction": float((status == 0).mean())},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "slab_cells": args.slab},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "pass_kernel<normal, float, moments>", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "launches": int(pass_launches), "avg_launch_ms": pass_ms / max(pass_launches, 1),
-                         "share_of_step": pass_ms / ms},
+                         "launches": args.steps, "avg_launch_ms": segments[dom]["ms"],
+                         "share_of_step": segments[dom]["share_of_step"]},
+            "segments": segments,
+            "fit_passes": {"launches": int(pass_launches), "avg_launch_ms": pass_ms / max(pass_launches, 1),
+                           "share_of_step": pass_ms / ms},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

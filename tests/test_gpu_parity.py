@@ -217,6 +217,42 @@ def test_ragged_batches_and_empty_cells(n_cells):
         assert np.isnan(cfact[:, 1]).all()
 
 
+def test_gapped_time_axis_takes_the_daywise_kernels():
+    """The phase-folded kernels need days[t] = days[0] + t; an axis with gaps must fall back to the day-by-day
+    kernels and agree with the oracle just the same.  The gap-free case without the y_scaled intermediate
+    (keep_scaled=False) must reproduce the path that keeps it bit for bit."""
+    T, C = 3200, 40
+    y = synthetic.tas_cells(C, T, seed=3, nan_fraction=0.1)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    keep = np.ones(T, dtype=bool)
+    keep[[59, 400, 401, 1519]] = False          # four missing calendar days
+    yg, gg, dg = y[keep], gmt[keep], days[keep]
+    s = CellBatchSolver("tas", device=DEV)
+    out = s.detrend_device(dev(yg), dg, gg)
+    status, logp, cfact = host(out["fit"].status), host(out["fit"].logp), host(out["cfact"])
+    assert (status == 0).all()
+    for j in (0, 17, C - 1):
+        ref = oracle.detrend_cell("tas", yg[:, j], gg, dg, helpers.MODES)
+        np.testing.assert_allclose(logp[j], ref["logp"], rtol=1e-9)
+        np.testing.assert_allclose(cfact[:, j], ref["cfact"], rtol=1e-5, equal_nan=True)
+    # keep_scaled=False is honoured only on a gap-free axis; on this one it silently keeps the intermediate
+    out2 = s.detrend_device(dev(yg), dg, gg, keep_scaled=False)
+    assert out2["y_scaled"] is not None
+    np.testing.assert_allclose(host(out2["cfact"]), cfact, rtol=1e-8, equal_nan=True)
+    # gap-free axis: with and without the intermediate
+    s = CellBatchSolver("tas", device=DEV)
+    a = s.detrend_device(dev(y), days, gmt, fit_window=(100, T - 50))
+    b = s.detrend_device(dev(y), days, gmt, fit_window=(100, T - 50), keep_scaled=False)
+    assert b["y_scaled"] is None
+    assert np.array_equal(host(a["cfact"]), host(b["cfact"]), equal_nan=True)
+    assert np.array_equal(host(a["replaced"]), host(b["replaced"]))
+    assert np.array_equal(host(a["fit"].params), host(b["fit"].params))
+    for j in (1, C - 2):
+        ref = oracle.detrend_cell("tas", y[:, j], gmt, days, helpers.MODES, fit_start=100, fit_stop=T - 50)
+        np.testing.assert_allclose(host(a["fit"].logp)[j], ref["logp"], rtol=1e-9)
+        np.testing.assert_allclose(host(a["cfact"])[:, j], ref["cfact"], rtol=1e-5, equal_nan=True)
+
+
 @pytest.mark.parametrize("variable,modes", [("sfcWind", 1), ("sfcWind", 3), ("hurs", 2), ("tasrange", 4), ("rsds", 4),
                                             ("tas", 2)])
 def test_synthetic_families_and_modes_sweep(variable, modes):
