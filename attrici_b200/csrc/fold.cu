@@ -45,26 +45,34 @@ struct FoldArgs {
     double* part_acc;        // [chunk][NACC][Pp]
 };
 
-__device__ __forceinline__ void fcp_async16(void* smem, const void* gmem) {
+__device__ __forceinline__ void fcp_async8(void* smem, const void* gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
 }
 
-// acc[0] += w, acc[1 + k] += w cos_{k+1}, acc[1 + K + k] += w sin_{k+1}; row = phase row {n, cos 1..8, sin 1..8, ..}
-template <int K, typename A> __device__ __forceinline__ void fold_accumulate(A* acc, A w, const double* row) {
+constexpr int FOLD_RING = 8;     // phases whose sums are in flight per thread (cp.async ring)
+constexpr int FOLD_TILE = 64;    // phase rows per shared-memory tile
+
+// acc[0] += w, acc[1 + k] += w cos_{k+1}, acc[1 + K + k] += w sin_{k+1}; trig = {cos 1..8, sin 1..8} of the phase
+template <int K, typename A> __device__ __forceinline__ void fold_accumulate(A* acc, A w, const A* trig) {
     acc[0] += w;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        acc[1 + k] = fma(w, (A)row[1 + k], acc[1 + k]);
-        acc[1 + K + k] = fma(w, (A)row[1 + NH + k], acc[1 + K + k]);
+        acc[1 + k] = fma(w, trig[k], acc[1 + k]);
+        acc[1 + K + k] = fma(w, trig[NH + k], acc[1 + K + k]);
     }
 }
 
 template <bool MOMENTS, typename RW>
 __global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_normal_kernel(FoldArgs a) {
-    __shared__ __align__(16) double tile[2][PASS_TILE * B_STRIDE];
+    // phase rows of the current tile: FP64 {n, cos 1..8, sin 1..8, sum gmt, sum gmt^2, 0} and an RW copy of the
+    // 16 trig columns for the Fisher moments; per-thread ring of the three sums of the next FOLD_RING phases
+    __shared__ __align__(16) double tile[FOLD_TILE * B_STRIDE];
+    __shared__ __align__(16) RW trig_w[FOLD_TILE * 2 * NH];
+    __shared__ double ring[FOLD_RING][3][PASS_CELLS];
 
-    const int pos = blockIdx.x * PASS_CELLS + threadIdx.x;
+    const int tid = threadIdx.x;
+    const int pos = blockIdx.x * PASS_CELLS + tid;
     const int chunk = blockIdx.y;
     const int d_begin = chunk * a.chunk_len;
     const int d_end = min(a.n_ph, d_begin + a.chunk_len);
@@ -96,77 +104,83 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_normal_kernel(FoldArg
     }
     double nll = 0.0;
 
-    const int n_tiles = (d_end - d_begin + PASS_TILE - 1) / PASS_TILE;
-    constexpr int VEC_PER_TILE = PASS_TILE * B_STRIDE * (int)sizeof(double) / 16;
-    auto issue_tile = [&](int it) {
-        const char* src = reinterpret_cast<const char*>(a.pb64 + (size_t)(d_begin + it * PASS_TILE) * B_STRIDE);
-        char* dst = reinterpret_cast<char*>(tile[it & 1]);
-        for (int v = threadIdx.x; v < VEC_PER_TILE; v += PASS_CELLS) fcp_async16(dst + 16 * v, src + 16 * v);
-        asm volatile("cp.async.commit_group;\n" ::);
-    };
-    issue_tile(0);
-
     const size_t cp = (size_t)a.Cp;
     const double* ys_p = a.ystat + cell;
     const double* gs_p = a.gstat + cell;
+    const int n_ph = d_end - d_begin;
+    // one cp.async group per phase (possibly empty) keeps the wait count uniform
+    auto issue = [&](int q) {
+        if (q < n_ph && active) {
+            const double* src = ys_p + (size_t)(d_begin + q) * 3 * cp;
+            double* dst = &ring[q % FOLD_RING][0][tid];
+            fcp_async8(dst, src);
+            fcp_async8(dst + PASS_CELLS, src + cp);
+            fcp_async8(dst + 2 * PASS_CELLS, src + 2 * cp);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+#pragma unroll
+    for (int q = 0; q < FOLD_RING - 1; ++q) issue(q);
 
-    for (int it = 0; it < n_tiles; ++it) {
-        if (it + 1 < n_tiles) {
-            issue_tile(it + 1);
-            asm volatile("cp.async.wait_group 1;\n" ::);
-        } else {
-            asm volatile("cp.async.wait_group 0;\n" ::);
+    for (int q0 = 0; q0 < n_ph; q0 += FOLD_TILE) {
+        const int n_rows = min(FOLD_TILE, n_ph - q0);
+        __syncthreads();   // the previous tile is no longer read
+        for (int i = tid; i < n_rows * B_STRIDE; i += PASS_CELLS) {
+            const double v = a.pb64[(size_t)(d_begin + q0) * B_STRIDE + i];
+            tile[i] = v;
+            const int r = i / B_STRIDE, c = i - r * B_STRIDE;
+            if (MOMENTS && c >= 1 && c <= 2 * NH) trig_w[r * 2 * NH + (c - 1)] = (RW)v;
         }
         __syncthreads();
-        if (warp_active) {
-            const double* tb = tile[it & 1];
-            const int d_tile = d_begin + it * PASS_TILE;
-            const int n_rows = min(PASS_TILE, d_end - d_tile);
-            // the three sums of the first phase; the next phase's are requested while this one is reduced
-            size_t o = (size_t)d_tile * 3 * cp;
-            double sy = active ? ys_p[o] : 0.0, syy = active ? ys_p[o + cp] : 0.0, syg = active ? ys_p[o + 2 * cp] : 0.0;
-            for (int r = 0; r < n_rows; ++r) {
-                const double* row = tb + r * B_STRIDE;
-                const double c_sy = sy, c_syy = syy, c_syg = syg;
-                const size_t oc = (size_t)(d_tile + r) * 3 * cp;
-                if (r + 1 < n_rows && active) {
-                    const size_t on = oc + 3 * cp;
-                    sy = ys_p[on]; syy = ys_p[on + cp]; syg = ys_p[on + 2 * cp];
-                }
-                double n = row[0], sg = row[1 + 2 * NH], sgg = row[2 + 2 * NH];
-                if (own_g) { n = gs_p[oc]; sg = gs_p[oc + cp]; sgg = gs_p[oc + 2 * cp]; }
-                if (!active) n = sg = sgg = 0.0;
-                // a_d, b_d, c_d: two chains each (cos / sin halves) to shorten the dependent FMA depth
-                double ac = thA[0], as = 0.0, bc = thA[1], bs = 0.0, cc = thB[0], cs = 0.0;
+        if (!warp_active) {   // keep the group accounting of this warp's (empty) ring consistent
+            for (int r = 0; r < n_rows; ++r) issue(q0 + r + FOLD_RING - 1);
+            continue;
+        }
+        for (int r = 0; r < n_rows; ++r) {
+            const int q = q0 + r;
+            issue(q + FOLD_RING - 1);
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(FOLD_RING - 1));
+            const double* row = tile + r * B_STRIDE;
+            const double* slot = &ring[q % FOLD_RING][0][tid];
+            const double c_sy = active ? slot[0] : 0.0, c_syy = active ? slot[PASS_CELLS] : 0.0,
+                         c_syg = active ? slot[2 * PASS_CELLS] : 0.0;
+            double n = row[0], sg = row[1 + 2 * NH], sgg = row[2 + 2 * NH];
+            if (own_g) {
+                const size_t oc = (size_t)(d_begin + q) * 3 * cp;
+                n = gs_p[oc]; sg = gs_p[oc + cp]; sgg = gs_p[oc + 2 * cp];
+            }
+            if (!active) n = sg = sgg = 0.0;
+            // a_d, b_d, c_d: two chains each (cos / sin halves) to shorten the dependent FMA depth
+            double ac = thA[0], as = 0.0, bc = thA[1], bs = 0.0, cc = thB[0], cs = 0.0;
 #pragma unroll
-                for (int k = 0; k < MAXM; ++k) {
-                    const double ck = row[1 + k], sk = row[1 + NH + k];
-                    ac = fma(thA[2 + k], ck, ac);
-                    as = fma(thA[2 + MAXM + k], sk, as);
-                    bc = fma(thA[2 + 2 * MAXM + k], ck, bc);
-                    bs = fma(thA[2 + 3 * MAXM + k], sk, bs);
-                    cc = fma(thB[1 + k], ck, cc);
-                    cs = fma(thB[1 + MAXM + k], sk, cs);
-                }
-                const double av = ac + as, bv = bc + bs, cv = cc + cs;
-                const double e2 = exp(-2.0 * cv);
-                const double R0 = c_sy - av * n - bv * sg;
-                const double R1 = c_syg - av * sg - bv * sgg;
-                const double Q = c_syy - av * c_sy - bv * c_syg - av * R0 - bv * R1;
-                nll += n * (cv + 0.91893853320467274178) + 0.5 * e2 * Q;
-                if (MOMENTS) {
-                    fold_accumulate<NH, RW>(AA, (RW)(e2 * n), row);
-                    fold_accumulate<NH, RW>(AA + NTRIG, (RW)(e2 * sg), row);
-                    fold_accumulate<NH, RW>(AA + 2 * NTRIG, (RW)(e2 * sgg), row);
-                    fold_accumulate<NH, RW>(BB, (RW)(2.0 * n), row);
-                    fold_accumulate<MAXM, double>(GA, -e2 * R0, row);
-                    fold_accumulate<MAXM, double>(GA + NB, -e2 * R1, row);
-                    fold_accumulate<MAXM, double>(GB, n - e2 * Q, row);
-                }
+            for (int k = 0; k < MAXM; ++k) {
+                const double ck = row[1 + k], sk = row[1 + NH + k];
+                ac = fma(thA[2 + k], ck, ac);
+                as = fma(thA[2 + MAXM + k], sk, as);
+                bc = fma(thA[2 + 2 * MAXM + k], ck, bc);
+                bs = fma(thA[2 + 3 * MAXM + k], sk, bs);
+                cc = fma(thB[1 + k], ck, cc);
+                cs = fma(thB[1 + MAXM + k], sk, cs);
+            }
+            const double av = ac + as, bv = bc + bs, cv = cc + cs;
+            const double e2 = exp(-2.0 * cv);
+            const double R0 = c_sy - av * n - bv * sg;
+            const double R1 = c_syg - av * sg - bv * sgg;
+            const double Q = c_syy - av * c_sy - bv * c_syg - av * R0 - bv * R1;
+            nll += n * (cv + 0.91893853320467274178) + 0.5 * e2 * Q;
+            if (MOMENTS) {
+                const RW* tw = trig_w + r * 2 * NH;
+                fold_accumulate<NH, RW>(AA, (RW)(e2 * n), tw);
+                fold_accumulate<NH, RW>(AA + NTRIG, (RW)(e2 * sg), tw);
+                fold_accumulate<NH, RW>(AA + 2 * NTRIG, (RW)(e2 * sgg), tw);
+                fold_accumulate<NH, RW>(BB, (RW)(2.0 * n), tw);
+                fold_accumulate<MAXM, double>(GA, -e2 * R0, row + 1);
+                fold_accumulate<MAXM, double>(GA + NB, -e2 * R1, row + 1);
+                fold_accumulate<MAXM, double>(GB, n - e2 * Q, row + 1);
             }
         }
-        __syncthreads();
     }
+    asm volatile("cp.async.wait_group 0;\n" ::);
 
     if (in_range) {
         a.part_nll[(size_t)chunk * a.Pp + pos] = nll;
