@@ -84,7 +84,7 @@ def _dist_info():
 def gather_cells(local, counts, dist=None, device=None):
     """Final gather of per-cell arrays to every rank: the one collective of the path.
 
-    ``local``: dict name -> array whose LAST axis... no: whose FIRST axis is this rank's cells;
+    ``local``: dict name -> array whose first axis is this rank's cells;
     ``counts``: cells per rank.  Uses ``all_gather`` on tensors padded to the largest shard (shards are
     uneven under the reference's partition rule)."""
     import torch
