@@ -139,13 +139,13 @@ int run_pass(Workspace& ws, bool fold, const int* list, int n_active, int term, 
         if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
         ATTRICI_TRY(launch_fold_pass(ws, ps, with_moments, exact, status, s));
         if (e1) ATTRICI_CUDA_CHECK(cudaEventRecord(e1, s));
-        return launch_reduce(ws, ps, true, with_moments, s);
+        return launch_reduce(ws, ps, true, with_moments, s, status);
     }
     PassShape ps = plan_pass(ws, list, n_active, i0, i1, fp64);
     if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
     ATTRICI_TRY(launch_pass(ws, ps, term, fp64, with_moments, y_scaled, ld, i0, i1, status, s));
     if (e1) ATTRICI_CUDA_CHECK(cudaEventRecord(e1, s));
-    return launch_reduce(ws, ps, fp64, with_moments, s);
+    return launch_reduce(ws, ps, fp64, with_moments, s, status);
 }
 
 // Fisher-scoring iteration of one likelihood term over the whole batch.  Cells still iterating are kept in
@@ -163,21 +163,32 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
     ATTRICI_TRY(read_counter(ws.counters + cur, &running, s));
     const bool profile = o.profile != 0;
     std::vector<cudaEvent_t> ev;
-    // a cell may spend passes on rejected trial points: the cap counts passes, not accepted steps
-    for (int it = 0; running > 0 && it < o.max_pass; ++it) {
-        const bool use_list = 2 * running < ws.C;
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (profile) {
-            ATTRICI_CUDA_CHECK(cudaEventCreate(&e0));
-            ATTRICI_CUDA_CHECK(cudaEventCreate(&e1));
-            ev.push_back(e0);
-            ev.push_back(e1);
-            g_profile.cell_days += (double)running * (double)(i1 - i0);
+    // a cell may spend passes on rejected trial points: the cap counts passes, not accepted steps.
+    // The folded passes are cheap enough that reading the number of running cells back after every pass (a host
+    // round trip with the GPU idle) costs more than a pass over cells that are already done: they are issued in
+    // blocks (6, then 2 at a time) over all cells with the status mask, and the host synchronises once per block.
+    for (int it = 0; running > 0 && it < o.max_pass;) {
+        int block = fold ? (it == 0 ? 6 : 2) : 1;
+        if (block > o.max_pass - it) block = o.max_pass - it;
+        for (int b = 0; b < block; ++b) {
+            const bool use_list = (block == 1) && (2 * running < ws.C);
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (profile) {
+                ATTRICI_CUDA_CHECK(cudaEventCreate(&e0));
+                ATTRICI_CUDA_CHECK(cudaEventCreate(&e1));
+                ev.push_back(e0);
+                ev.push_back(e1);
+                g_profile.cell_days += (double)running * (double)(i1 - i0);
+            }
+            ATTRICI_TRY(run_pass(ws, fold, use_list ? ws.list[cur] : nullptr, use_list ? running : ws.C, sp.term, fp64,
+                                 true, false, y_scaled, ld, i0, i1, use_list ? nullptr : ws.status, s, e0, e1));
+            if (block == 1)
+                ATTRICI_TRY(launch_fit_step(ws, sp, ws.list[cur], running, ws.list[cur ^ 1], ws.counters + (cur ^ 1), s));
+            else   // every cell's warp looks at its own status
+                ATTRICI_TRY(launch_fit_step(ws, sp, nullptr, ws.C, ws.list[cur ^ 1], ws.counters + (cur ^ 1), s));
+            cur ^= 1;
         }
-        ATTRICI_TRY(run_pass(ws, fold, use_list ? ws.list[cur] : nullptr, use_list ? running : ws.C, sp.term, fp64, true,
-                             false, y_scaled, ld, i0, i1, use_list ? nullptr : ws.status, s, e0, e1));
-        ATTRICI_TRY(launch_fit_step(ws, sp, ws.list[cur], running, ws.list[cur ^ 1], ws.counters + (cur ^ 1), s));
-        cur ^= 1;
+        it += block;
         ATTRICI_TRY(read_counter(ws.counters + cur, &running, s));
     }
     for (size_t k = 0; k + 1 < ev.size(); k += 2) {

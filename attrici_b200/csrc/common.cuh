@@ -208,7 +208,9 @@ int fold_phases(const Workspace& ws);
 int launch_fold_pass(Workspace& ws, const PassShape& ps, bool with_moments, bool exact, const int* status,
                      cudaStream_t s);
 // cross-chunk reduction of the partials of the last pass into ws.momd
-int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_moments, cudaStream_t s);
+// status != nullptr (only without a list): cells whose status is not RUNNING are skipped
+int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_moments, cudaStream_t s,
+                  const int* status = nullptr);
 
 struct StepParams {
     int term;

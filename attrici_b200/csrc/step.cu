@@ -15,7 +15,9 @@ constexpr int RED_GROUP = 2;    // accumulators per thread of the reduction kern
 
 struct WarpCtx {
     static constexpr int W = 32;
+    static constexpr bool kRegisterSolve = true;
     __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    __device__ bool solve(CellScratch& S, double lam) const;
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
@@ -24,6 +26,72 @@ struct WarpCtx {
     }
     __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
 };
+
+// (H + lam D) delta = -g with lane = row: the lane's row of H (then of the Cholesky factor L) lives in registers,
+// the factorisation is right-looking (column j is scaled, then every later column k takes its rank-1 update with
+// L[k][j] fetched from lane k by a shuffle), the forward substitution is column-oriented, the backward one a warp
+// sum per row.  Same mathematics as lm_solve() (step_impl.cuh) in about a third of the instructions; returns false
+// if a pivot is not positive.  Every loop is fully unrolled so that the row stays in registers.
+__device__ bool WarpCtx::solve(CellScratch& S, double lam) const {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int l = lane();
+    const bool row = l < NP;
+    double a[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        double v = (row && k <= l) ? S.H[l * (l + 1) / 2 + k] : 0.0;
+        if (k == l) v += lam * fmax(fabs(v), 1e-12);
+        a[k] = v;
+    }
+    double inv_diag = 1.0;   // 1 / L[l][l]
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        const double d = __shfl_sync(FULL, a[j], j);
+        if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }   // uniform: d is the same in every lane
+        const double ljj = sqrt(d), inv = 1.0 / ljj;
+        if (l == j) { a[j] = ljj; inv_diag = inv; }
+        else a[j] *= inv;                                  // L[l][j] for l > j (rows l < j hold zeros)
+#pragma unroll
+        for (int k = j + 1; k < NP; ++k) {
+            const double lkj = __shfl_sync(FULL, a[j], k);
+            a[k] = fma(-a[j], lkj, a[k]);                  // only entries k <= l of a row are ever read
+        }
+    }
+    if (!ok) return false;
+    // L y = -g, column-oriented: once y[i] is known every later row subtracts L[.][i] y[i]
+    double r = row ? -S.g[l] : 0.0, y = 0.0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const double yi = __shfl_sync(FULL, r * inv_diag, i);
+        if (l == i) y = yi;
+        if (l > i) r = fma(-a[i], yi, r);
+    }
+    // L^T delta = y, rows from the last: delta[i] = (y[i] - sum_{k > i} L[k][i] delta[k]) / L[i][i]
+    double delta = 0.0;
+#pragma unroll
+    for (int i = NP - 1; i >= 0; --i) {
+        double t = (row && l > i) ? a[i] * delta : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+        if (l == i) delta = (y - t) * inv_diag;
+    }
+    if (row) S.delta[l] = delta;
+    __syncwarp();
+    return true;
+}
+
+// table of the information-matrix entries for this launch's (term, modes), built once per CTA
+__device__ __forceinline__ void build_h_table(const StepArgs& a, HEntry* tab) {
+    for (int e = threadIdx.x; e < NTRI; e += blockDim.x) {
+        // e = i (i + 1) / 2 + j, j <= i
+        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+        while (i * (i + 1) / 2 > e) --i;
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        tab[e] = h_entry(a.term, a.modes, i, e - i * (i + 1) / 2);
+    }
+    __syncthreads();
+}
 
 // cell handled by this warp: position in the active list (or the identity), -1 if none
 __device__ __forceinline__ int warp_cell(const int* list, int n) {
@@ -44,10 +112,12 @@ __global__ void __launch_bounds__(STEP_THREADS) fit_init_kernel(StepArgs a, int*
 __global__ void __launch_bounds__(STEP_THREADS) fit_step_kernel(StepArgs a, const int* list_in, int n_in,
                                                                 int* list_out, int* counter) {
     __shared__ CellScratch S[STEP_WARPS];
+    __shared__ HEntry tab[NTRI];
+    build_h_table(a, tab);
     int cell = warp_cell(list_in, n_in);
     if (cell < 0) return;
     WarpCtx ctx;
-    bool run = cell_step(a, cell, S[threadIdx.x >> 5], ctx);
+    bool run = cell_step(a, cell, S[threadIdx.x >> 5], ctx, tab);
     if (run && ctx.lane() == 0) list_out[atomicAdd(counter, 1)] = cell;
 }
 
@@ -71,13 +141,15 @@ __global__ void __launch_bounds__(STEP_THREADS) fit_store_kernel(StepArgs a) {
 __global__ void __launch_bounds__(STEP_THREADS) assemble_kernel(StepArgs a, double* nll, double* grad /*[Cp][NP]*/,
                                                                 double* fisher /*[Cp][NTRI], nullable*/) {
     __shared__ CellScratch Ss[STEP_WARPS];
+    __shared__ HEntry tab[NTRI];
+    build_h_table(a, tab);
     int cell = warp_cell(nullptr, a.C);
     if (cell < 0) return;
     WarpCtx ctx;
     CellScratch& S = Ss[threadIdx.x >> 5];
     for (int i = ctx.lane(); i < NP; i += 32) S.th[i] = a.th_trial[(size_t)cell * NP + i];
     load_moments(a, cell, S, ctx);
-    double f = assemble(a, S, fisher != nullptr, ctx);
+    double f = assemble(a, S, fisher != nullptr, ctx, tab);
     if (ctx.lane() == 0) nll[cell] = f;
     if (grad) for (int i = ctx.lane(); i < NP; i += 32) grad[(size_t)cell * NP + i] = S.g[i];
     if (fisher) for (int i = ctx.lane(); i < NTRI; i += 32) fisher[(size_t)cell * NTRI + i] = S.H[i];
@@ -109,10 +181,12 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_partials_kernel(const int*
                                                                       int n_chunks, int row0,
                                                                       const double* __restrict__ part_nll,
                                                                       const R* __restrict__ part_acc,
-                                                                      double* __restrict__ momd) {
+                                                                      double* __restrict__ momd,
+                                                                      const int* __restrict__ status) {
     int pos = blockIdx.x * RED_THREADS + threadIdx.x;
     if (pos >= n) return;
     int cell = list ? list[pos] : pos;
+    if (status && status[cell] != ATTRICI_STATUS_RUNNING) return;
     int i0 = row0 + blockIdx.y * RED_GROUP;
     for (int i = i0; i < i0 + RED_GROUP && i <= NACC; ++i) {
         double s = 0.0;
@@ -251,7 +325,7 @@ int launch_fit_store(Workspace& ws, const StepParams& sp, cudaStream_t s) {
     return 0;
 }
 
-int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_moments, cudaStream_t s) {
+int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_moments, cudaStream_t s, const int* status) {
     if (ps.n_active <= 0) return 0;
     dim3 grid((ps.n_active + RED_THREADS - 1) / RED_THREADS, (NACC + 1 + RED_GROUP - 1) / RED_GROUP);
     // without moments only row NACC (the sum of the day terms of the nll) is reduced
@@ -260,11 +334,11 @@ int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_momen
     if (fp64)
         reduce_partials_kernel<double><<<grid, RED_THREADS, 0, s>>>(ps.list, ps.n_active, ps.Pp, ws.Cp, ps.n_chunks,
                                                                    row0, ws.part_nll,
-                                                                   (const double*)ws.part_acc, ws.momd);
+                                                                   (const double*)ws.part_acc, ws.momd, status);
     else
         reduce_partials_kernel<float><<<grid, RED_THREADS, 0, s>>>(ps.list, ps.n_active, ps.Pp, ws.Cp, ps.n_chunks,
                                                                   row0, ws.part_nll,
-                                                                  (const float*)ws.part_acc, ws.momd);
+                                                                  (const float*)ws.part_acc, ws.momd, status);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }

@@ -42,9 +42,11 @@ struct StepArgs {
     double* th_out; double* logp_part; int* status_part; int* npass_part;   // [2][NP][Cp], [2][Cp] ...
 };
 
+constexpr int H_ZERO = NACC + 1;   // CellScratch::mom slot that holds 0
+
 // per-cell scratch (shared memory on the device)
 struct CellScratch {
-    double mom[NACC + 1];
+    double mom[NACC + 2];   // [NACC] = sum of the day terms of the nll, [NACC + 1] = 0 (the "no moment" slot of HEntry)
     double H[NTRI];
     double L[NTRI];
     double g[NP], th[NP], delta[NP], y[NP];
@@ -53,6 +55,7 @@ struct CellScratch {
 // serial "group" of one lane (CPU unit tests)
 struct SerialCtx {
     static constexpr int W = 1;
+    static constexpr bool kRegisterSolve = false;
     ATTRICI_HD int lane() const { return 0; }
     ATTRICI_HD void sync() const {}
     ATTRICI_HD double sum(double v) const { return v; }
@@ -106,6 +109,7 @@ ATTRICI_HD void rotate_to_shared(const StepArgs& a, int cell, const double* th_c
 template <class Ctx> ATTRICI_HD void load_moments(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
     const size_t cp = a.Cp;
     for (int i = ctx.lane(); i <= NACC; i += Ctx::W) S.mom[i] = a.momd[(size_t)i * cp + cell];
+    if (ctx.lane() == 0) S.mom[H_ZERO] = 0.0;
     ctx.sync();
     const double* rot = a.rot + (size_t)cell * 2 * NH;
     // 9 (block, harmonic) families: AA p0..2, AB p0..1, BB carry 8 harmonics; GA p0, GA p1, GB carry 4
@@ -136,9 +140,44 @@ ATTRICI_HD double trig_product(const double* m, const Col& a, const Col& b) {
     return 0.5 * (Sm[sum] + lo);
 }
 
+// Packed entry e = tri(i, j) of the information matrix as a table row: H[e] = 0.5 (mom[i1] + s2 mom[i2]) + add
+// (the same case analysis as trig_product / assemble, resolved once per launch instead of once per cell)
+struct HEntry {
+    short i1, i2;
+    float s2, add;
+};
+
+ATTRICI_HD HEntry h_entry(int term, int modes, int i, int j) {
+    HEntry e;
+    e.i1 = H_ZERO; e.i2 = H_ZERO; e.s2 = 0.f; e.add = 0.f;
+    const Col ci = col_of(i), cj = col_of(j);
+    if (!col_active(ci, term, modes) || !col_active(cj, term, modes)) {
+        e.add = (i == j) ? 1.f : 0.f;
+        return e;
+    }
+    const int pw = ci.pw + cj.pw;
+    int base;
+    if (ci.blk == 0 && cj.blk == 0) base = ACC_AA + pw * NTRIG;
+    else if (ci.blk == 1 && cj.blk == 1) base = ACC_BB;
+    else base = ACC_AB + pw * NTRIG;
+    const int cm = base, sm = base + NH;   // cm + k: cos k moment (k = 0: constant), sm + k: sin k moment
+    const int sum = ci.k + cj.k, dif = ci.k - cj.k;
+    const int ad = dif < 0 ? -dif : dif;
+    if (!ci.sn && !cj.sn) { e.i1 = (short)(cm + ad); e.i2 = (short)(cm + sum); e.s2 = 1.f; }
+    else if (ci.sn && cj.sn) { e.i1 = (short)(cm + ad); e.i2 = (short)(cm + sum); e.s2 = -1.f; }
+    else {
+        const int sgn = ci.sn ? dif : -dif;
+        e.i1 = (short)(sm + sum);
+        if (ad != 0) { e.i2 = (short)(sm + ad); e.s2 = sgn > 0 ? 1.f : -1.f; }
+    }
+    if (i == j) e.add = (float)prior_prec(ci);
+    return e;
+}
+
 // objective, gradient (S.g) and Fisher information + prior (S.H, packed lower triangle) of one cell in
 // the cell frame, canonical layout, at S.th.  Needs S.mom (load_moments).  Returns the objective.
-template <class Ctx> ATTRICI_HD double assemble(const StepArgs& a, CellScratch& S, bool want_H, const Ctx& ctx) {
+template <class Ctx>
+ATTRICI_HD double assemble(const StepArgs& a, CellScratch& S, bool want_H, const Ctx& ctx, const HEntry* tab = nullptr) {
     double fp = 0.0;
     for (int i = ctx.lane(); i < NP; i += Ctx::W) {
         Col ci = col_of(i);
@@ -152,7 +191,12 @@ template <class Ctx> ATTRICI_HD double assemble(const StepArgs& a, CellScratch& 
         }
         S.g[i] = gi;
     }
-    if (want_H) {
+    if (want_H && tab) {
+        for (int e = ctx.lane(); e < NTRI; e += Ctx::W) {
+            const HEntry t = tab[e];
+            S.H[e] = 0.5 * (S.mom[t.i1] + (double)t.s2 * S.mom[t.i2]) + (double)t.add;
+        }
+    } else if (want_H) {
         for (int i = 0; i < NP; ++i) {
             Col ci = col_of(i);
             bool act_i = col_active(ci, a.term, a.modes);
@@ -239,7 +283,8 @@ ATTRICI_HD int propose(const StepArgs& a, int cell, CellScratch& S, const Ctx& c
     double lam = a.lam[cell];
     bool ok = false;
     for (int tries = 0; tries < 40 && !ok; ++tries) {
-        ok = lm_solve(S, lam, ctx);
+        if constexpr (Ctx::kRegisterSolve) ok = ctx.solve(S, lam);
+        else ok = lm_solve(S, lam, ctx);
         if (ok) {
             bool fin = true;
             for (int i = ctx.lane(); i < NP; i += Ctx::W) fin = fin && isfinite(S.delta[i]);
@@ -252,12 +297,12 @@ ATTRICI_HD int propose(const StepArgs& a, int cell, CellScratch& S, const Ctx& c
     if (!ok) {
         status = ATTRICI_STATUS_STALLED;
     } else {
-        // predicted decrease of the quadratic model: -g.d - 0.5 d.H.d
+        // predicted decrease of the quadratic model, -g.d - 0.5 d.H.d, with H d = -g - lam D d from the solve:
+        // -0.5 g.d + 0.5 lam d.D.d
         double part = 0.0;
         for (int i = ctx.lane(); i < NP; i += Ctx::W) {
-            double hi = 0.0;
-            for (int j = 0; j < NP; ++j) hi += S.H[tri(i, j)] * S.delta[j];
-            part += -S.g[i] * S.delta[i] - 0.5 * S.delta[i] * hi;
+            const double di = S.delta[i], hii = S.H[tri(i, i)];
+            part += -0.5 * S.g[i] * di + 0.5 * lam * fmax(fabs(hii), 1e-12) * di * di;
         }
         pred = ctx.sum(part);
         double f = a.f_acc[cell];
@@ -378,11 +423,12 @@ template <class Ctx> ATTRICI_HD bool cell_init(const StepArgs& a, int cell, Cell
 
 // after a pass at th_trial (moments reduced into momd): accept / reject, update damping, propose the
 // next trial.  Returns true if the cell needs another pass.
-template <class Ctx> ATTRICI_HD bool cell_step(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
+template <class Ctx>
+ATTRICI_HD bool cell_step(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx, const HEntry* tab = nullptr) {
     if (a.status[cell] != ATTRICI_STATUS_RUNNING) return false;
     for (int i = ctx.lane(); i < NP; i += Ctx::W) S.th[i] = a.th_trial[(size_t)cell * NP + i];
     load_moments(a, cell, S, ctx);
-    double f_t = assemble(a, S, true, ctx);
+    double f_t = assemble(a, S, true, ctx, tab);
     bool fin = isfinite(f_t);
     for (int i = ctx.lane(); i < NP; i += Ctx::W) fin = fin && isfinite(S.g[i]);
     const bool finite = ctx.all(fin);
