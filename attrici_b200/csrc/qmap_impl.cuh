@@ -56,9 +56,10 @@ ATTRICI_HD double gamma_cdf(double y, double a, double scale) {
     if (x <= 0.0) return 0.0;
     return gamma_p(a, x);
 }
-ATTRICI_HD double gamma_ppf(double q, double a, double scale) {
+// x0: optional starting value for the standardised quantile (<= 0: none)
+ATTRICI_HD double gamma_ppf(double q, double a, double scale, double x0 = -1.0) {
     if (isnan(q) || isnan(a) || isnan(scale) || !(a > 0.0) || !(scale > 0.0) || q < 0.0 || q > 1.0) return NAN;
-    return gamma_p_inv(a, q) * scale;
+    return gamma_p_inv(a, q, x0) * scale;
 }
 
 // distribution parameters of the family (the values `report_variables` would store)
@@ -115,20 +116,44 @@ ATTRICI_HD double dist_cdf(int family, const DistPar& p, double y) {
     }
 }
 
-ATTRICI_HD double dist_invcdf(int family, const DistPar& p, double q) {
+// y_hint: a value whose quantile under these parameters is close to q (<= 0: none); it only seeds the
+// iterations of the gamma / beta inverses, the result is the same root
+ATTRICI_HD double dist_invcdf(int family, const DistPar& p, double q, double y_hint = -1.0) {
     switch (family) {
         case ATTRICI_NORMAL: return ndtri(q) * p.p1 + p.p0;
-        case ATTRICI_GAMMA: { double a = p.p1 * p.p1; return gamma_ppf(q, a, p.p0 / a); }
+        case ATTRICI_GAMMA: { double a = p.p1 * p.p1; return gamma_ppf(q, a, p.p0 / a, y_hint * a / p.p0); }
         case ATTRICI_BETA: {
             double A = p.p0 * p.p1, B = (1.0 - p.p0) * p.p1;
-            return beta_i_inv(A, B, q);
+            return beta_i_inv(A, B, q, y_hint);
         }
         case ATTRICI_WEIBULL: {
             if (isnan(q) || q < 0.0 || q > 1.0) return NAN;
             return pow(-log1p(-q), 1.0 / p.p0) * p.p1;
         }
-        default: { double a = p.p2 * p.p2; return gamma_ppf((q - p.p0) / (1.0 - p.p0), a, p.p1 / a); }
+        default: {
+            double a = p.p2 * p.p2;
+            return gamma_ppf((q - p.p0) / (1.0 - p.p0), a, p.p1 / a, y_hint * a / p.p1);
+        }
     }
+}
+
+// Gamma family shortcut.  The shape a = nu^2 does not depend on the predictor, so factual and counterfactual
+// distributions differ by their scale only and F_cf^-1(F_ref(y)) = y mu_cf / mu_ref exactly; the reference's
+// gammainc -> gammaincinv round trip only adds its own rounding, which stays below ~1e-9 relative while the upper
+// tail probability Q(a, x) is above ~1e-7 (1.1e-16 / Q).  Days further out in the upper tail keep the full
+// evaluation, which reproduces the reference's saturation (cdf rounds to 1 -> ppf = Inf -> `replaced`).
+// Leading term of ln Q for x > a + 1:  (a - 1) ln x - x - lgamma(a).
+ATTRICI_HD bool gamma_fast_path(const DistPar& ref, const DistPar& cf, double ys, double* cs) {
+    if (!(ys > 0.0) || !(ref.p0 > 0.0) || !(cf.p0 > 0.0) || !(ref.p1 > 0.0) || !isfinite(ref.p0) || !isfinite(cf.p0)) return false;
+    const double a = ref.p1 * ref.p1;
+    const double x = ys * a / ref.p0;
+    if (!isfinite(x)) return false;
+    if (x > a + 1.0) {
+        const double ln_q = (a - 1.0) * log(x) - x - lgamma(a);
+        if (!(ln_q > -16.0)) return false;
+    }
+    *cs = ys * (cf.p0 / ref.p0);
+    return true;
 }
 
 // Normal family shortcut.  sigma does not depend on the predictor, so F_cf^-1(F_ref(y)) = mu_cf + sigma z
@@ -199,8 +224,11 @@ ATTRICI_HD QmapOut qmap_day(int family, int scaling, int post_rule, float y, flo
     double cs;
     if (family != ATTRICI_BERNOULLI_GAMMA) {
         // variables.py:303: invcdf_cf(cdf_ref(y_scaled)); NaN in -> NaN out
-        double q = dist_cdf(family, ref, (double)ys);
-        cs = dist_invcdf(family, cf, q);
+        if (!(family == ATTRICI_GAMMA && gamma_fast_path(ref, cf, (double)ys, &cs))) {
+            double q = dist_cdf(family, ref, (double)ys);
+            // the counterfactual value is close to the observation: start the gamma / beta inverses there
+            cs = dist_invcdf(family, cf, q, (double)ys);
+        }
     } else {
         // Pr.quantile_mapping, variables.py:422-480
         const bool dry = (ys != ys);
@@ -211,7 +239,7 @@ ATTRICI_HD QmapOut qmap_day(int family, int scaling, int post_rule, float y, flo
         const bool qm1 = !drier_cf && !dry;
         const bool to_wet = !qm1 && (u * ref.p0 > cf.p0);
         cs = 0.0;
-        if (qm0 || qm1 || to_wet) cs = dist_invcdf(family, cf, q);
+        if (qm0 || qm1 || to_wet) cs = dist_invcdf(family, cf, q, dry ? -1.0 : y0);
     }
     return qmap_finish(scaling, post_rule, cs, y, datamin, scale);
 }

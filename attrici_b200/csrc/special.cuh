@@ -146,7 +146,8 @@ ATTRICI_HD double gamma_q(double a, double x) {
 }
 
 // x with P(a, x) = p   (scipy.special.gammaincinv); safeguarded Halley iteration
-ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p) {
+// x0 > 0: starting value supplied by the caller (the quantile map knows a point whose quantile is close)
+ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p, double x0 = -1.0) {
     if (isnan(a) || isnan(p) || a <= 0.0 || p < 0.0 || p > 1.0) return NAN;
     if (p == 0.0) return 0.0;
     if (p == 1.0) return INFINITY;
@@ -154,7 +155,9 @@ ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p) {
     const double a1 = a - 1.0;
     double x;
     // starting value (Abramowitz & Stegun 26.2.22 / 26.4.17, as in Numerical Recipes invgammp)
-    if (a > 1.0) {
+    if (x0 > 0.0 && isfinite(x0)) {
+        x = x0;
+    } else if (a > 1.0) {
         double pp = p < 0.5 ? p : 1.0 - p;
         double t = sqrt(-2.0 * log(pp));
         x = (2.30753 + t * 0.27061) / (1.0 + t * (0.99229 + t * 0.04481)) - t;
@@ -255,13 +258,16 @@ ATTRICI_HD_NOINLINE double beta_i2(double a, double b, double x, double* comp) {
 ATTRICI_HD double beta_i(double a, double b, double x) { return beta_i2(a, b, x, nullptr); }
 
 // x with I_x(a, b) = p   (scipy.special.betaincinv); safeguarded Halley iteration
-ATTRICI_HD_NOINLINE double beta_i_inv(double a, double b, double p) {
+// x0 in (0, 1): starting value supplied by the caller
+ATTRICI_HD_NOINLINE double beta_i_inv(double a, double b, double p, double x0 = -1.0) {
     if (isnan(a) || isnan(b) || isnan(p) || a <= 0.0 || b <= 0.0 || p < 0.0 || p > 1.0) return NAN;
     if (p == 0.0) return 0.0;
     if (p == 1.0) return 1.0;
     const double a1 = a - 1.0, b1 = b - 1.0;
     double x;
-    if (a >= 1.0 && b >= 1.0) {
+    if (x0 > 0.0 && x0 < 1.0) {
+        x = x0;
+    } else if (a >= 1.0 && b >= 1.0) {
         double pp = p < 0.5 ? p : 1.0 - p;
         double t = sqrt(-2.0 * log(pp));
         x = (2.30753 + t * 0.27061) / (1.0 + t * (0.99229 + t * 0.04481)) - t;
