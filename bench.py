@@ -41,6 +41,21 @@ METRIC = "gridcell-fits/sec (43k-day series, modes=4)"
 UNIT = "cells/s"
 
 
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/r1_traffic.json, same tile)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    if d.get("cells") != TILE_CELLS or d.get("days") != T_DAYS:
+        return None
+    for name, v in d["kernels"].items():
+        if name.startswith(kernel_prefix):
+            return v["dram_bytes"]
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -64,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -303,6 +318,10 @@ def run_cuda(args):
         dom_kernel = {"scale": "prep_minmax_kernel + prep_scale_fold_kernel (2 launches)",
                       "quantile_map": "qmap_fold_normal_kernel"}[dom]
         achieved = segments[dom]["algorithmic_gbs"]
+        traffic = None
+        if C == TILE_CELLS:
+            traffic = (ncu_traffic("qmap_fold_normal_kernel") if dom == "quantile_map" else
+                       sum(filter(None, [ncu_traffic("prep_minmax_kernel"), ncu_traffic("prep_scale_fold_kernel")])) or None)
         cpu = None
         if not args.no_cpu_baseline:
             cores = min(host_cores(), 64)
@@ -327,7 +346,8 @@ def run_cuda(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read + write, profiles/r1_traffic.json)",
+                         "algorithmic_bytes": seg_bytes[dom], "peak_source": peak_src,
                          "launches": args.steps, "avg_launch_ms": segments[dom]["ms"],
                          "share_of_step": segments[dom]["share_of_step"]},
             "segments": segments,
@@ -344,7 +364,7 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--cells", type=int, default=TILE_CELLS, help="cells per GPU (default: the 100x100 tile)")

@@ -2,7 +2,7 @@
 # Runs on the GPU box (via gpurun): ncu launch list and one full capture of the chosen kernels, exported to
 # CSV on the box (the .ncu-rep is kept only if small; gpurun_out/ is capped at 64 MiB).
 mkdir -p gpurun_out
-CELLS=${CELLS:-4096}
+CELLS=${CELLS:-10000}
 KREGEX=${KREGEX:-pass_kernel}
 SKIP=${SKIP:-0}
 COUNT=${COUNT:-3}
