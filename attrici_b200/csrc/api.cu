@@ -470,14 +470,25 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
         ATTRICI_CUDA_CHECK(cudaMemcpyAsync(d_days, days_host, 4 * (size_t)T, cudaMemcpyHostToDevice, st[0]));
         ATTRICI_CUDA_CHECK(cudaMemcpyAsync(d_gmt, gmt_host, 8 * (size_t)T, cudaMemcpyHostToDevice, st[0]));
         ATTRICI_CUDA_CHECK(cudaStreamSynchronize(st[0]));
-        int n_slabs = (C + slab_cells - 1) / slab_cells;
+        // cell ranges of the slabs.  The pipeline is bound by the D2H copies, which can only start once the first
+        // slab has been uploaded and detrended: a short first slab shortens that fill time.
+        std::vector<int> start;
+        {
+            int first = slab_cells / 4;
+            if (first < 256) first = slab_cells;
+            int c = 0;
+            if (first < slab_cells && C > slab_cells) { start.push_back(0); c = first; }
+            for (; c < C; c += slab_cells) start.push_back(c);
+            start.push_back(C);
+        }
+        const int n_slabs = (int)start.size() - 1;
         // upload of slab k is issued before the (host-synchronising) fit of slab k-1 starts, on the
         // stream that owns its buffer set: stream order serialises the reuse of that set, and the copy
         // overlaps the other stream's kernels and downloads
         auto upload = [&](int k) -> int {
             const int bb = k & 1;
-            const int cc0 = k * slab_cells;
-            const int ncc = (C - cc0 < slab_cells) ? C - cc0 : slab_cells;
+            const int cc0 = start[k];
+            const int ncc = start[k + 1] - cc0;
             ATTRICI_CUDA_CHECK(cudaMemcpy2DAsync(buf[bb].y, 4 * (size_t)ncc, y_host + cc0, 4 * (size_t)ld_host,
                                                  4 * (size_t)ncc, T, cudaMemcpyHostToDevice, st[bb]));
             if (seeds_host)
@@ -491,8 +502,8 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
             const int b = is & 1;
             cudaStream_t s = st[b];
             SlabBuffers& B = buf[b];
-            const int c0 = is * slab_cells;
-            const int nc = (C - c0 < slab_cells) ? C - c0 : slab_cells;
+            const int c0 = start[is];
+            const int nc = start[is + 1] - c0;
             if (is + 1 < n_slabs) ATTRICI_TRY(upload(is + 1));
             ATTRICI_TRY(attrici_build_basis(B.ws, B.ws_bytes, var->family, d_days, d_gmt, T, nc, s));
             // Normal family on a gap-free daily axis: the fit runs on the per-phase sums and the quantile map
