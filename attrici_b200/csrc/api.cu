@@ -131,22 +131,31 @@ int fold_applies(Workspace& ws, int term, int i0, int i1, cudaStream_t s, bool* 
 }
 
 // one likelihood pass + cross-chunk reduction at ws.th_pass, by whichever kernel applies
-int run_pass(Workspace& ws, bool fold, const int* list, int n_active, int term, bool fp64, bool with_moments,
+// mode: PASS_NLL / PASS_GRAD / PASS_FULL (the day-by-day kernels have no gradient-only form: PASS_GRAD = PASS_FULL)
+int run_pass(Workspace& ws, bool fold, const int* list, int n_active, int term, bool fp64, int mode,
              bool exact, const float* y_scaled, int64_t ld, int i0, int i1, const int* status, cudaStream_t s,
              cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr) {
     if (fold) {
         PassShape ps = plan_pass(ws, list, n_active, 0, fold_phases(ws), true);
         if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
-        ATTRICI_TRY(launch_fold_pass(ws, ps, with_moments, exact, status, s));
+        ATTRICI_TRY(launch_fold_pass(ws, ps, mode, exact, status, s));
         if (e1) ATTRICI_CUDA_CHECK(cudaEventRecord(e1, s));
-        return launch_reduce(ws, ps, true, with_moments, s, status);
+        return launch_reduce(ws, ps, true, mode, s, status);
     }
+    if (mode == PASS_GRAD) mode = PASS_FULL;
     PassShape ps = plan_pass(ws, list, n_active, i0, i1, fp64);
     if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
-    ATTRICI_TRY(launch_pass(ws, ps, term, fp64, with_moments, y_scaled, ld, i0, i1, status, s));
+    ATTRICI_TRY(launch_pass(ws, ps, term, fp64, mode != PASS_NLL, y_scaled, ld, i0, i1, status, s));
     if (e1) ATTRICI_CUDA_CHECK(cudaEventRecord(e1, s));
-    return launch_reduce(ws, ps, fp64, with_moments, s, status);
+    return launch_reduce(ws, ps, fp64, mode, s, status);
 }
+
+// Passes FISHER_PASSES .. FISHER_PASSES + CHORD_PASSES - 1 of the folded iteration reuse the information matrix of
+// the accepted point instead of refreshing the Fisher moments: the matrix depends on the coefficients only through
+// sigma(d), which has settled by then for a typical cell, and those are its last passes.  Cells that are still
+// iterating afterwards (strong seasonal cycle of sigma) go back to fresh moments.
+constexpr int FISHER_PASSES = 3;
+constexpr int CHORD_PASSES = 2;
 
 // Fisher-scoring iteration of one likelihood term over the whole batch.  Cells still iterating are kept in
 // a compact list (ping-pong); once fewer than half of the batch is left the likelihood pass runs over the
@@ -180,12 +189,14 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
                 ev.push_back(e1);
                 g_profile.cell_days += (double)running * (double)(i1 - i0);
             }
+            const bool fresh = !fold || (it + b < FISHER_PASSES) || (it + b >= FISHER_PASSES + CHORD_PASSES);
             ATTRICI_TRY(run_pass(ws, fold, use_list ? ws.list[cur] : nullptr, use_list ? running : ws.C, sp.term, fp64,
-                                 true, false, y_scaled, ld, i0, i1, use_list ? nullptr : ws.status, s, e0, e1));
+                                 fresh ? PASS_FULL : PASS_GRAD, false, y_scaled, ld, i0, i1,
+                                 use_list ? nullptr : ws.status, s, e0, e1));
             if (block == 1)
-                ATTRICI_TRY(launch_fit_step(ws, sp, ws.list[cur], running, ws.list[cur ^ 1], ws.counters + (cur ^ 1), s));
+                ATTRICI_TRY(launch_fit_step(ws, sp, ws.list[cur], running, ws.list[cur ^ 1], ws.counters + (cur ^ 1), s, fresh));
             else   // every cell's warp looks at its own status
-                ATTRICI_TRY(launch_fit_step(ws, sp, nullptr, ws.C, ws.list[cur ^ 1], ws.counters + (cur ^ 1), s));
+                ATTRICI_TRY(launch_fit_step(ws, sp, nullptr, ws.C, ws.list[cur ^ 1], ws.counters + (cur ^ 1), s, fresh));
             cur ^= 1;
         }
         it += block;
@@ -202,7 +213,7 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
     }
     // log posterior of the accepted point in FP64 (model_scipy.py:525: trace["logp"] = -res.fun)
     ATTRICI_TRY(launch_fit_final_point(ws, sp, s));
-    ATTRICI_TRY(run_pass(ws, fold, nullptr, ws.C, sp.term, true, false, false, y_scaled, ld, i0, i1, nullptr, s));
+    ATTRICI_TRY(run_pass(ws, fold, nullptr, ws.C, sp.term, true, PASS_NLL, false, y_scaled, ld, i0, i1, nullptr, s));
     ATTRICI_TRY(launch_fit_store(ws, sp, s));
     return 0;
 }
@@ -297,7 +308,7 @@ int attrici_nll_grad(void* workspace, size_t workspace_bytes, const attrici_vari
         ATTRICI_TRY(launch_rotate(ws, sp, s));
         bool fold = false;
         ATTRICI_TRY(fold_applies(ws, sp.term, i0, i1, s, &fold));
-        ATTRICI_TRY(run_pass(ws, fold, nullptr, ws.C, sp.term, use_fp64 != 0, true, true, y_scaled, ld, i0, i1, nullptr, s));
+        ATTRICI_TRY(run_pass(ws, fold, nullptr, ws.C, sp.term, use_fp64 != 0, PASS_FULL, true, y_scaled, ld, i0, i1, nullptr, s));
         // canonical results go through idle fit-state buffers: f_acc, g_acc [Cp][NP], h_acc [Cp][NTRI]
         ATTRICI_TRY(launch_assemble(ws, sp, ws.f_acc, ws.g_acc, fisher ? ws.h_acc : nullptr, s));
         ATTRICI_TRY(launch_scatter_kat(ws, var->family, var->modes, slot, ws.f_acc, ws.g_acc,

@@ -204,12 +204,13 @@ int launch_pass_mma(Workspace& ws, const PassShape& ps, const float* y_scaled, i
                     const int* status, cudaStream_t s);
 // phase-folded pass of the Normal family over the per-phase sums of prep (fold.cu); `ps` is planned over
 // [0, fold_phases(ws)); partials are FP64
+// what a pass produces: the nll only, nll + gradient moments, or nll + gradient + Fisher moments
+enum { PASS_NLL = 0, PASS_GRAD = 1, PASS_FULL = 2 };
 int fold_phases(const Workspace& ws);
-int launch_fold_pass(Workspace& ws, const PassShape& ps, bool with_moments, bool exact, const int* status,
-                     cudaStream_t s);
+int launch_fold_pass(Workspace& ws, const PassShape& ps, int mode, bool exact, const int* status, cudaStream_t s);
 // cross-chunk reduction of the partials of the last pass into ws.momd
 // status != nullptr (only without a list): cells whose status is not RUNNING are skipped
-int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_moments, cudaStream_t s,
+int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, int mode, cudaStream_t s,
                   const int* status = nullptr);
 
 struct StepParams {
@@ -224,8 +225,10 @@ struct StepParams {
 // start values and phase origins; list_out / counter receive the cells that iterate
 int launch_fit_init(Workspace& ws, const StepParams& sp, int* list_out, int* counter, cudaStream_t s);
 // accept / reject / propose for the cells of list_in; list_out / counter receive those that go on
+// fresh_fisher = false: the pass before only produced gradient moments, the information matrix of the accepted
+// point is reused
 int launch_fit_step(Workspace& ws, const StepParams& sp, const int* list_in, int n_in, int* list_out, int* counter,
-                    cudaStream_t s);
+                    cudaStream_t s, bool fresh_fisher = true);
 // th_trial := th_acc, rotated into th_pass (before the final FP64 evaluation)
 int launch_fit_final_point(Workspace& ws, const StepParams& sp, cudaStream_t s);
 // after an FP64 pass without moments at th_acc (+ reduce): store coefficients / logp / status of this term slot

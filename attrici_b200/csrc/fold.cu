@@ -63,8 +63,11 @@ template <int K, typename A> __device__ __forceinline__ void fold_accumulate(A* 
     }
 }
 
-template <bool MOMENTS, typename RW>
-__global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_normal_kernel(FoldArgs a) {
+// MODE 0: nll only; 1: nll + gradient moments (the Fisher moments of an earlier pass are reused); 2: everything
+template <int MODE, typename RW>
+__global__ void __launch_bounds__(PASS_CELLS, MODE == 2 ? 2 : 3) fold_pass_normal_kernel(FoldArgs a) {
+    constexpr bool MOMENTS = MODE >= 1;   // gradient moments
+    constexpr bool FISHER = MODE >= 2;    // Fisher moments
     // phase rows of the current tile: FP64 {n, cos 1..8, sin 1..8, sum gmt, sum gmt^2, 0} and an RW copy of the
     // 16 trig columns for the Fisher moments; per-thread ring of the three sums of the next FOLD_RING phases
     __shared__ __align__(16) double tile[FOLD_TILE * B_STRIDE];
@@ -92,11 +95,13 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_normal_kernel(FoldArg
 
     RW AA[3 * NTRIG], BB[NTRIG];
     double GA[2 * NB], GB[NB];
-    if (MOMENTS) {
+    if (FISHER) {
 #pragma unroll
         for (int i = 0; i < 3 * NTRIG; ++i) AA[i] = RW(0);
 #pragma unroll
         for (int i = 0; i < NTRIG; ++i) BB[i] = RW(0);
+    }
+    if (MOMENTS) {
 #pragma unroll
         for (int i = 0; i < 2 * NB; ++i) GA[i] = 0.0;
 #pragma unroll
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_normal_kernel(FoldArg
             const double v = a.pb64[(size_t)(d_begin + q0) * B_STRIDE + i];
             tile[i] = v;
             const int r = i / B_STRIDE, c = i - r * B_STRIDE;
-            if (MOMENTS && c >= 1 && c <= 2 * NH) trig_w[r * 2 * NH + (c - 1)] = (RW)v;
+            if (FISHER && c >= 1 && c <= 2 * NH) trig_w[r * 2 * NH + (c - 1)] = (RW)v;
         }
         __syncthreads();
         if (!warp_active) {   // keep the group accounting of this warp's (empty) ring consistent
@@ -168,12 +173,14 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_normal_kernel(FoldArg
             const double R1 = c_syg - av * sg - bv * sgg;
             const double Q = c_syy - av * c_sy - bv * c_syg - av * R0 - bv * R1;
             nll += n * (cv + 0.91893853320467274178) + 0.5 * e2 * Q;
-            if (MOMENTS) {
+            if (FISHER) {
                 const RW* tw = trig_w + r * 2 * NH;
                 fold_accumulate<NH, RW>(AA, (RW)(e2 * n), tw);
                 fold_accumulate<NH, RW>(AA + NTRIG, (RW)(e2 * sg), tw);
                 fold_accumulate<NH, RW>(AA + 2 * NTRIG, (RW)(e2 * sgg), tw);
                 fold_accumulate<NH, RW>(BB, (RW)(2.0 * n), tw);
+            }
+            if (MOMENTS) {
                 fold_accumulate<MAXM, double>(GA, -e2 * R0, row + 1);
                 fold_accumulate<MAXM, double>(GA + NB, -e2 * R1, row + 1);
                 fold_accumulate<MAXM, double>(GB, n - e2 * Q, row + 1);
@@ -186,12 +193,14 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_normal_kernel(FoldArg
         a.part_nll[(size_t)chunk * a.Pp + pos] = nll;
         if (MOMENTS) {
             double* out = a.part_acc + (size_t)chunk * NACC * a.Pp + pos;
+            if (FISHER) {
 #pragma unroll
-            for (int i = 0; i < 3 * NTRIG; ++i) out[(size_t)(ACC_AA + i) * a.Pp] = (double)AA[i];
+                for (int i = 0; i < 3 * NTRIG; ++i) out[(size_t)(ACC_AA + i) * a.Pp] = (double)AA[i];
 #pragma unroll
-            for (int i = 0; i < 2 * NTRIG; ++i) out[(size_t)(ACC_AB + i) * a.Pp] = 0.0;
+                for (int i = 0; i < 2 * NTRIG; ++i) out[(size_t)(ACC_AB + i) * a.Pp] = 0.0;
 #pragma unroll
-            for (int i = 0; i < NTRIG; ++i) out[(size_t)(ACC_BB + i) * a.Pp] = (double)BB[i];
+                for (int i = 0; i < NTRIG; ++i) out[(size_t)(ACC_BB + i) * a.Pp] = (double)BB[i];
+            }
 #pragma unroll
             for (int i = 0; i < 2 * NB; ++i) out[(size_t)(ACC_GA + i) * a.Pp] = GA[i];
 #pragma unroll
@@ -204,9 +213,8 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_normal_kernel(FoldArg
 
 int fold_phases(const Workspace& ws) { return ws.T < NPHASE ? ws.T : NPHASE; }
 
-// exact = true: Fisher moments accumulated in FP64 too (known-answer entry)
-int launch_fold_pass(Workspace& ws, const PassShape& ps, bool with_moments, bool exact, const int* status,
-                     cudaStream_t s) {
+// mode: PASS_NLL / PASS_GRAD / PASS_FULL; exact = true: Fisher moments accumulated in FP64 too (known-answer entry)
+int launch_fold_pass(Workspace& ws, const PassShape& ps, int mode, bool exact, const int* status, cudaStream_t s) {
     if (ps.n_active <= 0) return 0;
     if (!ws.ystat) { set_error("workspace was sized for another family"); return ATTRICI_EWORKSPACE; }
     FoldArgs a;
@@ -225,9 +233,10 @@ int launch_fold_pass(Workspace& ws, const PassShape& ps, bool with_moments, bool
     a.part_nll = ws.part_nll;
     a.part_acc = (double*)ws.part_acc;
     dim3 grid((ps.n_active + PASS_CELLS - 1) / PASS_CELLS, ps.n_chunks);
-    if (!with_moments) fold_pass_normal_kernel<false, float><<<grid, PASS_CELLS, 0, s>>>(a);
-    else if (exact) fold_pass_normal_kernel<true, double><<<grid, PASS_CELLS, 0, s>>>(a);
-    else fold_pass_normal_kernel<true, float><<<grid, PASS_CELLS, 0, s>>>(a);
+    if (mode == PASS_NLL) fold_pass_normal_kernel<0, float><<<grid, PASS_CELLS, 0, s>>>(a);
+    else if (mode == PASS_GRAD) fold_pass_normal_kernel<1, float><<<grid, PASS_CELLS, 0, s>>>(a);
+    else if (exact) fold_pass_normal_kernel<2, double><<<grid, PASS_CELLS, 0, s>>>(a);
+    else fold_pass_normal_kernel<2, float><<<grid, PASS_CELLS, 0, s>>>(a);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }

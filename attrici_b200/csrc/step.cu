@@ -110,14 +110,14 @@ __global__ void __launch_bounds__(STEP_THREADS) fit_init_kernel(StepArgs a, int*
 }
 
 __global__ void __launch_bounds__(STEP_THREADS) fit_step_kernel(StepArgs a, const int* list_in, int n_in,
-                                                                int* list_out, int* counter) {
+                                                                int* list_out, int* counter, int fresh_fisher) {
     __shared__ CellScratch S[STEP_WARPS];
     __shared__ HEntry tab[NTRI];
     build_h_table(a, tab);
     int cell = warp_cell(list_in, n_in);
     if (cell < 0) return;
     WarpCtx ctx;
-    bool run = cell_step(a, cell, S[threadIdx.x >> 5], ctx, tab);
+    bool run = cell_step(a, cell, S[threadIdx.x >> 5], ctx, tab, fresh_fisher != 0);
     if (run && ctx.lane() == 0) list_out[atomicAdd(counter, 1)] = cell;
 }
 
@@ -305,10 +305,11 @@ int launch_fit_init(Workspace& ws, const StepParams& sp, int* list_out, int* cou
 }
 
 int launch_fit_step(Workspace& ws, const StepParams& sp, const int* list_in, int n_in, int* list_out, int* counter,
-                    cudaStream_t s) {
+                    cudaStream_t s, bool fresh_fisher) {
     ATTRICI_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), s));
     if (n_in <= 0) return 0;
-    fit_step_kernel<<<warp_blocks(n_in), STEP_THREADS, 0, s>>>(make_args(ws, sp), list_in, n_in, list_out, counter);
+    fit_step_kernel<<<warp_blocks(n_in), STEP_THREADS, 0, s>>>(make_args(ws, sp), list_in, n_in, list_out, counter,
+                                                               fresh_fisher ? 1 : 0);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
@@ -325,12 +326,11 @@ int launch_fit_store(Workspace& ws, const StepParams& sp, cudaStream_t s) {
     return 0;
 }
 
-int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, bool with_moments, cudaStream_t s, const int* status) {
+int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, int mode, cudaStream_t s, const int* status) {
     if (ps.n_active <= 0) return 0;
-    dim3 grid((ps.n_active + RED_THREADS - 1) / RED_THREADS, (NACC + 1 + RED_GROUP - 1) / RED_GROUP);
-    // without moments only row NACC (the sum of the day terms of the nll) is reduced
-    const int row0 = with_moments ? 0 : NACC;
-    if (!with_moments) grid.y = 1;
+    // rows reduced: everything, the gradient moments + nll, or only row NACC (the sum of the day terms of the nll)
+    const int row0 = mode == PASS_FULL ? 0 : (mode == PASS_GRAD ? ACC_GA : NACC);
+    dim3 grid((ps.n_active + RED_THREADS - 1) / RED_THREADS, (NACC + 1 - row0 + RED_GROUP - 1) / RED_GROUP);
     if (fp64)
         reduce_partials_kernel<double><<<grid, RED_THREADS, 0, s>>>(ps.list, ps.n_active, ps.Pp, ws.Cp, ps.n_chunks,
                                                                    row0, ws.part_nll,

@@ -424,11 +424,18 @@ template <class Ctx> ATTRICI_HD bool cell_init(const StepArgs& a, int cell, Cell
 // after a pass at th_trial (moments reduced into momd): accept / reject, update damping, propose the
 // next trial.  Returns true if the cell needs another pass.
 template <class Ctx>
-ATTRICI_HD bool cell_step(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx, const HEntry* tab = nullptr) {
+ATTRICI_HD bool cell_step(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx, const HEntry* tab = nullptr,
+                          bool fresh_fisher = true) {
     if (a.status[cell] != ATTRICI_STATUS_RUNNING) return false;
     for (int i = ctx.lane(); i < NP; i += Ctx::W) S.th[i] = a.th_trial[(size_t)cell * NP + i];
     load_moments(a, cell, S, ctx);
-    double f_t = assemble(a, S, true, ctx, tab);
+    // without fresh Fisher moments the information matrix of the accepted point stays in use (the matrix only
+    // steers the step; near the optimum it changes by less than the damping does)
+    double f_t = assemble(a, S, fresh_fisher, ctx, tab);
+    if (!fresh_fisher) {
+        for (int i = ctx.lane(); i < NTRI; i += Ctx::W) S.H[i] = a.h_acc[(size_t)cell * NTRI + i];
+        ctx.sync();
+    }
     bool fin = isfinite(f_t);
     for (int i = ctx.lane(); i < NP; i += Ctx::W) fin = fin && isfinite(S.g[i]);
     const bool finite = ctx.all(fin);
@@ -471,7 +478,8 @@ ATTRICI_HD bool cell_step(const StepArgs& a, int cell, CellScratch& S, const Ctx
             a.th_acc[(size_t)cell * NP + i] = S.th[i];
             a.g_acc[(size_t)cell * NP + i] = S.g[i];
         }
-        for (int i = ctx.lane(); i < NTRI; i += Ctx::W) a.h_acc[(size_t)cell * NTRI + i] = S.H[i];
+        if (fresh_fisher)
+            for (int i = ctx.lane(); i < NTRI; i += Ctx::W) a.h_acc[(size_t)cell * NTRI + i] = S.H[i];
     } else {
         for (int i = ctx.lane(); i < NP; i += Ctx::W) {
             S.th[i] = a.th_acc[(size_t)cell * NP + i];
