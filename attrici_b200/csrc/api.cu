@@ -120,22 +120,39 @@ bool fold_enabled() {
 
 // does the phase-folded pass apply?  Normal term on a gap-free daily axis (flag left by attrici_build_basis)
 // whose per-phase sums were gathered by attrici_prep_scale_mask on this workspace.  Synchronises `s`.
-int fold_applies(Workspace& ws, int term, int i0, int i1, cudaStream_t s, bool* fold) {
-    *fold = false;
-    if (term != T_NORMAL || !ws.ystat || !fold_enabled()) return 0;
-    int h[3] = {1, -1, -1};   // {days off the gap-free axis, fit window the sums were gathered for}
+// how a term's likelihood passes run: FOLD_SUMS = Normal term from the per-phase sums of prep (fold.cu),
+// FOLD_STREAM = the other terms streamed in phase order, FOLD_NONE = day-by-day kernels
+enum { FOLD_NONE = 0, FOLD_SUMS = 1, FOLD_STREAM = 2 };
+int fold_applies(Workspace& ws, int term, int i0, int i1, cudaStream_t s, int* fold) {
+    *fold = FOLD_NONE;
+    if (!fold_enabled()) return 0;
+    if (term == T_NORMAL && !ws.ystat) return 0;
+    int h[3] = {1, -1, -1};   // {days off the gap-free axis, fit window the phase rows / sums were gathered for}
     ATTRICI_CUDA_CHECK(cudaMemcpyAsync(h, ws.fold_bad, sizeof(h), cudaMemcpyDeviceToHost, s));
     ATTRICI_CUDA_CHECK(cudaStreamSynchronize(s));
-    *fold = (h[0] == 0 && h[1] == i0 && h[2] == i1);
+    if (h[0] == 0 && h[1] == i0 && h[2] == i1) {
+        // measured (scripts/bench_families.py): the phase-ordered stream wins for the Gamma and Bernoulli terms
+        // (tasrange fit 2.1x, pr 1.5x); the Beta and Weibull terms spend their time in per-day special functions and
+        // run faster in the day-ordered kernel, which keeps more warps resident
+        if (term == T_NORMAL) *fold = FOLD_SUMS;
+        else if (term == T_GAMMA || term == T_BERNOULLI) *fold = FOLD_STREAM;
+    }
     return 0;
 }
 
 // one likelihood pass + cross-chunk reduction at ws.th_pass, by whichever kernel applies
 // mode: PASS_NLL / PASS_GRAD / PASS_FULL (the day-by-day kernels have no gradient-only form: PASS_GRAD = PASS_FULL)
-int run_pass(Workspace& ws, bool fold, const int* list, int n_active, int term, bool fp64, int mode,
+int run_pass(Workspace& ws, int fold, const int* list, int n_active, int term, bool fp64, int mode,
              bool exact, const float* y_scaled, int64_t ld, int i0, int i1, const int* status, cudaStream_t s,
              cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr) {
-    if (fold) {
+    if (fold == FOLD_STREAM && !fp64 && mode != PASS_NLL) {
+        PassShape ps = plan_pass(ws, list, n_active, 0, fold_phases(ws), false);
+        if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
+        ATTRICI_TRY(launch_fold_pass_generic(ws, ps, term, y_scaled, ld, i0, i1, status, s));
+        if (e1) ATTRICI_CUDA_CHECK(cudaEventRecord(e1, s));
+        return launch_reduce(ws, ps, false, PASS_FULL, s, status);
+    }
+    if (fold == FOLD_SUMS) {
         PassShape ps = plan_pass(ws, list, n_active, 0, fold_phases(ws), true);
         if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
         ATTRICI_TRY(launch_fold_pass(ws, ps, mode, exact, status, s));
@@ -165,10 +182,10 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
     StepParams sp = step_params(var, o, slot);
     const bool fp64 = o.use_fp64 != 0;
     int cur = 0, running = 0;
-    bool fold = false;
+    int fold = FOLD_NONE;
     ATTRICI_TRY(launch_fit_init(ws, sp, ws.list[cur], ws.counters + cur, s));
     ATTRICI_TRY(fold_applies(ws, sp.term, i0, i1, s, &fold));
-    if (!fold && !y_scaled) { set_error("y_scaled is needed: the phase-folded pass does not apply"); return ATTRICI_EINVAL; }
+    if (fold != FOLD_SUMS && !y_scaled) { set_error("y_scaled is needed: the phase-folded pass does not apply"); return ATTRICI_EINVAL; }
     ATTRICI_TRY(read_counter(ws.counters + cur, &running, s));
     const bool profile = o.profile != 0;
     std::vector<cudaEvent_t> ev;
@@ -177,7 +194,7 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
     // round trip with the GPU idle) costs more than a pass over cells that are already done: they are issued in
     // blocks (6, then 2 at a time) over all cells with the status mask, and the host synchronises once per block.
     for (int it = 0; running > 0 && it < o.max_pass;) {
-        int block = fold ? (it == 0 ? 6 : 2) : 1;
+        int block = fold == FOLD_SUMS ? (it == 0 ? 6 : 2) : 1;
         if (block > o.max_pass - it) block = o.max_pass - it;
         for (int b = 0; b < block; ++b) {
             const bool use_list = (block == 1) && (2 * running < ws.C);
@@ -189,7 +206,7 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
                 ev.push_back(e1);
                 g_profile.cell_days += (double)running * (double)(i1 - i0);
             }
-            const bool fresh = !fold || (it + b < FISHER_PASSES) || (it + b >= FISHER_PASSES + CHORD_PASSES);
+            const bool fresh = fold != FOLD_SUMS || (it + b < FISHER_PASSES) || (it + b >= FISHER_PASSES + CHORD_PASSES);
             ATTRICI_TRY(run_pass(ws, fold, use_list ? ws.list[cur] : nullptr, use_list ? running : ws.C, sp.term, fp64,
                                  fresh ? PASS_FULL : PASS_GRAD, false, y_scaled, ld, i0, i1,
                                  use_list ? nullptr : ws.status, s, e0, e1));
@@ -306,7 +323,7 @@ int attrici_nll_grad(void* workspace, size_t workspace_bytes, const attrici_vari
         ATTRICI_TRY(launch_phase_only(ws, sp, s));
         ATTRICI_TRY(launch_load_theta(ws, var->family, var->modes, slot, theta, s));
         ATTRICI_TRY(launch_rotate(ws, sp, s));
-        bool fold = false;
+        int fold = FOLD_NONE;
         ATTRICI_TRY(fold_applies(ws, sp.term, i0, i1, s, &fold));
         ATTRICI_TRY(run_pass(ws, fold, nullptr, ws.C, sp.term, use_fp64 != 0, PASS_FULL, true, y_scaled, ld, i0, i1, nullptr, s));
         // canonical results go through idle fit-state buffers: f_acc, g_acc [Cp][NP], h_acc [Cp][NTRI]

@@ -241,4 +241,235 @@ int launch_fold_pass(Workspace& ws, const PassShape& ps, int mode, bool exact, c
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Phase-folded pass of the other families (Gamma, Weibull, Beta, Bernoulli).
+//
+// Their likelihoods are not functions of a few sums, so the series is still streamed once per pass, but in phase
+// order: for the days t = d + 1461 j of one phase the 27-term predictor sums collapse to
+//     eta_A(t) = a_d + gmt(t) b_d ,  eta_B(t) = c_d ,
+// everything that depends on eta_B only (e^c, lgamma / digamma / trigamma of the Gamma shape) is evaluated once
+// per phase, and the 129 moment accumulators of pass.cu are updated once per phase from ten per-phase sums
+//     sum w_AA {1, g, g^2}, sum w_AB {1, g}, sum w_BB, sum r_A {1, g}, sum r_B, sum nll
+// instead of once per day: a day costs one load, one FMA, the family's day terms and ten accumulations, against
+// 27 + 129 FMAs in pass.cu.  FP32 day arithmetic with FP64 accumulation of the nll, as pass_kernel<KIND, float>.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct GenArgs {
+    const float* ys;
+    int64_t ld;
+    int T, Cp;
+    const int* list;
+    int n_active, Pp;
+    int i0, i1;
+    int n_ph, chunk_len, nj_max;
+    const double* pb64;      // phase rows (trig columns)
+    const float* basis32;    // gmt(t) = basis32[t * B_STRIDE]
+    const double* th_pass;
+    const int* status;
+    double* part_nll;        // [chunk][Pp]
+    float* part_acc;         // [chunk][NACC][Pp]
+};
+
+constexpr int GEN_TILE = 32;   // phases per shared-memory tile
+constexpr int GEN_U = 8;       // days per batch of loads
+
+// terms of the Gamma family that depend on eta_B only (shape a = nu^2 = e^{2 eta_B})
+struct GammaPhase { float a, lna, lgam_a, psi_a, wbb; };
+
+template <int KIND>
+__device__ __forceinline__ DayTerms<float> gen_day(float y, float ea, float eb, const GammaPhase& gp) {
+    if (KIND == K_GAMMA) {
+        DayTerms<float> d;
+        const float ly = logf(y);
+        const float lnu = ly - ea;
+        const float u = expf(lnu);
+        const float dd = lnu + gp.lna + 1.f - u - gp.psi_a;
+        d.nll = -((gp.a - 1.f) * ly - gp.a * u - gp.lgam_a - gp.a * ea + gp.a * gp.lna);
+        d.rA = -gp.a * (u - 1.f);
+        d.rB = -2.f * gp.a * dd;
+        d.wAA = gp.a;
+        d.wAB = 0.f;
+        d.wBB = gp.wbb;
+        return d;
+    }
+    return family_day_t<KIND, float>(y, ea, eb);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_generic_kernel(GenArgs a) {
+    constexpr bool HAS_B = (KIND != K_BERNOULLI);
+    constexpr bool HAS_AB = (KIND == K_WEIBULL || KIND == K_BETA);
+    extern __shared__ __align__(16) unsigned char gen_smem[];
+    float* trig = reinterpret_cast<float*>(gen_smem);      // [GEN_TILE][16] cos 1..8, sin 1..8
+    float* g_s = trig + GEN_TILE * 2 * NH;                 // [GEN_TILE][nj_max] gmt of day d + 1461 j
+
+    const int tid = threadIdx.x;
+    const int pos = blockIdx.x * PASS_CELLS + tid;
+    const int chunk = blockIdx.y;
+    const int d_begin = chunk * a.chunk_len;
+    const int d_end = min(a.n_ph, d_begin + a.chunk_len);
+    const bool in_range = pos < a.n_active;
+    const int cell = a.list ? a.list[in_range ? pos : 0] : (in_range ? pos : a.n_active - 1);
+    bool active = in_range;
+    if (active && a.status) active = (a.status[cell] == ATTRICI_STATUS_RUNNING);
+    if (__syncthreads_or(active) == 0 || d_begin >= d_end) return;   // uniform per CTA
+    const bool warp_active = __any_sync(0xffffffffu, active);
+
+    float thA[NA], thB[NB];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) thA[i] = active ? (float)a.th_pass[(size_t)i * a.Cp + cell] : 0.f;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) thB[i] = (active && HAS_B) ? (float)a.th_pass[(size_t)(NA + i) * a.Cp + cell] : 0.f;
+
+    PassAcc<float> acc;
+    acc.clear();
+    double nll = 0.0;
+    const float* yp0 = a.ys + cell;
+    const size_t jstride = (size_t)NPHASE * a.ld;
+    const float qnan = __int_as_float(0x7fc00000);
+
+    for (int q0 = d_begin; q0 < d_end; q0 += GEN_TILE) {
+        const int n_rows = min(GEN_TILE, d_end - q0);
+        __syncthreads();
+        for (int i = tid; i < n_rows * 2 * NH; i += PASS_CELLS) {
+            const int r = i / (2 * NH), c = i - r * 2 * NH;
+            trig[i] = (float)a.pb64[(size_t)(q0 + r) * B_STRIDE + 1 + c];
+        }
+        for (int i = tid; i < n_rows * a.nj_max; i += PASS_CELLS) {
+            const int r = i / a.nj_max, j = i - r * a.nj_max;
+            const int t = q0 + r + j * NPHASE;
+            g_s[i] = (t < a.T) ? a.basis32[(size_t)t * B_STRIDE] : 0.f;
+        }
+        __syncthreads();
+        if (!warp_active) continue;
+        for (int r = 0; r < n_rows; ++r) {
+            const int d = q0 + r;
+            const float* tr = trig + r * 2 * NH;
+            // days of this phase inside the fit window: j in [ja, jb)
+            const int nj = (a.T - d + NPHASE - 1) / NPHASE;
+            const int ja = a.i0 > d ? (a.i0 - d + NPHASE - 1) / NPHASE : 0;
+            const int jb = a.i1 > d ? min(nj, (a.i1 - d + NPHASE - 1) / NPHASE) : 0;
+            if (ja >= jb) continue;
+            float av = thA[0], bv = thA[1], cv = HAS_B ? thB[0] : 0.f;
+#pragma unroll
+            for (int k = 0; k < MAXM; ++k) {
+                const float ck = tr[k], sk = tr[NH + k];
+                av = fmaf(thA[2 + k], ck, av);
+                av = fmaf(thA[2 + MAXM + k], sk, av);
+                bv = fmaf(thA[2 + 2 * MAXM + k], ck, bv);
+                bv = fmaf(thA[2 + 3 * MAXM + k], sk, bv);
+                if (HAS_B) {
+                    cv = fmaf(thB[1 + k], ck, cv);
+                    cv = fmaf(thB[1 + MAXM + k], sk, cv);
+                }
+            }
+            GammaPhase gp = {0.f, 0.f, 0.f, 0.f, 0.f};
+            if (KIND == K_GAMMA) {
+                gp.a = expf(2.f * cv);
+                gp.lna = 2.f * cv;
+                gp.lgam_a = lgammaf(gp.a);
+                gp.psi_a = digamma<float>(gp.a);
+                gp.wbb = 4.f * gp.a * (gp.a * trigamma<float>(gp.a) - 1.f);
+            }
+            float w0 = 0.f, w1 = 0.f, w2 = 0.f, ab0 = 0.f, ab1 = 0.f, bb = 0.f, ra0 = 0.f, ra1 = 0.f, rb = 0.f, nl = 0.f;
+            const float* gr = g_s + r * a.nj_max;
+            const float* yp = yp0 + (size_t)d * a.ld + (size_t)ja * jstride;
+            for (int j0 = ja; j0 < jb; j0 += GEN_U, yp += GEN_U * jstride) {
+                float yv[GEN_U];
+                const int last = jb - 1 - j0;
+#pragma unroll
+                for (int u = 0; u < GEN_U; ++u) yv[u] = (active && u <= last) ? __ldg(yp + (size_t)u * jstride) : qnan;
+#pragma unroll
+                for (int u = 0; u < GEN_U; ++u) {
+                    if (u <= last) {
+                        const float yf = yv[u];
+                        bool valid;
+                        float y;
+                        if (KIND == K_BERNOULLI) {
+                            valid = active;                       // every day of the window counts; NaN (dry) is the event
+                            y = (yf != yf) ? 1.f : 0.f;
+                        } else {
+                            valid = active && (yf == yf);
+                            y = valid ? yf : 0.5f;
+                        }
+                        const float g = gr[j0 + u];
+                        DayTerms<float> dt = gen_day<KIND>(y, fmaf(g, bv, av), cv, gp);
+                        if (valid) {
+                            nl += dt.nll;
+                            w0 += dt.wAA; w1 = fmaf(dt.wAA, g, w1); w2 = fmaf(dt.wAA * g, g, w2);
+                            ra0 += dt.rA; ra1 = fmaf(dt.rA, g, ra1);
+                            if (HAS_AB) { ab0 += dt.wAB; ab1 = fmaf(dt.wAB, g, ab1); }
+                            if (HAS_B) { bb += dt.wBB; rb += dt.rB; }
+                        }
+                    }
+                }
+            }
+            nll += (double)nl;
+            // fold the per-phase sums into the moment accumulators (layout of pass.cu)
+            fold_accumulate<NH, float>(acc.AA, w0, tr);
+            fold_accumulate<NH, float>(acc.AA + NTRIG, w1, tr);
+            fold_accumulate<NH, float>(acc.AA + 2 * NTRIG, w2, tr);
+            if (HAS_AB) {
+                fold_accumulate<NH, float>(acc.AB, ab0, tr);
+                fold_accumulate<NH, float>(acc.AB + NTRIG, ab1, tr);
+            }
+            if (HAS_B) {
+                fold_accumulate<NH, float>(acc.BB, bb, tr);
+                fold_accumulate<MAXM, float>(acc.GB, rb, tr);
+            }
+            fold_accumulate<MAXM, float>(acc.GA, ra0, tr);
+            fold_accumulate<MAXM, float>(acc.GA + NB, ra1, tr);
+        }
+    }
+
+    if (in_range) {
+        a.part_nll[(size_t)chunk * a.Pp + pos] = nll;
+        float* out = a.part_acc + (size_t)chunk * NACC * a.Pp + pos;
+#pragma unroll
+        for (int i = 0; i < 3 * NTRIG; ++i) out[(size_t)(ACC_AA + i) * a.Pp] = acc.AA[i];
+#pragma unroll
+        for (int i = 0; i < 2 * NTRIG; ++i) out[(size_t)(ACC_AB + i) * a.Pp] = HAS_AB ? acc.AB[i] : 0.f;
+#pragma unroll
+        for (int i = 0; i < NTRIG; ++i) out[(size_t)(ACC_BB + i) * a.Pp] = HAS_B ? acc.BB[i] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 2 * NB; ++i) out[(size_t)(ACC_GA + i) * a.Pp] = acc.GA[i];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) out[(size_t)(ACC_GB + i) * a.Pp] = HAS_B ? acc.GB[i] : 0.f;
+    }
+}
+
+}  // namespace
+
+// FP32 pass with all moments for the non-Normal terms on a gap-free daily axis; `ps` planned over the phases
+int launch_fold_pass_generic(Workspace& ws, const PassShape& ps, int term, const float* y_scaled, int64_t ld, int i0,
+                             int i1, const int* status, cudaStream_t s) {
+    if (ps.n_active <= 0) return 0;
+    GenArgs a;
+    a.ys = y_scaled; a.ld = ld; a.T = ws.T; a.Cp = ws.Cp;
+    a.list = ps.list; a.n_active = ps.n_active; a.Pp = ps.Pp;
+    a.i0 = i0; a.i1 = i1;
+    a.n_ph = fold_phases(ws); a.chunk_len = ps.chunk_len; a.nj_max = (ws.T + NPHASE - 1) / NPHASE;
+    a.pb64 = ws.pb64; a.basis32 = ws.basis32; a.th_pass = ws.th_pass; a.status = status;
+    a.part_nll = ws.part_nll; a.part_acc = (float*)ws.part_acc;
+    const size_t smem = sizeof(float) * GEN_TILE * (2 * NH + (size_t)a.nj_max);
+    if (smem > 200 * 1024) { set_error("series too long for the phase-ordered pass (T=%d)", ws.T); return ATTRICI_EUNSUPPORTED; }
+    dim3 grid((ps.n_active + PASS_CELLS - 1) / PASS_CELLS, ps.n_chunks);
+    auto launch = [&](auto kernel) -> int {
+        ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, PASS_CELLS, smem, s>>>(a);
+        return 0;
+    };
+    switch (term) {
+        case T_GAMMA: ATTRICI_TRY(launch(fold_pass_generic_kernel<K_GAMMA>)); break;
+        case T_BETA: ATTRICI_TRY(launch(fold_pass_generic_kernel<K_BETA>)); break;
+        case T_WEIBULL: ATTRICI_TRY(launch(fold_pass_generic_kernel<K_WEIBULL>)); break;
+        case T_BERNOULLI: ATTRICI_TRY(launch(fold_pass_generic_kernel<K_BERNOULLI>)); break;
+        default: set_error("no phase-ordered generic pass for term %d", term); return ATTRICI_EINVAL;
+    }
+    ATTRICI_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace attrici

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(STEP_THREADS) fit_init_kernel(StepArgs a, int*
     if (run && ctx.lane() == 0) list_out[atomicAdd(counter, 1)] = cell;
 }
 
-__global__ void __launch_bounds__(STEP_THREADS) fit_step_kernel(StepArgs a, const int* list_in, int n_in,
+__global__ void __launch_bounds__(STEP_THREADS, 5) fit_step_kernel(StepArgs a, const int* list_in, int n_in,
                                                                 int* list_out, int* counter, int fresh_fisher) {
     __shared__ CellScratch S[STEP_WARPS];
     __shared__ HEntry tab[NTRI];
