@@ -23,6 +23,16 @@
 
 namespace attrici {
 
+// correctly rounded reciprocal without the special-case handling of an IEEE division (one rounding more than
+// x / y when used as x * rcp(y); the series and continued fractions below run to 1e-16 regardless)
+ATTRICI_HD double rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
+
 template <typename R> ATTRICI_HD R lgam(R x);
 template <> ATTRICI_HD double lgam<double>(double x) { return lgamma(x); }
 template <> ATTRICI_HD float lgam<float>(float x) { return lgammaf(x); }
@@ -96,22 +106,23 @@ ATTRICI_HD_NOINLINE double ndtri(double p) {
 // regularised incomplete gamma P(a, x), Q(a, x) and the inverse of P
 // ---------------------------------------------------------------------------------------
 // x^a e^-x / Gamma(a)
-ATTRICI_HD double gamma_prefactor(double a, double x) { return exp(a * log(x) - x - lgamma(a)); }
+// gln = lgamma(a), hoisted by callers that evaluate several times at the same shape
+ATTRICI_HD double gamma_prefactor(double a, double x, double gln) { return exp(a * log(x) - x - gln); }
 
 // series for P, converges quickly for x < a + 1
-ATTRICI_HD_NOINLINE double gamma_p_series(double a, double x) {
+ATTRICI_HD_NOINLINE double gamma_p_series(double a, double x, double gln) {
     double ap = a, del = 1.0 / a, sum = del;
     for (int n = 0; n < 2000; ++n) {
         ap += 1.0;
-        del *= x / ap;
+        del *= x * rcp(ap);
         sum += del;
         if (fabs(del) < fabs(sum) * 1e-17) break;
     }
-    return sum * gamma_prefactor(a, x);
+    return sum * gamma_prefactor(a, x, gln);
 }
 
 // modified Lentz continued fraction for Q, converges quickly for x > a + 1
-ATTRICI_HD_NOINLINE double gamma_q_cf(double a, double x) {
+ATTRICI_HD_NOINLINE double gamma_q_cf(double a, double x, double gln) {
     const double tiny = 1e-300;
     double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
     for (int i = 1; i < 2000; ++i) {
@@ -119,31 +130,35 @@ ATTRICI_HD_NOINLINE double gamma_q_cf(double a, double x) {
         b += 2.0;
         d = an * d + b;
         if (fabs(d) < tiny) d = tiny;
-        c = b + an / c;
+        c = b + an * rcp(c);
         if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
+        d = rcp(d);
         double del = d * c;
         h *= del;
         if (fabs(del - 1.0) < 1e-16) break;
     }
-    return h * gamma_prefactor(a, x);
+    return h * gamma_prefactor(a, x, gln);
 }
 
-ATTRICI_HD double gamma_p(double a, double x) {
+// P and Q with lgamma(a) supplied
+ATTRICI_HD double gamma_p_l(double a, double x, double gln) {
     if (isnan(a) || isnan(x) || a <= 0.0 || x < 0.0) return NAN;
     if (x == 0.0) return 0.0;
     if (isinf(x)) return 1.0;
-    if (x < a + 1.0) return gamma_p_series(a, x);
-    return 1.0 - gamma_q_cf(a, x);
+    if (x < a + 1.0) return gamma_p_series(a, x, gln);
+    return 1.0 - gamma_q_cf(a, x, gln);
 }
 
-ATTRICI_HD double gamma_q(double a, double x) {
+ATTRICI_HD double gamma_q_l(double a, double x, double gln) {
     if (isnan(a) || isnan(x) || a <= 0.0 || x < 0.0) return NAN;
     if (x == 0.0) return 1.0;
     if (isinf(x)) return 0.0;
-    if (x < a + 1.0) return 1.0 - gamma_p_series(a, x);
-    return gamma_q_cf(a, x);
+    if (x < a + 1.0) return 1.0 - gamma_p_series(a, x, gln);
+    return gamma_q_cf(a, x, gln);
 }
+
+ATTRICI_HD double gamma_p(double a, double x) { return gamma_p_l(a, x, lgamma(a)); }
+ATTRICI_HD double gamma_q(double a, double x) { return gamma_q_l(a, x, lgamma(a)); }
 
 // x with P(a, x) = p   (scipy.special.gammaincinv); safeguarded Halley iteration
 // x0 > 0: starting value supplied by the caller (the quantile map knows a point whose quantile is close)
@@ -178,7 +193,7 @@ ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p, double x0 = -1.0) {
     for (int it = 0; it < 60; ++it) {
         if (x <= 0.0) x = 0.5 * (lo + (isinf(hi) ? lo + 1e-300 : hi));
         // error in the better-conditioned tail
-        double err = (p < 0.5) ? gamma_p(a, x) - p : (1.0 - p) - gamma_q(a, x);
+        double err = (p < 0.5) ? gamma_p_l(a, x, gln) - p : (1.0 - p) - gamma_q_l(a, x, gln);
         if (err > 0.0) hi = x; else lo = x;
         double dens;  // dP/dx
         if (a > 1.0)
@@ -216,19 +231,21 @@ ATTRICI_HD_NOINLINE double beta_cf(double a, double b, double x) {
     double h = d;
     for (int m = 1; m < 3000; ++m) {
         int m2 = 2 * m;
-        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        // both coefficients of this double step share the factor 1 / (a + 2m)
+        const double r0 = rcp(a + m2);
+        double aa = m * (b - m) * x * rcp(qam + m2) * r0;
         d = 1.0 + aa * d;
         if (fabs(d) < tiny) d = tiny;
-        c = 1.0 + aa / c;
+        c = 1.0 + aa * rcp(c);
         if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
+        d = rcp(d);
         h *= d * c;
-        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        aa = -(a + m) * (qab + m) * x * r0 * rcp(qap + m2);
         d = 1.0 + aa * d;
         if (fabs(d) < tiny) d = tiny;
-        c = 1.0 + aa / c;
+        c = 1.0 + aa * rcp(c);
         if (fabs(c) < tiny) c = tiny;
-        d = 1.0 / d;
+        d = rcp(d);
         double del = d * c;
         h *= del;
         if (fabs(del - 1.0) < 1e-16) break;
@@ -236,15 +253,16 @@ ATTRICI_HD_NOINLINE double beta_cf(double a, double b, double x) {
     return h;
 }
 
-// returns I_x(a,b); if comp != nullptr also 1 - I_x(a,b) computed without cancellation
-ATTRICI_HD_NOINLINE double beta_i2(double a, double b, double x, double* comp) {
+// returns I_x(a,b); if comp != nullptr also 1 - I_x(a,b) computed without cancellation.
+// lnb = lgamma(a + b) - lgamma(a) - lgamma(b), hoisted by callers that evaluate several times at the same (a, b)
+ATTRICI_HD_NOINLINE double beta_i2_l(double a, double b, double x, double lnb, double* comp) {
     if (isnan(a) || isnan(b) || isnan(x) || a <= 0.0 || b <= 0.0 || x < 0.0 || x > 1.0) {
         if (comp) *comp = NAN;
         return NAN;
     }
     if (x == 0.0) { if (comp) *comp = 1.0; return 0.0; }
     if (x == 1.0) { if (comp) *comp = 0.0; return 1.0; }
-    double bt = exp(lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log1p(-x));
+    double bt = exp(lnb + a * log(x) + b * log1p(-x));
     double p, q;
     if (x < (a + 1.0) / (a + b + 2.0)) {
         p = bt * beta_cf(a, b, x) / a;
@@ -255,6 +273,10 @@ ATTRICI_HD_NOINLINE double beta_i2(double a, double b, double x, double* comp) {
     }
     if (comp) *comp = q;
     return p;
+}
+
+ATTRICI_HD double beta_i2(double a, double b, double x, double* comp) {
+    return beta_i2_l(a, b, x, lgamma(a + b) - lgamma(a) - lgamma(b), comp);
 }
 
 ATTRICI_HD double beta_i(double a, double b, double x) { return beta_i2(a, b, x, nullptr); }
@@ -291,7 +313,7 @@ ATTRICI_HD_NOINLINE double beta_i_inv(double a, double b, double p, double x0 = 
     for (int it = 0; it < 80; ++it) {
         if (!(x > 0.0) || !(x < 1.0)) x = 0.5 * (lo + hi);
         double q;
-        double pv = beta_i2(a, b, x, &q);
+        double pv = beta_i2_l(a, b, x, afac, &q);
         double err = (p < 0.5) ? pv - p : (1.0 - p) - q;
         if (err > 0.0) hi = x; else lo = x;
         double dens = exp(a1 * log(x) + b1 * log1p(-x) + afac);
