@@ -414,6 +414,28 @@ def test_full_length_series_properties():
     np.testing.assert_allclose(cfact[:, 5].cpu().numpy(), ref["cfact"], rtol=1e-5, equal_nan=True)
 
 
+def test_global_land_size_batch():
+    """BASELINE configs[4] on one GPU: 67 420 cells x 43 464 days in one batch (2.9e9 elements: offsets beyond
+    32 bits).  Cells at the start, middle and end must agree with the same cells detrended as a small batch."""
+    T, C = synthetic.DAYS_1901_2019, 67420
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~45 GB of device memory")
+    y = synthetic.tas_tile_torch(C, T, device=DEV, nan_fraction=0.001)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    s = CellBatchSolver("tas", device=DEV)
+    big = s.detrend_device(y, days, gmt, keep_scaled=False)
+    assert (big["fit"].status == 0).all()
+    pick = [0, 1, 33709, 33710, C - 2, C - 1]
+    ysub = y[:, pick].contiguous()
+    small = CellBatchSolver("tas", device=DEV).detrend_device(ysub, days, gmt, keep_scaled=False)
+    np.testing.assert_allclose(host(big["fit"].params[pick]), host(small["fit"].params), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(host(big["fit"].logp[pick]), host(small["fit"].logp), rtol=1e-12)
+    np.testing.assert_allclose(host(big["cfact"][:, pick]), host(small["cfact"]), rtol=1e-9, equal_nan=True)
+    assert torch.equal(big["replaced"][:, pick], small["replaced"])
+    assert torch.equal(torch.isnan(big["cfact"]), torch.isnan(y))
+
+
 def test_model_cuda_plugin_interface():
     """ModelCuda behind the reference's Model interface: fit / estimate_logp / estimate_distribution."""
     from dataclasses import dataclass
