@@ -213,6 +213,9 @@ def run_cuda(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     torch.cuda.set_device(local_rank)
     device = f"cuda:{local_rank}"
+    from attrici_b200.detrend import bind_to_gpu_cpus
+
+    bound_cpus = bind_to_gpu_cpus(local_rank)  # pinned host buffers on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(device))
 
@@ -342,7 +345,7 @@ def run_cuda(args):
                        "passes_per_cell_mean": float(n_pass.mean()), "passes_per_cell_max": int(n_pass.max()),
                        "converged_fraction": float((status == 0).mean())},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "slab_cells": args.slab},
+                    "steps": e2e_steps, "slab_cells": args.slab, "cpus_bound_per_rank": bound_cpus},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak,

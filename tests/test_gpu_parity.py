@@ -414,6 +414,23 @@ def test_full_length_series_properties():
     np.testing.assert_allclose(cfact[:, 5].cpu().numpy(), ref["cfact"], rtol=1e-5, equal_nan=True)
 
 
+@pytest.mark.parametrize("T", [400, 1461, 1462])
+def test_series_shorter_than_one_phase_cycle(T):
+    """Phase folding with fewer days than phases (every phase holds at most one day) and right at the 1461-day
+    boundary."""
+    C = 12
+    y = synthetic.tas_cells(C, T, seed=17)
+    y[5:40, 3] = np.nan
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    s = CellBatchSolver("tas", device=DEV)
+    out = s.detrend_device(dev(y), days, gmt, keep_scaled=False)
+    assert (host(out["fit"].status) == 0).all()
+    for j in (0, 3, C - 1):
+        ref = oracle.detrend_cell("tas", y[:, j], gmt, days, helpers.MODES)
+        np.testing.assert_allclose(host(out["fit"].logp)[j], ref["logp"], rtol=1e-9)
+        np.testing.assert_allclose(host(out["cfact"])[:, j], ref["cfact"], rtol=1e-5, equal_nan=True)
+
+
 def test_global_land_size_batch():
     """BASELINE configs[4] on one GPU: 67 420 cells x 43 464 days in one batch (2.9e9 elements: offsets beyond
     32 bits).  Cells at the start, middle and end must agree with the same cells detrended as a small batch."""
