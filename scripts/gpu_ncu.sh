@@ -16,8 +16,8 @@ ncu --set full --clock-control none --import-source on -k regex:"$KREGEX" -s $SK
 echo "ncu full exit $?"
 ncu -i /tmp/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
 ncu -i /tmp/prof_$TAG.ncu-rep --page details --csv > gpurun_out/prof_${TAG}_details.csv 2>/dev/null
-ncu -i /tmp/prof_$TAG.ncu-rep --page source --csv > gpurun_out/prof_${TAG}_source.csv 2>/dev/null
+if [ "${NOSRC:-0}" != "1" ]; then ncu -i /tmp/prof_$TAG.ncu-rep --page source --csv > gpurun_out/prof_${TAG}_source.csv 2>/dev/null; fi
 SZ=$(stat -c %s /tmp/prof_$TAG.ncu-rep)
 echo "rep size $SZ"
-if [ "$SZ" -lt 30000000 ]; then cp /tmp/prof_$TAG.ncu-rep gpurun_out/; fi
+if [ "$SZ" -lt 30000000 ] && [ "${NOSRC:-0}" != "1" ]; then cp /tmp/prof_$TAG.ncu-rep gpurun_out/; fi
 ls -la gpurun_out
