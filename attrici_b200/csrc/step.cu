@@ -28,10 +28,12 @@ struct WarpCtx {
 };
 
 // (H + lam D) delta = -g with lane = row: the lane's row of H (then of the Cholesky factor L) lives in registers,
-// the factorisation is right-looking (column j is scaled, then every later column k takes its rank-1 update with
-// L[k][j] fetched from lane k by a shuffle), the forward substitution is column-oriented, the backward one a warp
-// sum per row.  Same mathematics as lm_solve() (step_impl.cuh) in about a third of the instructions; returns false
-// if a pivot is not positive.  Every loop is fully unrolled so that the row stays in registers.
+// the factorisation is right-looking: column j is scaled and published through shared memory (S.y), then every
+// later column k takes its rank-1 update with L[k][j] read back as a warp-wide broadcast.  The forward
+// substitution is column-oriented in registers; for the backward one the rows of L are parked in S.L so that
+// lane k can read L[i][k] while delta[i] is broadcast.  Same mathematics as lm_solve() (step_impl.cuh) in about a
+// quarter of the instructions; returns false if a pivot is not positive.  Every loop is fully unrolled so that
+// the row stays in registers.
 __device__ bool WarpCtx::solve(CellScratch& S, double lam) const {
     constexpr unsigned FULL = 0xffffffffu;
     const int l = lane();
@@ -45,6 +47,7 @@ __device__ bool WarpCtx::solve(CellScratch& S, double lam) const {
     }
     double inv_diag = 1.0;   // 1 / L[l][l]
     bool ok = true;
+    double* col = S.y;       // column j of L, indexed by row (free until the substitutions)
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
         const double d = __shfl_sync(FULL, a[j], j);
@@ -52,13 +55,21 @@ __device__ bool WarpCtx::solve(CellScratch& S, double lam) const {
         const double ljj = sqrt(d), inv = 1.0 / ljj;
         if (l == j) { a[j] = ljj; inv_diag = inv; }
         else a[j] *= inv;                                  // L[l][j] for l > j (rows l < j hold zeros)
+        if (j + 1 < NP) {
+            if (row) col[l] = a[j];
+            __syncwarp();
 #pragma unroll
-        for (int k = j + 1; k < NP; ++k) {
-            const double lkj = __shfl_sync(FULL, a[j], k);
-            a[k] = fma(-a[j], lkj, a[k]);                  // only entries k <= l of a row are ever read
+            for (int k = j + 1; k < NP; ++k) a[k] = fma(-a[j], col[k], a[k]);   // only entries k <= l are ever read
+            __syncwarp();
         }
     }
     if (!ok) return false;
+    // rows of L for the backward substitution
+    if (row) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+            if (k <= l) S.L[l * (l + 1) / 2 + k] = a[k];
+    }
     // L y = -g, column-oriented: once y[i] is known every later row subtracts L[.][i] y[i]
     double r = row ? -S.g[l] : 0.0, y = 0.0;
 #pragma unroll
@@ -67,14 +78,14 @@ __device__ bool WarpCtx::solve(CellScratch& S, double lam) const {
         if (l == i) y = yi;
         if (l > i) r = fma(-a[i], yi, r);
     }
-    // L^T delta = y, rows from the last: delta[i] = (y[i] - sum_{k > i} L[k][i] delta[k]) / L[i][i]
-    double delta = 0.0;
+    __syncwarp();
+    // L^T delta = y, column-oriented from the last row: delta[i] = r[i] / L[i][i], then r[k] -= L[i][k] delta[i], k < i
+    double rb = y, delta = 0.0;
 #pragma unroll
     for (int i = NP - 1; i >= 0; --i) {
-        double t = (row && l > i) ? a[i] * delta : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-        if (l == i) delta = (y - t) * inv_diag;
+        const double di = __shfl_sync(FULL, rb * inv_diag, i);
+        if (l == i) delta = di;
+        if (l < i) rb = fma(-S.L[i * (i + 1) / 2 + l], di, rb);
     }
     if (row) S.delta[l] = delta;
     __syncwarp();
