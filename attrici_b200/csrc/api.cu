@@ -146,6 +146,7 @@ int run_pass(Workspace& ws, int fold, const int* list, int n_active, int term, b
              bool exact, const float* y_scaled, int64_t ld, int i0, int i1, const int* status, cudaStream_t s,
              cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr) {
     if (fold == FOLD_STREAM && !fp64 && mode != PASS_NLL) {
+        mode = PASS_FULL;
         PassShape ps = plan_pass(ws, list, n_active, 0, fold_phases(ws), false);
         if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
         ATTRICI_TRY(launch_fold_pass_generic(ws, ps, term, y_scaled, ld, i0, i1, status, s));
@@ -159,7 +160,7 @@ int run_pass(Workspace& ws, int fold, const int* list, int n_active, int term, b
         if (e1) ATTRICI_CUDA_CHECK(cudaEventRecord(e1, s));
         return launch_reduce(ws, ps, true, mode, s, status);
     }
-    if (mode == PASS_GRAD) mode = PASS_FULL;
+    if (mode == PASS_GRAD || mode == PASS_FLAT) mode = PASS_FULL;
     PassShape ps = plan_pass(ws, list, n_active, i0, i1, fp64);
     if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
     ATTRICI_TRY(launch_pass(ws, ps, term, fp64, mode != PASS_NLL, y_scaled, ld, i0, i1, status, s));
@@ -207,8 +208,10 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
                 g_profile.cell_days += (double)running * (double)(i1 - i0);
             }
             const bool fresh = fold != FOLD_SUMS || (it + b < FISHER_PASSES) || (it + b >= FISHER_PASSES + CHORD_PASSES);
+            // pass 0 evaluates the point fit_init leaves: only the two intercepts are non-zero
+            const int mode = (it + b == 0) ? PASS_FLAT : (fresh ? PASS_FULL : PASS_GRAD);
             ATTRICI_TRY(run_pass(ws, fold, use_list ? ws.list[cur] : nullptr, use_list ? running : ws.C, sp.term, fp64,
-                                 fresh ? PASS_FULL : PASS_GRAD, false, y_scaled, ld, i0, i1,
+                                 mode, false, y_scaled, ld, i0, i1,
                                  use_list ? nullptr : ws.status, s, e0, e1));
             if (block == 1)
                 ATTRICI_TRY(launch_fit_step(ws, sp, ws.list[cur], running, ws.list[cur ^ 1], ws.counters + (cur ^ 1), s, fresh));

@@ -205,7 +205,8 @@ int launch_pass_mma(Workspace& ws, const PassShape& ps, const float* y_scaled, i
 // phase-folded pass of the Normal family over the per-phase sums of prep (fold.cu); `ps` is planned over
 // [0, fold_phases(ws)); partials are FP64
 // what a pass produces: the nll only, nll + gradient moments, or nll + gradient + Fisher moments
-enum { PASS_NLL = 0, PASS_GRAD = 1, PASS_FULL = 2 };
+// PASS_FLAT = PASS_FULL at a point whose only non-zero coefficients are the two intercepts (folded Normal pass)
+enum { PASS_NLL = 0, PASS_GRAD = 1, PASS_FULL = 2, PASS_FLAT = 3 };
 int fold_phases(const Workspace& ws);
 int launch_fold_pass(Workspace& ws, const PassShape& ps, int mode, bool exact, const int* status, cudaStream_t s);
 // phase-ordered FP32 pass (all moments) of the Gamma / Weibull / Beta / Bernoulli terms over the scaled series

@@ -63,11 +63,16 @@ template <int K, typename A> __device__ __forceinline__ void fold_accumulate(A* 
     }
 }
 
-// MODE 0: nll only; 1: nll + gradient moments (the Fisher moments of an earlier pass are reused); 2: everything
+// MODE 0: nll only; 1: nll + gradient moments (the Fisher moments of an earlier pass are reused); 2: everything;
+// 3: everything at a flat point (only the two intercepts are non-zero, the state fit_init leaves): mu and sigma do
+// not depend on the phase, so there is no predictor chain and no exp per phase, and for cells without missing
+// days the Fisher moments are e^{-2c} times sums of the phase rows alone, formed once per CTA
 template <int MODE, typename RW>
-__global__ void __launch_bounds__(PASS_CELLS, MODE == 2 ? 2 : 3) fold_pass_normal_kernel(FoldArgs a) {
+__global__ void __launch_bounds__(PASS_CELLS, MODE >= 2 ? 2 : 3) fold_pass_normal_kernel(FoldArgs a) {
+    constexpr bool FLAT = MODE == 3;
     constexpr bool MOMENTS = MODE >= 1;   // gradient moments
     constexpr bool FISHER = MODE >= 2;    // Fisher moments
+    __shared__ double flat_sums[FLAT ? 4 * NTRIG : 1];   // sum over the chunk's phases of {n, Sg, Sgg, 2 n} x trig17
     // phase rows of the current tile: FP64 {n, cos 1..8, sin 1..8, sum gmt, sum gmt^2, 0} and an RW copy of the
     // 16 trig columns for the Fisher moments; per-thread ring of the three sums of the next FOLD_RING phases
     __shared__ __align__(16) double tile[FOLD_TILE * B_STRIDE];
@@ -89,9 +94,11 @@ __global__ void __launch_bounds__(PASS_CELLS, MODE == 2 ? 2 : 3) fold_pass_norma
 
     double thA[NA], thB[NB];
 #pragma unroll
-    for (int i = 0; i < NA; ++i) thA[i] = active ? a.th_pass[(size_t)i * a.Cp + cell] : 0.0;
+    for (int i = 0; i < NA; ++i) thA[i] = (active && (!FLAT || i == 0)) ? a.th_pass[(size_t)i * a.Cp + cell] : 0.0;
 #pragma unroll
-    for (int i = 0; i < NB; ++i) thB[i] = active ? a.th_pass[(size_t)(NA + i) * a.Cp + cell] : 0.0;
+    for (int i = 0; i < NB; ++i) thB[i] = (active && (!FLAT || i == 0)) ? a.th_pass[(size_t)(NA + i) * a.Cp + cell] : 0.0;
+    const double e2_flat = FLAT ? exp(-2.0 * thB[0]) : 0.0;
+    double flat_acc = 0.0;   // threads 0 .. 67: one of the 4 x 17 sums each, gathered tile by tile
 
     RW AA[3 * NTRIG], BB[NTRIG];
     double GA[2 * NB], GB[NB];
@@ -137,6 +144,15 @@ __global__ void __launch_bounds__(PASS_CELLS, MODE == 2 ? 2 : 3) fold_pass_norma
             if (FISHER && c >= 1 && c <= 2 * NH) trig_w[r * 2 * NH + (c - 1)] = (RW)v;
         }
         __syncthreads();
+        if (FLAT && tid < 4 * NTRIG) {
+            const int p = tid / NTRIG, j = tid % NTRIG;
+            const int wcol = p == 0 ? 0 : (p == 1 ? 1 + 2 * NH : (p == 2 ? 2 + 2 * NH : 0));
+            const double wscale = p == 3 ? 2.0 : 1.0;
+            for (int r = 0; r < n_rows; ++r) {
+                const double* row = tile + r * B_STRIDE;
+                flat_acc = fma(wscale * row[wcol], j == 0 ? 1.0 : row[j], flat_acc);
+            }
+        }
         if (!warp_active) {   // keep the group accounting of this warp's (empty) ring consistent
             for (int r = 0; r < n_rows; ++r) issue(q0 + r + FOLD_RING - 1);
             continue;
@@ -155,25 +171,30 @@ __global__ void __launch_bounds__(PASS_CELLS, MODE == 2 ? 2 : 3) fold_pass_norma
                 n = gs_p[oc]; sg = gs_p[oc + cp]; sgg = gs_p[oc + 2 * cp];
             }
             if (!active) n = sg = sgg = 0.0;
-            // a_d, b_d, c_d: two chains each (cos / sin halves) to shorten the dependent FMA depth
-            double ac = thA[0], as = 0.0, bc = thA[1], bs = 0.0, cc = thB[0], cs = 0.0;
+            double av, bv, cv, e2;
+            if (FLAT) {
+                av = thA[0]; bv = 0.0; cv = thB[0]; e2 = e2_flat;
+            } else {
+                // a_d, b_d, c_d: two chains each (cos / sin halves) to shorten the dependent FMA depth
+                double ac = thA[0], as = 0.0, bc = thA[1], bs = 0.0, cc = thB[0], cs = 0.0;
 #pragma unroll
-            for (int k = 0; k < MAXM; ++k) {
-                const double ck = row[1 + k], sk = row[1 + NH + k];
-                ac = fma(thA[2 + k], ck, ac);
-                as = fma(thA[2 + MAXM + k], sk, as);
-                bc = fma(thA[2 + 2 * MAXM + k], ck, bc);
-                bs = fma(thA[2 + 3 * MAXM + k], sk, bs);
-                cc = fma(thB[1 + k], ck, cc);
-                cs = fma(thB[1 + MAXM + k], sk, cs);
+                for (int k = 0; k < MAXM; ++k) {
+                    const double ck = row[1 + k], sk = row[1 + NH + k];
+                    ac = fma(thA[2 + k], ck, ac);
+                    as = fma(thA[2 + MAXM + k], sk, as);
+                    bc = fma(thA[2 + 2 * MAXM + k], ck, bc);
+                    bs = fma(thA[2 + 3 * MAXM + k], sk, bs);
+                    cc = fma(thB[1 + k], ck, cc);
+                    cs = fma(thB[1 + MAXM + k], sk, cs);
+                }
+                av = ac + as; bv = bc + bs; cv = cc + cs;
+                e2 = exp(-2.0 * cv);
             }
-            const double av = ac + as, bv = bc + bs, cv = cc + cs;
-            const double e2 = exp(-2.0 * cv);
             const double R0 = c_sy - av * n - bv * sg;
             const double R1 = c_syg - av * sg - bv * sgg;
             const double Q = c_syy - av * c_sy - bv * c_syg - av * R0 - bv * R1;
             nll += n * (cv + 0.91893853320467274178) + 0.5 * e2 * Q;
-            if (FISHER) {
+            if (FISHER && (!FLAT || own_g)) {   // flat point, no missing day: formed from flat_sums after the loop
                 const RW* tw = trig_w + r * 2 * NH;
                 fold_accumulate<NH, RW>(AA, (RW)(e2 * n), tw);
                 fold_accumulate<NH, RW>(AA + NTRIG, (RW)(e2 * sg), tw);
@@ -188,18 +209,26 @@ __global__ void __launch_bounds__(PASS_CELLS, MODE == 2 ? 2 : 3) fold_pass_norma
         }
     }
     asm volatile("cp.async.wait_group 0;\n" ::);
+    if (FLAT) {
+        if (tid < 4 * NTRIG) flat_sums[tid] = flat_acc;
+        __syncthreads();
+    }
 
     if (in_range) {
         a.part_nll[(size_t)chunk * a.Pp + pos] = nll;
         if (MOMENTS) {
             double* out = a.part_acc + (size_t)chunk * NACC * a.Pp + pos;
             if (FISHER) {
+                const bool from_sums = FLAT && !own_g;
+                const double fs = active ? 1.0 : 0.0;
 #pragma unroll
-                for (int i = 0; i < 3 * NTRIG; ++i) out[(size_t)(ACC_AA + i) * a.Pp] = (double)AA[i];
+                for (int i = 0; i < 3 * NTRIG; ++i)
+                    out[(size_t)(ACC_AA + i) * a.Pp] = from_sums ? fs * e2_flat * flat_sums[i] : (double)AA[i];
 #pragma unroll
                 for (int i = 0; i < 2 * NTRIG; ++i) out[(size_t)(ACC_AB + i) * a.Pp] = 0.0;
 #pragma unroll
-                for (int i = 0; i < NTRIG; ++i) out[(size_t)(ACC_BB + i) * a.Pp] = (double)BB[i];
+                for (int i = 0; i < NTRIG; ++i)
+                    out[(size_t)(ACC_BB + i) * a.Pp] = from_sums ? fs * flat_sums[3 * NTRIG + i] : (double)BB[i];
             }
 #pragma unroll
             for (int i = 0; i < 2 * NB; ++i) out[(size_t)(ACC_GA + i) * a.Pp] = GA[i];
@@ -233,7 +262,8 @@ int launch_fold_pass(Workspace& ws, const PassShape& ps, int mode, bool exact, c
     a.part_nll = ws.part_nll;
     a.part_acc = (double*)ws.part_acc;
     dim3 grid((ps.n_active + PASS_CELLS - 1) / PASS_CELLS, ps.n_chunks);
-    if (mode == PASS_NLL) fold_pass_normal_kernel<0, float><<<grid, PASS_CELLS, 0, s>>>(a);
+    if (mode == PASS_FLAT && !exact) fold_pass_normal_kernel<3, float><<<grid, PASS_CELLS, 0, s>>>(a);
+    else if (mode == PASS_NLL) fold_pass_normal_kernel<0, float><<<grid, PASS_CELLS, 0, s>>>(a);
     else if (mode == PASS_GRAD) fold_pass_normal_kernel<1, float><<<grid, PASS_CELLS, 0, s>>>(a);
     else if (exact) fold_pass_normal_kernel<2, double><<<grid, PASS_CELLS, 0, s>>>(a);
     else fold_pass_normal_kernel<2, float><<<grid, PASS_CELLS, 0, s>>>(a);

@@ -340,7 +340,7 @@ int launch_fit_store(Workspace& ws, const StepParams& sp, cudaStream_t s) {
 int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, int mode, cudaStream_t s, const int* status) {
     if (ps.n_active <= 0) return 0;
     // rows reduced: everything, the gradient moments + nll, or only row NACC (the sum of the day terms of the nll)
-    const int row0 = mode == PASS_FULL ? 0 : (mode == PASS_GRAD ? ACC_GA : NACC);
+    const int row0 = (mode == PASS_FULL || mode == PASS_FLAT) ? 0 : (mode == PASS_GRAD ? ACC_GA : NACC);
     dim3 grid((ps.n_active + RED_THREADS - 1) / RED_THREADS, (NACC + 1 - row0 + RED_GROUP - 1) / RED_GROUP);
     if (fp64)
         reduce_partials_kernel<double><<<grid, RED_THREADS, 0, s>>>(ps.list, ps.n_active, ps.Pp, ws.Cp, ps.n_chunks,
