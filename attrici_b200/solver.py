@@ -120,7 +120,9 @@ class CellBatchSolver:
         T, C_, ld = self._check_series(y, "y")
         self._need_basis(T, C_)
         i0, i1 = (0, T) if fit_window is None else fit_window
-        ys = torch.empty((T, C_), dtype=torch.float32, device=self.device) if keep_scaled else None
+        # the C ABI has one leading dimension for y and y_scaled: the scaled series takes the layout of its input
+        ys = (torch.empty_strided((T, C_), (ld, 1), dtype=torch.float32, device=self.device)
+              if keep_scaled else None)
         scaling = torch.empty((C_, 2), dtype=torch.float64, device=self.device)
         ws = self._ws
         with torch.cuda.device(self.device):

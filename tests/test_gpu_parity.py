@@ -414,6 +414,28 @@ def test_full_length_series_properties():
     np.testing.assert_allclose(cfact[:, 5].cpu().numpy(), ref["cfact"], rtol=1e-5, equal_nan=True)
 
 
+@pytest.mark.parametrize("offset,width", [(3, 41), (4, 64), (1, 130)])
+def test_strided_unaligned_input_matches_contiguous(offset, width):
+    """A column window of a wider array (leading dimension > cells, base pointer off the 8 / 16-byte grid): the
+    vectorised kernels must fall back to scalar accesses and produce the same bits."""
+    T = 3000
+    wide = synthetic.tas_cells(width + 7, T, seed=23, nan_fraction=0.05)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    wide_d = dev(wide)
+    window = wide_d[:, offset:offset + width]
+    assert window.stride(0) == width + 7 and window.data_ptr() % 16 != 0 or offset % 4 == 0
+    a = CellBatchSolver("tas", device=DEV).detrend_device(window, days, gmt, keep_scaled=False)
+    b = CellBatchSolver("tas", device=DEV).detrend_device(window.contiguous(), days, gmt, keep_scaled=False)
+    assert torch.equal(a["fit"].params, b["fit"].params)
+    assert torch.equal(a["scaling"], b["scaling"])
+    assert np.array_equal(host(a["cfact"]), host(b["cfact"]), equal_nan=True)
+    assert torch.equal(a["replaced"], b["replaced"])
+    c = CellBatchSolver("tas", device=DEV).detrend_device(window, days, gmt)          # keeps y_scaled
+    d = CellBatchSolver("tas", device=DEV).detrend_device(window.contiguous(), days, gmt)
+    assert np.array_equal(host(c["y_scaled"]), host(d["y_scaled"]), equal_nan=True)
+    assert np.array_equal(host(c["cfact"]), host(a["cfact"]), equal_nan=True)
+
+
 @pytest.mark.parametrize("T", [400, 1461, 1462])
 def test_series_shorter_than_one_phase_cycle(T):
     """Phase folding with fewer days than phases (every phase holds at most one day) and right at the 1461-day
