@@ -350,6 +350,30 @@ def test_host_pipeline_matches_device_path():
     assert np.array_equal(host(a["scaling"]), b["scaling"].numpy())
 
 
+@pytest.mark.parametrize("variable", ["pr", "hurs"])
+def test_host_pipeline_other_families(variable):
+    """attrici_detrend_host for families that keep the scaled series and (pr) consume per-cell seeds."""
+    T, C = 2600, 70
+    y = synthetic.GENERATORS[variable](C, T)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    lat, lon = synthetic.tile_coordinates(7, 10)
+    seeds = cell_seeds(0, lat, lon) if variable == "pr" else None
+    a = CellBatchSolver(variable, device=DEV).detrend_device(dev(y), days, gmt, seeds=seeds)
+    b = CellBatchSolver(variable, device=DEV).detrend_host(torch.from_numpy(y).pin_memory(), days, gmt, seeds=seeds,
+                                                           slab_cells=32)  # 32 + 32 + 6
+    assert np.array_equal(host(a["fit"].status), b["status"].numpy())
+    # FP32 day arithmetic: the time chunking differs between the 70-cell batch and the 32-cell slabs, so the two
+    # runs stop at points that agree to the accuracy of the float32 objective, not bit for bit
+    np.testing.assert_allclose(host(a["fit"].params), b["params"].numpy(), rtol=0, atol=5e-6)
+    ca, cb = host(a["cfact"]), b["cfact"].numpy()
+    assert np.array_equal(np.isnan(ca), np.isnan(cb))
+    same_zero = (ca == 0) == (cb == 0)
+    assert (~same_zero).sum() <= 2          # pr: a day within the fit tolerance of the dry / wet boundary
+    m = same_zero & ~np.isnan(ca)
+    np.testing.assert_allclose(ca[m], cb[m], rtol=2e-5)
+    assert (host(a["replaced"]) != b["replaced"].numpy()).sum() <= 2
+
+
 def test_host_pipeline_short_first_slab():
     """Slabs of >= 1024 cells start with a quarter-size slab (pipeline fill); every cell must still land in its
     own column."""
