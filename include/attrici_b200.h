@@ -130,9 +130,13 @@ ATTRICI_API int attrici_build_basis(void* workspace, size_t workspace_bytes, int
  * replaces create_variable -> <Variable>.__init__ (attrici/variables.py:92-111, 354-403, 565-591,
  * 619-623, 712-732, 760-780) and the Inf -> NaN step of attrici/detrend.py:311.
  *   y[T x ld]         float32 observations
- *   y_scaled[T x ld]  float32 out; NaN = masked / dry / missing (bit-exact float32 arithmetic)
+ *   y_scaled[T x ld]  float32 out; NaN = masked / dry / missing (bit-exact float32 arithmetic).
+ *                     May be NULL for the Normal family: the scaled series is then not materialised (the fit
+ *                     runs on the per-phase sums gathered here, the quantile map recomputes the values)
  *   scaling[C x 2]    float64 out: {datamin, scale} (datamin = 0 where the reference has none)
- * Also gathers the per-cell start values / phase origins of the fit window [i0, i1) into the workspace. */
+ * Also gathers, into the workspace, the per-cell start values / phase origins of the fit window [i0, i1) and,
+ * for the Normal family, the per-phase sums {sum y, sum y^2, sum y gmt} (FP64) of the phase-folded likelihood
+ * passes (used when the time axis is gap-free daily, as attrici_build_basis found). */
 ATTRICI_API int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
                             const float* y, float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
                             double* scaling, void* stream);
@@ -149,7 +153,9 @@ ATTRICI_API int attrici_nll_grad(void* workspace, size_t workspace_bytes, const 
 /* batched MAP fit: Fisher-scoring Levenberg-Marquardt with per-cell convergence masks.
  * replaces ModelScipy.fit (model_scipy.py:505-527: scipy L-BFGS-B with finite differences).
  *   params[C x P] out, logp[C] out (log posterior, FP64 evaluation at the returned point),
- *   status[C] out, n_pass[C] out (nullable).  Synchronises `stream` internally between passes. */
+ *   status[C] out, n_pass[C] out (nullable).  Synchronises `stream` internally (once per block of passes).
+ *   y_scaled may be NULL for the Normal family on a gap-free daily axis when attrici_prep_scale_mask ran on
+ *   this workspace with the same window (the passes then read the per-phase sums); otherwise ATTRICI_EINVAL. */
 ATTRICI_API int attrici_fit_batch(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
                       const float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
                       const attrici_fit_options_t* opts, double* params, double* logp, int32_t* status,
@@ -160,7 +166,8 @@ ATTRICI_API int attrici_fit_batch(void* workspace, size_t workspace_bytes, const
  * Variable.quantile_mapping and overrides (attrici/variables.py:287-303, 422-480, 645-653, 691-698),
  * attrici/distributions.py:81-216, rescale (variables.py:71-89, 114-131, 483-486) and the NaN/Inf
  * replacement of attrici/detrend.py:392-411.
- *   y, y_scaled [T x ld]   ; params[C x P] ; scaling[C x 2]
+ *   y, y_scaled [T x ld]   ; params[C x P] ; scaling[C x 2]     (y_scaled may be NULL for the Normal family:
+ *                            it is recomputed from y and scaling with the float32 arithmetic of the scaling step)
  *   seeds[C] uint32  (pr only; attrici/detrend.py:285, consumed by np.random.rand in variables.py:458)
  *   cfact[T x ld_out] float64 out ; replaced[T x ld_out] uint8 out (nullable) ;
  *   cfact_scaled[T x ld_out] float64 out (nullable) */
