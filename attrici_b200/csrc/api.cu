@@ -135,7 +135,7 @@ int fold_applies(Workspace& ws, int term, int i0, int i1, cudaStream_t s, int* f
         // (tasrange fit 2.1x, pr 1.5x); the Beta and Weibull terms spend their time in per-day special functions and
         // run faster in the day-ordered kernel, which keeps more warps resident
         if (term == T_NORMAL) *fold = FOLD_SUMS;
-        else if (term == T_GAMMA || term == T_BERNOULLI) *fold = FOLD_STREAM;
+        else *fold = FOLD_STREAM;
     }
     return 0;
 }

@@ -87,6 +87,7 @@ struct Workspace {
     int* miss;         // [Cp] 1: the cell has missing days inside the fit window
     double* ystat;     // [NPHASE][3][Cp] per-phase sums {y, y^2, y gmt} over the cell's valid window days (Normal only)
     double* gstat;     // [NPHASE][3][Cp] per-phase {n, sum gmt, sum gmt^2} of cells with missing days (Normal only)
+    float* psums;      // [NPHASE][11][Cp] per-phase sums of the day terms (two-stage pass of the other families)
 
     static size_t align(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -143,6 +144,7 @@ struct Workspace {
         miss = (int*)take(4 * c);
         ystat = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)NPHASE * c) : nullptr;
         gstat = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)NPHASE * c) : nullptr;
+        psums = (family != ATTRICI_NORMAL) ? (float*)take(4 * 11 * (size_t)NPHASE * c) : nullptr;
         bytes = off;
         return off;
     }

@@ -273,37 +273,44 @@ int launch_fold_pass(Workspace& ws, const PassShape& ps, int mode, bool exact, c
 
 
 // ---------------------------------------------------------------------------------------------------------
-// Phase-folded pass of the other families (Gamma, Weibull, Beta, Bernoulli).
+// Phase-folded pass of the other families (Gamma, Weibull, Beta, Bernoulli), in two stages.
 //
 // Their likelihoods are not functions of a few sums, so the series is still streamed once per pass, but in phase
 // order: for the days t = d + 1461 j of one phase the 27-term predictor sums collapse to
 //     eta_A(t) = a_d + gmt(t) b_d ,  eta_B(t) = c_d ,
 // everything that depends on eta_B only (e^c, lgamma / digamma / trigamma of the Gamma shape) is evaluated once
-// per phase, and the 129 moment accumulators of pass.cu are updated once per phase from ten per-phase sums
-//     sum w_AA {1, g, g^2}, sum w_AB {1, g}, sum w_BB, sum r_A {1, g}, sum r_B, sum nll
-// instead of once per day: a day costs one load, one FMA, the family's day terms and ten accumulations, against
-// 27 + 129 FMAs in pass.cu.  FP32 day arithmetic with FP64 accumulation of the nll, as pass_kernel<KIND, float>.
+// per phase, and a day contributes to eleven per-phase sums
+//     sum w_AA {1, g, g^2}, sum w_AB {1, g}, sum w_BB, sum r_A {1, g}, sum r_B, sum nll, (count)
+// instead of 129 moment accumulators.
+//   stage 1  fold_stream_sums_kernel<KIND>: thread = cell, CTA = 128 cells x <= 16 phases; one load, one FMA, the
+//            family's day terms and ten accumulations per day; ~60 registers, so enough warps stay resident to hide
+//            the latency of the per-day special functions (the day-ordered pass.cu kernel carries the 129
+//            accumulators in registers and runs 8 warps per SM).  Writes psums[phase][11][cell] (FP32).
+//   stage 2  fold_sums_moments_kernel: folds the per-phase sums into the 129 moments of pass.cu with the trig
+//            columns of each phase (once per phase instead of once per day) and writes the chunk partials, so the
+//            reduction and the Fisher-scoring step are unchanged.
+// FP32 day arithmetic with FP64 accumulation of the nll across phases, as pass_kernel<KIND, float>.
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
-struct GenArgs {
+constexpr int NSUM = 11;        // per-phase sums: wAA {1,g,g2}, wAB {1,g}, wBB, rA {1,g}, rB, nll, spare
+constexpr int ST_MAXPH = 16;    // phases per CTA of stage 1
+constexpr int ST_U = 10;        // days per batch of loads
+
+struct StreamArgs {
     const float* ys;
     int64_t ld;
     int T, Cp;
     const int* list;
     int n_active, Pp;
     int i0, i1;
-    int n_ph, chunk_len, nj_max;
+    int n_ph, ph_len, njp;   // njp: days per phase rounded up to whole batches
     const double* pb64;      // phase rows (trig columns)
     const float* basis32;    // gmt(t) = basis32[t * B_STRIDE]
     const double* th_pass;
     const int* status;
-    double* part_nll;        // [chunk][Pp]
-    float* part_acc;         // [chunk][NACC][Pp]
+    float* psums;            // [n_ph][NSUM][Pp]
 };
-
-constexpr int GEN_TILE = 32;   // phases per shared-memory tile
-constexpr int GEN_U = 8;       // days per batch of loads
 
 // terms of the Gamma family that depend on eta_B only (shape a = nu^2 = e^{2 eta_B})
 struct GammaPhase { float a, lna, lgam_a, psi_a, wbb; };
@@ -328,71 +335,62 @@ __device__ __forceinline__ DayTerms<float> gen_day(float y, float ea, float eb, 
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_generic_kernel(GenArgs a) {
+__global__ void __launch_bounds__(PASS_CELLS) fold_stream_sums_kernel(StreamArgs a) {
     constexpr bool HAS_B = (KIND != K_BERNOULLI);
     constexpr bool HAS_AB = (KIND == K_WEIBULL || KIND == K_BETA);
-    extern __shared__ __align__(16) unsigned char gen_smem[];
-    float* trig = reinterpret_cast<float*>(gen_smem);      // [GEN_TILE][16] cos 1..8, sin 1..8
-    float* g_s = trig + GEN_TILE * 2 * NH;                 // [GEN_TILE][nj_max] gmt of day d + 1461 j
+    extern __shared__ __align__(16) unsigned char st_smem[];
+    float* coef = reinterpret_cast<float*>(st_smem);       // [NP][128]
+    float* trig = coef + NP * PASS_CELLS;                  // [ST_MAXPH][8]: cos 1..4, sin 1..4
+    float* g_s = trig + ST_MAXPH * 2 * MAXM;               // [ST_MAXPH][njp] gmt of day d + 1461 j
 
     const int tid = threadIdx.x;
     const int pos = blockIdx.x * PASS_CELLS + tid;
-    const int chunk = blockIdx.y;
-    const int d_begin = chunk * a.chunk_len;
-    const int d_end = min(a.n_ph, d_begin + a.chunk_len);
+    const int d0 = blockIdx.y * a.ph_len, d1 = min(a.n_ph, d0 + a.ph_len);
     const bool in_range = pos < a.n_active;
     const int cell = a.list ? a.list[in_range ? pos : 0] : (in_range ? pos : a.n_active - 1);
     bool active = in_range;
     if (active && a.status) active = (a.status[cell] == ATTRICI_STATUS_RUNNING);
-    if (__syncthreads_or(active) == 0 || d_begin >= d_end) return;   // uniform per CTA
-    const bool warp_active = __any_sync(0xffffffffu, active);
+    if (__syncthreads_or(active) == 0 || d0 >= d1) return;   // uniform per CTA
+    const int nph = d1 - d0;
 
-    float thA[NA], thB[NB];
 #pragma unroll
-    for (int i = 0; i < NA; ++i) thA[i] = active ? (float)a.th_pass[(size_t)i * a.Cp + cell] : 0.f;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) thB[i] = (active && HAS_B) ? (float)a.th_pass[(size_t)(NA + i) * a.Cp + cell] : 0.f;
+    for (int i = 0; i < NP; ++i)
+        coef[i * PASS_CELLS + tid] = (active && (HAS_B || i < NA)) ? (float)a.th_pass[(size_t)i * a.Cp + cell] : 0.f;
+    for (int i = tid; i < nph * 2 * MAXM; i += PASS_CELLS) {
+        const int r = i / (2 * MAXM), k = i - r * 2 * MAXM;
+        trig[i] = (float)a.pb64[(size_t)(d0 + r) * B_STRIDE + (k < MAXM ? 1 + k : 1 + NH + (k - MAXM))];
+    }
+    for (int i = tid; i < nph * a.njp; i += PASS_CELLS) {
+        const int r = i / a.njp, j = i - r * a.njp;
+        const int t = d0 + r + j * NPHASE;
+        g_s[i] = (t < a.T) ? a.basis32[(size_t)t * B_STRIDE] : 0.f;
+    }
+    __syncthreads();
+    if (!active) return;
 
-    PassAcc<float> acc;
-    acc.clear();
-    double nll = 0.0;
+    const float* cf = coef + tid;
     const float* yp0 = a.ys + cell;
     const size_t jstride = (size_t)NPHASE * a.ld;
-    const float qnan = __int_as_float(0x7fc00000);
-
-    for (int q0 = d_begin; q0 < d_end; q0 += GEN_TILE) {
-        const int n_rows = min(GEN_TILE, d_end - q0);
-        __syncthreads();
-        for (int i = tid; i < n_rows * 2 * NH; i += PASS_CELLS) {
-            const int r = i / (2 * NH), c = i - r * 2 * NH;
-            trig[i] = (float)a.pb64[(size_t)(q0 + r) * B_STRIDE + 1 + c];
-        }
-        for (int i = tid; i < n_rows * a.nj_max; i += PASS_CELLS) {
-            const int r = i / a.nj_max, j = i - r * a.nj_max;
-            const int t = q0 + r + j * NPHASE;
-            g_s[i] = (t < a.T) ? a.basis32[(size_t)t * B_STRIDE] : 0.f;
-        }
-        __syncthreads();
-        if (!warp_active) continue;
-        for (int r = 0; r < n_rows; ++r) {
-            const int d = q0 + r;
-            const float* tr = trig + r * 2 * NH;
-            // days of this phase inside the fit window: j in [ja, jb)
-            const int nj = (a.T - d + NPHASE - 1) / NPHASE;
-            const int ja = a.i0 > d ? (a.i0 - d + NPHASE - 1) / NPHASE : 0;
-            const int jb = a.i1 > d ? min(nj, (a.i1 - d + NPHASE - 1) / NPHASE) : 0;
-            if (ja >= jb) continue;
-            float av = thA[0], bv = thA[1], cv = HAS_B ? thB[0] : 0.f;
+    for (int r = 0; r < nph; ++r) {
+        const int d = d0 + r;
+        // days of this phase inside the fit window: j in [ja, jb)
+        const int nj = (a.T - d + NPHASE - 1) / NPHASE;
+        const int ja = a.i0 > d ? (a.i0 - d + NPHASE - 1) / NPHASE : 0;
+        const int jb = a.i1 > d ? min(nj, (a.i1 - d + NPHASE - 1) / NPHASE) : 0;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f, ab0 = 0.f, ab1 = 0.f, bb = 0.f, ra0 = 0.f, ra1 = 0.f, rb = 0.f, nl = 0.f;
+        if (ja < jb) {
+            const float* tr = trig + r * 2 * MAXM;
+            float av = cf[0], bv = cf[1 * PASS_CELLS], cv = HAS_B ? cf[NA * PASS_CELLS] : 0.f;
 #pragma unroll
             for (int k = 0; k < MAXM; ++k) {
-                const float ck = tr[k], sk = tr[NH + k];
-                av = fmaf(thA[2 + k], ck, av);
-                av = fmaf(thA[2 + MAXM + k], sk, av);
-                bv = fmaf(thA[2 + 2 * MAXM + k], ck, bv);
-                bv = fmaf(thA[2 + 3 * MAXM + k], sk, bv);
+                const float ck = tr[k], sk = tr[MAXM + k];
+                av = fmaf(cf[(2 + k) * PASS_CELLS], ck, av);
+                av = fmaf(cf[(2 + MAXM + k) * PASS_CELLS], sk, av);
+                bv = fmaf(cf[(2 + 2 * MAXM + k) * PASS_CELLS], ck, bv);
+                bv = fmaf(cf[(2 + 3 * MAXM + k) * PASS_CELLS], sk, bv);
                 if (HAS_B) {
-                    cv = fmaf(thB[1 + k], ck, cv);
-                    cv = fmaf(thB[1 + MAXM + k], sk, cv);
+                    cv = fmaf(cf[(NA + 1 + k) * PASS_CELLS], ck, cv);
+                    cv = fmaf(cf[(NA + 1 + MAXM + k) * PASS_CELLS], sk, cv);
                 }
             }
             GammaPhase gp = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -403,29 +401,28 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_generic_kernel(GenArg
                 gp.psi_a = digamma<float>(gp.a);
                 gp.wbb = 4.f * gp.a * (gp.a * trigamma<float>(gp.a) - 1.f);
             }
-            float w0 = 0.f, w1 = 0.f, w2 = 0.f, ab0 = 0.f, ab1 = 0.f, bb = 0.f, ra0 = 0.f, ra1 = 0.f, rb = 0.f, nl = 0.f;
-            const float* gr = g_s + r * a.nj_max;
+            const float* gr = g_s + r * a.njp;
             const float* yp = yp0 + (size_t)d * a.ld + (size_t)ja * jstride;
-            for (int j0 = ja; j0 < jb; j0 += GEN_U, yp += GEN_U * jstride) {
-                float yv[GEN_U];
+            for (int j0 = ja; j0 < jb; j0 += ST_U, yp += ST_U * jstride) {
+                float yv[ST_U];
                 const int last = jb - 1 - j0;
 #pragma unroll
-                for (int u = 0; u < GEN_U; ++u) yv[u] = (active && u <= last) ? __ldg(yp + (size_t)u * jstride) : qnan;
+                for (int u = 0; u < ST_U; ++u) yv[u] = (u <= last) ? __ldg(yp + (size_t)u * jstride) : 0.f;
 #pragma unroll
-                for (int u = 0; u < GEN_U; ++u) {
+                for (int u = 0; u < ST_U; ++u) {
                     if (u <= last) {
                         const float yf = yv[u];
                         bool valid;
                         float y;
                         if (KIND == K_BERNOULLI) {
-                            valid = active;                       // every day of the window counts; NaN (dry) is the event
+                            valid = true;                         // every day of the window counts; NaN (dry) is the event
                             y = (yf != yf) ? 1.f : 0.f;
                         } else {
-                            valid = active && (yf == yf);
+                            valid = (yf == yf);
                             y = valid ? yf : 0.5f;
                         }
                         const float g = gr[j0 + u];
-                        DayTerms<float> dt = gen_day<KIND>(y, fmaf(g, bv, av), cv, gp);
+                        const DayTerms<float> dt = gen_day<KIND>(y, fmaf(g, bv, av), cv, gp);
                         if (valid) {
                             nl += dt.nll;
                             w0 += dt.wAA; w1 = fmaf(dt.wAA, g, w1); w2 = fmaf(dt.wAA * g, g, w2);
@@ -436,21 +433,81 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_generic_kernel(GenArg
                     }
                 }
             }
-            nll += (double)nl;
-            // fold the per-phase sums into the moment accumulators (layout of pass.cu)
-            fold_accumulate<NH, float>(acc.AA, w0, tr);
-            fold_accumulate<NH, float>(acc.AA + NTRIG, w1, tr);
-            fold_accumulate<NH, float>(acc.AA + 2 * NTRIG, w2, tr);
+        }
+        float* out = a.psums + (size_t)d * NSUM * a.Pp + pos;
+        out[0] = w0; out[(size_t)1 * a.Pp] = w1; out[(size_t)2 * a.Pp] = w2;
+        out[(size_t)3 * a.Pp] = ab0; out[(size_t)4 * a.Pp] = ab1; out[(size_t)5 * a.Pp] = bb;
+        out[(size_t)6 * a.Pp] = ra0; out[(size_t)7 * a.Pp] = ra1; out[(size_t)8 * a.Pp] = rb;
+        out[(size_t)9 * a.Pp] = nl;
+    }
+}
+
+struct SumsArgs {
+    int Cp;
+    const int* list;
+    int n_active, Pp;
+    int n_ph, chunk_len;
+    const double* pb64;
+    const int* status;
+    const float* psums;      // [n_ph][NSUM][Pp]
+    double* part_nll;        // [chunk][Pp]
+    float* part_acc;         // [chunk][NACC][Pp]
+};
+
+template <bool HAS_B, bool HAS_AB>
+__global__ void __launch_bounds__(PASS_CELLS, 2) fold_sums_moments_kernel(SumsArgs a) {
+    __shared__ float trig[FOLD_TILE * 2 * NH];   // cos 1..8, sin 1..8 per phase
+    const int tid = threadIdx.x;
+    const int pos = blockIdx.x * PASS_CELLS + tid;
+    const int chunk = blockIdx.y;
+    const int d_begin = chunk * a.chunk_len;
+    const int d_end = min(a.n_ph, d_begin + a.chunk_len);
+    const bool in_range = pos < a.n_active;
+    const int cell = a.list ? a.list[in_range ? pos : 0] : (in_range ? pos : a.n_active - 1);
+    bool active = in_range;
+    if (active && a.status) active = (a.status[cell] == ATTRICI_STATUS_RUNNING);
+    if (__syncthreads_or(active) == 0 || d_begin >= d_end) return;   // uniform per CTA
+
+    PassAcc<float> acc;
+    acc.clear();
+    double nll = 0.0;
+    const float* ps = a.psums + pos;
+    const size_t pp = (size_t)a.Pp;
+    for (int q0 = d_begin; q0 < d_end; q0 += FOLD_TILE) {
+        const int n_rows = min(FOLD_TILE, d_end - q0);
+        __syncthreads();
+        for (int i = tid; i < n_rows * 2 * NH; i += PASS_CELLS) {
+            const int r = i / (2 * NH), c = i - r * 2 * NH;
+            trig[i] = (float)a.pb64[(size_t)(q0 + r) * B_STRIDE + 1 + c];
+        }
+        __syncthreads();
+        if (!active) continue;
+        // the sums of the next phase are requested while this one is folded
+        float cur[10], nxt[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) cur[k] = ps[((size_t)q0 * NSUM + k) * pp];
+        for (int r = 0; r < n_rows; ++r) {
+            if (r + 1 < n_rows) {
+#pragma unroll
+                for (int k = 0; k < 10; ++k) nxt[k] = ps[((size_t)(q0 + r + 1) * NSUM + k) * pp];
+            }
+            const float* tr = trig + r * 2 * NH;
+            fold_accumulate<NH, float>(acc.AA, cur[0], tr);
+            fold_accumulate<NH, float>(acc.AA + NTRIG, cur[1], tr);
+            fold_accumulate<NH, float>(acc.AA + 2 * NTRIG, cur[2], tr);
             if (HAS_AB) {
-                fold_accumulate<NH, float>(acc.AB, ab0, tr);
-                fold_accumulate<NH, float>(acc.AB + NTRIG, ab1, tr);
+                fold_accumulate<NH, float>(acc.AB, cur[3], tr);
+                fold_accumulate<NH, float>(acc.AB + NTRIG, cur[4], tr);
             }
             if (HAS_B) {
-                fold_accumulate<NH, float>(acc.BB, bb, tr);
-                fold_accumulate<MAXM, float>(acc.GB, rb, tr);
+                fold_accumulate<NH, float>(acc.BB, cur[5], tr);
+                fold_accumulate<MAXM, float>(acc.GB, cur[8], tr);
             }
-            fold_accumulate<MAXM, float>(acc.GA, ra0, tr);
-            fold_accumulate<MAXM, float>(acc.GA + NB, ra1, tr);
+            fold_accumulate<MAXM, float>(acc.GA, cur[6], tr);
+            fold_accumulate<MAXM, float>(acc.GA + NB, cur[7], tr);
+            nll += (double)cur[9];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) cur[k] = nxt[k];
         }
     }
 
@@ -476,28 +533,46 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) fold_pass_generic_kernel(GenArg
 int launch_fold_pass_generic(Workspace& ws, const PassShape& ps, int term, const float* y_scaled, int64_t ld, int i0,
                              int i1, const int* status, cudaStream_t s) {
     if (ps.n_active <= 0) return 0;
-    GenArgs a;
+    if (!ws.psums) { set_error("workspace was sized for another family"); return ATTRICI_EWORKSPACE; }
+    StreamArgs a;
     a.ys = y_scaled; a.ld = ld; a.T = ws.T; a.Cp = ws.Cp;
     a.list = ps.list; a.n_active = ps.n_active; a.Pp = ps.Pp;
     a.i0 = i0; a.i1 = i1;
-    a.n_ph = fold_phases(ws); a.chunk_len = ps.chunk_len; a.nj_max = (ws.T + NPHASE - 1) / NPHASE;
+    a.n_ph = fold_phases(ws);
+    a.njp = ((ws.T + NPHASE - 1) / NPHASE + ST_U - 1) / ST_U * ST_U;
     a.pb64 = ws.pb64; a.basis32 = ws.basis32; a.th_pass = ws.th_pass; a.status = status;
-    a.part_nll = ws.part_nll; a.part_acc = (float*)ws.part_acc;
-    const size_t smem = sizeof(float) * GEN_TILE * (2 * NH + (size_t)a.nj_max);
+    a.psums = ws.psums;
+    const int n_cb = (ps.n_active + PASS_CELLS - 1) / PASS_CELLS;
+    int want = (148 * 16 + n_cb - 1) / n_cb;
+    if (want > a.n_ph) want = a.n_ph;
+    if (want < 1) want = 1;
+    a.ph_len = (a.n_ph + want - 1) / want;
+    if (a.ph_len > ST_MAXPH) a.ph_len = ST_MAXPH;
+    const size_t smem = sizeof(float) * ((size_t)NP * PASS_CELLS + ST_MAXPH * 2 * MAXM + (size_t)ST_MAXPH * a.njp);
     if (smem > 200 * 1024) { set_error("series too long for the phase-ordered pass (T=%d)", ws.T); return ATTRICI_EUNSUPPORTED; }
-    dim3 grid((ps.n_active + PASS_CELLS - 1) / PASS_CELLS, ps.n_chunks);
+    dim3 grid1(n_cb, (a.n_ph + a.ph_len - 1) / a.ph_len);
     auto launch = [&](auto kernel) -> int {
         ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<grid, PASS_CELLS, smem, s>>>(a);
+        kernel<<<grid1, PASS_CELLS, smem, s>>>(a);
         return 0;
     };
+    bool has_b = true, has_ab = false;
     switch (term) {
-        case T_GAMMA: ATTRICI_TRY(launch(fold_pass_generic_kernel<K_GAMMA>)); break;
-        case T_BETA: ATTRICI_TRY(launch(fold_pass_generic_kernel<K_BETA>)); break;
-        case T_WEIBULL: ATTRICI_TRY(launch(fold_pass_generic_kernel<K_WEIBULL>)); break;
-        case T_BERNOULLI: ATTRICI_TRY(launch(fold_pass_generic_kernel<K_BERNOULLI>)); break;
+        case T_GAMMA: ATTRICI_TRY(launch(fold_stream_sums_kernel<K_GAMMA>)); break;
+        case T_BETA: ATTRICI_TRY(launch(fold_stream_sums_kernel<K_BETA>)); has_ab = true; break;
+        case T_WEIBULL: ATTRICI_TRY(launch(fold_stream_sums_kernel<K_WEIBULL>)); has_ab = true; break;
+        case T_BERNOULLI: ATTRICI_TRY(launch(fold_stream_sums_kernel<K_BERNOULLI>)); has_b = false; break;
         default: set_error("no phase-ordered generic pass for term %d", term); return ATTRICI_EINVAL;
     }
+    ATTRICI_LAUNCH_CHECK();
+    SumsArgs b;
+    b.Cp = ws.Cp; b.list = ps.list; b.n_active = ps.n_active; b.Pp = ps.Pp;
+    b.n_ph = a.n_ph; b.chunk_len = ps.chunk_len; b.pb64 = ws.pb64; b.status = status; b.psums = ws.psums;
+    b.part_nll = ws.part_nll; b.part_acc = (float*)ws.part_acc;
+    dim3 grid2(n_cb, ps.n_chunks);
+    if (has_ab) fold_sums_moments_kernel<true, true><<<grid2, PASS_CELLS, 0, s>>>(b);
+    else if (has_b) fold_sums_moments_kernel<true, false><<<grid2, PASS_CELLS, 0, s>>>(b);
+    else fold_sums_moments_kernel<false, false><<<grid2, PASS_CELLS, 0, s>>>(b);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }

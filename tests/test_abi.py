@@ -44,10 +44,11 @@ def test_workspace_query_and_argument_errors():
     lib = _lib.load()
     n = _lib.workspace_bytes(_lib.NORMAL, 43464, 10000)
     assert 50e6 < n < 1.2e9
-    # the Normal family also holds the per-phase sums of the folded pass: 2 x [1461][3][C] float64
+    # per-phase buffers of the folded passes: Normal 2 x [1461][3][C] float64, other families [1461][11][C] float32
     n_gamma = _lib.workspace_bytes(_lib.GAMMA, 43464, 10000)
-    assert n >= n_gamma + 2 * 3 * 8 * 1461 * 10000
-    # the Bernoulli-Gamma family the [T x C] MT19937 uniforms
+    assert n - 2 * 3 * 8 * 1461 * 10000 > 50e6 and n_gamma - 4 * 11 * 1461 * 10000 > 50e6
+    assert abs((n - 2 * 3 * 8 * 1461 * 10016) - (n_gamma - 4 * 11 * 1461 * 10016)) < 4096
+    # the Bernoulli-Gamma family also holds the [T x C] MT19937 uniforms
     assert _lib.workspace_bytes(_lib.BERNOULLI_GAMMA, 43464, 10000) > n_gamma + 8 * 43464 * 10000 - 1
     with pytest.raises(_lib.AttriciCudaError, match="T >= 2"):
         _lib.workspace_bytes(_lib.NORMAL, 1, 10)
