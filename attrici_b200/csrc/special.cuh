@@ -140,12 +140,18 @@ ATTRICI_HD_NOINLINE double gamma_q_cf(double a, double x, double gln) {
     return h * gamma_prefactor(a, x, gln);
 }
 
+// Switch between the series for P and the continued fraction for Q.  The textbook switch is x = a + 1; the series
+// still converges quickly (about x + 6 sqrt(x) + 20 positive terms, no cancellation) far beyond it, and a warp
+// whose lanes fall on both sides of the switch pays for both branches, so the series is kept up to x = 30: for the
+// shapes of pr / tasrange (a ~ 0.3 .. 3) practically every lane then takes the same branch.
+ATTRICI_HD bool gamma_use_series(double a, double x) { return x < a + 1.0 || x < 30.0; }
+
 // P and Q with lgamma(a) supplied
 ATTRICI_HD double gamma_p_l(double a, double x, double gln) {
     if (isnan(a) || isnan(x) || a <= 0.0 || x < 0.0) return NAN;
     if (x == 0.0) return 0.0;
     if (isinf(x)) return 1.0;
-    if (x < a + 1.0) return gamma_p_series(a, x, gln);
+    if (gamma_use_series(a, x)) return gamma_p_series(a, x, gln);
     return 1.0 - gamma_q_cf(a, x, gln);
 }
 
@@ -153,7 +159,12 @@ ATTRICI_HD double gamma_q_l(double a, double x, double gln) {
     if (isnan(a) || isnan(x) || a <= 0.0 || x < 0.0) return NAN;
     if (x == 0.0) return 1.0;
     if (isinf(x)) return 0.0;
-    if (x < a + 1.0) return 1.0 - gamma_p_series(a, x, gln);
+    if (gamma_use_series(a, x)) {
+        // 1 - P keeps full relative accuracy only while Q is not small; the far upper tail (rare) takes the
+        // continued fraction, which computes Q itself
+        const double p = gamma_p_series(a, x, gln);
+        if (p < 0.99 || x < a + 1.0) return 1.0 - p;
+    }
     return gamma_q_cf(a, x, gln);
 }
 
