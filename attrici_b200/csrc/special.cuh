@@ -274,14 +274,12 @@ ATTRICI_HD_NOINLINE double beta_i2_l(double a, double b, double x, double lnb, d
     if (x == 0.0) { if (comp) *comp = 1.0; return 0.0; }
     if (x == 1.0) { if (comp) *comp = 0.0; return 1.0; }
     double bt = exp(lnb + a * log(x) + b * log1p(-x));
-    double p, q;
-    if (x < (a + 1.0) / (a + b + 2.0)) {
-        p = bt * beta_cf(a, b, x) / a;
-        q = 1.0 - p;
-    } else {
-        q = bt * beta_cf(b, a, 1.0 - x) / b;
-        p = 1.0 - q;
-    }
+    // one continued-fraction call with the arguments swapped where needed: lanes on either side of the switch
+    // then run the same code instead of two divergent calls
+    const bool flip = !(x < (a + 1.0) / (a + b + 2.0));
+    const double fa = flip ? b : a, fb = flip ? a : b, fx = flip ? 1.0 - x : x;
+    const double v = bt * beta_cf(fa, fb, fx) / fa;
+    const double p = flip ? 1.0 - v : v, q = flip ? v : 1.0 - v;
     if (comp) *comp = q;
     return p;
 }
