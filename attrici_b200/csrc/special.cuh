@@ -168,6 +168,20 @@ ATTRICI_HD double gamma_q_l(double a, double x, double gln) {
     return gamma_q_cf(a, x, gln);
 }
 
+// P and Q from one series evaluation (one call site: the lanes of a warp do not diverge on which of the two is
+// wanted); the far upper tail takes the continued fraction for Q
+ATTRICI_HD void gamma_pq_l(double a, double x, double gln, double* p, double* q) {
+    if (isnan(a) || isnan(x) || a <= 0.0 || x < 0.0) { *p = NAN; *q = NAN; return; }
+    if (x == 0.0) { *p = 0.0; *q = 1.0; return; }
+    if (isinf(x)) { *p = 1.0; *q = 0.0; return; }
+    if (gamma_use_series(a, x)) {
+        const double pp = gamma_p_series(a, x, gln);
+        if (pp < 0.99 || x < a + 1.0) { *p = pp; *q = 1.0 - pp; return; }
+    }
+    *q = gamma_q_cf(a, x, gln);
+    *p = 1.0 - *q;
+}
+
 ATTRICI_HD double gamma_p(double a, double x) { return gamma_p_l(a, x, lgamma(a)); }
 ATTRICI_HD double gamma_q(double a, double x) { return gamma_q_l(a, x, lgamma(a)); }
 
@@ -204,7 +218,9 @@ ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p, double x0 = -1.0) {
     for (int it = 0; it < 60; ++it) {
         if (x <= 0.0) x = 0.5 * (lo + (isinf(hi) ? lo + 1e-300 : hi));
         // error in the better-conditioned tail
-        double err = (p < 0.5) ? gamma_p_l(a, x, gln) - p : (1.0 - p) - gamma_q_l(a, x, gln);
+        double pv, qv;
+        gamma_pq_l(a, x, gln, &pv, &qv);
+        double err = (p < 0.5) ? pv - p : (1.0 - p) - qv;
         if (err > 0.0) hi = x; else lo = x;
         double dens;  // dP/dx
         if (a > 1.0)
