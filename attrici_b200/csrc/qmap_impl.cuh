@@ -156,6 +156,22 @@ ATTRICI_HD bool gamma_fast_path(const DistPar& ref, const DistPar& cf, double ys
     return true;
 }
 
+// Weibull family shortcut.  The shape alpha does not depend on the predictor, so factual and counterfactual
+// distributions differ by their scale only and F_cf^-1(F_ref(y)) = y beta_cf / beta_ref exactly (with
+// r = (y / beta_ref)^alpha: q = -expm1(-r), invcdf = beta_cf (-log1p(-q))^(1/alpha) = beta_cf r^(1/alpha)).
+// The reference's round trip only adds its own rounding while r stays below ~16 (1 - q = e^-r > 1e-7); beyond
+// that it loses digits of 1 - q and finally saturates (q rounds to 1 -> Inf -> `replaced`), so those days keep
+// the full evaluation.  r is only needed as a classifier: float32 is ample.
+ATTRICI_HD bool weibull_fast_path(const DistPar& ref, const DistPar& cf, double ys, double* cs) {
+    if (!(ys > 0.0) || !(ref.p0 > 0.0) || !(ref.p1 > 0.0) || !(cf.p1 > 0.0) || !(cf.p0 == ref.p0) || !isfinite(ref.p1) ||
+        !isfinite(cf.p1) || !isfinite(ref.p0))
+        return false;
+    const float r = powf((float)(ys / ref.p1), (float)ref.p0);
+    if (!(r < 16.0f)) return false;
+    *cs = ys * (cf.p1 / ref.p1);
+    return true;
+}
+
 // Normal family shortcut.  sigma does not depend on the predictor, so F_cf^-1(F_ref(y)) = mu_cf + sigma z
 // with z = (y - mu_ref) / sigma, i.e. y + (mu_cf - mu_ref): the reference's ndtri(ndtr(z)) round trip only
 // adds its own rounding, at most 1.1e-16 / pdf(z) in z (8e-13 at |z| = 4).  Days with |z| < 4 (float32
@@ -224,7 +240,8 @@ ATTRICI_HD QmapOut qmap_day(int family, int scaling, int post_rule, float y, flo
     double cs;
     if (family != ATTRICI_BERNOULLI_GAMMA) {
         // variables.py:303: invcdf_cf(cdf_ref(y_scaled)); NaN in -> NaN out
-        if (!(family == ATTRICI_GAMMA && gamma_fast_path(ref, cf, (double)ys, &cs))) {
+        if (!(family == ATTRICI_GAMMA && gamma_fast_path(ref, cf, (double)ys, &cs)) &&
+            !(family == ATTRICI_WEIBULL && weibull_fast_path(ref, cf, (double)ys, &cs))) {
             double q = dist_cdf(family, ref, (double)ys);
             // the counterfactual value is close to the observation: start the gamma / beta inverses there
             cs = dist_invcdf(family, cf, q, (double)ys);
