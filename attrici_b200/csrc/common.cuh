@@ -261,6 +261,10 @@ int launch_qmap(Workspace& ws, const attrici_variable_t& var, const float* y, co
 int launch_qmap_fold(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled, int64_t ld,
                      const double* params, const double* scaling, double* cfact, uint8_t* replaced,
                      double* cfact_scaled, int64_t ld_out, cudaStream_t s);
+// Gamma / Weibull families in phase order (scale shortcut), same device-side dispatch; needs y_scaled
+int launch_qmap_fold_scale(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled, int64_t ld,
+                           const double* params, const double* scaling, double* cfact, uint8_t* replaced,
+                           double* cfact_scaled, int64_t ld_out, cudaStream_t s);
 int launch_eval_parameter(Workspace& ws, const attrici_variable_t& var, const double* params, int which,
                           int counterfactual, double* out, int64_t ld_out, cudaStream_t s);
 int launch_mt19937(const uint32_t* seeds, int C, int n, double* out, int64_t ld, cudaStream_t s);

@@ -259,6 +259,9 @@ int launch_qmap(Workspace& ws, const attrici_variable_t& var, const float* y, co
         // (gap-free daily axis) and the day-ordered one below, the one that does not apply returns at once
         ATTRICI_TRY(launch_qmap_fold(ws, var, y, y_scaled, ld, params, scaling, cfact, replaced, cfact_scaled, ld_out, s));
         a.want_fold = 0;
+    } else if (fold_on && y_scaled && (var.family == ATTRICI_GAMMA || var.family == ATTRICI_WEIBULL)) {
+        ATTRICI_TRY(launch_qmap_fold_scale(ws, var, y, y_scaled, ld, params, scaling, cfact, replaced, cfact_scaled, ld_out, s));
+        a.want_fold = 0;
     }
     int n_chunks = qmap_chunks(ws.T, ws.C, &a.chunk_len);
     dim3 grid(n_cb, n_chunks);
