@@ -149,9 +149,14 @@ int run_pass(Workspace& ws, int fold, const int* list, int n_active, int term, b
         mode = PASS_FULL;
         PassShape ps = plan_pass(ws, list, n_active, 0, fold_phases(ws), false);
         if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
-        ATTRICI_TRY(launch_fold_pass_generic(ws, ps, term, y_scaled, ld, i0, i1, status, s));
+        ATTRICI_TRY(launch_fold_pass_generic(ws, ps, term, false, y_scaled, ld, i0, i1, status, s));
         if (e1) ATTRICI_CUDA_CHECK(cudaEventRecord(e1, s));
         return launch_reduce(ws, ps, false, PASS_FULL, s, status);
+    }
+    if (fold == FOLD_STREAM && fp64 && mode == PASS_NLL) {   // the FP64 log posterior of the returned point
+        PassShape ps = plan_pass(ws, list, n_active, 0, fold_phases(ws), true);
+        ATTRICI_TRY(launch_fold_pass_generic(ws, ps, term, true, y_scaled, ld, i0, i1, status, s));
+        return launch_reduce(ws, ps, true, PASS_NLL, s, status);
     }
     if (fold == FOLD_SUMS) {
         PassShape ps = plan_pass(ws, list, n_active, 0, fold_phases(ws), true);

@@ -211,9 +211,10 @@ int launch_pass_mma(Workspace& ws, const PassShape& ps, const float* y_scaled, i
 enum { PASS_NLL = 0, PASS_GRAD = 1, PASS_FULL = 2, PASS_FLAT = 3 };
 int fold_phases(const Workspace& ws);
 int launch_fold_pass(Workspace& ws, const PassShape& ps, int mode, bool exact, const int* status, cudaStream_t s);
-// phase-ordered FP32 pass (all moments) of the Gamma / Weibull / Beta / Bernoulli terms over the scaled series
-int launch_fold_pass_generic(Workspace& ws, const PassShape& ps, int term, const float* y_scaled, int64_t ld, int i0,
-                             int i1, const int* status, cudaStream_t s);
+// phase-ordered pass of the Gamma / Weibull / Beta / Bernoulli terms over the scaled series: FP32 with all moments,
+// or (nll_only) the FP64 nll of the returned point
+int launch_fold_pass_generic(Workspace& ws, const PassShape& ps, int term, bool nll_only, const float* y_scaled, int64_t ld,
+                             int i0, int i1, const int* status, cudaStream_t s);
 // cross-chunk reduction of the partials of the last pass into ws.momd
 // status != nullptr (only without a list): cells whose status is not RUNNING are skipped
 int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, int mode, cudaStream_t s,

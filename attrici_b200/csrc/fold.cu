@@ -282,7 +282,7 @@ int launch_fold_pass(Workspace& ws, const PassShape& ps, int mode, bool exact, c
 // per phase, and a day contributes to eleven per-phase sums
 //     sum w_AA {1, g, g^2}, sum w_AB {1, g}, sum w_BB, sum r_A {1, g}, sum r_B, sum nll, (count)
 // instead of 129 moment accumulators.
-//   stage 1  fold_stream_sums_kernel<KIND>: thread = cell, CTA = 128 cells x <= 16 phases; one load, one FMA, the
+//   stage 1  fold_stream_kernel<KIND, float, false>: thread = cell, CTA = 128 cells x <= 16 phases; one load, one FMA, the
 //            family's day terms and ten accumulations per day; ~60 registers, so enough warps stay resident to hide
 //            the latency of the per-day special functions (the day-ordered pass.cu kernel carries the 129
 //            accumulators in registers and runs 8 warps per SM).  Writes psums[phase][11][cell] (FP32).
@@ -304,142 +304,159 @@ struct StreamArgs {
     const int* list;
     int n_active, Pp;
     int i0, i1;
-    int n_ph, ph_len, njp;   // njp: days per phase rounded up to whole batches
+    int n_ph, ph_len, njp;   // ph_len: phases per CTA; njp: days per phase rounded up to whole batches
     const double* pb64;      // phase rows (trig columns)
     const float* basis32;    // gmt(t) = basis32[t * B_STRIDE]
+    const double* basis64;
     const double* th_pass;
     const int* status;
-    float* psums;            // [n_ph][NSUM][Pp]
+    float* psums;            // [n_ph][NSUM][Pp]           (sums mode)
+    double* part_nll;        // [chunk][Pp]                 (nll-only mode: one chunk per CTA row)
 };
 
 // terms of the Gamma family that depend on eta_B only (shape a = nu^2 = e^{2 eta_B})
-struct GammaPhase { float a, lna, lgam_a, psi_a, wbb; };
+template <typename R> struct GammaPhase { R a, lna, lgam_a, psi_a, wbb; };
 
-template <int KIND>
-__device__ __forceinline__ DayTerms<float> gen_day(float y, float ea, float eb, const GammaPhase& gp) {
+template <int KIND, typename R>
+__device__ __forceinline__ DayTerms<R> gen_day(R y, R ea, R eb, const GammaPhase<R>& gp) {
     if (KIND == K_GAMMA) {
-        DayTerms<float> d;
-        const float ly = logf(y);
-        const float lnu = ly - ea;
-        const float u = expf(lnu);
-        const float dd = lnu + gp.lna + 1.f - u - gp.psi_a;
-        d.nll = -((gp.a - 1.f) * ly - gp.a * u - gp.lgam_a - gp.a * ea + gp.a * gp.lna);
-        d.rA = -gp.a * (u - 1.f);
-        d.rB = -2.f * gp.a * dd;
+        DayTerms<R> d;
+        const R ly = log(y);
+        const R lnu = ly - ea;
+        const R u = exp(lnu);
+        const R dd = lnu + gp.lna + R(1) - u - gp.psi_a;
+        d.nll = -((gp.a - R(1)) * ly - gp.a * u - gp.lgam_a - gp.a * ea + gp.a * gp.lna);
+        d.rA = -gp.a * (u - R(1));
+        d.rB = R(-2) * gp.a * dd;
         d.wAA = gp.a;
-        d.wAB = 0.f;
+        d.wAB = R(0);
         d.wBB = gp.wbb;
         return d;
     }
-    return family_day_t<KIND, float>(y, ea, eb);
+    return family_day_t<KIND, R>(y, ea, eb);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(PASS_CELLS) fold_stream_sums_kernel(StreamArgs a) {
+// R = float, NLL_ONLY = false: per-phase sums of all day terms (stage 1 of a likelihood pass)
+// R = double, NLL_ONLY = true: the FP64 log posterior of the returned point (model_scipy.py:525), summed per CTA row
+template <int KIND, typename R, bool NLL_ONLY>
+__global__ void __launch_bounds__(PASS_CELLS) fold_stream_kernel(StreamArgs a) {
     constexpr bool HAS_B = (KIND != K_BERNOULLI);
     constexpr bool HAS_AB = (KIND == K_WEIBULL || KIND == K_BETA);
     extern __shared__ __align__(16) unsigned char st_smem[];
-    float* coef = reinterpret_cast<float*>(st_smem);       // [NP][128]
-    float* trig = coef + NP * PASS_CELLS;                  // [ST_MAXPH][8]: cos 1..4, sin 1..4
-    float* g_s = trig + ST_MAXPH * 2 * MAXM;               // [ST_MAXPH][njp] gmt of day d + 1461 j
+    R* coef = reinterpret_cast<R*>(st_smem);               // [NP][128]
+    R* trig = coef + NP * PASS_CELLS;                      // [ST_MAXPH][8]: cos 1..4, sin 1..4
+    R* g_s = trig + ST_MAXPH * 2 * MAXM;                   // [ST_MAXPH][njp] gmt of day d + 1461 j
 
     const int tid = threadIdx.x;
     const int pos = blockIdx.x * PASS_CELLS + tid;
-    const int d0 = blockIdx.y * a.ph_len, d1 = min(a.n_ph, d0 + a.ph_len);
+    const int d_begin = blockIdx.y * a.ph_len, d_end = min(a.n_ph, d_begin + a.ph_len);
     const bool in_range = pos < a.n_active;
     const int cell = a.list ? a.list[in_range ? pos : 0] : (in_range ? pos : a.n_active - 1);
     bool active = in_range;
     if (active && a.status) active = (a.status[cell] == ATTRICI_STATUS_RUNNING);
-    if (__syncthreads_or(active) == 0 || d0 >= d1) return;   // uniform per CTA
-    const int nph = d1 - d0;
+    if (__syncthreads_or(active) == 0 || d_begin >= d_end) return;   // uniform per CTA
 
 #pragma unroll
     for (int i = 0; i < NP; ++i)
-        coef[i * PASS_CELLS + tid] = (active && (HAS_B || i < NA)) ? (float)a.th_pass[(size_t)i * a.Cp + cell] : 0.f;
-    for (int i = tid; i < nph * 2 * MAXM; i += PASS_CELLS) {
-        const int r = i / (2 * MAXM), k = i - r * 2 * MAXM;
-        trig[i] = (float)a.pb64[(size_t)(d0 + r) * B_STRIDE + (k < MAXM ? 1 + k : 1 + NH + (k - MAXM))];
-    }
-    for (int i = tid; i < nph * a.njp; i += PASS_CELLS) {
-        const int r = i / a.njp, j = i - r * a.njp;
-        const int t = d0 + r + j * NPHASE;
-        g_s[i] = (t < a.T) ? a.basis32[(size_t)t * B_STRIDE] : 0.f;
-    }
-    __syncthreads();
-    if (!active) return;
-
-    const float* cf = coef + tid;
+        coef[i * PASS_CELLS + tid] = (active && (HAS_B || i < NA)) ? (R)a.th_pass[(size_t)i * a.Cp + cell] : R(0);
+    const R* cf = coef + tid;
     const float* yp0 = a.ys + cell;
     const size_t jstride = (size_t)NPHASE * a.ld;
-    for (int r = 0; r < nph; ++r) {
-        const int d = d0 + r;
-        // days of this phase inside the fit window: j in [ja, jb)
-        const int nj = (a.T - d + NPHASE - 1) / NPHASE;
-        const int ja = a.i0 > d ? (a.i0 - d + NPHASE - 1) / NPHASE : 0;
-        const int jb = a.i1 > d ? min(nj, (a.i1 - d + NPHASE - 1) / NPHASE) : 0;
-        float w0 = 0.f, w1 = 0.f, w2 = 0.f, ab0 = 0.f, ab1 = 0.f, bb = 0.f, ra0 = 0.f, ra1 = 0.f, rb = 0.f, nl = 0.f;
-        if (ja < jb) {
-            const float* tr = trig + r * 2 * MAXM;
-            float av = cf[0], bv = cf[1 * PASS_CELLS], cv = HAS_B ? cf[NA * PASS_CELLS] : 0.f;
+    double nll_total = 0.0;
+
+    for (int d0 = d_begin; d0 < d_end; d0 += ST_MAXPH) {
+        const int nph = min(ST_MAXPH, d_end - d0);
+        __syncthreads();   // the previous tile (and, the first time, the coefficient columns) are settled
+        for (int i = tid; i < nph * 2 * MAXM; i += PASS_CELLS) {
+            const int r = i / (2 * MAXM), k = i - r * 2 * MAXM;
+            trig[i] = (R)a.pb64[(size_t)(d0 + r) * B_STRIDE + (k < MAXM ? 1 + k : 1 + NH + (k - MAXM))];
+        }
+        for (int i = tid; i < nph * a.njp; i += PASS_CELLS) {
+            const int r = i / a.njp, j = i - r * a.njp;
+            const int t = d0 + r + j * NPHASE;
+            R g = R(0);
+            if (t < a.T) g = (sizeof(R) == 8) ? (R)a.basis64[(size_t)t * B_STRIDE] : (R)a.basis32[(size_t)t * B_STRIDE];
+            g_s[i] = g;
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int r = 0; r < nph; ++r) {
+            const int d = d0 + r;
+            // days of this phase inside the fit window: j in [ja, jb)
+            const int nj = (a.T - d + NPHASE - 1) / NPHASE;
+            const int ja = a.i0 > d ? (a.i0 - d + NPHASE - 1) / NPHASE : 0;
+            const int jb = a.i1 > d ? min(nj, (a.i1 - d + NPHASE - 1) / NPHASE) : 0;
+            R w0 = 0, w1 = 0, w2 = 0, ab0 = 0, ab1 = 0, bb = 0, ra0 = 0, ra1 = 0, rb = 0, nl = 0;
+            if (ja < jb) {
+                const R* tr = trig + r * 2 * MAXM;
+                R av = cf[0], bv = cf[1 * PASS_CELLS], cv = HAS_B ? cf[NA * PASS_CELLS] : R(0);
 #pragma unroll
-            for (int k = 0; k < MAXM; ++k) {
-                const float ck = tr[k], sk = tr[MAXM + k];
-                av = fmaf(cf[(2 + k) * PASS_CELLS], ck, av);
-                av = fmaf(cf[(2 + MAXM + k) * PASS_CELLS], sk, av);
-                bv = fmaf(cf[(2 + 2 * MAXM + k) * PASS_CELLS], ck, bv);
-                bv = fmaf(cf[(2 + 3 * MAXM + k) * PASS_CELLS], sk, bv);
-                if (HAS_B) {
-                    cv = fmaf(cf[(NA + 1 + k) * PASS_CELLS], ck, cv);
-                    cv = fmaf(cf[(NA + 1 + MAXM + k) * PASS_CELLS], sk, cv);
+                for (int k = 0; k < MAXM; ++k) {
+                    const R ck = tr[k], sk = tr[MAXM + k];
+                    av = fma(cf[(2 + k) * PASS_CELLS], ck, av);
+                    av = fma(cf[(2 + MAXM + k) * PASS_CELLS], sk, av);
+                    bv = fma(cf[(2 + 2 * MAXM + k) * PASS_CELLS], ck, bv);
+                    bv = fma(cf[(2 + 3 * MAXM + k) * PASS_CELLS], sk, bv);
+                    if (HAS_B) {
+                        cv = fma(cf[(NA + 1 + k) * PASS_CELLS], ck, cv);
+                        cv = fma(cf[(NA + 1 + MAXM + k) * PASS_CELLS], sk, cv);
+                    }
                 }
-            }
-            GammaPhase gp = {0.f, 0.f, 0.f, 0.f, 0.f};
-            if (KIND == K_GAMMA) {
-                gp.a = expf(2.f * cv);
-                gp.lna = 2.f * cv;
-                gp.lgam_a = lgammaf(gp.a);
-                gp.psi_a = digamma<float>(gp.a);
-                gp.wbb = 4.f * gp.a * (gp.a * trigamma<float>(gp.a) - 1.f);
-            }
-            const float* gr = g_s + r * a.njp;
-            const float* yp = yp0 + (size_t)d * a.ld + (size_t)ja * jstride;
-            for (int j0 = ja; j0 < jb; j0 += ST_U, yp += ST_U * jstride) {
-                float yv[ST_U];
-                const int last = jb - 1 - j0;
+                GammaPhase<R> gp = {R(0), R(0), R(0), R(0), R(0)};
+                if (KIND == K_GAMMA) {
+                    gp.a = exp(R(2) * cv);
+                    gp.lna = R(2) * cv;
+                    gp.lgam_a = lgam<R>(gp.a);
+                    gp.psi_a = digamma<R>(gp.a);
+                    gp.wbb = NLL_ONLY ? R(0) : R(4) * gp.a * (gp.a * trigamma<R>(gp.a) - R(1));
+                }
+                const R* gr = g_s + r * a.njp;
+                const float* yp = yp0 + (size_t)d * a.ld + (size_t)ja * jstride;
+                for (int j0 = ja; j0 < jb; j0 += ST_U, yp += ST_U * jstride) {
+                    float yv[ST_U];
+                    const int last = jb - 1 - j0;
 #pragma unroll
-                for (int u = 0; u < ST_U; ++u) yv[u] = (u <= last) ? __ldg(yp + (size_t)u * jstride) : 0.f;
+                    for (int u = 0; u < ST_U; ++u) yv[u] = (u <= last) ? __ldg(yp + (size_t)u * jstride) : 0.f;
 #pragma unroll
-                for (int u = 0; u < ST_U; ++u) {
-                    if (u <= last) {
-                        const float yf = yv[u];
-                        bool valid;
-                        float y;
-                        if (KIND == K_BERNOULLI) {
-                            valid = true;                         // every day of the window counts; NaN (dry) is the event
-                            y = (yf != yf) ? 1.f : 0.f;
-                        } else {
-                            valid = (yf == yf);
-                            y = valid ? yf : 0.5f;
-                        }
-                        const float g = gr[j0 + u];
-                        const DayTerms<float> dt = gen_day<KIND>(y, fmaf(g, bv, av), cv, gp);
-                        if (valid) {
-                            nl += dt.nll;
-                            w0 += dt.wAA; w1 = fmaf(dt.wAA, g, w1); w2 = fmaf(dt.wAA * g, g, w2);
-                            ra0 += dt.rA; ra1 = fmaf(dt.rA, g, ra1);
-                            if (HAS_AB) { ab0 += dt.wAB; ab1 = fmaf(dt.wAB, g, ab1); }
-                            if (HAS_B) { bb += dt.wBB; rb += dt.rB; }
+                    for (int u = 0; u < ST_U; ++u) {
+                        if (u <= last) {
+                            const float yf = yv[u];
+                            bool valid;
+                            R y;
+                            if (KIND == K_BERNOULLI) {
+                                valid = true;                     // every day of the window counts; NaN (dry) is the event
+                                y = (yf != yf) ? R(1) : R(0);
+                            } else {
+                                valid = (yf == yf);
+                                y = valid ? (R)yf : R(0.5);
+                            }
+                            const R g = gr[j0 + u];
+                            const DayTerms<R> dt = gen_day<KIND, R>(y, fma(g, bv, av), cv, gp);
+                            if (valid) {
+                                nl += dt.nll;
+                                if (!NLL_ONLY) {
+                                    w0 += dt.wAA; w1 = fma(dt.wAA, g, w1); w2 = fma(dt.wAA * g, g, w2);
+                                    ra0 += dt.rA; ra1 = fma(dt.rA, g, ra1);
+                                    if (HAS_AB) { ab0 += dt.wAB; ab1 = fma(dt.wAB, g, ab1); }
+                                    if (HAS_B) { bb += dt.wBB; rb += dt.rB; }
+                                }
+                            }
                         }
                     }
                 }
             }
+            if (NLL_ONLY) {
+                nll_total += (double)nl;
+            } else {
+                float* out = a.psums + (size_t)d * NSUM * a.Pp + pos;
+                out[0] = (float)w0; out[(size_t)1 * a.Pp] = (float)w1; out[(size_t)2 * a.Pp] = (float)w2;
+                out[(size_t)3 * a.Pp] = (float)ab0; out[(size_t)4 * a.Pp] = (float)ab1; out[(size_t)5 * a.Pp] = (float)bb;
+                out[(size_t)6 * a.Pp] = (float)ra0; out[(size_t)7 * a.Pp] = (float)ra1; out[(size_t)8 * a.Pp] = (float)rb;
+                out[(size_t)9 * a.Pp] = (float)nl;
+            }
         }
-        float* out = a.psums + (size_t)d * NSUM * a.Pp + pos;
-        out[0] = w0; out[(size_t)1 * a.Pp] = w1; out[(size_t)2 * a.Pp] = w2;
-        out[(size_t)3 * a.Pp] = ab0; out[(size_t)4 * a.Pp] = ab1; out[(size_t)5 * a.Pp] = bb;
-        out[(size_t)6 * a.Pp] = ra0; out[(size_t)7 * a.Pp] = ra1; out[(size_t)8 * a.Pp] = rb;
-        out[(size_t)9 * a.Pp] = nl;
     }
+    if (NLL_ONLY && in_range) a.part_nll[(size_t)blockIdx.y * a.Pp + pos] = nll_total;
 }
 
 struct SumsArgs {
@@ -529,9 +546,11 @@ __global__ void __launch_bounds__(PASS_CELLS, 2) fold_sums_moments_kernel(SumsAr
 
 }  // namespace
 
-// FP32 pass with all moments for the non-Normal terms on a gap-free daily axis; `ps` planned over the phases
-int launch_fold_pass_generic(Workspace& ws, const PassShape& ps, int term, const float* y_scaled, int64_t ld, int i0,
-                             int i1, const int* status, cudaStream_t s) {
+// Pass of the non-Normal terms on a gap-free daily axis; `ps` planned over the phases.
+//   nll_only = false: FP32 pass with all moments (stage 1 sums, stage 2 moments; partials in float)
+//   nll_only = true : FP64 day arithmetic, nll only (part_nll per chunk of `ps`)
+int launch_fold_pass_generic(Workspace& ws, const PassShape& ps, int term, bool nll_only, const float* y_scaled, int64_t ld,
+                             int i0, int i1, const int* status, cudaStream_t s) {
     if (ps.n_active <= 0) return 0;
     if (!ws.psums) { set_error("workspace was sized for another family"); return ATTRICI_EWORKSPACE; }
     StreamArgs a;
@@ -540,28 +559,42 @@ int launch_fold_pass_generic(Workspace& ws, const PassShape& ps, int term, const
     a.i0 = i0; a.i1 = i1;
     a.n_ph = fold_phases(ws);
     a.njp = ((ws.T + NPHASE - 1) / NPHASE + ST_U - 1) / ST_U * ST_U;
-    a.pb64 = ws.pb64; a.basis32 = ws.basis32; a.th_pass = ws.th_pass; a.status = status;
-    a.psums = ws.psums;
+    a.pb64 = ws.pb64; a.basis32 = ws.basis32; a.basis64 = ws.basis64; a.th_pass = ws.th_pass; a.status = status;
+    a.psums = ws.psums; a.part_nll = ws.part_nll;
     const int n_cb = (ps.n_active + PASS_CELLS - 1) / PASS_CELLS;
+    const size_t elem = nll_only ? sizeof(double) : sizeof(float);
+    const size_t smem = elem * ((size_t)NP * PASS_CELLS + ST_MAXPH * 2 * MAXM + (size_t)ST_MAXPH * a.njp);
+    if (smem > 200 * 1024) { set_error("series too long for the phase-ordered pass (T=%d)", ws.T); return ATTRICI_EUNSUPPORTED; }
+    auto launch = [&](auto kernel, dim3 grid) -> int {
+        ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, PASS_CELLS, smem, s>>>(a);
+        return 0;
+    };
+    if (nll_only) {
+        a.ph_len = ps.chunk_len;   // one CTA row per chunk of the plan: part_nll[chunk][Pp]
+        dim3 grid(n_cb, ps.n_chunks);
+        switch (term) {
+            case T_GAMMA: ATTRICI_TRY(launch(fold_stream_kernel<K_GAMMA, double, true>, grid)); break;
+            case T_BETA: ATTRICI_TRY(launch(fold_stream_kernel<K_BETA, double, true>, grid)); break;
+            case T_WEIBULL: ATTRICI_TRY(launch(fold_stream_kernel<K_WEIBULL, double, true>, grid)); break;
+            case T_BERNOULLI: ATTRICI_TRY(launch(fold_stream_kernel<K_BERNOULLI, double, true>, grid)); break;
+            default: set_error("no phase-ordered generic pass for term %d", term); return ATTRICI_EINVAL;
+        }
+        ATTRICI_LAUNCH_CHECK();
+        return 0;
+    }
     int want = (148 * 16 + n_cb - 1) / n_cb;
     if (want > a.n_ph) want = a.n_ph;
     if (want < 1) want = 1;
     a.ph_len = (a.n_ph + want - 1) / want;
     if (a.ph_len > ST_MAXPH) a.ph_len = ST_MAXPH;
-    const size_t smem = sizeof(float) * ((size_t)NP * PASS_CELLS + ST_MAXPH * 2 * MAXM + (size_t)ST_MAXPH * a.njp);
-    if (smem > 200 * 1024) { set_error("series too long for the phase-ordered pass (T=%d)", ws.T); return ATTRICI_EUNSUPPORTED; }
     dim3 grid1(n_cb, (a.n_ph + a.ph_len - 1) / a.ph_len);
-    auto launch = [&](auto kernel) -> int {
-        ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<grid1, PASS_CELLS, smem, s>>>(a);
-        return 0;
-    };
     bool has_b = true, has_ab = false;
     switch (term) {
-        case T_GAMMA: ATTRICI_TRY(launch(fold_stream_sums_kernel<K_GAMMA>)); break;
-        case T_BETA: ATTRICI_TRY(launch(fold_stream_sums_kernel<K_BETA>)); has_ab = true; break;
-        case T_WEIBULL: ATTRICI_TRY(launch(fold_stream_sums_kernel<K_WEIBULL>)); has_ab = true; break;
-        case T_BERNOULLI: ATTRICI_TRY(launch(fold_stream_sums_kernel<K_BERNOULLI>)); has_b = false; break;
+        case T_GAMMA: ATTRICI_TRY(launch(fold_stream_kernel<K_GAMMA, float, false>, grid1)); break;
+        case T_BETA: ATTRICI_TRY(launch(fold_stream_kernel<K_BETA, float, false>, grid1)); has_ab = true; break;
+        case T_WEIBULL: ATTRICI_TRY(launch(fold_stream_kernel<K_WEIBULL, float, false>, grid1)); has_ab = true; break;
+        case T_BERNOULLI: ATTRICI_TRY(launch(fold_stream_kernel<K_BERNOULLI, float, false>, grid1)); has_b = false; break;
         default: set_error("no phase-ordered generic pass for term %d", term); return ATTRICI_EINVAL;
     }
     ATTRICI_LAUNCH_CHECK();
