@@ -70,11 +70,15 @@ template <int KIND, typename R> ATTRICI_HD DayTerms<R> family_day_t(R y, R ea, R
         R phi = exp(eb);
         R A = mu * phi, B = (R(1) - mu) * phi;
         R ly = log(y), l1y = log1p(-y);
-        R psiA = digamma<R>(A), psiB = digamma<R>(B), psiP = digamma<R>(phi);
-        R tA = trigamma<R>(A), tB = trigamma<R>(B), tP = trigamma<R>(phi);
+        // digamma and trigamma of each argument from one shared recurrence
+        R psiA, tA, psiB, tB, psiP, tP;
+        psi_tri<R>(A, psiA, tA);
+        psi_tri<R>(B, psiB, tB);
+        psi_tri<R>(phi, psiP, tP);
+        const R lgA = lgam<R>(A), lgB = lgam<R>(B), lgP = lgam<R>(phi);
         R m1 = mu * (R(1) - mu);
         R delta = ly - l1y - psiA + psiB;
-        d.nll = -((A - R(1)) * ly + (B - R(1)) * l1y - lgam<R>(A) - lgam<R>(B) + lgam<R>(phi));
+        d.nll = -((A - R(1)) * ly + (B - R(1)) * l1y - lgA - lgB + lgP);
         d.rA = -phi * m1 * delta;
         d.rB = -(A * (ly - psiA) + B * (l1y - psiB) + phi * psiP);
         R pm = phi * m1;

@@ -63,6 +63,26 @@ template <typename R> ATTRICI_HD R trigamma(R x) {
     return acc + s;
 }
 
+// digamma and trigamma of one argument x > 0 together: one upward recurrence to X >= X0 shared by both (sum of
+// 1 / (x + k) for digamma, of its square for trigamma), then their asymptotic series on the shared powers of 1 / X.
+// The Beta likelihood needs both at A, B and phi every day.  (lgamma stays with the library function: a float32
+// Stirling form loses too much of the nll to cancellation.)
+template <typename R> ATTRICI_HD void psi_tri(R x, R& psi, R& tri) {
+    const R X0 = (sizeof(R) == 8) ? R(10) : R(6);
+    R s1 = R(0), s2 = R(0);
+    while (x < X0) {
+        const R i = R(1) / x;
+        s1 += i;
+        s2 = fma(i, i, s2);
+        x += R(1);
+    }
+    const R inv = R(1) / x, inv2 = inv * inv;
+    const R ps = inv2 * (R(1.0 / 12) - inv2 * (R(1.0 / 120) - inv2 * (R(1.0 / 252) - inv2 * (R(1.0 / 240) - inv2 * (R(1.0 / 132) - inv2 * R(691.0 / 32760))))));
+    psi = log(x) - R(0.5) * inv - ps - s1;
+    const R ts = inv * (R(1) + inv * (R(0.5) + inv * (R(1.0 / 6) - inv2 * (R(1.0 / 30) - inv2 * (R(1.0 / 42) - inv2 * (R(1.0 / 30) - inv2 * (R(5.0 / 66) - inv2 * R(691.0 / 2730))))))));
+    tri = ts + s2;
+}
+
 // ---------------------------------------------------------------------------------------
 // normal distribution
 // ---------------------------------------------------------------------------------------
