@@ -159,7 +159,7 @@ int run_pass(Workspace& ws, int fold, const int* list, int n_active, int term, b
         return launch_reduce(ws, ps, true, PASS_NLL, s, status);
     }
     if (fold == FOLD_SUMS) {
-        PassShape ps = plan_pass(ws, list, n_active, 0, fold_phases(ws), true);
+        PassShape ps = plan_pass(ws, list, n_active, 0, fold_items(ws, mode, exact), true);
         if (e0) ATTRICI_CUDA_CHECK(cudaEventRecord(e0, s));
         ATTRICI_TRY(launch_fold_pass(ws, ps, mode, exact, status, s));
         if (e1) ATTRICI_CUDA_CHECK(cudaEventRecord(e1, s));

@@ -210,6 +210,8 @@ int launch_pass_mma(Workspace& ws, const PassShape& ps, const float* y_scaled, i
 // PASS_FLAT = PASS_FULL at a point whose only non-zero coefficients are the two intercepts (folded Normal pass)
 enum { PASS_NLL = 0, PASS_GRAD = 1, PASS_FULL = 2, PASS_FLAT = 3 };
 int fold_phases(const Workspace& ws);
+// items a folded Normal pass of this mode is planned over (phases, or phase pairs: fold.cu)
+int fold_items(const Workspace& ws, int mode, bool exact);
 int launch_fold_pass(Workspace& ws, const PassShape& ps, int mode, bool exact, const int* status, cudaStream_t s);
 // phase-ordered pass of the Gamma / Weibull / Beta / Bernoulli terms over the scaled series: FP32 with all moments,
 // or (nll_only) the FP64 nll of the returned point
