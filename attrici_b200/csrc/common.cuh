@@ -88,6 +88,7 @@ struct Workspace {
     double* ystat;     // [NPHASE][3][Cp] per-phase sums {y, y^2, y gmt} over the cell's valid window days (Normal only)
     double* gstat;     // [NPHASE][3][Cp] per-phase {n, sum gmt, sum gmt^2} of cells with missing days (Normal only)
     float* psums;      // [NPHASE][11][Cp] per-phase sums of the day terms (two-stage pass of the other families)
+    void* h_tab;       // [NTRI] moment indices of the information-matrix entries of the term being fitted (step.cu)
 
     static size_t align(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -145,6 +146,7 @@ struct Workspace {
         ystat = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)NPHASE * c) : nullptr;
         gstat = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)NPHASE * c) : nullptr;
         psums = (family != ATTRICI_NORMAL) ? (float*)take(4 * 11 * (size_t)NPHASE * c) : nullptr;
+        h_tab = take(16 * (size_t)NTRI);
         bytes = off;
         return off;
     }

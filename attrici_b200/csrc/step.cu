@@ -52,7 +52,7 @@ __device__ bool WarpCtx::solve(CellScratch& S, double lam) const {
     for (int j = 0; j < NP; ++j) {
         const double d = __shfl_sync(FULL, a[j], j);
         if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }   // uniform: d is the same in every lane
-        const double ljj = sqrt(d), inv = 1.0 / ljj;
+        const double inv = rsqrt(d), ljj = d * inv;   // 1 ulp-level: the factor only shapes a damped step
         if (l == j) { a[j] = ljj; inv_diag = inv; }
         else a[j] *= inv;                                  // L[l][j] for l > j (rows l < j hold zeros)
         if (j + 1 < NP) {
@@ -120,11 +120,25 @@ __global__ void __launch_bounds__(STEP_THREADS) fit_init_kernel(StepArgs a, int*
     if (run && ctx.lane() == 0) list_out[atomicAdd(counter, 1)] = cell;
 }
 
+// the table once per term (launch_fit_init), so that the step kernel only copies it
+__global__ void h_table_kernel(StepArgs a, HEntry* tab) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < NTRI; e += gridDim.x * blockDim.x) {
+        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+        while (i * (i + 1) / 2 > e) --i;
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        tab[e] = h_entry(a.term, a.modes, i, e - i * (i + 1) / 2);
+    }
+}
+
 __global__ void __launch_bounds__(STEP_THREADS, 5) fit_step_kernel(StepArgs a, const int* list_in, int n_in,
-                                                                int* list_out, int* counter, int fresh_fisher) {
+                                                                int* list_out, int* counter, int fresh_fisher,
+                                                                const HEntry* __restrict__ tab_g) {
     __shared__ CellScratch S[STEP_WARPS];
     __shared__ HEntry tab[NTRI];
-    build_h_table(a, tab);
+    static_assert(sizeof(HEntry) == 12, "HEntry is copied as three words");
+    for (int i = threadIdx.x; i < NTRI * 3; i += STEP_THREADS)
+        reinterpret_cast<int*>(tab)[i] = __ldg(reinterpret_cast<const int*>(tab_g) + i);
+    __syncthreads();
     int cell = warp_cell(list_in, n_in);
     if (cell < 0) return;
     WarpCtx ctx;
@@ -312,6 +326,8 @@ int launch_fit_init(Workspace& ws, const StepParams& sp, int* list_out, int* cou
     ATTRICI_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), s));
     fit_init_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp), list_out, counter);
     ATTRICI_LAUNCH_CHECK();
+    h_table_kernel<<<3, 128, 0, s>>>(make_args(ws, sp), reinterpret_cast<HEntry*>(ws.h_tab));
+    ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
@@ -320,7 +336,8 @@ int launch_fit_step(Workspace& ws, const StepParams& sp, const int* list_in, int
     ATTRICI_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), s));
     if (n_in <= 0) return 0;
     fit_step_kernel<<<warp_blocks(n_in), STEP_THREADS, 0, s>>>(make_args(ws, sp), list_in, n_in, list_out, counter,
-                                                               fresh_fisher ? 1 : 0);
+                                                               fresh_fisher ? 1 : 0,
+                                                               reinterpret_cast<const HEntry*>(ws.h_tab));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }

@@ -474,7 +474,9 @@ def test_series_shorter_than_one_phase_cycle(T):
     for j in (0, 3, C - 1):
         ref = oracle.detrend_cell("tas", y[:, j], gmt, days, helpers.MODES)
         np.testing.assert_allclose(host(out["fit"].logp)[j], ref["logp"], rtol=1e-9)
-        np.testing.assert_allclose(host(out["cfact"])[:, j], ref["cfact"], rtol=1e-5, equal_nan=True)
+        # 400 days barely identify the GMT slope: the optimum is flat in that direction, so equal logp (1e-9) still
+        # leaves the counterfactual a few 1e-5 apart
+        np.testing.assert_allclose(host(out["cfact"])[:, j], ref["cfact"], rtol=5e-5 if T < 1000 else 1e-5, equal_nan=True)
 
 
 def test_global_land_size_batch():
