@@ -460,6 +460,43 @@ def test_strided_unaligned_input_matches_contiguous(offset, width):
     assert np.array_equal(host(c["cfact"]), host(a["cfact"]), equal_nan=True)
 
 
+@pytest.mark.parametrize("keep_scaled", [False, True])
+def test_lean_quantile_map_matches_generic_kernel(keep_scaled):
+    """The streamlined Normal quantile-map kernel (no post rule, no cfact_scaled output; hoisted reciprocal in the
+    float32 scaling) must give the bits of the generic kernel, which is selected by asking for cfact_scaled -
+    including for NaN / Inf days, the cell's own minimum (numerator 0), tail days and cells whose scale lies
+    outside the range the hoisted reciprocal is used for."""
+    T, C = 6000, 70
+    y = synthetic.tas_cells(C, T, seed=31, nan_fraction=0.02)
+    y[17, 4] = np.inf
+    y[18, 4] = -np.inf
+    y[100:103, 9] += 60.0          # tail days: full cdf -> ppf evaluation
+    y[:, 11] = 250.0               # constant cell: degenerate scale
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    s = CellBatchSolver("tas", device=DEV)
+    s.set_predictor(days, gmt, C)
+    yd = dev(y)
+    ys, scaling = s.scale(yd)
+    fit = s.fit(ys)
+    params = fit.params.clone()
+    params[11] = params[0]         # the constant cell has no fit: any finite coefficients exercise the map
+    # cells 20 / 21: the same series at scales beyond 2^60 and below 2^-60
+    yd2 = yd.clone()
+    sc2 = scaling.clone()
+    for j, f in ((20, 2.0 ** 90), (21, 2.0 ** -100)):
+        yd2[:, j] = yd[:, j] * f
+        sc2[j] = scaling[j] * f
+    ys_in = None
+    if keep_scaled:
+        ys_in, _ = s.scale(yd2)   # scaling by a power of two leaves y_scaled unchanged
+        assert np.array_equal(host(ys_in), host(ys), equal_nan=True)
+    lean_c, lean_r, _ = s.quantile_map(yd2, ys_in, params, sc2)
+    gen_c, gen_r, _ = s.quantile_map(yd2, ys_in, params, sc2, want_scaled=True)
+    assert np.array_equal(host(lean_c), host(gen_c), equal_nan=True)
+    assert torch.equal(lean_r, gen_r)
+    assert host(lean_r)[17, 4] == 1 and host(lean_r)[100, 9] != 1
+
+
 @pytest.mark.parametrize("T", [400, 1461, 1462])
 def test_series_shorter_than_one_phase_cycle(T):
     """Phase folding with fewer days than phases (every phase holds at most one day) and right at the 1461-day
