@@ -106,11 +106,48 @@ StepParams step_params(const attrici_variable_t& var, const attrici_fit_options_
     return sp;
 }
 
-int read_counter(const int* dev, int* host, cudaStream_t s) {
-    ATTRICI_CUDA_CHECK(cudaMemcpyAsync(host, dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+// Small device -> host read-backs (numbers of running cells, the fold flags) go through a pinned, mapped host
+// mailbox written by a one-warp kernel, not through cudaMemcpyAsync: a copy would queue on the D2H copy engine
+// behind the bulk download of the previous slab of attrici_detrend_host (tens of ms) and stall the fit.
+struct Mailbox { int* host = nullptr; int* dev = nullptr; bool tried = false; };
+Mailbox& mailbox() {
+    static thread_local Mailbox m;
+    if (!m.tried) {
+        m.tried = true;
+        void* h = nullptr;
+        void* d = nullptr;
+        if (cudaHostAlloc(&h, 256, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+            cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+            m.host = (int*)h;
+            m.dev = (int*)d;
+        } else {
+            if (h) cudaFreeHost(h);
+            cudaGetLastError();
+        }
+    }
+    return m;
+}
+
+__global__ void post_ints_kernel(const int* __restrict__ src, int n, volatile int* dst) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
+int read_ints(const int* dev, int* host, int n, cudaStream_t s) {
+    Mailbox& m = mailbox();
+    if (m.host && n <= 32) {
+        post_ints_kernel<<<1, 32, 0, s>>>(dev, n, m.dev);
+        ATTRICI_LAUNCH_CHECK();
+        ATTRICI_CUDA_CHECK(cudaStreamSynchronize(s));
+        for (int i = 0; i < n; ++i) host[i] = ((volatile int*)m.host)[i];
+        return 0;
+    }
+    ATTRICI_CUDA_CHECK(cudaMemcpyAsync(host, dev, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
     ATTRICI_CUDA_CHECK(cudaStreamSynchronize(s));
     return 0;
 }
+
+int read_counter(const int* dev, int* host, cudaStream_t s) { return read_ints(dev, host, 1, s); }
 
 // ATTRICI_NO_FOLD=1 keeps every family on the day-by-day kernels (A/B measurements only)
 bool fold_enabled() {
@@ -128,8 +165,7 @@ int fold_applies(Workspace& ws, int term, int i0, int i1, cudaStream_t s, int* f
     if (!fold_enabled()) return 0;
     if (term == T_NORMAL && !ws.ystat) return 0;
     int h[3] = {1, -1, -1};   // {days off the gap-free axis, fit window the phase rows / sums were gathered for}
-    ATTRICI_CUDA_CHECK(cudaMemcpyAsync(h, ws.fold_bad, sizeof(h), cudaMemcpyDeviceToHost, s));
-    ATTRICI_CUDA_CHECK(cudaStreamSynchronize(s));
+    ATTRICI_TRY(read_ints(ws.fold_bad, h, 3, s));
     if (h[0] == 0 && h[1] == i0 && h[2] == i1) {
         // measured (scripts/bench_families.py): the phase-ordered stream wins for the Gamma and Bernoulli terms
         // (tasrange fit 2.1x, pr 1.5x); the Beta and Weibull terms spend their time in per-day special functions and
