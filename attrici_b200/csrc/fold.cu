@@ -261,8 +261,10 @@ template <int K, typename A> __device__ __forceinline__ void fold_accumulate2(A*
 
 template <int MODE, typename RW>
 __global__ void __launch_bounds__(PASS_CELLS, MODE >= 2 ? 2 : 3) fold_pass_pair_kernel(FoldArgs a) {
+    constexpr bool FLAT = MODE == 3;      // the flat start point: only the two intercepts are non-zero
     constexpr bool MOMENTS = MODE >= 1;   // gradient moments
     constexpr bool FISHER = MODE >= 2;    // Fisher moments
+    __shared__ double flat_sums[FLAT ? 4 * NTRIG : 1];   // sum over the chunk's phases of {n, Sg, Sgg, 2 n} x trig17
     __shared__ __align__(16) double tile[FOLD_TILE * B_STRIDE];   // rows of the phases d of the tile
     __shared__ double mirror[FOLD_TILE][4];                       // {n, Sg, Sgg} of the phases 1461 - d
     __shared__ __align__(16) RW trig_w[FOLD_TILE * 2 * NH];
@@ -283,9 +285,11 @@ __global__ void __launch_bounds__(PASS_CELLS, MODE >= 2 ? 2 : 3) fold_pass_pair_
 
     double thA[NA], thB[NB];
 #pragma unroll
-    for (int i = 0; i < NA; ++i) thA[i] = active ? a.th_pass[(size_t)i * a.Cp + cell] : 0.0;
+    for (int i = 0; i < NA; ++i) thA[i] = (active && (!FLAT || i == 0)) ? a.th_pass[(size_t)i * a.Cp + cell] : 0.0;
 #pragma unroll
-    for (int i = 0; i < NB; ++i) thB[i] = active ? a.th_pass[(size_t)(NA + i) * a.Cp + cell] : 0.0;
+    for (int i = 0; i < NB; ++i) thB[i] = (active && (!FLAT || i == 0)) ? a.th_pass[(size_t)(NA + i) * a.Cp + cell] : 0.0;
+    const double e2_flat = FLAT ? exp(-2.0 * thB[0]) : 0.0;
+    double flat_acc = 0.0;   // threads 0 .. 67: one of the 4 x 17 sums each, gathered tile by tile
 
     RW AA[3 * NTRIG], BB[NTRIG];
     double GA[2 * NB], GB[NB];
@@ -343,6 +347,19 @@ __global__ void __launch_bounds__(PASS_CELLS, MODE >= 2 ? 2 : 3) fold_pass_pair_
             mirror[r][c] = d > 0 ? a.pb64[(size_t)(NPHASE - d) * B_STRIDE + (c == 0 ? 0 : c + 2 * NH)] : 0.0;
         }
         __syncthreads();
+        if (FLAT && tid < 4 * NTRIG) {
+            // both phases of a pair: the mirrored phase has the same cosines and the negated sines
+            const int p = tid / NTRIG, j = tid % NTRIG;
+            const int wcol = p == 0 ? 0 : (p == 1 ? 1 + 2 * NH : (p == 2 ? 2 + 2 * NH : 0));
+            const int mcol = p == 0 ? 0 : (p == 1 ? 1 : (p == 2 ? 2 : 0));
+            const double wscale = p == 3 ? 2.0 : 1.0;
+            const double msign = j > NH ? -1.0 : 1.0;
+            for (int r = 0; r < n_rows; ++r) {
+                const double* row = tile + r * B_STRIDE;
+                const double w = wscale * fma(msign, mirror[r][mcol], row[wcol]);
+                flat_acc = fma(w, j == 0 ? 1.0 : row[j], flat_acc);
+            }
+        }
         if (!warp_active) {   // keep the group accounting of this warp's (empty) ring consistent
             for (int r = 0; r < n_rows; ++r) issue(q0 + r + PAIR_RING - 1);
             continue;
@@ -371,27 +388,32 @@ __global__ void __launch_bounds__(PASS_CELLS, MODE >= 2 ? 2 : 3) fold_pass_pair_
                 }
             }
             if (!active) n = sg = sgg = nm = sgm = sggm = 0.0;
-            // cosine and sine halves of the three predictors
-            double ca = thA[0], sa = 0.0, cb = thA[1], sb = 0.0, cc = thB[0], sc = 0.0;
+            double av, bv, cv, am, bm, cm, e2, e2m;
+            if (FLAT) {
+                av = am = thA[0]; bv = bm = 0.0; cv = cm = thB[0]; e2 = e2m = e2_flat;
+            } else {
+                // cosine and sine halves of the three predictors
+                double ca = thA[0], sa = 0.0, cb = thA[1], sb = 0.0, cc = thB[0], sc = 0.0;
 #pragma unroll
-            for (int k = 0; k < MAXM; ++k) {
-                const double ck = row[1 + k], sk = row[1 + NH + k];
-                ca = fma(thA[2 + k], ck, ca);
-                sa = fma(thA[2 + MAXM + k], sk, sa);
-                cb = fma(thA[2 + 2 * MAXM + k], ck, cb);
-                sb = fma(thA[2 + 3 * MAXM + k], sk, sb);
-                cc = fma(thB[1 + k], ck, cc);
-                sc = fma(thB[1 + MAXM + k], sk, sc);
+                for (int k = 0; k < MAXM; ++k) {
+                    const double ck = row[1 + k], sk = row[1 + NH + k];
+                    ca = fma(thA[2 + k], ck, ca);
+                    sa = fma(thA[2 + MAXM + k], sk, sa);
+                    cb = fma(thA[2 + 2 * MAXM + k], ck, cb);
+                    sb = fma(thA[2 + 3 * MAXM + k], sk, sb);
+                    cc = fma(thB[1 + k], ck, cc);
+                    sc = fma(thB[1 + MAXM + k], sk, sc);
+                }
+                av = ca + sa; bv = cb + sb; cv = cc + sc;      // phase d
+                am = ca - sa; bm = cb - sb; cm = cc - sc;      // phase 1461 - d
+                e2 = exp(-2.0 * cv); e2m = exp(-2.0 * cm);
             }
-            const double av = ca + sa, bv = cb + sb, cv = cc + sc;      // phase d
-            const double am = ca - sa, bm = cb - sb, cm = cc - sc;      // phase 1461 - d
-            const double e2 = exp(-2.0 * cv), e2m = exp(-2.0 * cm);
             const double R0 = sy - av * n - bv * sg, R0m = sym - am * nm - bm * sgm;
             const double R1 = syg - av * sg - bv * sgg, R1m = sygm - am * sgm - bm * sggm;
             const double Q = syy - av * sy - bv * syg - av * R0 - bv * R1;
             const double Qm = syym - am * sym - bm * sygm - am * R0m - bm * R1m;
             nll += n * (cv + 0.91893853320467274178) + 0.5 * e2 * Q + nm * (cm + 0.91893853320467274178) + 0.5 * e2m * Qm;
-            if (FISHER) {
+            if (FISHER && (!FLAT || own_g)) {   // flat point, no missing day: formed from flat_sums after the loop
                 const RW* tw = trig_w + r * 2 * NH;
                 const double w0 = e2 * n, w0m = e2m * nm, w1 = e2 * sg, w1m = e2m * sgm, w2 = e2 * sgg, w2m = e2m * sggm;
                 fold_accumulate2<NH, RW>(AA, (RW)(w0 + w0m), (RW)(w0 - w0m), tw);
@@ -409,18 +431,26 @@ __global__ void __launch_bounds__(PASS_CELLS, MODE >= 2 ? 2 : 3) fold_pass_pair_
         }
     }
     asm volatile("cp.async.wait_group 0;\n" ::);
+    if (FLAT) {
+        if (tid < 4 * NTRIG) flat_sums[tid] = flat_acc;
+        __syncthreads();
+    }
 
     if (in_range) {
         a.part_nll[(size_t)chunk * a.Pp + pos] = nll;
         if (MOMENTS) {
             double* out = a.part_acc + (size_t)chunk * NACC * a.Pp + pos;
             if (FISHER) {
+                const bool from_sums = FLAT && !own_g;
+                const double fs = active ? 1.0 : 0.0;
 #pragma unroll
-                for (int i = 0; i < 3 * NTRIG; ++i) out[(size_t)(ACC_AA + i) * a.Pp] = (double)AA[i];
+                for (int i = 0; i < 3 * NTRIG; ++i)
+                    out[(size_t)(ACC_AA + i) * a.Pp] = from_sums ? fs * e2_flat * flat_sums[i] : (double)AA[i];
 #pragma unroll
                 for (int i = 0; i < 2 * NTRIG; ++i) out[(size_t)(ACC_AB + i) * a.Pp] = 0.0;
 #pragma unroll
-                for (int i = 0; i < NTRIG; ++i) out[(size_t)(ACC_BB + i) * a.Pp] = (double)BB[i];
+                for (int i = 0; i < NTRIG; ++i)
+                    out[(size_t)(ACC_BB + i) * a.Pp] = from_sums ? fs * flat_sums[3 * NTRIG + i] : (double)BB[i];
             }
 #pragma unroll
             for (int i = 0; i < 2 * NB; ++i) out[(size_t)(ACC_GA + i) * a.Pp] = GA[i];
@@ -437,7 +467,7 @@ int fold_phases(const Workspace& ws) { return ws.T < NPHASE ? ws.T : NPHASE; }
 // number of items a folded Normal pass is planned over: phases, or phase pairs when the series covers a whole cycle
 int fold_items(const Workspace& ws, int mode, bool exact) {
     static const bool pair_on = [] { const char* e = getenv("ATTRICI_NO_PAIR"); return !(e && e[0] == '1'); }();
-    const bool pair = pair_on && ws.T >= NPHASE && !exact && mode != PASS_FLAT;
+    const bool pair = pair_on && ws.T >= NPHASE && !exact;
     return pair ? NPAIR : fold_phases(ws);
 }
 
@@ -462,7 +492,8 @@ int launch_fold_pass(Workspace& ws, const PassShape& ps, int mode, bool exact, c
     a.part_acc = (double*)ws.part_acc;
     dim3 grid((ps.n_active + PASS_CELLS - 1) / PASS_CELLS, ps.n_chunks);
     if (fold_items(ws, mode, exact) == NPAIR && ws.T >= NPHASE) {
-        if (mode == PASS_NLL) fold_pass_pair_kernel<0, float><<<grid, PASS_CELLS, 0, s>>>(a);
+        if (mode == PASS_FLAT) fold_pass_pair_kernel<3, float><<<grid, PASS_CELLS, 0, s>>>(a);
+        else if (mode == PASS_NLL) fold_pass_pair_kernel<0, float><<<grid, PASS_CELLS, 0, s>>>(a);
         else if (mode == PASS_GRAD) fold_pass_pair_kernel<1, float><<<grid, PASS_CELLS, 0, s>>>(a);
         else fold_pass_pair_kernel<2, float><<<grid, PASS_CELLS, 0, s>>>(a);
         ATTRICI_LAUNCH_CHECK();
