@@ -319,11 +319,11 @@ def run_cuda(args):
                     for i, n in enumerate(seg_names)}
         dom = max(("scale", "quantile_map"), key=lambda n: segments[n]["ms"])
         dom_kernel = {"scale": "prep_minmax_kernel + prep_scale_fold_kernel (2 launches)",
-                      "quantile_map": "qmap_fold_normal_kernel"}[dom]
+                      "quantile_map": "qmap_fold_lean_kernel"}[dom]
         achieved = segments[dom]["algorithmic_gbs"]
         traffic = None
         if C == TILE_CELLS:
-            traffic = (ncu_traffic("qmap_fold_normal_kernel") if dom == "quantile_map" else
+            traffic = (ncu_traffic("qmap_fold_lean_kernel") if dom == "quantile_map" else
                        sum(filter(None, [ncu_traffic("prep_minmax_kernel"), ncu_traffic("prep_scale_fold_kernel")])) or None)
         cpu = None
         if not args.no_cpu_baseline:
