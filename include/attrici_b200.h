@@ -187,6 +187,19 @@ ATTRICI_API int attrici_eval_parameter(void* workspace, size_t workspace_bytes, 
  *   out[n x ld] float64, cell-minor like every other series */
 ATTRICI_API int attrici_mt19937_uniform(const uint32_t* seeds, int C, int n, double* out, int64_t ld, void* stream);
 
+/* SSA smoothing of the GMT predictor: first elementary component of the singular spectrum analysis of x[n]
+ * (window W), i.e. row 0 of SingularSpectrumAnalysis(W).transform(x) as used by calc_gmt_by_ssa
+ * (attrici/preprocessing.py:13-40; attrici/vendored/singularspectrumanalysis.py:161-207, 51-76) - what
+ * `attrici ssa` (attrici/ssa.py:12-60) computes before `detrend` reads it with --gmt-file.
+ *   x, out: device float64 [n]; workspace: attrici_ssa_workspace_bytes(n, W) bytes, 256-byte aligned;
+ *   the leading eigenvector comes from a power iteration that stops at |G v - lambda v| <= tol lambda or after
+ *   max_iter steps; info (device int32 [2], nullable) = {iterations, converged}, eigenvalue (device float64 [1],
+ *   nullable) = lambda.  window outside [2, n] -> ATTRICI_EINVAL (pyts raises ValueError, :253-262) */
+ATTRICI_API int attrici_ssa_workspace_bytes(int n, int window, size_t* bytes);
+ATTRICI_API int attrici_ssa_first_component(const double* x, int n, int window, double* out, void* workspace,
+                                size_t workspace_bytes, int max_iter, double tol, int32_t* info, double* eigenvalue,
+                                void* stream);
+
 /* whole path for one batch with HOST buffers (pinned recommended): H2D of y, scale, fit,
  * quantile map, D2H of cfact / params / logp / status, cells processed in slabs of
  * `slab_cells` with copies and kernels overlapped on internal streams.

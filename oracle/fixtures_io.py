@@ -10,6 +10,10 @@ containers the reference's tests use are parsed directly:
 * ``tests/data/20CRv3-ERA5_germany_ssa_gmt.nc`` - netCDF-4 with two chunked
   (512 x f64, unfiltered) datasets indexed by version-1 B-trees.
 
+* ``tests/data/20crv3-era5_gmt_raw.nc`` - netCDF-4, ``tas(time, lat, lon)`` float32 with one value per
+  chunk (unlimited time axis), unfiltered, indexed by a version-1 B-tree; the input of reference
+  ``tests/test_ssa.py:27-44``.
+
 Only used by ``tests/golden/make_golden.py`` (run in the build container, where
 ``/root/reference`` exists) to produce the committed ``tests/golden/*.npz``.
 """
@@ -89,3 +93,29 @@ def read_ssa_gmt(path):
     if np.allclose(np.diff(a), np.diff(a)[0]):
         return a, b
     return b, a
+
+
+def read_raw_gmt(path):
+    """Return the daily raw GMT series ``tas[time]`` (float32) of ``20crv3-era5_gmt_raw.nc``.
+
+    Walks the leaf nodes of the 3-D chunk B-tree: key = chunk size (4 bytes), filter mask, offsets
+    (time, 0, 0, 0); one float32 per chunk.
+    """
+    buf = open(path, "rb").read()
+    vals = {}
+    for m in re.finditer(rb"TREE", buf):
+        pos = m.start()
+        node_type, level, used = struct.unpack_from("<BBH", buf, pos + 4)
+        if node_type != 1 or level != 0 or used == 0:
+            continue
+        p = pos + 24
+        for _ in range(used):
+            csize, mask, t, o1, o2, o3, addr = struct.unpack_from("<IIQQQQQ", buf, p)
+            p += 48
+            if csize != 4 or mask != 0 or o1 or o2 or o3 or addr + 4 > len(buf):
+                break
+            vals[t] = struct.unpack_from("<f", buf, addr)[0]
+    n = max(vals) + 1
+    if len(vals) != n:
+        raise ValueError(f"{n - len(vals)} chunks missing")
+    return np.array([vals[t] for t in range(n)], dtype=np.float32)
