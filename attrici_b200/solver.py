@@ -195,18 +195,23 @@ class CellBatchSolver:
                                                      _ptr(replaced), _ptr(cs), cfact.stride(0), self._stream()))
         return cfact, replaced, cs
 
-    def eval_parameter(self, params, which, counterfactual=False):
+    def eval_parameter(self, params, which, counterfactual=False, out=None):
         """Per-day distribution parameter (``report_variables``, detrend.py:462-467): ``which`` is a
-        name of ``self.spec.parameters`` or its index."""
+        name of ``self.spec.parameters`` or its index.  ``out``: optional [T, C] float64 CUDA view (unit stride
+        along cells) to write into."""
         if isinstance(which, str):
             which = self.spec.parameters.index(which)
         self._need_basis(self.T, self.C)
-        out = torch.empty((self.T, self.C), dtype=torch.float64, device=self.device)
+        if out is None:
+            out = torch.empty((self.T, self.C), dtype=torch.float64, device=self.device)
+        elif (out.dtype != torch.float64 or not out.is_cuda or tuple(out.shape) != (self.T, self.C)
+              or (self.C > 1 and out.stride(1) != 1)):
+            raise ValueError("out must be a [T, C] float64 CUDA tensor with unit stride along cells")
         ws = self._ws
         with torch.cuda.device(self.device):
             _lib.check(self.lib.attrici_eval_parameter(_ptr(ws), ws.numel(), C.byref(self.var), self.T, self.C,
                                                        _ptr(params), int(which), int(bool(counterfactual)),
-                                                       _ptr(out), self.C, self._stream()))
+                                                       _ptr(out), out.stride(0), self._stream()))
         return out
 
     def mt19937_uniform(self, seeds, n):

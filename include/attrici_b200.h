@@ -200,6 +200,35 @@ ATTRICI_API int attrici_ssa_first_component(const double* x, int n, int window, 
                                 size_t workspace_bytes, int max_iter, double tol, int32_t* info, double* eigenvalue,
                                 void* stream);
 
+/* ---- block bootstrap of the fitted trend (attrici/detrend.py:479-612; Normal family in this version) ----
+ * The samples of a batch of cells are refitted as extra cells of a [T x R C] series (column r C + c) through
+ * attrici_prep_scale_mask / attrici_fit_batch / attrici_eval_parameter; these four entries provide the rest.
+ *
+ * attrici_bootstrap_block_choices: np.random.seed(seeds[c]); choices[c][i] = np.random.randint(0, n_blocks),
+ *   i < n_draws = n_samples * n_blocks (sample-major, year-minor: the order of detrend.py:541-546), after
+ *   skip_words 32-bit generator outputs.  choices: device int16 [C][n_draws].
+ * attrici_bootstrap_scores: what a source day contributes (detrend.py:534): scores[t][c] = ndtri(F_ref,t(y_scaled))
+ *   (build_basis must have run on this workspace for (T, C)).
+ * attrici_bootstrap_resample: samples r0 .. r0+R-1 -> y_new[t][r C + c] = F_ref,t^-1(score of the source day),
+ *   invalid values replaced by y_scaled[t][c] and counted in replaced_count[t][c] (+=) (detrend.py:541-557,
+ *   get_random_block_indices :500-531).  block_start: device int32 [n_blocks + 1] first day of each calendar
+ *   year block (+ T), block_of_day: device int16 [T].
+ * attrici_bootstrap_stats: mean / std (ddof 0) / numpy.percentile(linear) at `levels` of the rescaled
+ *   expectations[t][r C + c] (detrend.py:574-612); mean, std_dev: [T x C], quantiles: [n_levels x T x C]. */
+ATTRICI_API int attrici_bootstrap_block_choices(const uint32_t* seeds, int C, int n_draws, int n_blocks, int skip_words,
+                                    int16_t* choices, void* stream);
+ATTRICI_API int attrici_bootstrap_scores(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                             const float* y_scaled, int64_t ld, int T, int C, const double* params, double* scores,
+                             int64_t ld_s, void* stream);
+ATTRICI_API int attrici_bootstrap_resample(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                               const float* y_scaled, int64_t ld, int T, int C, const double* params,
+                               const double* scores, int64_t ld_s, const int16_t* choices, int n_samples, int n_blocks,
+                               int r0, int R, const int32_t* block_start, const int16_t* block_of_day, float* y_new,
+                               int64_t ld_new, int32_t* replaced_count, int64_t ld_rc, void* stream);
+ATTRICI_API int attrici_bootstrap_stats(const attrici_variable_t* var, const double* expectations, int64_t ld_e, int T, int C,
+                            int n_samples, const double* scaling, const double* levels, int n_levels, double* mean,
+                            double* std_dev, double* quantiles, void* stream);
+
 /* whole path for one batch with HOST buffers (pinned recommended): H2D of y, scale, fit,
  * quantile map, D2H of cfact / params / logp / status, cells processed in slabs of
  * `slab_cells` with copies and kernels overlapped on internal streams.
