@@ -82,6 +82,7 @@ _SIGNATURES = {
     "attrici_detrend_host": (_i, [C.POINTER(Variable), C.POINTER(FitOptions), _vp, _i64, _i, _i, _i, _i, _vp, _vp,
                                    _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i]),
 }
+WHICH_EXPECTATION = -1   # attrici_eval_parameter: Distribution.expectation() instead of a parameter
 EXPORTS = tuple(_SIGNATURES)
 
 _lib = None

@@ -1,5 +1,5 @@
 """Block bootstrap of the fitted trend on the GPU (the bootstrap section of ``fit_and_detrend_cell``,
-attrici/detrend.py:479-612, for a batch of cells; Normal-family variables).
+attrici/detrend.py:479-612, for a batch of cells; every variable but pr).
 
 Per cell the reference reshuffles the factual quantiles of the observations in blocks of one calendar year,
 maps them back through the factual distribution of the target day, refits the model and collects the fitted
@@ -52,8 +52,8 @@ def bootstrap_cells(variable, y, days, gmt, years, seeds, n_samples, modes=4, de
     ``bootstrap_replaced`` [T, C] (int32), plus ``quantile`` (the levels) and the original ``fit``.
     The whole series is the fit window, as the reference demands (detrend.py:480-486)."""
     spec = create_variable(variable) if isinstance(variable, str) else variable
-    if spec.family != _lib.NORMAL:
-        raise NotImplementedError("the bootstrap is implemented for Normal-family variables (tas, ps, rlds, rsds, tasskew)")
+    if spec.family == _lib.BERNOULLI_GAMMA:
+        raise NotImplementedError("the bootstrap is not implemented for pr (Bernoulli-Gamma family)")
     n_samples = int(n_samples)
     if not 1 <= n_samples <= MAX_SAMPLES:
         raise ValueError(f"n_samples must be in 1..{MAX_SAMPLES}")
@@ -75,7 +75,7 @@ def bootstrap_cells(variable, y, days, gmt, years, seeds, n_samples, modes=4, de
     solver.set_predictor(days, gmt, Cn)
     ys, scaling = solver.scale(yt)
     fit = solver.fit(ys)
-    expected = solver.eval_parameter(fit.params, 0)   # Normal.expectation() = mu (distributions.py)
+    expected = solver.eval_parameter(fit.params, _lib.WHICH_EXPECTATION)   # Distribution.expectation()
     mul = scaling[:, 1] if spec.scaling != _lib.SCALE_NONE else torch.ones_like(scaling[:, 1])
     add = scaling[:, 0] if spec.scaling == _lib.SCALE_UNITY else torch.zeros_like(scaling[:, 0])
     expected = expected * mul + add
@@ -97,7 +97,9 @@ def bootstrap_cells(variable, y, days, gmt, years, seeds, n_samples, modes=4, de
 
         # samples as extra cells: R samples of all cells per refit batch, column r * C + c
         R = max(1, min(n_samples, int(max_columns) // Cn))
-        sample_spec = VariableSpec("bootstrap-sample", _lib.NORMAL, _lib.SCALE_NONE)
+        # the samples are already in scaled units: same family, no scaling, no masks
+        sample_spec = VariableSpec("bootstrap-sample", spec.family, _lib.SCALE_NONE)
+        folded = spec.family == _lib.NORMAL   # the Normal fit runs on per-phase sums and needs no scaled copy
         refit = {}
         y_new = torch.empty((T, R * Cn), dtype=torch.float32, device=dev)
         n_pass = []
@@ -113,10 +115,10 @@ def bootstrap_cells(variable, y, days, gmt, years, seeds, n_samples, modes=4, de
                 _ptr(ws), ws.numel(), C.byref(solver.var), _ptr(ys), ys.stride(0), T, Cn, _ptr(fit.params), _ptr(scores),
                 Cn, _ptr(choices), n_samples, n_blocks, r0, r, _ptr(start_d), _ptr(bod_d), _ptr(yb), yb.stride(0),
                 _ptr(replaced), Cn, stream))
-            sv.scale(yb, keep_scaled=False)
-            fb = sv.fit(None)
+            ysb, _ = sv.scale(yb, keep_scaled=not folded)
+            fb = sv.fit(ysb)
             n_pass.append(fb.n_pass)
-            sv.eval_parameter(fb.params, 0, out=E[:, r0 * Cn:r0 * Cn + cols])
+            sv.eval_parameter(fb.params, _lib.WHICH_EXPECTATION, out=E[:, r0 * Cn:r0 * Cn + cols])
         levels = torch.as_tensor(np.asarray(QUANTILES, dtype=np.float64)).to(dev)
         mean = torch.empty((T, Cn), dtype=torch.float64, device=dev)
         std = torch.empty((T, Cn), dtype=torch.float64, device=dev)

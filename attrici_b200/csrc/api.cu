@@ -431,7 +431,10 @@ int attrici_eval_parameter(void* workspace, size_t workspace_bytes, const attric
     ATTRICI_TRY(check_var(var));
     ATTRICI_TRY(check_shape(T, C, ld_out));
     const int n_par = var->family == ATTRICI_BERNOULLI_GAMMA ? 3 : 2;
-    if (which < 0 || which >= n_par) { set_error("parameter index %d outside 0..%d", which, n_par - 1); return ATTRICI_EINVAL; }
+    if (which < ATTRICI_WHICH_EXPECTATION || which >= n_par) {
+        set_error("parameter index %d outside -1..%d", which, n_par - 1);
+        return ATTRICI_EINVAL;
+    }
     if (!params || !out) { set_error("params / out is null"); return ATTRICI_EINVAL; }
     Workspace ws;
     ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, var->family));

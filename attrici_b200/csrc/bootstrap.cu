@@ -9,8 +9,10 @@
 //     MT19937 words; one stream per cell, seeded as detrend.py:285) - bit-identical indices,
 //   * the factual scores of the observed series and the resampled series,
 //   * mean / std / percentiles over the samples.
-// Normal family only in this round (its inverse cdf is ndtri(q) sigma_t + mu_t; the score stored per day is
-// ndtri(ndtr(z)), so that the sample uses exactly the reference's round trip including its saturation).
+// Every family but Bernoulli-Gamma (pr draws from the generator before its bootstrap and treats dry days apart).
+// Normal: the inverse cdf is ndtri(q) sigma_t + mu_t and the score stored per day is ndtri(ndtr(z)), so that the
+// sample uses exactly the reference's round trip including its saturation; Gamma / Beta / Weibull store the
+// quantile and invert it per sample-day with the functions of the quantile map (qmap_impl.cuh).
 #include "common.cuh"
 #include "special.cuh"
 #include "qmap_impl.cuh"
@@ -232,8 +234,9 @@ int bs_bind(Workspace& ws, void* workspace, size_t workspace_bytes, int T, int C
 
 int bs_check_family(const attrici_variable_t* var) {
     if (!var) { set_error("var is null"); return ATTRICI_EINVAL; }
-    if (var->family != ATTRICI_NORMAL) {
-        set_error("the bootstrap is implemented for the Normal family only (family %d)", var->family);
+    if (var->family < ATTRICI_NORMAL || var->family > ATTRICI_BERNOULLI_GAMMA) { set_error("unknown family %d", var->family); return ATTRICI_EINVAL; }
+    if (var->family == ATTRICI_BERNOULLI_GAMMA) {
+        set_error("the bootstrap is not implemented for the Bernoulli-Gamma family (pr)");
         return ATTRICI_EUNSUPPORTED;
     }
     if (var->modes < 1 || var->modes > ATTRICI_MAX_MODES) { set_error("bad modes %d", var->modes); return ATTRICI_EINVAL; }

@@ -175,7 +175,18 @@ __global__ void __launch_bounds__(QMAP_THREADS) eval_parameter_kernel(EvalArgs a
         DistPar ref, cf;
         family_params(a.family, d, ref, cf);
         const DistPar& p = a.counterfactual ? cf : ref;
-        a.out[(size_t)t * a.ld_out + cell] = a.which == 0 ? p.p0 : (a.which == 1 ? p.p1 : p.p2);
+        double v;
+        if (a.which < 0) {
+            // Distribution.expectation() (attrici/distributions.py:89-90, 128-129, 157-158, 186-187, 215-216)
+            switch (a.family) {
+                case ATTRICI_WEIBULL: v = p.p1 * tgamma(1.0 + 1.0 / p.p0); break;   // weibull_min.mean(alpha, scale=beta)
+                case ATTRICI_BERNOULLI_GAMMA: v = (1.0 - p.p0) * p.p1; break;
+                default: v = p.p0; break;                                           // mu
+            }
+        } else {
+            v = a.which == 0 ? p.p0 : (a.which == 1 ? p.p1 : p.p2);
+        }
+        a.out[(size_t)t * a.ld_out + cell] = v;
     }
 }
 

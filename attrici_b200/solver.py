@@ -200,7 +200,7 @@ class CellBatchSolver:
         name of ``self.spec.parameters`` or its index.  ``out``: optional [T, C] float64 CUDA view (unit stride
         along cells) to write into."""
         if isinstance(which, str):
-            which = self.spec.parameters.index(which)
+            which = _lib.WHICH_EXPECTATION if which == "expectation" else self.spec.parameters.index(which)
         self._need_basis(self.T, self.C)
         if out is None:
             out = torch.empty((self.T, self.C), dtype=torch.float64, device=self.device)

@@ -178,7 +178,9 @@ ATTRICI_API int attrici_quantile_map(void* workspace, size_t workspace_bytes, co
                          void* stream);
 
 /* per-day distribution parameters for report_variables (attrici/detrend.py:462-467):
- *   which = index of the parameter in the family's order, counterfactual != 0 -> predictor = 0 */
+ *   which = index of the parameter in the family's order, or ATTRICI_WHICH_EXPECTATION for
+ *   Distribution.expectation() (attrici/distributions.py:89-216); counterfactual != 0 -> predictor = 0 */
+#define ATTRICI_WHICH_EXPECTATION (-1)
 ATTRICI_API int attrici_eval_parameter(void* workspace, size_t workspace_bytes, const attrici_variable_t* var, int T,
                            int C, const double* params, int which, int counterfactual, double* out,
                            int64_t ld_out, void* stream);
@@ -207,8 +209,8 @@ ATTRICI_API int attrici_ssa_first_component(const double* x, int n, int window, 
  * attrici_bootstrap_block_choices: np.random.seed(seeds[c]); choices[c][i] = np.random.randint(0, n_blocks),
  *   i < n_draws = n_samples * n_blocks (sample-major, year-minor: the order of detrend.py:541-546), after
  *   skip_words 32-bit generator outputs.  choices: device int16 [C][n_draws].
- * attrici_bootstrap_scores: what a source day contributes (detrend.py:534): scores[t][c] = ndtri(F_ref,t(y_scaled))
- *   (build_basis must have run on this workspace for (T, C)).
+ * attrici_bootstrap_scores: what a source day contributes (detrend.py:534): scores[t][c] = F_ref,t(y_scaled), kept
+ *   as ndtri(F) for the Normal family (build_basis must have run on this workspace for (T, C)).
  * attrici_bootstrap_resample: samples r0 .. r0+R-1 -> y_new[t][r C + c] = F_ref,t^-1(score of the source day),
  *   invalid values replaced by y_scaled[t][c] and counted in replaced_count[t][c] (+=) (detrend.py:541-557,
  *   get_random_block_indices :500-531).  block_start: device int32 [n_blocks + 1] first day of each calendar

@@ -15,6 +15,7 @@ Only ``tests/`` import this module; the product never does.
 """
 
 import numpy as np
+from scipy import stats
 
 from . import attrici_oracle as ao
 
@@ -56,7 +57,9 @@ def bootstrap_cell(variable, y, gmt_scaled, days, years, n_samples, modes=4, see
     prob = ao.build_problem(family, ys, gmt_scaled, days, modes)
     trace = ao.fit_newton(prob)
     ref = ao.estimate_params(family, trace["params"], gmt_scaled, days, modes)
-    expectation = {"normal": lambda p: p["mu"]}[family]
+    # Distribution.expectation(), attrici/distributions.py:89-90, 157-158, 186-187, 215-216
+    expectation = {"normal": lambda p: p["mu"], "gamma": lambda p: p["mu"], "beta": lambda p: p["mu"],
+                   "weibull": lambda p: stats.weibull_min.mean(p["alpha"], scale=p["beta"])}[family]
     blocks = year_blocks(years)
     ys64 = np.asarray(ys, dtype=np.float64)
     with np.errstate(all="ignore"):

@@ -115,6 +115,30 @@ def test_bootstrap_statistics_against_oracle():
     assert int(out["bootstrap_replaced"][:, 2].sum()) > 0 and int(out["bootstrap_replaced"][:, 0].sum()) == 0
 
 
+@pytest.mark.parametrize("variable", ["tasrange", "sfcWind", "hurs"])
+def test_bootstrap_other_families_against_oracle(variable):
+    """Gamma / Weibull / Beta: quantiles inverted per sample-day by the quantile map's own functions, the samples
+    refitted by the day-ordered / phase-ordered kernels of those families."""
+    from attrici_b200.bootstrap import bootstrap_cells
+    from attrici_b200.solver import cell_seeds
+
+    T, Cn, N = 4 * 365 + 1, 2, 4
+    make = {"tasrange": synthetic.tasrange_cells, "sfcWind": synthetic.wind_cells, "hurs": synthetic.hurs_cells}[variable]
+    y = make(Cn, T)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    years = (np.datetime64("1901-01-01") + days.astype("timedelta64[D]")).astype("datetime64[Y]").astype(int) + 1970
+    lat, lon = np.array([50.75, 51.25]), np.array([9.25, 9.75])
+    out = bootstrap_cells(variable, y, days, gmt, years, cell_seeds(0, lat, lon), N, device=DEV, return_samples=True)
+    for j in range(Cn):
+        ref = bootstrap_oracle.bootstrap_cell(variable, y[:, j], gmt, days, years, N, modes=helpers.MODES, seed=0,
+                                              lat=lat[j], lon=lon[j], return_samples=True)
+        np.testing.assert_array_equal(out["bootstrap_replaced"][:, j].cpu().numpy(), ref["bootstrap_replaced"])
+        np.testing.assert_allclose(out["expected_values"][:, j].cpu().numpy(), ref["expected_values"], rtol=1e-4)
+        np.testing.assert_allclose(out["bootstrap_mean"][:, j].cpu().numpy(), ref["bootstrap_mean"], rtol=1e-4)
+        np.testing.assert_allclose(out["bootstrap_quantiles"][:, :, j].cpu().numpy(), ref["bootstrap_quantiles"], rtol=1e-4)
+        np.testing.assert_allclose(out["bootstrap_std"][:, j].cpu().numpy(), ref["bootstrap_std"], rtol=2e-2, atol=1e-6)
+
+
 def test_unsupported_family_is_refused():
     from attrici_b200.bootstrap import bootstrap_cells
 
