@@ -1,5 +1,5 @@
 """Block bootstrap of the fitted trend on the GPU (the bootstrap section of ``fit_and_detrend_cell``,
-attrici/detrend.py:479-612, for a batch of cells; every variable but pr).
+attrici/detrend.py:479-612, for a batch of cells).
 
 Per cell the reference reshuffles the factual quantiles of the observations in blocks of one calendar year,
 maps them back through the factual distribution of the target day, refits the model and collects the fitted
@@ -21,6 +21,7 @@ from .variables import VariableSpec, create_variable
 
 QUANTILES = (0, 0.01, 0.025, 0.05, 0.25, 0.5, 0.75, 0.95, 0.975, 0.99, 1)   # detrend.py:575
 MAX_SAMPLES = 256
+PR_THRESHOLD = 0.0000011574   # Pr.THRESHOLD, variables.py:350
 
 
 def _ptr(t):
@@ -52,8 +53,6 @@ def bootstrap_cells(variable, y, days, gmt, years, seeds, n_samples, modes=4, de
     ``bootstrap_replaced`` [T, C] (int32), plus ``quantile`` (the levels) and the original ``fit``.
     The whole series is the fit window, as the reference demands (detrend.py:480-486)."""
     spec = create_variable(variable) if isinstance(variable, str) else variable
-    if spec.family == _lib.BERNOULLI_GAMMA:
-        raise NotImplementedError("the bootstrap is not implemented for pr (Bernoulli-Gamma family)")
     n_samples = int(n_samples)
     if not 1 <= n_samples <= MAX_SAMPLES:
         raise ValueError(f"n_samples must be in 1..{MAX_SAMPLES}")
@@ -76,15 +75,21 @@ def bootstrap_cells(variable, y, days, gmt, years, seeds, n_samples, modes=4, de
     ys, scaling = solver.scale(yt)
     fit = solver.fit(ys)
     expected = solver.eval_parameter(fit.params, _lib.WHICH_EXPECTATION)   # Distribution.expectation()
+    # Variable.rescale (variables.py:114-131, 483-486)
     mul = scaling[:, 1] if spec.scaling != _lib.SCALE_NONE else torch.ones_like(scaling[:, 1])
     add = scaling[:, 0] if spec.scaling == _lib.SCALE_UNITY else torch.zeros_like(scaling[:, 0])
-    expected = expected * mul + add
+    if spec.scaling == _lib.SCALE_PR:
+        expected = torch.where(expected <= 0, torch.zeros_like(expected), expected * mul + PR_THRESHOLD)
+    else:
+        expected = expected * mul + add
 
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         seeds_d = torch.as_tensor(seeds.view(np.int32)).to(dev)
         choices = torch.empty((Cn, n_samples * n_blocks), dtype=torch.int16, device=dev)
-        _lib.check(lib.attrici_bootstrap_block_choices(_ptr(seeds_d), Cn, n_samples * n_blocks, n_blocks, 0,
+        # pr: the quantile map drew np.random.rand(T) from the cell's generator first (variables.py:458): 2 T words
+        skip_words = 2 * T if spec.family == _lib.BERNOULLI_GAMMA else 0
+        _lib.check(lib.attrici_bootstrap_block_choices(_ptr(seeds_d), Cn, n_samples * n_blocks, n_blocks, skip_words,
                                                        _ptr(choices), stream))
         scores = torch.empty((T, Cn), dtype=torch.float64, device=dev)
         ws = solver._ws

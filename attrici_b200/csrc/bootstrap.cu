@@ -9,10 +9,12 @@
 //     MT19937 words; one stream per cell, seeded as detrend.py:285) - bit-identical indices,
 //   * the factual scores of the observed series and the resampled series,
 //   * mean / std / percentiles over the samples.
-// Every family but Bernoulli-Gamma (pr draws from the generator before its bootstrap and treats dry days apart).
 // Normal: the inverse cdf is ndtri(q) sigma_t + mu_t and the score stored per day is ndtri(ndtr(z)), so that the
-// sample uses exactly the reference's round trip including its saturation; Gamma / Beta / Weibull store the
-// quantile and invert it per sample-day with the functions of the quantile map (qmap_impl.cuh).
+// sample uses exactly the reference's round trip including its saturation; the other families store the quantile
+// and invert it per sample-day with the functions of the quantile map (qmap_impl.cuh).  pr: a dry source day has
+// no quantile (NaN) and a quantile below the target day's dry probability has no inverse (NaN), so the sample
+// keeps the observed value there (detrend.py:553-557) - which may itself be dry; the caller skips the generator
+// words pr's quantile map consumed before the bootstrap (np.random.rand(T), variables.py:458).
 #include "common.cuh"
 #include "special.cuh"
 #include "qmap_impl.cuh"
@@ -173,13 +175,21 @@ struct StatsArgs {
 // costs O(N) on a nearly sorted sequence instead of O(N^2) (54 -> 4 ms for 100 cells x 100 samples x 43 464 days).
 constexpr int BS_STATS_DAYS = 64;
 
+// Variable.rescale (variables.py:114-131; Pr.rescale :483-486 maps non-positive scaled values to 0): multiply, then
+// add - two roundings like NumPy
+__device__ __forceinline__ double bs_rescale(double x, double mul, double add, bool is_pr) {
+    const double r = __dadd_rn(__dmul_rn(x, mul), add);
+    return (is_pr && x <= 0.0) ? 0.0 : r;
+}
+
 __global__ void __launch_bounds__(BS_THREADS) bootstrap_stats_kernel(StatsArgs a) {
     const int cell = blockIdx.x * BS_THREADS + threadIdx.x;
     if (cell >= a.C) return;
     const int t0 = blockIdx.y * BS_STATS_DAYS, t1 = min(a.T, t0 + BS_STATS_DAYS);
     const double datamin = a.scaling_v[2 * (size_t)cell], scale = a.scaling_v[2 * (size_t)cell + 1];
     const double mul = (a.scaling == ATTRICI_SCALE_NONE) ? 1.0 : scale;
-    const double add = a.unity ? datamin : 0.0;
+    const bool is_pr = a.scaling == ATTRICI_SCALE_PR;
+    const double add = a.unity ? datamin : (is_pr ? 0.0000011574 : 0.0);   // Pr.THRESHOLD, variables.py:350, 483-486
     double v[BS_MAX_SAMPLES];
     unsigned char perm[BS_MAX_SAMPLES];
     for (int r = 0; r < a.N; ++r) perm[r] = (unsigned char)r;
@@ -187,13 +197,13 @@ __global__ void __launch_bounds__(BS_THREADS) bootstrap_stats_kernel(StatsArgs a
         const double* e = a.E + (size_t)t * a.ld_e + cell;
         // mean in sample order (numpy.mean over axis 0 adds the samples one after the other)
         double sum = 0.0;
-        for (int r = 0; r < a.N; ++r) sum += __dadd_rn(__dmul_rn(e[(size_t)r * a.C], mul), add);
+        for (int r = 0; r < a.N; ++r) sum += bs_rescale(e[(size_t)r * a.C], mul, add, is_pr);
         const double mean = sum / (double)a.N;
         // values in yesterday's order, then insertion sort of (value, sample) pairs
         double ss = 0.0;
         for (int k = 0; k < a.N; ++k) {
             // rescale (variables.py:114-131): multiply, then add - two roundings like NumPy
-            const double x = __dadd_rn(__dmul_rn(e[(size_t)perm[k] * a.C], mul), add);
+            const double x = bs_rescale(e[(size_t)perm[k] * a.C], mul, add, is_pr);
             v[k] = x;
             const double d = x - mean;
             ss += d * d;
@@ -251,10 +261,6 @@ int bs_bind(Workspace& ws, void* workspace, size_t workspace_bytes, int T, int C
 int bs_check_family(const attrici_variable_t* var) {
     if (!var) { set_error("var is null"); return ATTRICI_EINVAL; }
     if (var->family < ATTRICI_NORMAL || var->family > ATTRICI_BERNOULLI_GAMMA) { set_error("unknown family %d", var->family); return ATTRICI_EINVAL; }
-    if (var->family == ATTRICI_BERNOULLI_GAMMA) {
-        set_error("the bootstrap is not implemented for the Bernoulli-Gamma family (pr)");
-        return ATTRICI_EUNSUPPORTED;
-    }
     if (var->modes < 1 || var->modes > ATTRICI_MAX_MODES) { set_error("bad modes %d", var->modes); return ATTRICI_EINVAL; }
     return 0;
 }

@@ -50,16 +50,17 @@ def bootstrap_cell(variable, y, gmt_scaled, days, years, n_samples, modes=4, see
                    return_samples=False):
     """detrend.py:479-612 for one cell (full time series, as the reference demands at :480-486)."""
     family = ao.VARIABLES[variable][0]
-    if family == "bernoulli_gamma":
-        raise NotImplementedError("pr consumes np.random.rand before the bootstrap; not restated here")
     np.random.seed(ao.cell_seed(seed, lat, lon))
+    if family == "bernoulli_gamma":
+        np.random.rand(len(y))   # consumed by Pr.quantile_mapping before the bootstrap starts (variables.py:458)
     ys, scaling, _ = ao.scale_variable(variable, y)
     prob = ao.build_problem(family, ys, gmt_scaled, days, modes)
     trace = ao.fit_newton(prob)
     ref = ao.estimate_params(family, trace["params"], gmt_scaled, days, modes)
     # Distribution.expectation(), attrici/distributions.py:89-90, 157-158, 186-187, 215-216
     expectation = {"normal": lambda p: p["mu"], "gamma": lambda p: p["mu"], "beta": lambda p: p["mu"],
-                   "weibull": lambda p: stats.weibull_min.mean(p["alpha"], scale=p["beta"])}[family]
+                   "weibull": lambda p: stats.weibull_min.mean(p["alpha"], scale=p["beta"]),
+                   "bernoulli_gamma": lambda p: (1 - p["p"]) * p["mu"]}[family]
     blocks = year_blocks(years)
     ys64 = np.asarray(ys, dtype=np.float64)
     with np.errstate(all="ignore"):

@@ -115,7 +115,7 @@ def test_bootstrap_statistics_against_oracle():
     assert int(out["bootstrap_replaced"][:, 2].sum()) > 0 and int(out["bootstrap_replaced"][:, 0].sum()) == 0
 
 
-@pytest.mark.parametrize("variable", ["tasrange", "sfcWind", "hurs"])
+@pytest.mark.parametrize("variable", ["tasrange", "sfcWind", "hurs", "pr"])
 def test_bootstrap_other_families_against_oracle(variable):
     """Gamma / Weibull / Beta: quantiles inverted per sample-day by the quantile map's own functions, the samples
     refitted by the day-ordered / phase-ordered kernels of those families."""
@@ -123,7 +123,8 @@ def test_bootstrap_other_families_against_oracle(variable):
     from attrici_b200.solver import cell_seeds
 
     T, Cn, N = 4 * 365 + 1, 2, 4
-    make = {"tasrange": synthetic.tasrange_cells, "sfcWind": synthetic.wind_cells, "hurs": synthetic.hurs_cells}[variable]
+    make = {"tasrange": synthetic.tasrange_cells, "sfcWind": synthetic.wind_cells, "hurs": synthetic.hurs_cells,
+            "pr": synthetic.pr_cells}[variable]
     y = make(Cn, T)
     gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
     years = (np.datetime64("1901-01-01") + days.astype("timedelta64[D]")).astype("datetime64[Y]").astype(int) + 1970
@@ -133,14 +134,11 @@ def test_bootstrap_other_families_against_oracle(variable):
         ref = bootstrap_oracle.bootstrap_cell(variable, y[:, j], gmt, days, years, N, modes=helpers.MODES, seed=0,
                                               lat=lat[j], lon=lon[j], return_samples=True)
         np.testing.assert_array_equal(out["bootstrap_replaced"][:, j].cpu().numpy(), ref["bootstrap_replaced"])
-        np.testing.assert_allclose(out["expected_values"][:, j].cpu().numpy(), ref["expected_values"], rtol=1e-4)
-        np.testing.assert_allclose(out["bootstrap_mean"][:, j].cpu().numpy(), ref["bootstrap_mean"], rtol=1e-4)
-        np.testing.assert_allclose(out["bootstrap_quantiles"][:, :, j].cpu().numpy(), ref["bootstrap_quantiles"], rtol=1e-4)
-        np.testing.assert_allclose(out["bootstrap_std"][:, j].cpu().numpy(), ref["bootstrap_std"], rtol=2e-2, atol=1e-6)
-
-
-def test_unsupported_family_is_refused():
-    from attrici_b200.bootstrap import bootstrap_cells
-
-    with pytest.raises(NotImplementedError):
-        bootstrap_cells("pr", np.zeros((10, 1), np.float32), np.arange(10), np.zeros(10), np.zeros(10), [0], 2, device=DEV)
+        # four years of pr (two likelihood terms, float32 day arithmetic, a third of the days dry) pin the optimum
+        # less sharply than the other variables
+        tol = 1e-3 if variable == "pr" else 1e-4
+        np.testing.assert_allclose(out["expected_values"][:, j].cpu().numpy(), ref["expected_values"], rtol=tol)
+        np.testing.assert_allclose(out["bootstrap_mean"][:, j].cpu().numpy(), ref["bootstrap_mean"], rtol=tol)
+        np.testing.assert_allclose(out["bootstrap_quantiles"][:, :, j].cpu().numpy(), ref["bootstrap_quantiles"], rtol=tol)
+        np.testing.assert_allclose(out["bootstrap_std"][:, j].cpu().numpy(), ref["bootstrap_std"], rtol=200 * tol,
+                                   atol=1e-6 * float(np.abs(ref["bootstrap_std"]).max()))
