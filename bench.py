@@ -66,15 +66,21 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
 
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    The sampler is started before the warm-up steps (nvidia-smi needs a few hundred ms to deliver its first line);
+    every line carries its timestamp and ``stop`` keeps those inside [t_begin, t_end] of the timed region.  If the
+    region is shorter than the sampling period, the samples taken since the warm-up began are used and the result
+    says so."""
+
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -83,6 +89,13 @@ class ClockSampler:
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
+        self.t_start = time.time()
+
+    def begin_region(self):
+        self.t_begin = time.time()
+
+    def end_region(self):
+        self.t_end = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -93,25 +106,36 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, smax, reasons = [], [], set()
+        import datetime
+
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), [n for n, v in zip(names, f[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        t0 = self.t_begin if self.t_begin is not None else self.t_start
+        t1 = self.t_end if self.t_end is not None else time.time()
+        inside = [r for r in rows if t0 - 0.01 <= r[0] <= t1 + 0.01]
+        note = None
+        if not inside:
+            inside = [r for r in rows if r[0] <= t1 + 0.01] or rows
+            note = "timed region shorter than the sampling period: samples since the warm-up steps began"
+        sm = [r[1] for r in inside]
+        smax = [r[2] for r in inside]
+        reasons = sorted({n for r in inside for n in r[3]})
         busy = [x for x in sm if x > 0.5 * max(smax)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        res = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": reasons, "samples": len(sm)}
+        if note:
+            res["note"] = note
+        return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -217,6 +241,11 @@ def run_cuda(args):
 
     bound_cpus = bind_to_gpu_cpus(local_rank)  # pinned host buffers on the GPU's NUMA node
     if world > 1:
+        # the image exports NCCL_DEBUG=VERSION, which makes NCCL print its version on stdout - the contract is
+        # one JSON line there; an explicit INFO / TRACE request of the caller is left alone
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # whatever level is asked for: not on stdout
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     C, T = args.cells, T_DAYS
@@ -254,6 +283,8 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         fit = step()
     barrier()
@@ -261,16 +292,16 @@ def run_cuda(args):
     status = fit.status.cpu().numpy()
     _lib.fit_profile(reset=True)
     launches0 = _lib.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     seg_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
+    sampler.begin_region()
     ev0.record()
     for k in range(args.steps):
         step(seg_ev[k])
     ev1.record()
     barrier()
+    sampler.end_region()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     seg_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in seg_ev) / args.steps for i in range(3)]
