@@ -78,6 +78,7 @@ _SIGNATURES = {
     "attrici_bootstrap_resample": (_i, [_vp, _sz, C.POINTER(Variable), _vp, _i64, _i, _i, _vp, _vp, _i64, _vp, _i, _i,
                                          _i, _i, _vp, _vp, _vp, _i64, _vp, _i64, _vp]),
     "attrici_bootstrap_stats": (_i, [C.POINTER(Variable), _vp, _i64, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "attrici_derive_huss": (_i, [_vp, _vp, _vp, _sz, _vp, _vp]),
     "attrici_detrend_host_scratch_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "attrici_detrend_host": (_i, [C.POINTER(Variable), C.POINTER(FitOptions), _vp, _i64, _i, _i, _i, _i, _vp, _vp,
                                    _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i]),

@@ -231,6 +231,11 @@ ATTRICI_API int attrici_bootstrap_stats(const attrici_variable_t* var, const dou
                             int n_samples, const double* scaling, const double* levels, int n_levels, double* mean,
                             double* std_dev, double* quantiles, void* stream);
 
+/* derive-huss: specific humidity [kg kg-1] from relative humidity [%], air pressure [Pa] and temperature [K],
+ * elementwise over n float64 values (device pointers): calc_huss_weedon2010, attrici/commands/derive_huss.py:27-99 */
+ATTRICI_API int attrici_derive_huss(const double* hurs, const double* ps, const double* tas, size_t n, double* huss,
+                        void* stream);
+
 /* whole path for one batch with HOST buffers (pinned recommended): H2D of y, scale, fit,
  * quantile map, D2H of cfact / params / logp / status, cells processed in slabs of
  * `slab_cells` with copies and kernels overlapped on internal streams.
