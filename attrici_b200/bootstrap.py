@@ -21,7 +21,6 @@ from .variables import VariableSpec, create_variable
 
 QUANTILES = (0, 0.01, 0.025, 0.05, 0.25, 0.5, 0.75, 0.95, 0.975, 0.99, 1)   # detrend.py:575
 MAX_SAMPLES = 256
-PR_THRESHOLD = 0.0000011574   # Pr.THRESHOLD, variables.py:350
 
 
 def _ptr(t):
@@ -74,14 +73,7 @@ def bootstrap_cells(variable, y, days, gmt, years, seeds, n_samples, modes=4, de
     solver.set_predictor(days, gmt, Cn)
     ys, scaling = solver.scale(yt)
     fit = solver.fit(ys)
-    expected = solver.eval_parameter(fit.params, _lib.WHICH_EXPECTATION)   # Distribution.expectation()
-    # Variable.rescale (variables.py:114-131, 483-486)
-    mul = scaling[:, 1] if spec.scaling != _lib.SCALE_NONE else torch.ones_like(scaling[:, 1])
-    add = scaling[:, 0] if spec.scaling == _lib.SCALE_UNITY else torch.zeros_like(scaling[:, 0])
-    if spec.scaling == _lib.SCALE_PR:
-        expected = torch.where(expected <= 0, torch.zeros_like(expected), expected * mul + PR_THRESHOLD)
-    else:
-        expected = expected * mul + add
+    expected_scaled = solver.eval_parameter(fit.params, _lib.WHICH_EXPECTATION)   # Distribution.expectation()
 
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -125,6 +117,14 @@ def bootstrap_cells(variable, y, days, gmt, years, seeds, n_samples, modes=4, de
             n_pass.append(fb.n_pass)
             sv.eval_parameter(fb.params, _lib.WHICH_EXPECTATION, out=E[:, r0 * Cn:r0 * Cn + cols])
         levels = torch.as_tensor(np.asarray(QUANTILES, dtype=np.float64)).to(dev)
+        # expected_values = Variable.rescale(expectation of the original fit) (detrend.py:579-581): the statistics
+        # kernel over a single "sample" (its mean is the rescaled value itself)
+        expected = torch.empty((T, Cn), dtype=torch.float64, device=dev)
+        scratch = torch.empty((len(QUANTILES) + 1, T, Cn), dtype=torch.float64, device=dev)
+        _lib.check(lib.attrici_bootstrap_stats(C.byref(solver.var), _ptr(expected_scaled), expected_scaled.stride(0), T, Cn,
+                                               1, _ptr(scaling), _ptr(levels), len(QUANTILES), _ptr(expected),
+                                               _ptr(scratch[0]), _ptr(scratch[1:]), stream))
+        del scratch
         mean = torch.empty((T, Cn), dtype=torch.float64, device=dev)
         std = torch.empty((T, Cn), dtype=torch.float64, device=dev)
         quant = torch.empty((len(QUANTILES), T, Cn), dtype=torch.float64, device=dev)
