@@ -90,6 +90,41 @@ def test_scale_and_masks_bit_exact(name):
         assert np.array_equal(ys[:, 0], c.d["y_scaled"], equal_nan=True)  # the reference's own y_scaled
 
 
+def test_float32_scaling_bit_exact_over_many_magnitudes():
+    """y_scaled = RN((y - min) / (max - min)) in float32: the streaming kernels form the reciprocal of the divisor
+    once per cell (the compiler's own div.rn.f32 sequence) - checked here against NumPy's float32 division bit for
+    bit for 512 cells whose offsets and ranges span 2^-40 .. 2^40 (plus ranges outside the guarded [2^-60, 2^60]),
+    on the folded path (3 000 gap-free days) with and without a materialised y_scaled."""
+    T, C = 3000, 512
+    rng = np.random.default_rng(123)
+    span = np.exp2(rng.uniform(-40, 40, C))
+    span[:4] = [2.0 ** -70, 2.0 ** 70, 2.0 ** -61, 2.0 ** 61]
+    offset = rng.normal(0, 4, C) * span
+    base = rng.random((T, C))
+    base[::97, 5] = np.nan
+    y = (offset[None, :] + span[None, :] * base).astype(np.float32)
+    y[7, :] = y.min(axis=0, where=~np.isnan(y), initial=np.inf)    # a repeated minimum: numerator exactly 0
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    s = CellBatchSolver("tas", device=DEV)
+    s.set_predictor(days, gmt, C)
+    yd = dev(y)
+    ys, scaling = s.scale(yd)
+    mn = np.nanmin(y, axis=0)
+    mx = np.nanmax(y, axis=0)
+    want = (y - mn[None, :]) / (mx - mn)[None, :]                     # float32 arithmetic, variables.py:108-110
+    assert want.dtype == np.float32
+    assert np.array_equal(host(ys), want, equal_nan=True)
+    assert np.array_equal(host(scaling)[:, 0], mn.astype(np.float64)) and np.array_equal(host(scaling)[:, 1], (mx - mn).astype(np.float64))
+    # the quantile map recomputes the scaled value when it is not handed one: same counterfactual bits
+    params = torch.zeros((C, s.n_params), dtype=torch.float64, device=DEV)
+    params[:, 0] = 0.5
+    params[:, 1] = 0.1
+    params[:, 18] = -1.5
+    a, ra, _ = s.quantile_map(yd, ys, params, scaling)
+    b, rb, _ = s.quantile_map(yd, None, params, scaling)
+    assert np.array_equal(host(a), host(b), equal_nan=True) and torch.equal(ra, rb)
+
+
 @pytest.mark.parametrize("name", helpers.ONE_PER_VARIABLE)
 @pytest.mark.parametrize("fp64", [True, False])
 def test_nll_grad_known_answers(name, fp64):
