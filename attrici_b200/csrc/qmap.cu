@@ -156,9 +156,29 @@ struct EvalArgs {
     const double* params;
     double* out;
     int64_t ld_out;
+    const int* fold_bad;   // [0] = days off the gap-free daily axis (Workspace::fold_bad)
+    int skip_if_fold;      // day-ordered kernel: return at once if the phase-ordered one applies
+    int n_ph, ph_len;      // phase-ordered kernel: phases, phases per CTA
 };
 
+// value of the requested field of the family's distribution (or its expectation) for one day
+__device__ __forceinline__ double eval_field(const EvalArgs& a, const DayParams& d) {
+    DistPar ref, cf;
+    family_params(a.family, d, ref, cf);
+    const DistPar& p = a.counterfactual ? cf : ref;
+    if (a.which < 0) {
+        // Distribution.expectation() (attrici/distributions.py:89-90, 128-129, 157-158, 186-187, 215-216)
+        switch (a.family) {
+            case ATTRICI_WEIBULL: return p.p1 * tgamma(1.0 + 1.0 / p.p0);   // weibull_min.mean(alpha, scale=beta)
+            case ATTRICI_BERNOULLI_GAMMA: return (1.0 - p.p0) * p.p1;
+            default: return p.p0;                                           // mu
+        }
+    }
+    return a.which == 0 ? p.p0 : (a.which == 1 ? p.p1 : p.p2);
+}
+
 __global__ void __launch_bounds__(QMAP_THREADS) eval_parameter_kernel(EvalArgs a) {
+    if (a.skip_if_fold && a.fold_bad[0] == 0) return;
     const int cell = blockIdx.x * QMAP_THREADS + threadIdx.x;
     if (cell >= a.C) return;
     const int t0 = blockIdx.y * a.chunk_len, t1 = min(a.T, t0 + a.chunk_len);
@@ -172,21 +192,69 @@ __global__ void __launch_bounds__(QMAP_THREADS) eval_parameter_kernel(EvalArgs a
         for (int i = 0; i < 1 + 2 * NH; ++i) r[i] = __ldg(row + i);
         DayParams d;
         day_predictors(coef, r, n_dep, d);
-        DistPar ref, cf;
-        family_params(a.family, d, ref, cf);
-        const DistPar& p = a.counterfactual ? cf : ref;
-        double v;
-        if (a.which < 0) {
-            // Distribution.expectation() (attrici/distributions.py:89-90, 128-129, 157-158, 186-187, 215-216)
-            switch (a.family) {
-                case ATTRICI_WEIBULL: v = p.p1 * tgamma(1.0 + 1.0 / p.p0); break;   // weibull_min.mean(alpha, scale=beta)
-                case ATTRICI_BERNOULLI_GAMMA: v = (1.0 - p.p0) * p.p1; break;
-                default: v = p.p0; break;                                           // mu
+        a.out[(size_t)t * a.ld_out + cell] = eval_field(a, d);
+    }
+}
+
+// The same on a gap-free daily axis, in phase order (see fold.cu): the Fourier sums of the predictors are formed once
+// per (cell, phase) - day_predictors with gmt = 0 gives base, with gmt = 1 base + trend - and so is everything that
+// does not depend on gmt (the GMT-independent parameter, every counterfactual field).  A day then costs one FMA and
+// the link of the one field that is asked for.
+enum { EV_CONST = 0, EV_IDENT, EV_EXP, EV_INVLOGIT, EV_EXP_TIMES, EV_BG_MEAN };
+
+__global__ void __launch_bounds__(QMAP_THREADS) eval_parameter_fold_kernel(EvalArgs a) {
+    if (a.fold_bad[0] != 0) return;
+    const int cell = blockIdx.x * QMAP_THREADS + threadIdx.x;
+    if (cell >= a.C) return;
+    const int d0 = blockIdx.y * a.ph_len, d1 = min(a.n_ph, d0 + a.ph_len);
+    CellCoef coef;
+    load_coef(a.family, a.modes, a.params, cell, coef);
+    const int n_dep = (a.family == ATTRICI_BERNOULLI_GAMMA) ? 2 : 1;
+    // which field: position of the GMT-independent parameter in the family's order, links of the dependent ones
+    // (family_params, qmap_impl.cuh)
+    const int indep = (a.family == ATTRICI_WEIBULL) ? 0 : (a.family == ATTRICI_BERNOULLI_GAMMA ? 2 : 1);
+    int kind, slot = 0;
+    if (a.which < 0) {
+        kind = (a.family == ATTRICI_WEIBULL) ? EV_EXP_TIMES : (a.family == ATTRICI_BERNOULLI_GAMMA ? EV_BG_MEAN
+               : (a.family == ATTRICI_NORMAL ? EV_IDENT : (a.family == ATTRICI_BETA ? EV_INVLOGIT : EV_EXP)));
+    } else if (a.which == indep) {
+        kind = EV_CONST;
+    } else {
+        slot = (a.family == ATTRICI_BERNOULLI_GAMMA && a.which == 1) ? 1 : 0;
+        kind = (a.family == ATTRICI_NORMAL) ? EV_IDENT
+               : ((a.family == ATTRICI_BETA || (a.family == ATTRICI_BERNOULLI_GAMMA && a.which == 0)) ? EV_INVLOGIT : EV_EXP);
+    }
+    for (int ph = d0; ph < d1; ++ph) {
+        const double* row = a.basis64 + (size_t)ph * B_STRIDE;
+        double r[1 + 2 * NH];
+#pragma unroll
+        for (int i = 0; i < 1 + 2 * NH; ++i) r[i] = __ldg(row + i);
+        DayParams base, one;
+        base.a_ref[1] = base.a_cf[1] = one.a_ref[1] = one.a_cf[1] = 0.0;
+        r[0] = 0.0;
+        day_predictors(coef, r, n_dep, base);      // a_ref = a_cf = base
+        r[0] = 1.0;
+        day_predictors(coef, r, n_dep, one);       // a_ref = base + trend
+        const double b0 = base.a_cf[0], b1 = base.a_cf[1];
+        // the counterfactual has gmt = 0 on every day (detrend.py:366-370): no trend
+        const double tr0 = a.counterfactual ? 0.0 : one.a_ref[0] - b0, tr1 = a.counterfactual ? 0.0 : one.a_ref[1] - b1;
+        const double vb = exp(base.b);                                               // the independent parameter
+        const double mean_factor = (kind == EV_EXP_TIMES) ? tgamma(1.0 + 1.0 / vb) : 0.0;   // weibull_min.mean
+        const double bs = slot ? b1 : b0, ts = slot ? tr1 : tr0;
+        for (int t = ph; t < a.T; t += NPHASE) {
+            const double g = __ldg(a.basis64 + (size_t)t * B_STRIDE);
+            const double eta = fma(g, ts, bs);
+            double v;
+            switch (kind) {
+                case EV_CONST: v = vb; break;
+                case EV_IDENT: v = eta; break;
+                case EV_EXP: v = exp(eta); break;
+                case EV_INVLOGIT: v = invlogit(eta); break;
+                case EV_EXP_TIMES: v = exp(eta) * mean_factor; break;
+                default: v = (1.0 - invlogit(fma(g, tr0, b0))) * exp(fma(g, tr1, b1)); break;   // (1 - p) mu
             }
-        } else {
-            v = a.which == 0 ? p.p0 : (a.which == 1 ? p.p1 : p.p2);
+            a.out[(size_t)t * a.ld_out + cell] = v;
         }
-        a.out[(size_t)t * a.ld_out + cell] = v;
     }
 }
 
@@ -287,9 +355,22 @@ int launch_eval_parameter(Workspace& ws, const attrici_variable_t& var, const do
     a.T = ws.T; a.C = ws.C; a.family = var.family; a.modes = var.modes; a.which = which;
     a.counterfactual = counterfactual;
     a.basis64 = ws.basis64; a.params = params; a.out = out; a.ld_out = ld_out;
+    a.fold_bad = ws.fold_bad; a.skip_if_fold = 0;
+    a.n_ph = ws.T < NPHASE ? ws.T : NPHASE; a.ph_len = 1;
+    const int n_cb = (ws.C + QMAP_THREADS - 1) / QMAP_THREADS;
+    static const bool fold_on = [] { const char* e = getenv("ATTRICI_NO_FOLD"); return !(e && e[0] == '1'); }();
+    if (fold_on) {
+        // device-side dispatch on the axis flag, as in launch_qmap: the kernel that does not apply returns at once
+        int want = (148 * 8 + n_cb - 1) / n_cb;
+        if (want > a.n_ph) want = a.n_ph;
+        if (want < 1) want = 1;
+        a.ph_len = (a.n_ph + want - 1) / want;
+        eval_parameter_fold_kernel<<<dim3(n_cb, (a.n_ph + a.ph_len - 1) / a.ph_len), QMAP_THREADS, 0, s>>>(a);
+        ATTRICI_LAUNCH_CHECK();
+        a.skip_if_fold = 1;
+    }
     int n_chunks = qmap_chunks(ws.T, ws.C, &a.chunk_len);
-    dim3 grid((ws.C + QMAP_THREADS - 1) / QMAP_THREADS, n_chunks);
-    eval_parameter_kernel<<<grid, QMAP_THREADS, 0, s>>>(a);
+    eval_parameter_kernel<<<dim3(n_cb, n_chunks), QMAP_THREADS, 0, s>>>(a);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
