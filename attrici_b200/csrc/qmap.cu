@@ -224,36 +224,70 @@ __global__ void __launch_bounds__(QMAP_THREADS) eval_parameter_fold_kernel(EvalA
         kind = (a.family == ATTRICI_NORMAL) ? EV_IDENT
                : ((a.family == ATTRICI_BETA || (a.family == ATTRICI_BERNOULLI_GAMMA && a.which == 0)) ? EV_INVLOGIT : EV_EXP);
     }
+    // coefficients in shared memory, [coefficient][thread]: the dynamically indexed CellCoef lives in local memory,
+    // and re-reading it for every phase (108 loads) is what the kernel would otherwise spend its time on
+    __shared__ double cs[(2 * NA + NB) * QMAP_THREADS];
+    {
+        double* c = cs + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) { c[i * QMAP_THREADS] = coef.a[0][i]; c[(NA + i) * QMAP_THREADS] = coef.a[1][i]; }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) c[(2 * NA + i) * QMAP_THREADS] = coef.b[i];
+    }
+    const double* c0 = cs + threadIdx.x;                       // slot 0
+    const double* c1 = cs + NA * QMAP_THREADS + threadIdx.x;   // slot 1 (pr's mu)
+    const double* cb = cs + 2 * NA * QMAP_THREADS + threadIdx.x;
     for (int ph = d0; ph < d1; ++ph) {
         const double* row = a.basis64 + (size_t)ph * B_STRIDE;
-        double r[1 + 2 * NH];
+        // base / trend of the dependent parameters and the independent predictor, in day_predictors' order
+        double b0 = c0[0], tr0 = c0[QMAP_THREADS], b1 = c1[0], tr1 = c1[QMAP_THREADS], eb = cb[0];
 #pragma unroll
-        for (int i = 0; i < 1 + 2 * NH; ++i) r[i] = __ldg(row + i);
-        DayParams base, one;
-        base.a_ref[1] = base.a_cf[1] = one.a_ref[1] = one.a_cf[1] = 0.0;
-        r[0] = 0.0;
-        day_predictors(coef, r, n_dep, base);      // a_ref = a_cf = base
-        r[0] = 1.0;
-        day_predictors(coef, r, n_dep, one);       // a_ref = base + trend
-        const double b0 = base.a_cf[0], b1 = base.a_cf[1];
+        for (int k = 0; k < MAXM; ++k) {
+            const double ck = __ldg(row + 1 + k), sk = __ldg(row + 1 + NH + k);
+            b0 = fma(c0[(2 + k) * QMAP_THREADS], ck, b0);
+            b0 = fma(c0[(2 + MAXM + k) * QMAP_THREADS], sk, b0);
+            tr0 = fma(c0[(2 + 2 * MAXM + k) * QMAP_THREADS], ck, tr0);
+            tr0 = fma(c0[(2 + 3 * MAXM + k) * QMAP_THREADS], sk, tr0);
+            if (n_dep > 1) {
+                b1 = fma(c1[(2 + k) * QMAP_THREADS], ck, b1);
+                b1 = fma(c1[(2 + MAXM + k) * QMAP_THREADS], sk, b1);
+                tr1 = fma(c1[(2 + 2 * MAXM + k) * QMAP_THREADS], ck, tr1);
+                tr1 = fma(c1[(2 + 3 * MAXM + k) * QMAP_THREADS], sk, tr1);
+            }
+            eb = fma(cb[(1 + k) * QMAP_THREADS], ck, eb);
+            eb = fma(cb[(1 + MAXM + k) * QMAP_THREADS], sk, eb);
+        }
         // the counterfactual has gmt = 0 on every day (detrend.py:366-370): no trend
-        const double tr0 = a.counterfactual ? 0.0 : one.a_ref[0] - b0, tr1 = a.counterfactual ? 0.0 : one.a_ref[1] - b1;
-        const double vb = exp(base.b);                                               // the independent parameter
+        if (a.counterfactual) { tr0 = 0.0; tr1 = 0.0; }
+        const double vb = exp(eb);                                                   // the independent parameter
         const double mean_factor = (kind == EV_EXP_TIMES) ? tgamma(1.0 + 1.0 / vb) : 0.0;   // weibull_min.mean
         const double bs = slot ? b1 : b0, ts = slot ? tr1 : tr0;
-        for (int t = ph; t < a.T; t += NPHASE) {
-            const double g = __ldg(a.basis64 + (size_t)t * B_STRIDE);
-            const double eta = fma(g, ts, bs);
-            double v;
-            switch (kind) {
-                case EV_CONST: v = vb; break;
-                case EV_IDENT: v = eta; break;
-                case EV_EXP: v = exp(eta); break;
-                case EV_INVLOGIT: v = invlogit(eta); break;
-                case EV_EXP_TIMES: v = exp(eta) * mean_factor; break;
-                default: v = (1.0 - invlogit(fma(g, tr0, b0))) * exp(fma(g, tr1, b1)); break;   // (1 - p) mu
+        // the days of the phase in batches of independent gmt loads (each is a different cache line, and a serial
+        // load -> store chain of ~2 900 L2 round trips per thread is what bounded the first version)
+        constexpr int EU = 10;
+        for (int t = ph; t < a.T; t += EU * NPHASE) {
+            double g[EU];
+#pragma unroll
+            for (int u = 0; u < EU; ++u) {
+                const int tt = t + u * NPHASE;
+                g[u] = tt < a.T ? __ldg(a.basis64 + (size_t)tt * B_STRIDE) : 0.0;
             }
-            a.out[(size_t)t * a.ld_out + cell] = v;
+#pragma unroll
+            for (int u = 0; u < EU; ++u) {
+                const int tt = t + u * NPHASE;
+                if (tt >= a.T) break;
+                const double eta = fma(g[u], ts, bs);
+                double v;
+                switch (kind) {
+                    case EV_CONST: v = vb; break;
+                    case EV_IDENT: v = eta; break;
+                    case EV_EXP: v = exp(eta); break;
+                    case EV_INVLOGIT: v = invlogit(eta); break;
+                    case EV_EXP_TIMES: v = exp(eta) * mean_factor; break;
+                    default: v = (1.0 - invlogit(fma(g[u], tr0, b0))) * exp(fma(g[u], tr1, b1)); break;   // (1 - p) mu
+                }
+                a.out[(size_t)tt * a.ld_out + cell] = v;
+            }
         }
     }
 }
