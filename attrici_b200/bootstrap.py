@@ -117,17 +117,15 @@ def bootstrap_cells(variable, y, days, gmt, years, seeds, n_samples, modes=4, de
             n_pass.append(fb.n_pass)
             sv.eval_parameter(fb.params, _lib.WHICH_EXPECTATION, out=E[:, r0 * Cn:r0 * Cn + cols])
         levels = torch.as_tensor(np.asarray(QUANTILES, dtype=np.float64)).to(dev)
-        # expected_values = Variable.rescale(expectation of the original fit) (detrend.py:579-581): the statistics
-        # kernel over a single "sample" (its mean is the rescaled value itself)
-        expected = torch.empty((T, Cn), dtype=torch.float64, device=dev)
-        scratch = torch.empty((len(QUANTILES) + 1, T, Cn), dtype=torch.float64, device=dev)
-        _lib.check(lib.attrici_bootstrap_stats(C.byref(solver.var), _ptr(expected_scaled), expected_scaled.stride(0), T, Cn,
-                                               1, _ptr(scaling), _ptr(levels), len(QUANTILES), _ptr(expected),
-                                               _ptr(scratch[0]), _ptr(scratch[1:]), stream))
-        del scratch
         mean = torch.empty((T, Cn), dtype=torch.float64, device=dev)
         std = torch.empty((T, Cn), dtype=torch.float64, device=dev)
         quant = torch.empty((len(QUANTILES), T, Cn), dtype=torch.float64, device=dev)
+        # expected_values = Variable.rescale(expectation of the original fit) (detrend.py:579-581): the statistics
+        # kernel over a single "sample" (its mean is the rescaled value itself; std / quant are overwritten below)
+        expected = torch.empty((T, Cn), dtype=torch.float64, device=dev)
+        _lib.check(lib.attrici_bootstrap_stats(C.byref(solver.var), _ptr(expected_scaled), expected_scaled.stride(0), T, Cn,
+                                               1, _ptr(scaling), _ptr(levels), len(QUANTILES), _ptr(expected), _ptr(std),
+                                               _ptr(quant), stream))
         _lib.check(lib.attrici_bootstrap_stats(C.byref(solver.var), _ptr(E), E.stride(0), T, Cn, n_samples, _ptr(scaling),
                                                _ptr(levels), len(QUANTILES), _ptr(mean), _ptr(std), _ptr(quant), stream))
     out = {"expected_values": expected, "bootstrap_mean": mean, "bootstrap_std": std, "bootstrap_quantiles": quant,
