@@ -52,6 +52,13 @@ __device__ __forceinline__ void bs_day_params(int family, const CellCoef& coef, 
     family_params(family, d, ref, cf);
 }
 
+// inverse cdf of the non-Normal families, out of line: the batched loop of the resampling kernel is unrolled
+__device__ __noinline__ double bs_invcdf(int family, double p0, double p1, double p2, double q) {
+    DistPar p;
+    p.p0 = p0; p.p1 = p1; p.p2 = p2;
+    return dist_invcdf(family, p, q);
+}
+
 struct LocalMt {
     uint32_t* p;
     __device__ uint32_t& operator()(int i) const { return p[i]; }
@@ -142,20 +149,35 @@ __global__ void __launch_bounds__(BS_THREADS) bootstrap_resample_kernel(Resample
         const int target = a.block_start[yb + 1] - b0;
         const int r_in = t - b0;
         int count = 0;
-        for (int r = 0; r < a.R; ++r) {
-            const int c = ch[(size_t)(a.r0 + r) * a.n_blocks + yb];
-            int start = a.block_start[c];
-            const int len = a.block_start[c + 1] - start;
-            if (len < target && c >= a.n_blocks - 1) start -= target - len;
-            const int src = start + r_in;
-            double v = NAN;
-            if (src >= 0 && src < a.T) {
-                const double sc = a.scores[(size_t)src * a.ld_s + cell];
-                v = (a.family == ATTRICI_NORMAL) ? sc * ref.p1 + ref.p0 : dist_invcdf(a.family, ref, sc);
+        // samples in batches: the choice -> block start -> score loads of one sample form a dependent chain of L2 round
+        // trips, and the store that ends it may alias the next sample's loads as far as the compiler knows - so the
+        // loads of RU samples are issued together before any of their stores
+        constexpr int RU = 8;
+        for (int r = 0; r < a.R; r += RU) {
+            int cidx[RU], src[RU];
+            double sc[RU];
+#pragma unroll
+            for (int u = 0; u < RU; ++u) cidx[u] = __ldg(ch + (size_t)(a.r0 + min(r + u, a.R - 1)) * a.n_blocks + yb);
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                int start = __ldg(a.block_start + cidx[u]);
+                const int len = __ldg(a.block_start + cidx[u] + 1) - start;
+                if (len < target && cidx[u] >= a.n_blocks - 1) start -= target - len;
+                src[u] = start + r_in;
             }
-            float out = (float)v;
-            if (isnan(v) || isinf(v)) { out = y0; ++count; }   // detrend.py:553-557
-            a.y_new[(size_t)t * a.ld_new + (size_t)r * a.C + cell] = out;
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+                sc[u] = (src[u] >= 0 && src[u] < a.T) ? __ldg(a.scores + (size_t)src[u] * a.ld_s + cell) : NAN;
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                if (r + u < a.R) {
+                    double v = sc[u];
+                    if (!isnan(v)) v = (a.family == ATTRICI_NORMAL) ? sc[u] * ref.p1 + ref.p0 : bs_invcdf(a.family, ref.p0, ref.p1, ref.p2, sc[u]);
+                    float out = (float)v;
+                    if (isnan(v) || isinf(v)) { out = y0; ++count; }   // detrend.py:553-557
+                    a.y_new[(size_t)t * a.ld_new + (size_t)(r + u) * a.C + cell] = out;
+                }
+            }
         }
         if (a.replaced) a.replaced[(size_t)t * a.ld_rc + cell] += count;
     }
