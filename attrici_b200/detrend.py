@@ -26,7 +26,7 @@ class Config:
     task_id: int = 0
     task_count: int = 1
     solver: str = "cuda"
-    slab_cells: int = 4096       # cells per device slab of the host pipeline
+    slab_cells: int = 2048       # cells per device slab of the host pipeline
     use_fp64: bool = False       # FP64 day arithmetic in the likelihood passes
     device: str = None           # default: cuda:<LOCAL_RANK>
 

@@ -239,7 +239,7 @@ class CellBatchSolver:
         cfact, replaced, _ = self.quantile_map(y, ys, fit.params, scaling, seeds, want_replaced)
         return {"y_scaled": ys, "scaling": scaling, "fit": fit, "cfact": cfact, "replaced": replaced}
 
-    def detrend_host(self, y_host, days, gmt, fit_window=None, seeds=None, slab_cells=4096, out=None,
+    def detrend_host(self, y_host, days, gmt, fit_window=None, seeds=None, slab_cells=2048, out=None,
                      want_replaced=True):
         """Whole hot path with HOST buffers (pinned recommended): slabs of cells, copies and kernels
         overlapped on the library's two internal streams (``attrici_detrend_host``).
