@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from .variables import create_variable
+from .variables import check_units, create_variable
 
 
 @dataclass
@@ -29,6 +29,7 @@ class Config:
     slab_cells: int = 2048       # cells per device slab of the host pipeline
     use_fp64: bool = False       # FP64 day arithmetic in the likelihood passes
     device: str = None           # default: cuda:<LOCAL_RANK>
+    validate: bool = False       # bounds checks of the input and of cfact on the host (see detrend_cells)
 
 
 def get_task_indices(indices_len, task_id, task_count):
@@ -87,14 +88,30 @@ def bind_to_gpu_cpus(device_index):
     return 0
 
 
-def validate_bounds(spec, values):
-    """``Variable.validate`` -> ``check_bounds`` (attrici/variables.py:17-37): same ValueError."""
+def validate_bounds(spec, values, skip_inf=False):
+    """``Variable.validate`` -> ``check_bounds`` (attrici/variables.py:17-37): same ``ValueError`` arguments.
+
+    The reference checks one cell at a time with xarray's NaN-skipping ``min`` / ``max``; here ``values`` is a
+    whole ``[T, C]`` batch (NumPy array or CPU tensor), reduced with ``fmin`` / ``fmax`` (NaN-skipping, no copy,
+    an all-NaN batch compares false like ``nan < bound``).  ``skip_inf``: the input check — the reference has set
+    infinite values to NaN before it builds the variable (detrend.py:311)."""
+    v = values.numpy() if hasattr(values, "numpy") else np.asarray(values)
+    if v.size == 0:
+        return
+
+    def extreme(ufunc):
+        m = ufunc.reduce(v, axis=None)
+        if skip_inf and np.isinf(m):
+            finite = v[np.isfinite(v)]
+            m = ufunc.reduce(finite) if finite.size else np.nan
+        return m
+
     if spec.lower_bound is not None:
-        m = np.nanmin(values)
+        m = extreme(np.fmin)
         if m < spec.lower_bound:
             raise ValueError(m, "is smaller than lower bound", spec.lower_bound, ".")
     if spec.upper_bound is not None:
-        m = np.nanmax(values)
+        m = extreme(np.fmax)
         if m > spec.upper_bound:
             raise ValueError(m, "is bigger than upper bound", spec.upper_bound, ".")
 
@@ -138,7 +155,7 @@ def gather_cells(local, counts, dist=None, device=None):
     return out
 
 
-def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather=True, out=None):
+def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather=True, out=None, units=None):
     """Detrend the cells of ``y`` ([T, C] float32 host array, time-major, cells stacked lat-major as
     attrici/detrend.py:672 does) that the reference's partition assigns to this rank.
 
@@ -146,6 +163,11 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
     ``replaced`` [T, n_local] uint8 for those cells, and per-cell ``params`` [C', P], ``logp``, ``status``,
     ``n_pass``, ``scaling`` — gathered over all ranks when ``gather`` and torch.distributed is
     initialised (then C' = C), else local.
+
+    ``units``: the ``units`` attribute of the input variable, checked like ``check_units``
+    (attrici/variables.py:134-156).  ``config.validate`` adds the reference's bounds checks of the input
+    (``<Variable>.__init__`` -> ``validate``, e.g. variables.py:317-320) and of ``cfact`` (detrend.py:411) for this
+    rank's cells — host reductions over the whole batch, which cost more than the device work, hence opt-in.
     """
     import os
 
@@ -156,6 +178,7 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
     if config.solver != "cuda":
         raise ValueError(f"attrici_b200 only provides solver='cuda', got {config.solver!r}")
     spec = create_variable(config.variable)
+    check_units(spec, units)
     y = np.asarray(y) if not isinstance(y, torch.Tensor) else y
     if y.ndim != 2:
         raise ValueError("y must be [T, C]")
@@ -179,8 +202,12 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
         y_local = y[:, sl]
         if isinstance(y_local, np.ndarray):
             y_local = torch.from_numpy(y_local)
+        if config.validate:
+            validate_bounds(spec, y_local, skip_inf=True)
         o = solver.detrend_host(y_local, days, gmt_scaled, fit_window, seeds, config.slab_cells, out=out)
         local = {k: (o[k].numpy() if o[k] is not None else None) for k in o}
+        if config.validate:
+            validate_bounds(spec, local["cfact"])
     else:
         local = {"cfact": np.empty((T, 0)), "replaced": np.empty((T, 0), dtype=np.uint8),
                  "params": np.empty((0, P)), "logp": np.empty(0), "scaling": np.empty((0, 2)),

@@ -41,6 +41,7 @@ class VariableSpec:
     lower_bound: float = None  # Variable.validate / check_bounds (variables.py:17-37)
     upper_bound: float = None
     scaling_keys: tuple = ()  # keys of Variable.scaling, i.e. the scaling_<k> variables of the trace file
+    units: object = None  # expected ``units`` attribute of the input (check_units, variables.py:134-156): str or set
 
     def descriptor(self, modes):
         if not 1 <= modes <= _lib.MAX_MODES:
@@ -59,24 +60,24 @@ class VariableSpec:
 # attrici/variables.py: Tas :306-338, Pr :341-486, Rlds :489-521, Ps :524-555, Hurs :558-609,
 # Tasskew :612-657, Rsds :660-702, Tasrange :705-750, Wind :753-798
 VARIABLES = {
-    "tas": VariableSpec("tas", _lib.NORMAL, _lib.SCALE_UNITY, lower_bound=0.0, scaling_keys=("datamin", "scale")),
-    "ps": VariableSpec("ps", _lib.NORMAL, _lib.SCALE_UNITY, lower_bound=0.0, scaling_keys=("datamin", "scale")),
-    "rlds": VariableSpec("rlds", _lib.NORMAL, _lib.SCALE_UNITY, lower_bound=0.0, scaling_keys=("datamin", "scale")),
+    "tas": VariableSpec("tas", _lib.NORMAL, _lib.SCALE_UNITY, lower_bound=0.0, scaling_keys=("datamin", "scale"), units="K"),
+    "ps": VariableSpec("ps", _lib.NORMAL, _lib.SCALE_UNITY, lower_bound=0.0, scaling_keys=("datamin", "scale"), units="Pa"),
+    "rlds": VariableSpec("rlds", _lib.NORMAL, _lib.SCALE_UNITY, lower_bound=0.0, scaling_keys=("datamin", "scale"), units="W m-2"),
     "rsds": VariableSpec("rsds", _lib.NORMAL, _lib.SCALE_UNITY, _lib.POST_LE0_NAN, lower_bound=0.0,
-                         scaling_keys=("datamin", "scale")),
+                         scaling_keys=("datamin", "scale"), units="W m-2"),
     "tasskew": VariableSpec("tasskew", _lib.NORMAL, _lib.SCALE_NONE, _lib.POST_OUTSIDE01_NAN, 0.0001, 0.9999,
-                            lower_bound=0.0, upper_bound=1.0),
-    "pr": VariableSpec("pr", _lib.BERNOULLI_GAMMA, _lib.SCALE_PR, lower_bound=0.0, scaling_keys=("scale",)),
+                            lower_bound=0.0, upper_bound=1.0, units=frozenset({"1", "K"})),
+    "pr": VariableSpec("pr", _lib.BERNOULLI_GAMMA, _lib.SCALE_PR, lower_bound=0.0, scaling_keys=("scale",), units="kg m-2 s-1"),
     "tasrange": VariableSpec("tasrange", _lib.GAMMA, _lib.SCALE_RANGE, lower_threshold=0.01, lower_bound=0.0,
-                             scaling_keys=("scale",)),
+                             scaling_keys=("scale",), units="K"),
     "hurs": VariableSpec("hurs", _lib.BETA, _lib.SCALE_PERCENT, lower_threshold=0.01, upper_threshold=99.99,
-                         lower_bound=0.0, upper_bound=100.0, scaling_keys=("scale",)),
+                         lower_bound=0.0, upper_bound=100.0, scaling_keys=("scale",), units="%"),
     "sfcWind": VariableSpec("sfcWind", _lib.WEIBULL, _lib.SCALE_RANGE, lower_threshold=0.01, lower_bound=0.0,
-                            scaling_keys=("scale",)),
+                            scaling_keys=("scale",), units="m s-1"),
 }
 VARIABLES["wind"] = VariableSpec("wind", *[getattr(VARIABLES["sfcWind"], f) for f in
                                            ("family", "scaling", "post_rule", "lower_threshold", "upper_threshold",
-                                            "lower_bound", "upper_bound", "scaling_keys")])
+                                            "lower_bound", "upper_bound", "scaling_keys", "units")])
 
 
 def create_variable(name):
@@ -86,3 +87,15 @@ def create_variable(name):
         return VARIABLES[name]
     except KeyError:
         raise ValueError(f"Variable {name} not supported") from None
+
+
+def check_units(spec, units):
+    """``check_units`` of the reference (attrici/variables.py:134-156) for the ``units`` attribute of an input
+    file: same ``ValueError`` texts; ``units=None`` (no attribute) passes, as there (it only logs a warning)."""
+    if units is None or spec.units is None:
+        return
+    if isinstance(spec.units, str):
+        if units != spec.units:
+            raise ValueError(f"Units of data are {units}, but expected {spec.units}.")
+    elif units not in spec.units:
+        raise ValueError(f"Units of data are {units}, but expected one of {set(spec.units)}.")
