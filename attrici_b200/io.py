@@ -3,9 +3,10 @@
 The reference writes one NetCDF file per cell (``ts_lat<lat>_lon<lon>.nc``, attrici/detrend.py:447-477; trace:
 ``write_trace`` :221-255) and later merges them with ``attrici merge-output`` (attrici/commands/merge_output.py:27-123)
 into one file with dimensions ``(time, lat, lon)``.  With the cells solved as one batch the merged layout can be
-written at once.  Files are NetCDF-3 (64-bit offset) through ``scipy.io.netcdf_file`` - this image has neither
-netCDF4 nor h5py, so the reference's zlib-compressed NetCDF-4 encoding is not available; xarray / netCDF4 open
-classic files transparently.  Layout (the one ``merge-output`` produces):
+written at once.  Files are NetCDF classic (64-bit offset) - this image has neither netCDF4 nor h5py, so the
+reference's zlib-compressed NetCDF-4 encoding is not available; xarray / netCDF4 open classic files transparently.
+The series file is streamed by ``MergedOutputWriter`` (``time`` as the record dimension, a block of days per write);
+the small trace file goes through ``scipy.io.netcdf_file``.  Layout (the one ``merge-output`` produces):
 
 * dimensions ``time, lat, lon`` (lat / lon = sorted unique coordinates of the cells, float32 like :53, :61),
 * ``time(time)`` with its ``units`` / ``calendar`` attributes, ``lat(lat)``, ``lon(lon)``,
@@ -60,53 +61,206 @@ def _nc_type(dtype):
     return ("f4", np.float32) if dtype == np.float32 else ("f8", np.float64)
 
 
+# NetCDF classic format, 64-bit-offset variant ("CDF-2"): tags and type codes of the file header
+_NC_DIMENSION, _NC_VARIABLE, _NC_ATTRIBUTE = 10, 11, 12
+_NC_CODE = {"i1": 1, "c": 2, "i4": 4, "f4": 5, "f8": 6}
+_BE = {"i1": ">i1", "i4": ">i4", "f4": ">f4", "f8": ">f8"}
+
+
+def _pad4(n):
+    return (n + 3) & ~3
+
+
+def _be32(n):
+    return int(n).to_bytes(4, "big", signed=True)
+
+
+def _nc_name(name):
+    b = name.encode("utf-8")
+    return _be32(len(b)) + b + b"\0" * (_pad4(len(b)) - len(b))
+
+
+def _nc_attributes(attrs):
+    """``att_list`` of the classic format: text attributes as NC_CHAR, numbers as one value of their own type."""
+    if not attrs:
+        return _be32(0) + _be32(0)
+    out = [_be32(_NC_ATTRIBUTE), _be32(len(attrs))]
+    for key, val in attrs.items():
+        out.append(_nc_name(key))
+        if isinstance(val, (str, bytes)):
+            b = val.encode("utf-8") if isinstance(val, str) else val
+            out += [_be32(_NC_CODE["c"]), _be32(len(b)), b + b"\0" * (_pad4(len(b)) - len(b))]
+        else:
+            code, cast = _nc_type(np.asarray(val).dtype)
+            b = np.asarray(val).astype(cast).astype(_BE[code]).tobytes()
+            out += [_be32(_NC_CODE[code]), _be32(len(b) // np.dtype(cast).itemsize), b + b"\0" * (_pad4(len(b)) - len(b))]
+    return b"".join(out)
+
+
+class MergedOutputWriter:
+    """Streams the ``merge-output`` layout to disk, a block of days at a time.
+
+    ``time`` is the record (unlimited) dimension of a NetCDF classic file in the 64-bit-offset variant, written by
+    hand: the format is a header followed by the fixed-size variables (``lat``, ``lon``, per-cell scalars) and then one
+    record per day holding that day's slice of every ``(time, ...)`` variable — which is the order the results
+    arrive in when cells are solved as batches, so a block of days is one contiguous write and memory stays at one
+    block whatever the grid (a global 0.5 degree ``cfact(time, lat, lon)`` is 90 GB; ``scipy.io.netcdf_file``
+    builds all variables in memory before writing, and the classic format caps a fixed-size variable at 4 GiB, a
+    record variable only per record).  xarray / netCDF4 / SciPy read the file like any other.
+
+    ``series``: name -> dtype of the ``(time, lat, lon)`` variables; ``shared``: name -> dtype of ``(time,)``
+    variables (``gmt_scaled``); ``scalars``: name -> [C] array of ``(lat, lon)`` variables, written at once."""
+
+    def __init__(self, path, lat, lon, series, shared=None, scalars=None, time_dtype=np.int32,
+                 time_units="days since 1901-01-01 00:00:00", calendar="proleptic_gregorian", attrs=None,
+                 block_bytes=64 << 20):
+        ulat, ulon, ilat, ilon = _grid(lat, lon)
+        self._flat = ilat * ulon.size + ilon
+        self._n_cells = ilat.size
+        self._identity = bool(np.array_equal(self._flat, np.arange(ulat.size * ulon.size)))
+        n_grid = ulat.size * ulon.size
+        self.block_bytes = int(block_bytes)
+        self.n_records = 0
+        self._block = None
+        dims = {"time": 0, "lat": ulat.size, "lon": ulon.size}
+        dim_id = {k: i for i, k in enumerate(dims)}
+        # (name, dims, nc type, attributes, payload of a fixed variable or None)
+        fixed = [("lat", ("lat",), "f4", {"units": "degrees_north"}, ulat.astype(">f4").tobytes()),
+                 ("lon", ("lon",), "f4", {"units": "degrees_east"}, ulon.astype(">f4").tobytes())]
+        for name, arr in (scalars or {}).items():
+            arr = np.asarray(arr)
+            if arr.shape != (self._n_cells,):
+                raise ValueError(f"scalar variable {name} must have shape [C]")
+            code, cast = _nc_type(arr.dtype)
+            full = np.full(n_grid, 0 if code in ("i1", "i4") else np.nan, dtype=_BE[code])
+            full[self._flat] = arr.astype(cast)
+            fixed.append((name, ("lat", "lon"), code, {}, full.tobytes()))
+        code, self._time_cast = _nc_type(time_dtype)
+        records = [("time", ("time",), code, {"units": time_units, "calendar": calendar}, 1)]
+        for name, dt in (shared or {}).items():
+            records.append((name, ("time",), _nc_type(dt)[0], {}, 1))
+        self._fill = {}
+        for name, dt in (series or {}).items():
+            code, cast = _nc_type(dt)
+            self._fill[name] = cast(0 if code in ("i1", "i4") else np.nan)
+            records.append((name, ("time", "lat", "lon"), code, {"_FillValue": self._fill[name]}, n_grid))
+        self._casts = {name: np.dtype(_BE[code]).newbyteorder("=").type for name, _, code, _, _ in records}
+        self._series = tuple(series or {})
+        self._shared = tuple(shared or {})
+
+        # record layout: every variable's slice of a record is padded to 4 bytes unless it is the only record variable
+        sizes = [np.dtype(_BE[code]).itemsize * n for _, _, code, _, n in records]
+        vsizes = sizes if len(records) == 1 else [_pad4(x) for x in sizes]
+        offsets = np.concatenate([[0], np.cumsum(vsizes)[:-1]]).tolist()
+        self._rec_size = int(sum(vsizes))
+        self._rec_dtype = np.dtype({
+            "names": [r[0] for r in records],
+            "formats": [(_BE[code], (n,)) if n > 1 else _BE[code] for _, _, code, _, n in records],
+            "offsets": offsets, "itemsize": self._rec_size})
+
+        def header(begins):
+            out = [b"CDF\x02", _be32(0), _be32(_NC_DIMENSION), _be32(len(dims))]
+            out += [_nc_name(k) + _be32(n) for k, n in dims.items()]
+            out.append(_nc_attributes(attrs))
+            out += [_be32(_NC_VARIABLE), _be32(len(fixed) + len(records))]
+            for (name, vdims, code, vattrs, _), vsize, begin in zip(
+                    fixed + records, [_pad4(len(f[4])) for f in fixed] + vsizes, begins):
+                out += [_nc_name(name), _be32(len(vdims))] + [_be32(dim_id[d]) for d in vdims]
+                out += [_nc_attributes(vattrs), _be32(_NC_CODE[code]), _be32(vsize), int(begin).to_bytes(8, "big")]
+            return b"".join(out)
+
+        n_var = len(fixed) + len(records)
+        pos = len(header([0] * n_var))            # the header's length does not depend on the offsets
+        begins = []
+        for f in fixed:
+            begins.append(pos)
+            pos += _pad4(len(f[4]))
+        self._rec_begin = pos
+        begins += [pos + o for o in offsets]
+        self._f = open(path, "wb")
+        self._f.write(header(begins))
+        for f in fixed:
+            self._f.write(f[4] + b"\0" * (_pad4(len(f[4])) - len(f[4])))
+        assert self._f.tell() == self._rec_begin
+
+    def append(self, time, series, shared=None):
+        """Write the next ``n`` days: ``time`` [n], ``series`` name -> [n, C], ``shared`` name -> [n]."""
+        time = np.asarray(time)
+        n = time.size
+        if set(series or {}) != set(self._series) or set(shared or {}) != set(self._shared):
+            raise ValueError("append needs exactly the variables the writer was created with")
+        for name in self._series:
+            if tuple(series[name].shape) != (n, self._n_cells):
+                raise ValueError(f"series {name} must have shape [{n}, {self._n_cells}], got {tuple(series[name].shape)}")
+        step = max(1, self.block_bytes // self._rec_size)
+        for a in range(0, n, step):
+            b = min(n, a + step)
+            if self._block is None or self._block.size < b - a:
+                # one record block, reused: its pages stay mapped, and the grid points without a cell keep the fill
+                # value written here (every append overwrites the same cell positions)
+                self._block = np.zeros(min(step, max(n, b - a)), dtype=self._rec_dtype)
+                if not self._identity:
+                    for name in self._series:
+                        self._block[name][...] = self._fill[name]
+            rec = self._block[: b - a]
+            rec["time"] = time[a:b].astype(self._time_cast)
+            for name in self._shared:
+                v = np.asarray(shared[name])
+                if v.shape != (n,):
+                    raise ValueError(f"shared variable {name} must have shape [{n}]")
+                rec[name] = v[a:b].astype(self._casts[name])
+            for name in self._series:
+                src = np.asarray(series[name][a:b])
+                if self._identity:
+                    rec[name] = src                      # cells already in grid order, no gaps
+                    continue
+                field = rec[name]                        # row-wise scatter: NumPy's 2-D fancy assignment is 6x slower
+                for i in range(b - a):
+                    field[i, self._flat] = src[i]
+            self._f.write(rec.view(np.uint8))
+        self.n_records += n
+
+    def close(self):
+        if self._f is not None:
+            if self._rec_size % 4:               # a lone, unpadded record variable: the file still ends on 4 bytes
+                self._f.write(b"\0" * (_pad4(self._f.tell()) - self._f.tell()))
+            self._f.seek(4)
+            self._f.write(_be32(self.n_records))
+            self._f.close()
+            self._f = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def write_merged_output(path, series, lat, lon, time, time_units="days since 1901-01-01 00:00:00",
                         calendar="proleptic_gregorian", scalars=None, shared=None, attrs=None):
     """One ``(time, lat, lon)`` file for a batch of cells.
 
     ``series``: dict name -> [T, C] array (e.g. ``{"y": y, "cfact": res["cfact"], "replaced": res["replaced"]}``, the
     ``report_variables`` of detrend.py:462-467); ``scalars``: dict name -> [C] (e.g. ``logp``); ``shared``: dict
-    name -> [T] (``gmt_scaled``)."""
-    ulat, ulon, ilat, ilon = _grid(lat, lon)
+    name -> [T] (``gmt_scaled``).  Streams through ``MergedOutputWriter``."""
     time = np.asarray(time)
-    T, C = time.size, ilat.size
-    nc = _create(path, ulat, ulon, attrs)
-    try:
-        nc.createDimension("time", T)
-        code, cast = _nc_type(time.dtype)
-        v = nc.createVariable("time", code, ("time",))
-        v[:] = time.astype(cast)
-        v.units = time_units
-        v.calendar = calendar
-        for name, arr in (shared or {}).items():
-            arr = np.asarray(arr)
-            if arr.shape != (T,):
-                raise ValueError(f"shared variable {name} must have shape [T]")
-            code, cast = _nc_type(arr.dtype)
-            nc.createVariable(name, code, ("time",))[:] = arr.astype(cast)
-        for name, arr in (series or {}).items():
-            arr = np.asarray(arr)
-            if arr.shape != (T, C):
-                raise ValueError(f"series {name} must have shape [T, C] = [{T}, {C}], got {arr.shape}")
-            code, cast = _nc_type(arr.dtype)
-            v = nc.createVariable(name, code, ("time", "lat", "lon"))
-            fill = 0 if code in ("i1", "i4") else np.nan
-            v._FillValue = cast(fill)
-            full = np.full((T, ulat.size, ulon.size), fill, dtype=cast)
-            full[:, ilat, ilon] = arr
-            v[:] = full
-        for name, arr in (scalars or {}).items():
-            arr = np.asarray(arr)
-            if arr.shape != (C,):
-                raise ValueError(f"scalar variable {name} must have shape [C]")
-            code, cast = _nc_type(arr.dtype)
-            v = nc.createVariable(name, code, ("lat", "lon"))
-            fill = 0 if code in ("i1", "i4") else np.nan
-            full = np.full((ulat.size, ulon.size), fill, dtype=cast)
-            full[ilat, ilon] = arr
-            v[:] = full
-    finally:
-        nc.close()
+    T = time.size
+    series = {k: (v.numpy() if hasattr(v, "numpy") else np.asarray(v)) for k, v in (series or {}).items()}
+    shared = {k: np.asarray(v) for k, v in (shared or {}).items()}
+    n_cells = np.asarray(lat).size
+    for name, arr in series.items():
+        if tuple(arr.shape) != (T, n_cells):
+            raise ValueError(f"series {name} must have shape [T, C] = [{T}, {n_cells}], got {tuple(arr.shape)}")
+    for name, arr in shared.items():
+        if arr.shape != (T,):
+            raise ValueError(f"shared variable {name} must have shape [T]")
+    with MergedOutputWriter(path, lat, lon, {k: v.dtype for k, v in series.items()},
+                            shared={k: v.dtype for k, v in shared.items()}, scalars=scalars, time_dtype=time.dtype,
+                            time_units=time_units, calendar=calendar, attrs=attrs) as w:
+        step = max(1, w.block_bytes // w._rec_size)
+        for a in range(0, T, step):
+            b = min(T, a + step)
+            w.append(time[a:b], {k: v[a:b] for k, v in series.items()}, {k: v[a:b] for k, v in shared.items()})
 
 
 def write_merged_trace(path, variable, params, logp, scaling, lat, lon, attrs=None):

@@ -25,7 +25,8 @@ def test_merged_output_layout(tmp_path):
     aio.write_merged_output(path, {"y": y, "cfact": cfact, "replaced": replaced}, lat, lon, np.arange(T, dtype=np.int32),
                             scalars={"logp": logp}, shared={"gmt_scaled": gmt}, attrs={"attrici_config": "variable = 'tas'"})
     nc = netcdf_file(path, "r", mmap=False)
-    assert nc.dimensions == {"lat": 2, "lon": 2, "time": T}
+    assert nc.dimensions == {"time": None, "lat": 2, "lon": 2}               # time is the record dimension
+    assert nc.variables["time"].shape == (T,) and nc.variables["cfact"].shape == (T, 2, 2)
     assert nc.variables["cfact"].dimensions == ("time", "lat", "lon")        # merge_output.py:79-86
     assert nc.variables["logp"].dimensions == ("lat", "lon")
     assert nc.variables["lat"].data.dtype.kind == "f" and nc.variables["lat"].data.dtype.itemsize == 4
@@ -72,3 +73,51 @@ def test_shape_and_duplicate_checks(tmp_path):
         aio.write_merged_output(str(tmp_path / "a.nc"), {"cfact": np.zeros((5, 2))}, lat, lon, np.arange(5))
     with pytest.raises(ValueError):
         aio.write_merged_output(str(tmp_path / "b.nc"), {}, [1.0, 1.0], [2.0, 2.0], np.arange(5))
+
+
+@pytest.mark.parametrize("block_bytes", [1, 100, 1 << 20])
+def test_streamed_records(tmp_path, block_bytes):
+    """Days appended block by block (and in several calls) give the same file; record slices of 1-byte variables
+    are padded to 4 bytes (3 grid points), a fully covered grid needs no fill."""
+    lat, lon = np.array([10.25, 10.25, 10.25]), np.array([1.25, 0.25, 0.75])   # one row, cells not in lon order
+    T, C = 23, 3
+    rng = np.random.default_rng(2)
+    cfact = rng.normal(size=(T, C))
+    replaced = rng.integers(0, 4, (T, C)).astype(np.uint8)
+    time = np.arange(100, 100 + T, dtype=np.int64)
+    path = str(tmp_path / "s.nc")
+    with aio.MergedOutputWriter(path, lat, lon, {"cfact": np.float64, "replaced": np.uint8}, shared={"gmt_scaled": np.float64},
+                                scalars={"status": np.int32([0, 2, 0])}, block_bytes=block_bytes) as w:
+        for a, b in ((0, 9), (9, 10), (10, T)):
+            w.append(time[a:b], {"cfact": cfact[a:b], "replaced": replaced[a:b]}, {"gmt_scaled": np.linspace(0, 1, T)[a:b]})
+        with pytest.raises(ValueError):
+            w.append(time[:2], {"cfact": cfact[:2]}, {"gmt_scaled": np.zeros(2)})
+        with pytest.raises(ValueError):
+            w.append(time[:2], {"cfact": cfact[:3], "replaced": replaced[:2]}, {"gmt_scaled": np.zeros(2)})
+    for mmap in (False, True):
+        nc = netcdf_file(path, "r", mmap=mmap)
+        order = np.argsort(lon)
+        np.testing.assert_array_equal(np.array(nc.variables["lon"][:]), np.float32(lon[order]))
+        np.testing.assert_array_equal(np.array(nc.variables["cfact"][:])[:, 0, :], cfact[:, order])
+        np.testing.assert_array_equal(np.array(nc.variables["replaced"][:])[:, 0, :], replaced[:, order].astype(np.int8))
+        np.testing.assert_array_equal(np.array(nc.variables["time"][:]), time.astype(np.int32))
+        np.testing.assert_array_equal(np.array(nc.variables["gmt_scaled"][:]), np.linspace(0, 1, T))
+        np.testing.assert_array_equal(np.array(nc.variables["status"][:]), np.int32([0, 2, 0])[order][None, :])
+        del nc  # mmap=True: SciPy warns if views outlive close()
+
+
+def test_lone_record_variable_and_torch_input(tmp_path):
+    """A file whose only record variable is ``time`` (no per-record padding rule), and CPU tensors as series."""
+    import torch
+
+    path = str(tmp_path / "t.nc")
+    with aio.MergedOutputWriter(path, [1.0], [2.0], {}) as w:
+        w.append(np.arange(5, dtype=np.int32), {})
+    nc = netcdf_file(path, "r", mmap=False)
+    np.testing.assert_array_equal(np.array(nc.variables["time"][:]), np.arange(5))
+    nc.close()
+    cf = torch.arange(12, dtype=torch.float64).reshape(6, 2)
+    aio.write_merged_output(path, {"cfact": cf}, [1.0, 1.5], [2.0, 2.0], np.arange(6))
+    nc = netcdf_file(path, "r", mmap=False)
+    np.testing.assert_array_equal(np.array(nc.variables["cfact"][:])[:, :, 0], cf.numpy())
+    nc.close()
