@@ -263,6 +263,71 @@ def write_merged_output(path, series, lat, lon, time, time_units="days since 190
             w.append(time[a:b], {k: v[a:b] for k, v in series.items()}, {k: v[a:b] for k, v in shared.items()})
 
 
+def write_merged_output_sharded(path, series_local, counts, lat, lon, time, dist, group=None, dst=0,
+                                block_bytes=64 << 20, **kwargs):
+    """The final host gather of a multi-rank run, straight into the merged file: every rank holds the series of its
+    contiguous cell range (``series_local``: name -> [T, counts[rank]], the ``cfact`` / ``replaced`` of
+    ``detrend_cells``); block of days by block of days the ranks' slices are gathered to rank ``dst`` over ``group``
+    (host tensors: a gloo group, e.g. ``dist.new_group(backend="gloo")`` next to the NCCL one) and appended to a
+    ``MergedOutputWriter`` there, so that no rank ever holds more than one block of the full ``[T, C]`` series.
+
+    ``lat`` / ``lon`` / ``time`` and the keyword arguments (``scalars``, ``shared``, ``attrs``, ...: full-size, as for
+    ``write_merged_output``) are only read on ``dst``.  Collective: all ranks of ``group`` must call it with the same
+    variable names.  Returns the number of days written (on ``dst``) or None."""
+    import torch
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    counts = [int(c) for c in counts]
+    if len(counts) != world:
+        raise ValueError("counts must have one entry per rank")
+    names = sorted(series_local)
+    local = {}
+    for k in names:
+        t = series_local[k]
+        t = t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t))
+        if t.dim() != 2 or t.shape[1] != counts[rank] or t.is_cuda:
+            raise ValueError(f"series {k} must be a host array [T, {counts[rank]}] on rank {rank}")
+        local[k] = t
+    T = int(np.asarray(time).size) if rank == dst else 0
+    n_days = torch.tensor([T if rank == dst else 0], dtype=torch.int64)
+    dist.broadcast(n_days, src=dst if group is None else dist.get_global_rank(group, dst), group=group)
+    T = int(n_days.item())
+    for k in names:
+        if local[k].shape[0] != T:
+            raise ValueError(f"series {k} has {local[k].shape[0]} days on rank {rank}, the time axis {T}")
+    cmax, n_cells = max(counts), sum(counts)
+    row_bytes = max(1, sum(local[k].element_size() for k in names) * max(n_cells, 1))
+    step = max(1, int(block_bytes) // row_bytes)
+    writer = None
+    if rank == dst:
+        shared = {k: np.asarray(v) for k, v in (kwargs.pop("shared", None) or {}).items()}
+        time = np.asarray(time)
+        writer = MergedOutputWriter(path, lat, lon, {k: local[k].numpy().dtype for k in names},
+                                    shared={k: v.dtype for k, v in shared.items()}, time_dtype=time.dtype,
+                                    block_bytes=block_bytes, **kwargs)
+    try:
+        for a in range(0, T, step):
+            b = min(T, a + step)
+            block = {}
+            for k in names:
+                part = local[k][a:b]
+                if counts[rank] < cmax:                      # gather needs equal shapes: pad the short shards
+                    pad = part.new_zeros((b - a, cmax))
+                    pad[:, : counts[rank]] = part
+                    part = pad
+                part = part.contiguous()
+                bucket = [torch.empty_like(part) for _ in range(world)] if rank == dst else None
+                dist.gather(part, bucket, dst=dst if group is None else dist.get_global_rank(group, dst), group=group)
+                if rank == dst:
+                    block[k] = torch.cat([t[:, :c] for t, c in zip(bucket, counts)], dim=1).numpy()
+            if rank == dst:
+                writer.append(time[a:b], block, {k: v[a:b] for k, v in shared.items()})
+    finally:
+        if writer is not None:
+            writer.close()
+    return T if rank == dst else None
+
+
 def write_merged_trace(path, variable, params, logp, scaling, lat, lon, attrs=None):
     """The traces of a batch of cells in merged form: ``params(lat, lon, params_dim_0)``, ``logp(lat, lon)`` and
     ``scaling_<key>(lat, lon)`` - the entries ``write_trace`` stores per cell (detrend.py:221-255 with the SciPy trace

@@ -91,3 +91,64 @@ def test_gather_world_size_2_gloo(n_cells):
         assert p.exitcode == 0
     got = sorted(q.get(timeout=5) for _ in range(2))
     assert got == [(0, True), (1, True)]
+
+
+def _writer_worker(rank, world, port, n_cells, path, q):
+    import torch.distributed as dist
+    from scipy.io import netcdf_file
+
+    from attrici_b200 import io as aio
+    from attrici_b200.synthetic import tile_coordinates
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T = 37
+        rng = np.random.default_rng(9)
+        cfact = rng.normal(size=(T, n_cells))
+        replaced = rng.integers(0, 4, (T, n_cells)).astype(np.uint8)
+        lat, lon = tile_coordinates(3, 5)
+        lat, lon = lat[:n_cells], lon[:n_cells]           # 15 grid points, the last ones without a cell
+        counts = [len(get_task_indices(n_cells, r, world)) for r in range(world)]
+        idx = get_task_indices(n_cells, rank, world)
+        group = dist.new_group(backend="gloo")             # what a run under NCCL adds for host tensors
+        n = aio.write_merged_output_sharded(
+            path, {"cfact": cfact[:, idx], "replaced": replaced[:, idx]}, counts, lat, lon, np.arange(T, dtype=np.int32),
+            dist, group=group, block_bytes=600, scalars={"logp": np.arange(n_cells, dtype=np.float64)},
+            shared={"gmt_scaled": np.linspace(0, 1, T)})
+        ok = True
+        if rank == 0:
+            nc = netcdf_file(path, "r", mmap=False)
+            full = np.array(nc.variables["cfact"][:]).reshape(T, -1)
+            rep = np.array(nc.variables["replaced"][:]).reshape(T, -1)
+            ok = (n == T and np.array_equal(full[:, :n_cells], cfact) and np.isnan(full[:, n_cells:]).all()
+                  and np.array_equal(rep[:, :n_cells], replaced.astype(np.int8)) and (rep[:, n_cells:] == 0).all()
+                  and np.array_equal(np.array(nc.variables["logp"][:]).ravel()[:n_cells], np.arange(n_cells))
+                  and np.array_equal(np.array(nc.variables["gmt_scaled"][:]), np.linspace(0, 1, T)))
+            nc.close()
+        else:
+            ok = n is None
+        dist.barrier()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_cells", [11, 14])
+def test_sharded_merged_output_world_size_2_gloo(n_cells, tmp_path):
+    """Final host gather to NetCDF (BASELINE configs[4]): uneven shards, several blocks of days."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + n_cells) % 2000
+    path = str(tmp_path / "merged.nc")
+    procs = [ctx.Process(target=_writer_worker, args=(r, 2, port, n_cells, path, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(2))
+    assert got == [(0, True), (1, True)]
