@@ -437,6 +437,16 @@ def test_batched_driver_single_rank():
     np.testing.assert_array_equal(part["cfact"], res["cfact"][:, 4:8])
     ref = oracle.detrend_cell("tas", y[:, 9], gmt, days, helpers.MODES)
     np.testing.assert_allclose(res["cfact"][:, 9], ref["cfact"], rtol=1e-5)
+    # the reference's units / bounds checks (variables.py:17-37, 134-156, 317-320; detrend.py:411)
+    checked = detrend_cells(Config("tas", slab_cells=8, validate=True), y, gmt, days, lat, lon, units="K")
+    np.testing.assert_array_equal(checked["cfact"], res["cfact"])
+    with pytest.raises(ValueError, match="Units of data are degC, but expected K"):
+        detrend_cells(Config("tas"), y, gmt, days, lat, lon, units="degC")
+    bad = y.copy()
+    bad[17, 3] = -1.0
+    with pytest.raises(ValueError) as e:
+        detrend_cells(Config("tas", validate=True), bad, gmt, days, lat, lon)
+    assert e.value.args[1:] == ("is smaller than lower bound", 0.0, ".")
 
 
 def test_full_length_series_properties():
