@@ -51,11 +51,47 @@ def get_task_indices(indices_len, task_id, task_count):
     return np.arange(start, end + 1)
 
 
-def scale_predictor(gmt, n_time):
-    """Predictor on the observation axis, attrici/detrend.py:698-707 (default branch): stretch the GMT
-    series over the normalised time index of a gap-free daily axis and min-max scale it to [0, 1]."""
-    t_scaled = np.arange(n_time, dtype=np.float64) / np.float64(n_time - 1)
-    g = np.interp(t_scaled, np.linspace(0, 1, len(gmt)), np.asarray(gmt, dtype=np.float64))
+def scale_predictor(gmt, n_time=None, days=None, gmt_days=None, full_extrapolation=False):
+    """Predictor on the observation axis, min-max scaled to [0, 1] (attrici/detrend.py:687-707).
+
+    Default branch (:698-707): the GMT series is stretched over the normalised observation times
+    ``(t - t.min()) / (t.max() - t.min())`` — whatever dates the GMT file carries — with ``np.interp``.  ``days``:
+    integer day offsets of the observation axis (any origin, gaps allowed); ``n_time`` alone means the gap-free
+    axis ``0 .. n_time-1``.
+    ``full_extrapolation`` (:688-696): the GMT values sit on a subset of the observation dates (``gmt_days``, same
+    origin as ``days``, e.g. every 10th day); linear interpolation in between and linear extrapolation of the first /
+    last segment beyond its ends — the arithmetic of ``scipy.interpolate.interp1d(kind="linear",
+    fill_value="extrapolate")`` that ``xarray.DataArray.interp`` runs on the dates as float64 nanoseconds since
+    the first GMT date."""
+    gmt = np.asarray(gmt, dtype=np.float64)
+    if days is None:
+        if n_time is None:
+            raise ValueError("give n_time or days")
+        days = np.arange(n_time, dtype=np.int64)
+    days = np.asarray(days)
+    if not np.issubdtype(days.dtype, np.integer):
+        raise TypeError("days must be integer day offsets")
+    days = days.astype(np.int64)
+    if n_time is not None and len(days) != n_time:
+        raise ValueError("days must have n_time entries")
+    if full_extrapolation:
+        if gmt_days is None:
+            raise ValueError("full_extrapolation needs the day offsets of the GMT values (gmt_days)")
+        gd = np.asarray(gmt_days).astype(np.int64)
+        if gd.shape != gmt.shape or gd.size < 2 or (np.diff(gd) <= 0).any():
+            raise ValueError("gmt_days must be increasing, one entry per GMT value, at least two")
+        ns = 86400.0e9                                   # xarray works on nanoseconds since the first GMT date
+        x = (gd - gd[0]).astype(np.float64) * ns
+        x_new = (days - gd[0]).astype(np.float64) * ns
+        hi = np.clip(np.searchsorted(x, x_new), 1, len(x) - 1)
+        lo = hi - 1
+        span = x[hi] - x[lo]                             # SciPy 1.18 `_call_linear`: two weights, no slope
+        g = ((x_new - x[lo]) / span) * gmt[hi] + ((x[hi] - x_new) / span) * gmt[lo]
+    else:
+        # timedelta64 / timedelta64 in the reference: a float64 quotient of integer tick counts, which for whole days
+        # equals the quotient of the day counts
+        t_scaled = (days - days.min()).astype(np.float64) / np.float64(days.max() - days.min())
+        g = np.interp(t_scaled, np.linspace(0, 1, len(gmt)), gmt)
     return (g - g.min()) / (g.max() - g.min())
 
 

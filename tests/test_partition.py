@@ -55,6 +55,36 @@ def test_predictor_and_seeds_match_oracle():
     assert cell_seeds(3, lat, lon).tolist() == want
 
 
+def test_predictor_on_datetime_axes_and_full_extrapolation():
+    """attrici/detrend.py:687-707 on real datetime64 arithmetic: the default branch's
+    ``(time - time.min()) / (time.max() - time.min())`` (also with gaps), and the ``full_extrapolation`` branch,
+    which is ``scipy.interpolate.interp1d(..., fill_value="extrapolate")`` on float64 nanoseconds inside xarray."""
+    from scipy.interpolate import interp1d
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ssa_gmt.npz"))["tas"]
+    time = np.arange("1901-01-01", "2024-01-01", dtype="datetime64[D]").astype("datetime64[ns]")
+    time = np.delete(time, slice(500, 730))                                  # an axis with a gap
+    days = ((time - time[0]) / np.timedelta64(1, "D")).astype(np.int64)
+    t_scaled = (time - time.min()) / (time.max() - time.min())               # the reference's expression
+    want = np.interp(t_scaled, np.linspace(0, 1, len(g)), g)
+    want = (want - want.min()) / (want.max() - want.min())
+    assert np.array_equal(scale_predictor(g, days=days + 17), want)          # any origin
+    # GMT on every 10th observation day, the last days extrapolated
+    gmt_time, gd = time[::10], days[::10]
+    g = g[: len(gd)]
+    assert gd[-1] < days[-1] and len(g) == len(gd)
+    x = (gmt_time - gmt_time.min()).astype(np.float64)                        # xarray's _floatize_x: ns as float64
+    x_new = (time - gmt_time.min()).astype(np.float64)
+    want = interp1d(x, g, kind="linear", fill_value="extrapolate", bounds_error=False)(x_new)
+    want = (want - want.min()) / (want.max() - want.min())
+    got = scale_predictor(g, days=days, gmt_days=gd, full_extrapolation=True)
+    assert np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        scale_predictor(g, days=days, full_extrapolation=True)
+    with pytest.raises(ValueError):
+        scale_predictor(g)
+
+
 def _worker(rank, world, port, n_cells, q):
     import torch.distributed as dist
 
