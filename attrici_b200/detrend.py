@@ -30,6 +30,8 @@ class Config:
     use_fp64: bool = False       # FP64 day arithmetic in the likelihood passes
     device: str = None           # default: cuda:<LOCAL_RANK>
     validate: bool = False       # bounds checks of the input and of cfact on the host (see detrend_cells)
+    fit_only: bool = False       # stop after the fit (attrici/detrend.py:353-354): no cfact / replaced
+    window_size: int = None      # rolling-window model: not implemented (like ModelScipy, model_scipy.py:58-59)
 
 
 def get_task_indices(indices_len, task_id, task_count):
@@ -93,6 +95,23 @@ def scale_predictor(gmt, n_time=None, days=None, gmt_days=None, full_extrapolati
         t_scaled = (days - days.min()).astype(np.float64) / np.float64(days.max() - days.min())
         g = np.interp(t_scaled, np.linspace(0, 1, len(gmt)), gmt)
     return (g - g.min()) / (g.max() - g.min())
+
+
+def fit_window_indices(time, start_date=None, stop_date=None):
+    """``[i0, i1)`` of the days the model is fitted on: ``subset_times = time[(time >= start) & (time <= stop)]``
+    (attrici/detrend.py:709-722), both ends inclusive, ``None`` = first / last day of the series.  ``time``:
+    increasing datetime64 axis; the dates anything ``np.datetime64`` accepts (``"1901-01-01"``, ``datetime.date``)."""
+    t = np.asarray(time)
+    if not np.issubdtype(t.dtype, np.datetime64):
+        raise TypeError("time must be a datetime64 axis")
+    start = t[0] if start_date is None else np.datetime64(start_date)
+    stop = t[-1] if stop_date is None else np.datetime64(stop_date)
+    keep = np.flatnonzero((t >= start) & (t <= stop))
+    if keep.size == 0:
+        raise ValueError(f"no day of the series lies in [{start}, {stop}]")
+    if keep[-1] - keep[0] + 1 != keep.size:
+        raise ValueError("time axis must be increasing")
+    return int(keep[0]), int(keep[-1]) + 1
 
 
 def bind_to_gpu_cpus(device_index):
@@ -191,7 +210,48 @@ def gather_cells(local, counts, dist=None, device=None):
     return out
 
 
-def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather=True, out=None, units=None):
+def _slabs_on_device(solver, config, y_local, days, gmt, fit_window, seeds, trace_local, want_map):
+    """The two modes of the reference's cell function that are not the whole path: ``fit_only`` (scale and fit,
+    attrici/detrend.py:353-354) and a given trace (no fit; the quantile map runs on the stored coefficients and
+    rescales with the stored scaling constants, :319-324, :335).  Slab by slab through the solver's device calls."""
+    import torch
+
+    T, n = y_local.shape
+    P = solver.n_params
+    pin = torch.cuda.is_available()
+    res = {"cfact": torch.empty((T, n), dtype=torch.float64, pin_memory=pin) if want_map else None,
+           "replaced": torch.empty((T, n), dtype=torch.uint8, pin_memory=pin) if want_map else None,
+           "params": torch.empty((n, P), dtype=torch.float64), "logp": torch.empty(n, dtype=torch.float64),
+           "scaling": torch.empty((n, 2), dtype=torch.float64), "status": torch.zeros(n, dtype=torch.int32),
+           "n_pass": torch.zeros(n, dtype=torch.int32)}
+    slab = max(1, int(config.slab_cells))
+    for a in range(0, n, slab):
+        b = min(n, a + slab)
+        yd = y_local[:, a:b].contiguous().to(solver.device, non_blocking=True)
+        if not getattr(solver, "_basis_ready", False) or (solver.T, solver.C) != (T, b - a):
+            solver.set_predictor(days, gmt, b - a)           # shared basis: once per slab shape
+        ys, scaling = solver.scale(yd, fit_window)
+        if trace_local is None:
+            fit = solver.fit(ys)
+            params, logp = fit.params, fit.logp
+            res["status"][a:b], res["n_pass"][a:b] = fit.status.cpu(), fit.n_pass.cpu()
+        else:
+            params = torch.from_numpy(np.ascontiguousarray(trace_local["params"][a:b], dtype=np.float64)).to(solver.device)
+            logp = torch.from_numpy(np.ascontiguousarray(trace_local["logp"][a:b], dtype=np.float64))
+            if trace_local.get("scaling") is not None:   # variable.scaling taken from the trace (:319-324)
+                scaling = torch.from_numpy(np.ascontiguousarray(trace_local["scaling"][a:b], dtype=np.float64)).to(solver.device)
+        res["params"][a:b], res["logp"][a:b], res["scaling"][a:b] = params.cpu(), logp.cpu(), scaling.cpu()
+        if want_map:
+            cfact, replaced, _ = solver.quantile_map(yd, ys, params, scaling, None if seeds is None else seeds[a:b])
+            res["cfact"][:, a:b].copy_(cfact)
+            res["replaced"][:, a:b].copy_(replaced)
+    if torch.device(solver.device).type == "cuda":
+        torch.cuda.synchronize(solver.device)
+    return res
+
+
+def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather=True, out=None, units=None,
+                  trace=None):
     """Detrend the cells of ``y`` ([T, C] float32 host array, time-major, cells stacked lat-major as
     attrici/detrend.py:672 does) that the reference's partition assigns to this rank.
 
@@ -204,6 +264,10 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
     (attrici/variables.py:134-156).  ``config.validate`` adds the reference's bounds checks of the input
     (``<Variable>.__init__`` -> ``validate``, e.g. variables.py:317-320) and of ``cfact`` (detrend.py:411) for this
     rank's cells — host reductions over the whole batch, which cost more than the device work, hence opt-in.
+    ``trace``: ``{"params": [C, P], "logp": [C], "scaling": [C, 2] (optional)}`` for all ``C`` cells, e.g. from
+    ``io.read_merged_trace`` — the ``--trace-file`` mode (detrend.py:741-751): no fit, the quantile map runs on
+    these coefficients.  ``config.fit_only`` stops after the fit (``cfact`` / ``replaced`` are None).
+    ``fit_window``: ``[i0, i1)`` on the time axis (``fit_window_indices`` for start / stop dates).
     """
     import os
 
@@ -213,6 +277,10 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
 
     if config.solver != "cuda":
         raise ValueError(f"attrici_b200 only provides solver='cuda', got {config.solver!r}")
+    if (config.modes is None) == (config.window_size is None):
+        raise ValueError("Exactly one of `modes` and `window_size` must be set")      # detrend.py:646-647
+    if config.window_size is not None:
+        raise NotImplementedError("Rolling window not implemented for the CUDA solver")
     spec = create_variable(config.variable)
     check_units(spec, units)
     y = np.asarray(y) if not isinstance(y, torch.Tensor) else y
@@ -240,12 +308,24 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
             y_local = torch.from_numpy(y_local)
         if config.validate:
             validate_bounds(spec, y_local, skip_inf=True)
-        o = solver.detrend_host(y_local, days, gmt_scaled, fit_window, seeds, config.slab_cells, out=out)
+        if trace is not None or config.fit_only:
+            if trace is not None:
+                tp = np.asarray(trace["params"])
+                if tp.shape != (C, P):
+                    raise ValueError(f"trace params must be [{C}, {P}], got {tp.shape}")
+            t_local = None if trace is None else {
+                "params": tp[sl], "logp": np.asarray(trace.get("logp", np.full(C, np.nan)))[sl],
+                "scaling": None if trace.get("scaling") is None else np.asarray(trace["scaling"])[sl]}
+            o = _slabs_on_device(solver, config, y_local, days, gmt_scaled, fit_window, seeds, t_local,
+                                 want_map=not config.fit_only)
+        else:
+            o = solver.detrend_host(y_local, days, gmt_scaled, fit_window, seeds, config.slab_cells, out=out)
         local = {k: (o[k].numpy() if o[k] is not None else None) for k in o}
-        if config.validate:
+        if config.validate and local["cfact"] is not None:
             validate_bounds(spec, local["cfact"])
     else:
-        local = {"cfact": np.empty((T, 0)), "replaced": np.empty((T, 0), dtype=np.uint8),
+        local = {"cfact": None if config.fit_only else np.empty((T, 0)),
+                 "replaced": None if config.fit_only else np.empty((T, 0), dtype=np.uint8),
                  "params": np.empty((0, P)), "logp": np.empty(0), "scaling": np.empty((0, 2)),
                  "status": np.empty(0, dtype=np.int32), "n_pass": np.empty(0, dtype=np.int32)}
     res["cfact"], res["replaced"] = local["cfact"], local["replaced"]

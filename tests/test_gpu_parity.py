@@ -449,6 +449,55 @@ def test_batched_driver_single_rank():
     assert e.value.args[1:] == ("is smaller than lower bound", 0.0, ".")
 
 
+@pytest.mark.parametrize("variable", ["tas", "pr"])
+def test_batched_driver_fit_only_and_trace_file(variable, tmp_path):
+    """``--fit-only --write-trace`` followed by ``--trace-file`` (attrici/detrend.py:319-324, 335, 347-354, 741-751)
+    gives the output of the one-step run: the merged trace file carries coefficients and scaling constants, the
+    second run skips the fit."""
+    from attrici_b200.io import read_merged_trace, write_merged_trace
+
+    T, n_lat, n_lon = 2600, 3, 5
+    C = n_lat * n_lon
+    lat, lon = synthetic.tile_coordinates(n_lat, n_lon)
+    y = synthetic.GENERATORS[variable](C, T)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    window = (100, 2400)
+    res = detrend_cells(Config(variable, slab_cells=8), y, gmt, days, lat, lon, fit_window=window)
+    fit = detrend_cells(Config(variable, slab_cells=8, fit_only=True), y, gmt, days, lat, lon, fit_window=window)
+    assert fit["cfact"] is None and fit["replaced"] is None
+    assert np.array_equal(fit["status"], res["status"]) and np.array_equal(fit["scaling"], res["scaling"])
+    np.testing.assert_allclose(fit["params"], res["params"], rtol=0, atol=1e-9 if variable == "tas" else 5e-6)
+    path = str(tmp_path / "trace.nc")
+    write_merged_trace(path, variable, res["params"], res["logp"], res["scaling"], lat, lon)
+    params, logp, scaling = read_merged_trace(path, lat, lon)
+    assert np.array_equal(params, res["params"]) and np.array_equal(scaling[:, 1], res["scaling"][:, 1])
+    again = detrend_cells(Config(variable, slab_cells=7), y, gmt, days, lat, lon, fit_window=window,
+                          trace={"params": params, "logp": logp, "scaling": res["scaling"]})
+    assert np.array_equal(again["params"], res["params"])
+    assert np.array_equal(again["logp"], res["logp"], equal_nan=True) and (again["n_pass"] == 0).all()
+
+    def same_output(got, want_cfact, want_replaced):
+        if variable == "tas":
+            np.testing.assert_allclose(got["cfact"], want_cfact, rtol=1e-9, equal_nan=True)
+            assert np.array_equal(got["replaced"], want_replaced)
+            return
+        # pr: the scaled series of a slab may differ in the last float32 bit between slab compositions (the gamma
+        # fit of Pr.scale is a chunked reduction), which a day on the dry / wet boundary can turn into a flip
+        ca, cb = got["cfact"], want_cfact
+        assert np.array_equal(np.isnan(ca), np.isnan(cb))
+        same_zero = (ca == 0) == (cb == 0)
+        assert (~same_zero).sum() <= 2
+        m = same_zero & ~np.isnan(ca)
+        np.testing.assert_allclose(ca[m], cb[m], rtol=2e-5)
+        assert (got["replaced"] != want_replaced).sum() <= 2
+
+    same_output(again, res["cfact"], res["replaced"])
+    part = detrend_cells(Config(variable, task_id=1, task_count=4), y, gmt, days, lat, lon, fit_window=window,
+                         trace={"params": params, "logp": logp, "scaling": res["scaling"]})
+    assert part["indices"].tolist() == [4, 5, 6, 7]
+    same_output(part, res["cfact"][:, 4:8], res["replaced"][:, 4:8])
+
+
 def test_full_length_series_properties():
     """BASELINE size in time (43 464 days), 1 024 cells: size-independent properties of the map."""
     T, C = synthetic.DAYS_1901_2019, 1024

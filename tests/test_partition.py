@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from attrici_b200.detrend import gather_cells, get_task_indices, scale_predictor
+from attrici_b200.detrend import Config, detrend_cells, fit_window_indices, gather_cells, get_task_indices, scale_predictor
 from attrici_b200.solver import cell_seeds
 from oracle import attrici_oracle as oracle
 
@@ -83,6 +83,104 @@ def test_predictor_on_datetime_axes_and_full_extrapolation():
         scale_predictor(g, days=days, full_extrapolation=True)
     with pytest.raises(ValueError):
         scale_predictor(g)
+
+
+def test_fit_window_from_dates():
+    """``subset_times`` of attrici/detrend.py:709-722: both ends inclusive, None = the whole series."""
+    import datetime
+
+    time = np.arange("1901-01-01", "1911-01-01", dtype="datetime64[D]").astype("datetime64[ns]")
+    assert fit_window_indices(time) == (0, len(time))
+    i0, i1 = fit_window_indices(time, "1902-01-01", datetime.date(1905, 12, 31))
+    want = np.flatnonzero((time >= np.datetime64("1902-01-01")) & (time <= np.datetime64("1905-12-31")))
+    assert (i0, i1) == (want[0], want[-1] + 1) and i1 - i0 == 4 * 365 + 1
+    assert fit_window_indices(time, None, "2021-12-31") == (0, len(time))     # the reference tests' stop date
+    with pytest.raises(ValueError):
+        fit_window_indices(time, "1950-01-01", None)
+    with pytest.raises(TypeError):
+        fit_window_indices(np.arange(10))
+
+
+def test_driver_rejects_what_the_reference_rejects():
+    """attrici/detrend.py:646-647 (modes xor window_size) and the window model's NotImplementedError
+    (model_scipy.py:58-59) are raised before anything touches the GPU."""
+    y = np.zeros((10, 2), dtype=np.float32)
+    args = (y, np.linspace(0, 1, 10), np.arange(10), [0.25, 0.25], [0.25, 0.75])
+    with pytest.raises(ValueError, match="Exactly one of `modes` and `window_size` must be set"):
+        detrend_cells(Config("tas", modes=4, window_size=31), *args)
+    with pytest.raises(ValueError, match="Exactly one of `modes` and `window_size` must be set"):
+        detrend_cells(Config("tas", modes=None), *args)
+    with pytest.raises(NotImplementedError):
+        detrend_cells(Config("tas", modes=None, window_size=31), *args)
+    with pytest.raises(ValueError, match="only provides solver='cuda'"):
+        detrend_cells(Config("tas", solver="scipy"), *args)
+    with pytest.raises(ValueError, match="Variable huss not supported"):
+        detrend_cells(Config("huss"), *args)
+
+
+class _StubSolver:
+    """Stands in for CellBatchSolver on the CPU: records the calls and returns arrays that encode which cells of
+    which slab they came from, so that the slab bookkeeping of ``detrend._slabs_on_device`` can be checked."""
+
+    def __init__(self):
+        import torch
+
+        self.device, self.n_params, self.calls, self.torch = torch.device("cpu"), 3, [], torch
+
+    def set_predictor(self, days, gmt, n_cells):
+        self.calls.append(("predictor", n_cells))
+
+    def scale(self, y, fit_window=None):
+        self.calls.append(("scale", tuple(y.shape), fit_window))
+        t = self.torch
+        return y * 0.5, t.stack([y[0].double(), t.full_like(y[0], 2.0).double()], dim=1)
+
+    def fit(self, ys):
+        t = self.torch
+        cells = ys[0] * 2.0                                     # the stub's y holds the cell number in every row
+        from attrici_b200.solver import FitResult
+
+        return FitResult(t.stack([cells, cells + 0.25, cells + 0.5], dim=1).double(), -cells.double(),
+                         t.ones(ys.shape[1], dtype=t.int32), t.full((ys.shape[1],), 5, dtype=t.int32))
+
+    def quantile_map(self, y, ys, params, scaling, seeds=None, want_replaced=True):
+        self.calls.append(("map", None if seeds is None else list(seeds)))
+        cfact = y.double() + params[:, 0][None, :] * 1000.0 + scaling[:, 1][None, :]
+        return cfact, (y > 3).to(self.torch.uint8), None
+
+
+def test_slab_loop_of_the_fit_only_and_trace_modes():
+    import torch
+
+    from attrici_b200 import detrend as D
+
+    T, n = 6, 7
+    y = torch.arange(n, dtype=torch.float32)[None, :].repeat(T, 1)
+    seeds = np.arange(100, 100 + n, dtype=np.uint32)
+    # fit only: three slabs (3 + 3 + 1), no map
+    s = _StubSolver()
+    out = D._slabs_on_device(s, D.Config("tas", slab_cells=3), y, np.arange(T), np.zeros(T), (1, 5), seeds, None, False)
+    assert out["cfact"] is None and out["replaced"] is None
+    assert out["params"][:, 0].tolist() == list(range(n)) and out["logp"].tolist() == [-float(i) for i in range(n)]
+    assert out["status"].tolist() == [1] * n and out["n_pass"].tolist() == [5] * n
+    assert out["scaling"][:, 0].tolist() == list(range(n))
+    assert [c for c in s.calls if c[0] == "scale"] == [("scale", (T, 3), (1, 5)), ("scale", (T, 3), (1, 5)), ("scale", (T, 1), (1, 5))]
+    assert not [c for c in s.calls if c[0] == "map"]
+    # given trace: no fit, the trace's coefficients and scaling reach the map of the right cells, seeds sliced alike
+    s = _StubSolver()
+    trace = {"params": np.arange(n)[:, None] + np.zeros((n, 3)) + 10.0, "logp": np.arange(n) * 1.5,
+             "scaling": np.column_stack([np.zeros(n), np.arange(n) + 0.125])}
+    out = D._slabs_on_device(s, D.Config("tas", slab_cells=4), y, np.arange(T), np.zeros(T), None, seeds, trace, True)
+    want = y.double() + (torch.arange(n) + 10.0)[None, :] * 1000.0 + (torch.arange(n) + 0.125)[None, :]
+    assert torch.equal(out["cfact"], want) and torch.equal(out["replaced"], (y > 3).to(torch.uint8))
+    assert np.array_equal(out["params"].numpy(), trace["params"]) and np.array_equal(out["logp"].numpy(), trace["logp"])
+    assert np.array_equal(out["scaling"].numpy(), trace["scaling"]) and out["n_pass"].tolist() == [0] * n
+    assert [c[1] for c in s.calls if c[0] == "map"] == [[100, 101, 102, 103], [104, 105, 106]]
+    # a trace without scaling constants keeps the ones of the data
+    s = _StubSolver()
+    del trace["scaling"]
+    out = D._slabs_on_device(s, D.Config("tas", slab_cells=4), y, np.arange(T), np.zeros(T), None, None, trace, True)
+    assert out["scaling"][:, 1].tolist() == [2.0] * n
 
 
 def _worker(rank, world, port, n_cells, q):
