@@ -31,6 +31,10 @@ class Config:
     device: str = None           # default: cuda:<LOCAL_RANK>
     validate: bool = False       # bounds checks of the input and of cfact on the host (see detrend_cells)
     fit_only: bool = False       # stop after the fit (attrici/detrend.py:353-354): no cfact / replaced
+    # variables of the per-cell output dataset to return (attrici/detrend.py:447-467; the reference's default is
+    # ("all",)): beyond cfact / replaced, "y_scaled", "cfact_scaled", the distribution fields ("mu", "sigma", ...)
+    # and their counterfactual twins ("mu_cfact", ...) come back in res["series"]
+    report_variables: tuple = ("cfact", "replaced")
     window_size: int = None      # rolling-window model: not implemented (like ModelScipy, model_scipy.py:58-59)
 
 
@@ -210,10 +214,25 @@ def gather_cells(local, counts, dist=None, device=None):
     return out
 
 
-def _slabs_on_device(solver, config, y_local, days, gmt, fit_window, seeds, trace_local, want_map):
+def report_series(spec, report_variables):
+    """Names of the extra per-day series a ``report_variables`` list asks for (everything of the reference's output
+    dataset, attrici/detrend.py:447-467, that is not an input, ``cfact``, ``replaced`` or ``logp``); unknown names
+    raise ``KeyError`` like the reference's ``ds[config.report_variables]``."""
+    fields = list(spec.parameters) + [f"{k}_cfact" for k in spec.parameters]
+    known = ["y", "gmt_scaled", "y_scaled", "cfact_scaled", "cfact", "logp", "replaced"] + fields
+    if "all" in report_variables:
+        return ["y_scaled", "cfact_scaled"] + fields
+    for name in report_variables:
+        if name not in known:
+            raise KeyError(name)
+    return [k for k in ["y_scaled", "cfact_scaled"] + fields if k in report_variables]
+
+
+def _slabs_on_device(solver, config, y_local, days, gmt, fit_window, seeds, trace_local, want_map, extras=()):
     """The two modes of the reference's cell function that are not the whole path: ``fit_only`` (scale and fit,
     attrici/detrend.py:353-354) and a given trace (no fit; the quantile map runs on the stored coefficients and
-    rescales with the stored scaling constants, :319-324, :335).  Slab by slab through the solver's device calls."""
+    rescales with the stored scaling constants, :319-324, :335) — and the runs that report more than ``cfact`` /
+    ``replaced`` (``extras``: names from ``report_series``).  Slab by slab through the solver's device calls."""
     import torch
 
     T, n = y_local.shape
@@ -224,6 +243,8 @@ def _slabs_on_device(solver, config, y_local, days, gmt, fit_window, seeds, trac
            "params": torch.empty((n, P), dtype=torch.float64), "logp": torch.empty(n, dtype=torch.float64),
            "scaling": torch.empty((n, 2), dtype=torch.float64), "status": torch.zeros(n, dtype=torch.int32),
            "n_pass": torch.zeros(n, dtype=torch.int32)}
+    series = {k: torch.empty((T, n), dtype=torch.float32 if k == "y_scaled" else torch.float64, pin_memory=pin)
+              for k in extras}
     slab = max(1, int(config.slab_cells))
     for a in range(0, n, slab):
         b = min(n, a + slab)
@@ -242,11 +263,21 @@ def _slabs_on_device(solver, config, y_local, days, gmt, fit_window, seeds, trac
                 scaling = torch.from_numpy(np.ascontiguousarray(trace_local["scaling"][a:b], dtype=np.float64)).to(solver.device)
         res["params"][a:b], res["logp"][a:b], res["scaling"][a:b] = params.cpu(), logp.cpu(), scaling.cpu()
         if want_map:
-            cfact, replaced, _ = solver.quantile_map(yd, ys, params, scaling, None if seeds is None else seeds[a:b])
+            cfact, replaced, cs = solver.quantile_map(yd, ys, params, scaling, None if seeds is None else seeds[a:b],
+                                                      want_scaled="cfact_scaled" in series)
             res["cfact"][:, a:b].copy_(cfact)
             res["replaced"][:, a:b].copy_(replaced)
+            if cs is not None:
+                series["cfact_scaled"][:, a:b].copy_(cs)
+        for k in series:
+            if k == "y_scaled":
+                series[k][:, a:b].copy_(ys)
+            elif k != "cfact_scaled":                        # distribution fields: estimate_distribution x2, :362-370
+                name, cf = (k[: -len("_cfact")], True) if k.endswith("_cfact") else (k, False)
+                series[k][:, a:b].copy_(solver.eval_parameter(params, name, counterfactual=cf))
     if torch.device(solver.device).type == "cuda":
         torch.cuda.synchronize(solver.device)
+    res["series"] = series
     return res
 
 
@@ -268,6 +299,8 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
     ``io.read_merged_trace`` — the ``--trace-file`` mode (detrend.py:741-751): no fit, the quantile map runs on
     these coefficients.  ``config.fit_only`` stops after the fit (``cfact`` / ``replaced`` are None).
     ``fit_window``: ``[i0, i1)`` on the time axis (``fit_window_indices`` for start / stop dates).
+    ``config.report_variables`` beyond ``cfact`` / ``replaced`` adds ``res["series"]``: name -> [T, n_local]
+    (``y_scaled`` float32, ``cfact_scaled``, distribution fields and ``<field>_cfact`` float64; detrend.py:447-467).
     """
     import os
 
@@ -283,6 +316,7 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
         raise NotImplementedError("Rolling window not implemented for the CUDA solver")
     spec = create_variable(config.variable)
     check_units(spec, units)
+    extras = [] if config.fit_only else report_series(spec, config.report_variables)
     y = np.asarray(y) if not isinstance(y, torch.Tensor) else y
     if y.ndim != 2:
         raise ValueError("y must be [T, C]")
@@ -308,7 +342,7 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
             y_local = torch.from_numpy(y_local)
         if config.validate:
             validate_bounds(spec, y_local, skip_inf=True)
-        if trace is not None or config.fit_only:
+        if trace is not None or config.fit_only or extras:
             if trace is not None:
                 tp = np.asarray(trace["params"])
                 if tp.shape != (C, P):
@@ -317,7 +351,8 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
                 "params": tp[sl], "logp": np.asarray(trace.get("logp", np.full(C, np.nan)))[sl],
                 "scaling": None if trace.get("scaling") is None else np.asarray(trace["scaling"])[sl]}
             o = _slabs_on_device(solver, config, y_local, days, gmt_scaled, fit_window, seeds, t_local,
-                                 want_map=not config.fit_only)
+                                 want_map=not config.fit_only, extras=extras)
+            res["series"] = {k: v.numpy() for k, v in o.pop("series").items()}
         else:
             o = solver.detrend_host(y_local, days, gmt_scaled, fit_window, seeds, config.slab_cells, out=out)
         local = {k: (o[k].numpy() if o[k] is not None else None) for k in o}
@@ -328,6 +363,8 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
                  "replaced": None if config.fit_only else np.empty((T, 0), dtype=np.uint8),
                  "params": np.empty((0, P)), "logp": np.empty(0), "scaling": np.empty((0, 2)),
                  "status": np.empty(0, dtype=np.int32), "n_pass": np.empty(0, dtype=np.int32)}
+        if extras:
+            res["series"] = {k: np.empty((T, 0), dtype=np.float32 if k == "y_scaled" else np.float64) for k in extras}
     res["cfact"], res["replaced"] = local["cfact"], local["replaced"]
     per_cell = {k: local[k] for k in ("params", "logp", "scaling", "status", "n_pass")}
     if gather and world > 1:

@@ -498,6 +498,46 @@ def test_batched_driver_fit_only_and_trace_file(variable, tmp_path):
     same_output(part, res["cfact"][:, 4:8], res["replaced"][:, 4:8])
 
 
+def test_batched_driver_report_variables():
+    """``report_variables = ("all",)`` (the reference's default, attrici/detrend.py:447-467): the scaled series, the
+    scaled counterfactual and the factual / counterfactual distribution fields come back next to ``cfact``."""
+    T, n_lat, n_lon = 2500, 3, 5
+    lat, lon = synthetic.tile_coordinates(n_lat, n_lon)
+    y = synthetic.tas_cells(n_lat * n_lon, T, seed=23, nan_fraction=0.2)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    lean = detrend_cells(Config("tas", slab_cells=8), y, gmt, days, lat, lon)
+    res = detrend_cells(Config("tas", slab_cells=8, report_variables=("all",)), y, gmt, days, lat, lon)
+    np.testing.assert_allclose(res["cfact"], lean["cfact"], rtol=1e-9, equal_nan=True)
+    assert np.array_equal(res["replaced"], lean["replaced"])
+    ser = res["series"]
+    assert set(ser) == {"y_scaled", "cfact_scaled", "mu", "sigma", "mu_cfact", "sigma_cfact"}
+    s = CellBatchSolver("tas", device=DEV)
+    out = s.detrend_device(dev(y), days, gmt)
+    assert np.array_equal(ser["y_scaled"], host(out["y_scaled"]), equal_nan=True)
+    for name in ("mu", "sigma"):
+        for cf in (False, True):
+            want = host(s.eval_parameter(out["fit"].params, name, counterfactual=cf))
+            np.testing.assert_allclose(ser[name + ("_cfact" if cf else "")], want, rtol=1e-9)
+    # sigma does not depend on the predictor, so the Normal map is a shift by the change of mu (SURVEY.md 8d iv)
+    # (days in the far tails go through the reference's ndtr -> ndtri round trip, which is not exact there)
+    ys64 = ser["y_scaled"].astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        ok = (res["replaced"] == 0) & ~np.isnan(ys64) & (np.abs(ys64 - ser["mu"]) < 3.5 * ser["sigma"])
+    assert ok.mean() > 0.9
+    shift = ser["cfact_scaled"] - ys64
+    np.testing.assert_allclose(shift[ok], (ser["mu_cfact"] - ser["mu"])[ok], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ser["sigma"], ser["sigma_cfact"], rtol=1e-14)
+    # rescale (variables.py:114-131): cfact = cfact_scaled * scale + datamin
+    c = 4
+    np.testing.assert_allclose(res["cfact"][ok[:, c], c],
+                               ser["cfact_scaled"][ok[:, c], c] * res["scaling"][c, 1] + res["scaling"][c, 0], rtol=1e-12)
+    one = detrend_cells(Config("tas", report_variables=("cfact", "mu_cfact")), y, gmt, days, lat, lon)
+    assert list(one["series"]) == ["mu_cfact"]
+    np.testing.assert_allclose(one["series"]["mu_cfact"], ser["mu_cfact"], rtol=1e-9)
+    with pytest.raises(KeyError):
+        detrend_cells(Config("tas", report_variables=("cfact", "nu")), y, gmt, days, lat, lon)
+
+
 def test_full_length_series_properties():
     """BASELINE size in time (43 464 days), 1 024 cells: size-independent properties of the map."""
     T, C = synthetic.DAYS_1901_2019, 1024

@@ -143,10 +143,14 @@ class _StubSolver:
         return FitResult(t.stack([cells, cells + 0.25, cells + 0.5], dim=1).double(), -cells.double(),
                          t.ones(ys.shape[1], dtype=t.int32), t.full((ys.shape[1],), 5, dtype=t.int32))
 
-    def quantile_map(self, y, ys, params, scaling, seeds=None, want_replaced=True):
+    def quantile_map(self, y, ys, params, scaling, seeds=None, want_replaced=True, want_scaled=False):
         self.calls.append(("map", None if seeds is None else list(seeds)))
         cfact = y.double() + params[:, 0][None, :] * 1000.0 + scaling[:, 1][None, :]
-        return cfact, (y > 3).to(self.torch.uint8), None
+        return cfact, (y > 3).to(self.torch.uint8), (cfact - 1.0 if want_scaled else None)
+
+    def eval_parameter(self, params, which, counterfactual=False):
+        base = {"mu": 1.0, "sigma": 2.0}[which] + (0.5 if counterfactual else 0.0)
+        return (params[:, 0] + base)[None, :].repeat(6, 1)
 
 
 def test_slab_loop_of_the_fit_only_and_trace_modes():
@@ -176,6 +180,20 @@ def test_slab_loop_of_the_fit_only_and_trace_modes():
     assert np.array_equal(out["params"].numpy(), trace["params"]) and np.array_equal(out["logp"].numpy(), trace["logp"])
     assert np.array_equal(out["scaling"].numpy(), trace["scaling"]) and out["n_pass"].tolist() == [0] * n
     assert [c[1] for c in s.calls if c[0] == "map"] == [[100, 101, 102, 103], [104, 105, 106]]
+    # report_variables beyond cfact / replaced: every series lands in the columns of its slab
+    s = _StubSolver()
+    names = D.report_series(D.create_variable("tas"), ("all",))
+    assert names == ["y_scaled", "cfact_scaled", "mu", "sigma", "mu_cfact", "sigma_cfact"]
+    assert D.report_series(D.create_variable("pr"), ("cfact", "p_cfact", "y", "nu")) == ["nu", "p_cfact"]
+    with pytest.raises(KeyError):
+        D.report_series(D.create_variable("tas"), ("cfact", "nu"))
+    out = D._slabs_on_device(s, D.Config("tas", slab_cells=4), y, np.arange(T), np.zeros(T), None, None, trace, True, names)
+    ser = out["series"]
+    assert ser["y_scaled"].dtype == torch.float32 and torch.equal(ser["y_scaled"], y * 0.5)
+    assert torch.equal(ser["cfact_scaled"], out["cfact"] - 1.0)
+    cells = torch.arange(n, dtype=torch.float64) + 10.0
+    for k, add in (("mu", 1.0), ("sigma", 2.0), ("mu_cfact", 1.5), ("sigma_cfact", 2.5)):
+        assert torch.equal(ser[k], (cells + add)[None, :].repeat(T, 1)), k
     # a trace without scaling constants keeps the ones of the data
     s = _StubSolver()
     del trace["scaling"]
