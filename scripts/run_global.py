@@ -73,10 +73,18 @@ for variable in args.variables.split(","):
     cfg = Config(variable, slab_cells=args.slab_cells, device=f"cuda:{local_rank}")
     solver = CellBatchSolver(variable, device=cfg.device)
     seeds = cell_seeds(cfg.seed, lat[idx], lon[idx]) if variable == "pr" else None
-    solver.detrend_host(y_local[:, : min(64, len(idx))], days, gmt, seeds=None if seeds is None else seeds[:64],
-                        slab_cells=64)                                        # warm-up: workspace, pinned mailbox
+    n, P = len(idx), solver.n_params
+    out = {"cfact": torch.empty((T, n), dtype=torch.float64, pin_memory=True),      # pinned outputs allocated (and
+           "replaced": torch.empty((T, n), dtype=torch.uint8, pin_memory=True),     # the scratch sized by a warm-up
+           "params": torch.empty((n, P), dtype=torch.float64, pin_memory=True),     # slab) outside the timed region
+           "logp": torch.empty(n, dtype=torch.float64, pin_memory=True),
+           "scaling": torch.empty((n, 2), dtype=torch.float64, pin_memory=True),
+           "status": torch.empty(n, dtype=torch.int32, pin_memory=True),
+           "n_pass": torch.empty(n, dtype=torch.int32, pin_memory=True)}
+    w = min(cfg.slab_cells, n)
+    solver.detrend_host(y_local[:, :w], days, gmt, seeds=None if seeds is None else seeds[:w], slab_cells=w)
     a = wall()
-    res = solver.detrend_host(y_local, days, gmt, seeds=seeds, slab_cells=cfg.slab_cells)
+    res = solver.detrend_host(y_local, days, gmt, seeds=seeds, slab_cells=cfg.slab_cells, out=out)
     b = wall()
     per_cell = {k: res[k].numpy() for k in ("params", "logp", "scaling", "status", "n_pass")}
     if world > 1:
