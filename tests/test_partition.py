@@ -40,6 +40,43 @@ def test_partition_rule(n, k):
         assert counts == [8428] * 7 + [8424]
 
 
+def _reference_function(name, path="/root/reference/attrici/detrend.py"):
+    """The unmodified source text of one top-level function of the reference, executed with NumPy and a silent
+    logger (the module itself needs xarray / tomlkit); None where the reference is not present."""
+    import ast
+
+    if not os.path.exists(path):
+        return None
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+
+    class _Quiet:
+        def __getattr__(self, _):
+            return lambda *a, **k: None
+
+    ns = {"np": np, "logger": _Quiet()}
+    exec(compile(ast.get_source_segment(src, node), path, "exec"), ns)
+    return ns[name]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/attrici/detrend.py"), reason="reference not present")
+def test_partition_rule_against_the_reference_function():
+    """``get_task_indices`` against the reference's own function (attrici/detrend.py:119-169) for every task of many
+    (cells, tasks) pairs, including more tasks than cells and the global land count."""
+    ref = _reference_function("get_task_indices")
+    rng = np.random.default_rng(0)
+    pairs = [(67420, 8), (67420, 7), (1, 1), (3, 8), (8, 8), (9, 8)] + [
+        (int(rng.integers(1, 3000)), int(rng.integers(1, 40))) for _ in range(150)]
+    for n, k in pairs:
+        for task in range(k):
+            assert np.array_equal(get_task_indices(n, task, k), ref(n, task, k)), (n, k, task)
+    for bad in (-1, 4):
+        with pytest.raises(ValueError):
+            ref(10, bad, 4)
+        with pytest.raises(ValueError):
+            get_task_indices(10, bad, 4)
+
+
 def test_partition_errors():
     with pytest.raises(ValueError):
         get_task_indices(10, 4, 4)
