@@ -192,6 +192,13 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def reference_cells_per_step(steps, cores, rounds=16):
+    """Cells per step of the reference arm: one per core, fewer once ``steps`` rounds of the pool would exceed
+    ``rounds`` (~11 s each)."""
+    budget_cells = rounds * cores
+    return cores if steps * cores <= budget_cells else max(1, budget_cells // steps)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -201,8 +208,7 @@ def run_reference(args):
     # (16 rounds of the pool); for more steps than that the per-step sample shrinks, and the steps' samples are fed
     # to the pool back to back (no barrier between steps: a step smaller than the pool would leave cores idle), so
     # that the K steps are timed as one region and all cores stay busy.
-    budget_cells = 16 * cores
-    n_cells = cores if args.steps * cores <= budget_cells else max(1, budget_cells // args.steps)
+    n_cells = reference_cells_per_step(args.steps, cores)
     with cpu_pool(cores) as pool:  # worker start-up and imports are the warm-up; the CPU path has no other
         total, _ = cpu_sample(pool, n_cells * args.steps)
     value = n_cells * args.steps / total

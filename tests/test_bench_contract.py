@@ -23,6 +23,18 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert "workload" in d["config"]
 
 
+def test_reference_arm_sample_is_bounded():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert bench.reference_cells_per_step(1, 16) == 16 and bench.reference_cells_per_step(16, 16) == 16
+    assert bench.reference_cells_per_step(40, 16) == 6 and bench.reference_cells_per_step(40, 32) == 12
+    assert bench.reference_cells_per_step(10_000, 16) == 1
+    for steps in (1, 3, 20, 40, 100, 256):
+        for cores in (8, 16, 32, 64):
+            assert steps * bench.reference_cells_per_step(steps, cores) <= max(16 * cores, steps)
+
+
 def test_clock_sampler_keeps_the_samples_of_the_timed_region(tmp_path, monkeypatch):
     sys.path.insert(0, ROOT)
     import bench
