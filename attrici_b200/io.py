@@ -155,7 +155,7 @@ class MergedOutputWriter:
         self._rec_size = int(sum(vsizes))
         self._rec_dtype = np.dtype({
             "names": [r[0] for r in records],
-            "formats": [(_BE[code], (n,)) if n > 1 else _BE[code] for _, _, code, _, n in records],
+            "formats": [(_BE[code], (n,)) if len(vdims) == 3 else _BE[code] for _, vdims, code, _, n in records],
             "offsets": offsets, "itemsize": self._rec_size})
 
         def header(begins):

@@ -121,3 +121,44 @@ def test_lone_record_variable_and_torch_input(tmp_path):
     nc = netcdf_file(path, "r", mmap=False)
     np.testing.assert_array_equal(np.array(nc.variables["cfact"][:])[:, :, 0], cf.numpy())
     nc.close()
+
+
+def test_streamed_writer_random_layouts(tmp_path):
+    """Random grids (cells in any order, any subset of the lat x lon box), dtypes, block sizes and append patterns:
+    the file read back with SciPy equals a dense array filled the straightforward way."""
+    rng = np.random.default_rng(42)
+    path = str(tmp_path / "r.nc")
+    for case in range(25):
+        n_lat, n_lon, T = int(rng.integers(1, 6)), int(rng.integers(1, 7)), int(rng.integers(1, 30))
+        ulat = np.sort(rng.choice(np.arange(-89.75, 90, 0.5), n_lat, replace=False))
+        ulon = np.sort(rng.choice(np.arange(-179.75, 180, 0.5), n_lon, replace=False))
+        n_grid = n_lat * n_lon
+        C = int(rng.integers(1, n_grid + 1))
+        cells = rng.permutation(n_grid)[:C]                      # any order, any subset
+        lat, lon = ulat[cells // n_lon], ulon[cells % n_lon]
+        dtypes = {"cfact": np.float64, "y": np.float32, "replaced": np.uint8, "count": np.int32}
+        names = [k for k in dtypes if rng.random() < 0.7] or ["cfact"]
+        data = {k: (rng.normal(size=(T, C)) * 50).astype(dtypes[k]) if dtypes[k] in (np.float64, np.float32)
+                else rng.integers(0, 100, (T, C)).astype(dtypes[k]) for k in names}
+        time = np.cumsum(rng.integers(1, 4, T)).astype(np.int32)
+        with aio.MergedOutputWriter(path, lat, lon, {k: dtypes[k] for k in names},
+                                    block_bytes=int(rng.choice([1, 64, 4096, 1 << 20]))) as w:
+            a = 0
+            while a < T:
+                b = min(T, a + int(rng.integers(1, T + 1)))
+                w.append(time[a:b], {k: data[k][a:b] for k in names})
+                a = b
+        nc = netcdf_file(path, "r", mmap=False)
+        # lat / lon of the file are the unique coordinates of the cells present, which may be fewer than the box
+        flat, flon = np.array(nc.variables["lat"][:]), np.array(nc.variables["lon"][:])
+        assert np.array_equal(flat, np.unique(lat).astype(np.float32)) and np.array_equal(flon, np.unique(lon).astype(np.float32))
+        assert np.array_equal(np.array(nc.variables["time"][:]), time)
+        ilat, ilon = np.searchsorted(np.unique(lat), lat), np.searchsorted(np.unique(lon), lon)
+        for k in names:
+            got = np.array(nc.variables[k][:])
+            cast = {np.uint8: np.int8}.get(dtypes[k], dtypes[k])
+            fill = 0 if np.dtype(cast).kind == "i" else np.nan
+            want = np.full((T, flat.size, flon.size), fill, dtype=cast)
+            want[:, ilat, ilon] = data[k].astype(cast)
+            assert got.shape == want.shape and np.array_equal(got, want, equal_nan=np.dtype(cast).kind == "f"), (case, k)
+        nc.close()
