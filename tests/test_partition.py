@@ -259,7 +259,7 @@ def _worker(rank, world, port, n_cells, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_cells", [11, 8])
+@pytest.mark.parametrize("n_cells", [11, 8, 1])
 def test_gather_world_size_2_gloo(n_cells):
     import torch.multiprocessing as mp
 
@@ -318,7 +318,7 @@ def _writer_worker(rank, world, port, n_cells, path, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_cells", [11, 14])
+@pytest.mark.parametrize("n_cells", [11, 14, 1])
 def test_sharded_merged_output_world_size_2_gloo(n_cells, tmp_path):
     """Final host gather to NetCDF (BASELINE configs[4]): uneven shards, several blocks of days."""
     import torch.multiprocessing as mp
