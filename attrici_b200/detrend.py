@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from .variables import check_units, create_variable
+from .variables import check_bounds, check_units, create_variable
 
 
 @dataclass
@@ -148,31 +148,9 @@ def bind_to_gpu_cpus(device_index):
 
 
 def validate_bounds(spec, values, skip_inf=False):
-    """``Variable.validate`` -> ``check_bounds`` (attrici/variables.py:17-37): same ``ValueError`` arguments.
-
-    The reference checks one cell at a time with xarray's NaN-skipping ``min`` / ``max``; here ``values`` is a
-    whole ``[T, C]`` batch (NumPy array or CPU tensor), reduced with ``fmin`` / ``fmax`` (NaN-skipping, no copy,
-    an all-NaN batch compares false like ``nan < bound``).  ``skip_inf``: the input check — the reference has set
-    infinite values to NaN before it builds the variable (detrend.py:311)."""
-    v = values.numpy() if hasattr(values, "numpy") else np.asarray(values)
-    if v.size == 0:
-        return
-
-    def extreme(ufunc):
-        m = ufunc.reduce(v, axis=None)
-        if skip_inf and np.isinf(m):
-            finite = v[np.isfinite(v)]
-            m = ufunc.reduce(finite) if finite.size else np.nan
-        return m
-
-    if spec.lower_bound is not None:
-        m = extreme(np.fmin)
-        if m < spec.lower_bound:
-            raise ValueError(m, "is smaller than lower bound", spec.lower_bound, ".")
-    if spec.upper_bound is not None:
-        m = extreme(np.fmax)
-        if m > spec.upper_bound:
-            raise ValueError(m, "is bigger than upper bound", spec.upper_bound, ".")
+    """``Variable.validate`` (attrici/variables.py:317-320 and the other classes): ``check_bounds`` with the
+    variable's bounds, for a whole ``[T, C]`` batch."""
+    check_bounds(values, spec.lower_bound, spec.upper_bound, skip_inf=skip_inf)
 
 
 def _dist_info():

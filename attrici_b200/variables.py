@@ -9,6 +9,8 @@ left on the host.
 
 from dataclasses import dataclass
 
+import numpy as np
+
 from . import _lib
 
 # distribution parameter names in the field order of attrici/distributions.py dataclasses
@@ -99,3 +101,32 @@ def check_units(spec, units):
             raise ValueError(f"Units of data are {units}, but expected {spec.units}.")
     elif units not in spec.units:
         raise ValueError(f"Units of data are {units}, but expected one of {set(spec.units)}.")
+
+
+def check_bounds(data, lower=None, upper=None, skip_inf=False):
+    """``check_bounds`` of the reference (attrici/variables.py:17-37): ``ValueError(value, "is smaller than lower
+    bound", lower, ".")`` / ``(value, "is bigger than upper bound", upper, ".")``.
+
+    The reference checks one cell at a time with xarray's NaN-skipping ``min`` / ``max``; here ``data`` may be a whole
+    ``[T, C]`` batch (NumPy array or CPU tensor), reduced with ``fmin`` / ``fmax`` (NaN-skipping, no copy; an all-NaN
+    or empty batch passes, as ``nan < bound`` is false).  ``skip_inf``: for the input check — the reference has set
+    infinite values to NaN before it builds the variable (attrici/detrend.py:311)."""
+    v = data.numpy() if hasattr(data, "numpy") else np.asarray(data)
+    if v.size == 0 or (lower is None and upper is None):
+        return
+
+    def extreme(ufunc):
+        m = ufunc.reduce(v, axis=None)
+        if skip_inf and np.isinf(m):
+            finite = v[np.isfinite(v)]
+            m = ufunc.reduce(finite) if finite.size else np.nan
+        return m
+
+    if lower is not None:
+        m = extreme(np.fmin)
+        if m < lower:
+            raise ValueError(m, "is smaller than lower bound", lower, ".")
+    if upper is not None:
+        m = extreme(np.fmax)
+        if m > upper:
+            raise ValueError(m, "is bigger than upper bound", upper, ".")

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from attrici_b200.detrend import validate_bounds
-from attrici_b200.variables import VARIABLES, check_units, create_variable
+from attrici_b200.variables import VARIABLES, check_bounds, check_units, create_variable
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
@@ -22,6 +22,21 @@ EXPECTED = {  # variable: (units, lower bound, upper bound)
     "hurs": ("%", 0.0, 100.0), "tasskew": ({"1", "K"}, 0.0, 1.0), "rsds": ("W m-2", 0.0, None),
     "tasrange": ("K", 0.0, None), "sfcWind": ("m s-1", 0.0, None), "wind": ("m s-1", 0.0, None),
 }
+
+
+# the cases of the reference's own unit tests of check_bounds (tests/test_variables.py:7-52), as one table:
+# data, lower, upper, raises
+@pytest.mark.parametrize("data,lower,upper,raises", [
+    ([1, 2, 3], None, None, False), ([1, 2, 3], 0, None, False), ([1, 2, 3], None, 4, False), ([1, 2, 3], 0, 4, False),
+    ([1, 2, 3], 2, None, True), ([1, 2, 3], None, 2, True), ([1, 2, 3], 2, 2, True), ([], None, None, False),
+    ([1], 0, 2, False),
+])
+def test_check_bounds_cases_of_the_reference_tests(data, lower, upper, raises):
+    if raises:
+        with pytest.raises(ValueError):
+            check_bounds(np.array(data), lower=lower, upper=upper)
+    else:
+        check_bounds(np.array(data), lower=lower, upper=upper)
 
 
 def test_table_of_units_and_bounds():
