@@ -1,6 +1,9 @@
-import sys, time, os
-sys.path.insert(0, '/root/repo')
-import numpy as np, torch
+"""eval_parameter (report variables): phase-ordered against day-ordered kernel, 10 000 cells x 43 464 days."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
 from attrici_b200 import synthetic
 from attrici_b200.solver import CellBatchSolver
 T, C = synthetic.DAYS_1901_2019, 10000

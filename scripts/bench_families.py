@@ -3,7 +3,6 @@
 Not a bench line (see bench.py); numbers go to profiles/ as context."""
 import os
 import sys
-import time
 
 import numpy as np
 import torch

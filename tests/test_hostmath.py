@@ -4,7 +4,7 @@ flow without a GPU; the CUDA kernels themselves are covered by the `-m gpu` test
 
 import numpy as np
 import pytest
-from scipy import special, stats
+from scipy import special
 
 import helpers
 import hostmath_lib as hm
