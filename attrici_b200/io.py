@@ -18,6 +18,8 @@ the small trace file goes through ``scipy.io.netcdf_file``.  Layout (the one ``m
 Pure host code (NumPy + SciPy); nothing here touches the GPU.
 """
 
+import os
+
 import numpy as np
 from scipy.io import netcdf_file
 
@@ -378,3 +380,52 @@ def read_merged_trace(path, lat, lon):
         return params, logp, scaling
     finally:
         nc.close()
+
+
+def replaced_flags(codes):
+    """The library's ``replaced`` codes (``ATTRICI_REPLACED_*``: 0 none, 1 NaN, 2 +Inf, 3 -Inf) as the float64 flags
+    the reference stores (attrici/detrend.py:396-409: 0, NaN, +Inf, -Inf; ``_FillValue`` 0)."""
+    table = np.array([0.0, np.nan, np.inf, -np.inf])
+    return table[np.asarray(codes).astype(np.intp)]
+
+
+def cell_paths(output_dir, variable, lat, lon):
+    """``(timeseries file, trace file)`` of one cell, the reference's layout (attrici/detrend.py:236-242, 287-293):
+    ``<out>/timeseries/<var>/lat_<lat:g>/ts_lat<lat:g>_lon<lon:g>.nc`` and
+    ``<out>/trace/<var>/lat_<lat:g>/trace_lat<lat:g>_lon<lon:g>.nc``."""
+    lat, lon = float(lat), float(lon)
+    return (os.path.join(str(output_dir), "timeseries", variable, f"lat_{lat:g}", f"ts_lat{lat:g}_lon{lon:g}.nc"),
+            os.path.join(str(output_dir), "trace", variable, f"lat_{lat:g}", f"trace_lat{lat:g}_lon{lon:g}.nc"))
+
+
+def write_cell_files(output_dir, variable, lat, lon, time, series, logp, params=None, scaling=None, shared=None,
+                     cells=None, overwrite=True, attrs=None, **time_kwargs):
+    """Per-cell files at the reference's paths, for runs whose downstream tools expect them: for every cell one
+    timeseries file with dimensions ``(time, lat, lon)`` of lengths ``(T, 1, 1)`` holding ``series`` (name -> [T, C];
+    ``replaced`` codes are stored as the reference's NaN / Inf flags), ``logp(lat, lon)`` and the ``shared`` ``(time,)``
+    variables (attrici/detrend.py:447-477), and - if ``params`` is given - one trace file (``write_trace``, :221-255).
+    ``cells``: indices to write (default all).  An existing timeseries file is skipped unless ``overwrite``
+    (:296-305).  Returns the list of timeseries paths written.  A global run should prefer ``write_merged_output``:
+    67 k small files are the reference's scalability wall."""
+    spec = create_variable(variable) if isinstance(variable, str) else variable
+    lat, lon = np.asarray(lat, dtype=np.float64), np.asarray(lon, dtype=np.float64)
+    written = []
+    for c in (range(lat.size) if cells is None else cells):
+        ts_path, trace_path = cell_paths(output_dir, spec.name, lat[c], lon[c])
+        if params is not None:
+            os.makedirs(os.path.dirname(trace_path), exist_ok=True)
+            write_merged_trace(trace_path, spec, np.asarray(params)[c:c + 1], np.asarray(logp)[c:c + 1],
+                               np.asarray(scaling)[c:c + 1], lat[c:c + 1], lon[c:c + 1], attrs=attrs)
+        if not series:
+            continue
+        if os.path.exists(ts_path) and not overwrite:
+            continue
+        os.makedirs(os.path.dirname(ts_path), exist_ok=True)
+        cell = {}
+        for k, v in series.items():
+            col = (v.numpy() if hasattr(v, "numpy") else np.asarray(v))[:, c:c + 1]
+            cell[k] = replaced_flags(col) if k == "replaced" and col.dtype.kind in "iub" else col
+        write_merged_output(ts_path, cell, lat[c:c + 1], lon[c:c + 1], time, scalars={"logp": np.asarray(logp)[c:c + 1]},
+                            shared=shared, attrs=attrs, **time_kwargs)
+        written.append(ts_path)
+    return written

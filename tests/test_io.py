@@ -162,3 +162,42 @@ def test_streamed_writer_random_layouts(tmp_path):
             want[:, ilat, ilon] = data[k].astype(cast)
             assert got.shape == want.shape and np.array_equal(got, want, equal_nan=np.dtype(cast).kind == "f"), (case, k)
         nc.close()
+
+
+def test_per_cell_files_at_the_reference_paths(tmp_path):
+    """attrici/detrend.py:236-242, 287-293 (paths), 447-477 (timeseries file), 221-255 (trace file)."""
+    lat, lon = np.array([50.75, 51.25, -0.25]), np.array([9.25, 9.75, 100.0])
+    T, C = 12, 3
+    rng = np.random.default_rng(3)
+    y = rng.normal(280, 5, (T, C)).astype(np.float32)
+    cfact = y.astype(np.float64) + 0.5
+    codes = rng.integers(0, 4, (T, C)).astype(np.uint8)
+    params, logp = rng.normal(size=(C, 27)), rng.normal(size=C)
+    scaling = np.column_stack([rng.uniform(250, 260, C), rng.uniform(40, 60, C)])
+    ts, tr = aio.cell_paths(tmp_path, "tas", 50.75, 9.25)
+    assert ts == str(tmp_path / "timeseries" / "tas" / "lat_50.75" / "ts_lat50.75_lon9.25.nc")
+    assert tr == str(tmp_path / "trace" / "tas" / "lat_50.75" / "trace_lat50.75_lon9.25.nc")
+    assert aio.cell_paths(tmp_path, "tas", -0.25, 100.0)[0].endswith("lat_-0.25/ts_lat-0.25_lon100.nc")   # ":g"
+    written = aio.write_cell_files(tmp_path, "tas", lat, lon, np.arange(T, dtype=np.int32),
+                                   {"y": y, "cfact": cfact, "replaced": codes}, logp, params=params, scaling=scaling,
+                                   shared={"gmt_scaled": np.linspace(0, 1, T)})
+    assert len(written) == C and written[0] == ts
+    for c in range(C):
+        ts, tr = aio.cell_paths(tmp_path, "tas", lat[c], lon[c])
+        nc = netcdf_file(ts, "r", mmap=False)
+        assert nc.variables["cfact"].shape == (T, 1, 1) and nc.variables["cfact"].dimensions == ("time", "lat", "lon")
+        np.testing.assert_array_equal(np.array(nc.variables["cfact"][:])[:, 0, 0], cfact[:, c])
+        np.testing.assert_array_equal(np.array(nc.variables["y"][:])[:, 0, 0], y[:, c])
+        rep = np.array(nc.variables["replaced"][:])[:, 0, 0]
+        np.testing.assert_array_equal(rep, aio.replaced_flags(codes[:, c]))       # 0 / NaN / +Inf / -Inf
+        assert nc.variables["replaced"].data.dtype.itemsize == 8
+        assert np.array(nc.variables["logp"][:]).ravel()[0] == logp[c]
+        assert np.array(nc.variables["lat"][:])[0] == np.float32(lat[c])
+        nc.close()
+        p, l, sc = aio.read_merged_trace(tr, lat[c:c + 1], lon[c:c + 1])
+        np.testing.assert_array_equal(p[0], params[c])
+        np.testing.assert_array_equal(sc[0], scaling[c])
+    # existing output is skipped unless overwrite (detrend.py:296-305)
+    assert aio.write_cell_files(tmp_path, "tas", lat, lon, np.arange(T), {"cfact": cfact}, logp, overwrite=False) == []
+    assert len(aio.write_cell_files(tmp_path, "tas", lat, lon, np.arange(T), {"cfact": cfact}, logp, cells=[1])) == 1
+    assert np.array_equal(aio.replaced_flags([0, 1, 2, 3]), [0.0, np.nan, np.inf, -np.inf], equal_nan=True)
