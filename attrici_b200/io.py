@@ -382,6 +382,41 @@ def read_merged_trace(path, lat, lon):
         nc.close()
 
 
+def provenance_attrs(config=None, **other_metadata):
+    """Global attributes of the output files, the keys of ``get_data_provenance_metadata`` (attrici/util.py:17-41):
+    package version, installed distributions, Python version, creation time, and ``attrici_config`` = the run's
+    configuration as TOML ``key = value`` lines (``Config.to_toml``, attrici/detrend.py:106-116: ``None`` omitted)."""
+    import dataclasses
+    import importlib.metadata
+    import sys
+    from datetime import datetime
+
+    from . import __version__
+
+    res = {
+        "attrici_version": f"attrici_b200 {__version__}",
+        "attrici_packages": "\n".join(sorted({f"{d.name}=={d.version}" for d in importlib.metadata.distributions()},
+                                             key=str.casefold)),
+        "attrici_python_version": sys.version,
+        "created_at": datetime.now().isoformat(),
+    }
+    if config is not None:
+        items = dataclasses.asdict(config) if dataclasses.is_dataclass(config) else dict(config)
+
+        def toml(v):
+            if isinstance(v, bool):
+                return "true" if v else "false"
+            if isinstance(v, (int, float)):
+                return repr(v)
+            if isinstance(v, (list, tuple)):
+                return "[" + ", ".join(toml(x) for x in v) + "]"
+            return '"' + str(v).replace("\\", "\\\\").replace('"', '\\"') + '"'
+
+        res["attrici_config"] = "\n".join(f"{k} = {toml(v)}" for k, v in items.items() if v is not None) + "\n"
+    res.update(other_metadata)
+    return res
+
+
 def replaced_flags(codes):
     """The library's ``replaced`` codes (``ATTRICI_REPLACED_*``: 0 none, 1 NaN, 2 +Inf, 3 -Inf) as the float64 flags
     the reference stores (attrici/detrend.py:396-409: 0, NaN, +Inf, -Inf; ``_FillValue`` 0)."""

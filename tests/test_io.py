@@ -201,3 +201,24 @@ def test_per_cell_files_at_the_reference_paths(tmp_path):
     assert aio.write_cell_files(tmp_path, "tas", lat, lon, np.arange(T), {"cfact": cfact}, logp, overwrite=False) == []
     assert len(aio.write_cell_files(tmp_path, "tas", lat, lon, np.arange(T), {"cfact": cfact}, logp, cells=[1])) == 1
     assert np.array_equal(aio.replaced_flags([0, 1, 2, 3]), [0.0, np.nan, np.inf, -np.inf], equal_nan=True)
+
+
+def test_provenance_attributes(tmp_path):
+    """Keys of get_data_provenance_metadata (attrici/util.py:17-41) + the configuration as TOML, stored as global
+    attributes."""
+    import tomllib
+
+    from attrici_b200.detrend import Config
+
+    cfg = Config("tas", modes=4, seed=3, report_variables=("cfact", 'mu "x"'))
+    a = aio.provenance_attrs(cfg, note="synthetic")
+    assert set(a) == {"attrici_version", "attrici_packages", "attrici_python_version", "created_at", "attrici_config", "note"}
+    parsed = tomllib.loads(a["attrici_config"])
+    assert parsed["variable"] == "tas" and parsed["modes"] == 4 and parsed["seed"] == 3 and parsed["fit_only"] is False
+    assert parsed["report_variables"] == ["cfact", 'mu "x"'] and "window_size" not in parsed and "device" not in parsed
+    assert "numpy==" in a["attrici_packages"]
+    path = str(tmp_path / "p.nc")
+    aio.write_merged_output(path, {"cfact": np.zeros((2, 1))}, [1.0], [2.0], np.arange(2), attrs=a)
+    nc = netcdf_file(path, "r", mmap=False)
+    assert tomllib.loads(nc.attrici_config.decode())["variable"] == "tas" and nc.note == b"synthetic"
+    nc.close()
