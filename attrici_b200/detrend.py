@@ -101,6 +101,43 @@ def scale_predictor(gmt, n_time=None, days=None, gmt_days=None, full_extrapolati
     return (g - g.min()) / (g.max() - g.min())
 
 
+def stack_latlon(lat, lon):
+    """Coordinates of the stacked cells, ``obs_data.stack(latlon=("lat", "lon"))`` (attrici/detrend.py:672): lat-major,
+    lon-minor; cell ``i * len(lon) + j`` is ``(lat[i], lon[j])``, i.e. column ``i * len(lon) + j`` of the ``[T, C]``
+    view of a ``(time, lat, lon)`` array."""
+    la, lo = np.meshgrid(np.asarray(lat), np.asarray(lon), indexing="ij")
+    return la.ravel(), lo.ravel()
+
+
+def select_cells(lat, lon, cells=None, mask=None, mask_lat=None, mask_lon=None):
+    """Indices of the stacked cells a run works on (attrici/detrend.py:674-685): ``cells`` - a list of
+    ``(lat, lon)`` tuples, taken in the order given, ``KeyError`` if one is not a cell of the input
+    (``obs_data.sel(latlon=[...])``) - and then ``mask`` - a ``(lat, lon)`` array on ``mask_lat`` x ``mask_lon``
+    whose cells equal to 1 are kept, in the mask's stacked order (``mask.where(mask == 1).dropna("latlon")``; a
+    masked-in cell that is not among the (selected) input cells is a ``KeyError`` as well).  ``lat`` / ``lon``: the
+    coordinates of the stacked cells (``stack_latlon``).  Coordinates are compared exactly, as xarray's index does."""
+    lat, lon = np.asarray(lat), np.asarray(lon)
+    index = {(a, b): i for i, (a, b) in enumerate(zip(lat.tolist(), lon.tolist()))}
+    chosen = np.arange(lat.size)
+    if cells:
+        try:
+            chosen = np.array([index[(float(a), float(b))] for a, b in cells], dtype=np.int64)
+        except KeyError as e:
+            raise KeyError(f"Not all cells could be found in input data: {e.args[0]}") from None
+    if mask is not None:
+        mask = np.asarray(mask)
+        mla, mlo = stack_latlon(mask_lat, mask_lon)
+        if mask.shape != (np.asarray(mask_lat).size, np.asarray(mask_lon).size):
+            raise ValueError("mask must be a (lat, lon) array on mask_lat x mask_lon")
+        keep = np.flatnonzero(mask.ravel() == 1)
+        available = {(lat[i].item(), lon[i].item()): i for i in chosen.tolist()}
+        try:
+            chosen = np.array([available[(mla[k].item(), mlo[k].item())] for k in keep], dtype=np.int64)
+        except KeyError as e:
+            raise KeyError(f"masked-in cell {e.args[0]} is not a cell of the input data") from None
+    return chosen
+
+
 def fit_window_indices(time, start_date=None, stop_date=None):
     """``[i0, i1)`` of the days the model is fitted on: ``subset_times = time[(time >= start) & (time <= stop)]``
     (attrici/detrend.py:709-722), both ends inclusive, ``None`` = first / last day of the series.  ``time``:

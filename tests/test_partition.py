@@ -6,7 +6,8 @@ import os
 import numpy as np
 import pytest
 
-from attrici_b200.detrend import Config, detrend_cells, fit_window_indices, gather_cells, get_task_indices, scale_predictor
+from attrici_b200.detrend import (Config, detrend_cells, fit_window_indices, gather_cells, get_task_indices,
+                                  scale_predictor, select_cells, stack_latlon)
 from attrici_b200.solver import cell_seeds
 from oracle import attrici_oracle as oracle
 
@@ -120,6 +121,36 @@ def test_predictor_on_datetime_axes_and_full_extrapolation():
         scale_predictor(g, days=days, full_extrapolation=True)
     with pytest.raises(ValueError):
         scale_predictor(g)
+
+
+def test_cell_selection_by_list_and_mask():
+    """attrici/detrend.py:672-685: stacking order, ``--cells`` and the mask file."""
+    glat, glon = np.array([50.75, 51.25, 51.75]), np.array([9.25, 9.75])
+    lat, lon = stack_latlon(glat, glon)
+    assert lat.tolist() == [50.75, 50.75, 51.25, 51.25, 51.75, 51.75] and lon.tolist() == [9.25, 9.75] * 3
+    cube = np.arange(4 * 3 * 2).reshape(4, 3, 2)                                  # (time, lat, lon)
+    assert np.array_equal(cube.reshape(4, -1)[:, 3], cube[:, 1, 1])               # column i * n_lon + j
+    assert select_cells(lat, lon).tolist() == list(range(6))
+    assert select_cells(lat, lon, cells=[(51.75, 9.25), (50.75, 9.75)]).tolist() == [4, 1]     # order as given
+    with pytest.raises(KeyError):
+        select_cells(lat, lon, cells=[(51.75, 9.25), (52.0, 9.75)])
+    mask = np.array([[0, 1], [1, 1], [np.nan, 2]])                                # only == 1 counts
+    assert select_cells(lat, lon, mask=mask, mask_lat=glat, mask_lon=glon).tolist() == [1, 2, 3]
+    # a mask on a different (larger) grid: stacked order of the mask, cells outside the input are an error
+    big_lat, big_lon = np.array([50.25, 50.75, 51.25]), np.array([9.25, 9.75])
+    m = np.zeros((3, 2))
+    m[1, 1] = m[2, 0] = 1
+    assert select_cells(lat, lon, mask=m, mask_lat=big_lat, mask_lon=big_lon).tolist() == [1, 2]
+    m[0, 0] = 1
+    with pytest.raises(KeyError):
+        select_cells(lat, lon, mask=m, mask_lat=big_lat, mask_lon=big_lon)
+    # cells first, then the mask on what is left (a masked-in cell that was not selected is an error)
+    assert select_cells(lat, lon, cells=[(51.25, 9.75), (50.75, 9.75)], mask=np.array([[0, 1], [0, 1], [0, 0]]),
+                        mask_lat=glat, mask_lon=glon).tolist() == [1, 3]
+    with pytest.raises(KeyError):
+        select_cells(lat, lon, cells=[(51.25, 9.75)], mask=mask, mask_lat=glat, mask_lon=glon)
+    with pytest.raises(ValueError):
+        select_cells(lat, lon, mask=np.ones((2, 2)), mask_lat=glat, mask_lon=glon)
 
 
 def test_fit_window_from_dates():
