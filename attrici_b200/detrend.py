@@ -327,8 +327,15 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
         raise ValueError(f"attrici_b200 only provides solver='cuda', got {config.solver!r}")
     if (config.modes is None) == (config.window_size is None):
         raise ValueError("Exactly one of `modes` and `window_size` must be set")      # detrend.py:646-647
+    if config.window_size is not None and config.window_size % 2 == 0:
+        raise ValueError("Window size must be an odd number")                          # detrend.py:648-649
     if config.window_size is not None:
         raise NotImplementedError("Rolling window not implemented for the CUDA solver")
+    g = np.asarray(gmt_scaled, dtype=np.float64)
+    if g.ndim != 1:
+        raise ValueError("GMT data must have dimension 'time'")                         # detrend.py:654-655
+    if np.any(np.isnan(g)) or np.any(np.isinf(g)):
+        raise ValueError("GMT data must not contain NaN or infinite values")           # detrend.py:656-657
     spec = create_variable(config.variable)
     check_units(spec, units)
     extras = [] if config.fit_only else report_series(spec, config.report_variables)

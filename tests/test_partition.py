@@ -180,6 +180,14 @@ def test_driver_rejects_what_the_reference_rejects():
         detrend_cells(Config("tas", modes=None), *args)
     with pytest.raises(NotImplementedError):
         detrend_cells(Config("tas", modes=None, window_size=31), *args)
+    with pytest.raises(ValueError, match="Window size must be an odd number"):
+        detrend_cells(Config("tas", modes=None, window_size=30), *args)
+    bad_gmt = np.linspace(0, 1, 10)
+    bad_gmt[3] = np.nan
+    with pytest.raises(ValueError, match="GMT data must not contain NaN or infinite values"):
+        detrend_cells(Config("tas"), y, bad_gmt, *args[2:])
+    with pytest.raises(ValueError, match="GMT data must have dimension 'time'"):
+        detrend_cells(Config("tas"), y, np.zeros((10, 2)), *args[2:])
     with pytest.raises(ValueError, match="only provides solver='cuda'"):
         detrend_cells(Config("tas", solver="scipy"), *args)
     with pytest.raises(ValueError, match="Variable huss not supported"):
