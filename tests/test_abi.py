@@ -27,6 +27,46 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == syms  # the ctypes stub binds exactly the header
 
 
+def header_prototypes():
+    """name -> (return type, [argument types]) of every ATTRICI_API declaration, comments stripped."""
+    src = open(os.path.join(ROOT, "include", "attrici_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    out = {}
+    for ret, name, args in re.findall(r"ATTRICI_API\s+([\w\s\*]+?)\b(attrici_\w+)\s*\(([^)]*)\)\s*;", src):
+        args = [a.strip() for a in args.split(",")] if args.strip() not in ("", "void") else []
+        out[name] = (" ".join(ret.split()), [re.sub(r"\s*\b\w+$", "", a).strip() if not a.endswith("*") else a for a in args])
+    return out
+
+
+def _ctype_of(c_type):
+    t = c_type.replace("const ", "").strip()
+    if t.endswith("*"):
+        return "pointer"
+    return {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "size_t": C.c_size_t, "double": C.c_double,
+            "float": C.c_float, "long long": C.c_longlong}[t]
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every binding of attrici_b200/_lib.py has the argument count and the scalar / pointer kinds of its
+    declaration in include/attrici_b200.h (a mismatch would corrupt the call silently under ctypes)."""
+    protos = header_prototypes()
+    assert sorted(protos) == sorted(_lib._SIGNATURES)
+    for name, (res, args) in _lib._SIGNATURES.items():
+        ret, c_args = protos[name]
+        assert len(args) == len(c_args), (name, len(args), c_args)
+        for i, (bound, declared) in enumerate(zip(args, c_args)):
+            kind = _ctype_of(declared)
+            if kind == "pointer":
+                assert bound is C.c_void_p or bound is C.c_char_p or issubclass(bound, C._Pointer), (name, i, declared)
+            else:
+                assert C.sizeof(bound) == C.sizeof(kind) and not issubclass(bound, C._Pointer) and bound is not C.c_void_p, \
+                    (name, i, declared, bound)
+        if ret.endswith("*"):
+            assert res is C.c_char_p
+        else:
+            assert C.sizeof(res) == C.sizeof(_ctype_of(ret)), (name, ret)
+
+
 def test_abi_version_and_param_counts():
     lib = _lib.load()
     assert lib.attrici_abi_version() == _lib.ABI_VERSION
