@@ -374,3 +374,100 @@ def test_sharded_merged_output_world_size_2_gloo(n_cells, tmp_path):
         assert p.exitcode == 0
     got = sorted(q.get(timeout=5) for _ in range(2))
     assert got == [(0, True), (1, True)]
+
+
+class _StubBatchSolver(_StubSolver):
+    """``CellBatchSolver`` stand-in for the driver under gloo: ``detrend_host`` returns results that encode the cell
+    (the first row of ``y`` holds the global cell number), the slab calls are those of ``_StubSolver``."""
+
+    def __init__(self, spec, modes=4, device="cpu", use_fp64=False):
+        super().__init__()
+        self.spec, self.n_params = spec, spec.n_params(modes)
+
+    def fit(self, ys):
+        import torch
+
+        from attrici_b200.solver import FitResult
+
+        cells = ys[0].double() * 2.0
+        params = cells[:, None] + torch.arange(self.n_params, dtype=torch.float64)[None, :] / 100.0
+        n = ys.shape[1]
+        return FitResult(params, -cells, torch.zeros(n, dtype=torch.int32), torch.full((n,), 5, dtype=torch.int32))
+
+    def eval_parameter(self, params, which, counterfactual=False):
+        base = {"mu": 1.0, "sigma": 2.0}[which] + (0.5 if counterfactual else 0.0)
+        return (params[:, 0] + base)[None, :].repeat(self._T, 1)
+
+    def scale(self, y, fit_window=None):
+        self._T = y.shape[0]
+        return super().scale(y, fit_window)
+
+    def detrend_host(self, y, days, gmt, fit_window=None, seeds=None, slab_cells=2048, out=None, want_replaced=True):
+        import torch
+
+        cells = y[0].double()
+        n = y.shape[1]
+        return {"cfact": y.double() + 1000.0 * cells[None, :], "replaced": (y > 3).to(torch.uint8),
+                "params": cells[:, None] + torch.arange(self.n_params, dtype=torch.float64)[None, :] / 100.0,
+                "logp": -cells, "scaling": torch.stack([cells, cells + 0.5], dim=1),
+                "status": torch.zeros(n, dtype=torch.int32), "n_pass": torch.full((n,), 5, dtype=torch.int32)}
+
+
+def _driver_worker(rank, world, port, n_cells, q):
+    import torch
+    import torch.distributed as dist
+
+    import attrici_b200.solver as solver_module
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        solver_module.CellBatchSolver = _StubBatchSolver      # the GPU stays out of this test: host logic only
+        T = 6
+        y = np.arange(n_cells, dtype=np.float32)[None, :].repeat(T, 0)
+        lat, lon = np.arange(n_cells) * 0.5, np.zeros(n_cells)
+        args = (y, np.linspace(0, 1, T), np.arange(T), lat, lon)
+        idx = get_task_indices(n_cells, rank, world)
+        cells = np.arange(n_cells, dtype=np.float64)
+        res = detrend_cells(Config("tas", device="cpu"), *args)
+        ok = [res["indices"].tolist() == idx.tolist(),
+              res["cfact"].shape == (T, len(idx)) and np.array_equal(res["cfact"][0], 1001.0 * idx),
+              res["params"].shape == (n_cells, 27) and np.array_equal(res["params"][:, 0], cells),   # gathered
+              np.array_equal(res["logp"], -cells), np.array_equal(res["scaling"][:, 1], cells + 0.5),
+              res["status"].dtype == np.int32 and res["n_pass"].tolist() == [5] * n_cells]
+        local = detrend_cells(Config("tas", device="cpu"), *args, gather=False)
+        ok.append(local["params"].shape == (len(idx), 27))
+        # trace-file and report_variables modes: every rank slices the full-size trace by its own cell range
+        trace = {"params": cells[:, None] * 3.0 + np.zeros((n_cells, 27)), "logp": cells * 7.0}
+        tr = detrend_cells(Config("tas", device="cpu", slab_cells=2, report_variables=("cfact", "mu_cfact")), *args,
+                           trace=trace)
+        ok += [np.array_equal(tr["params"], trace["params"]), np.array_equal(tr["logp"], trace["logp"]),
+               list(tr["series"]) == ["mu_cfact"] and tr["series"]["mu_cfact"].shape == (T, len(idx)),
+               len(idx) == 0 or np.array_equal(tr["series"]["mu_cfact"][0], 3.0 * idx + 1.5),
+               (tr["n_pass"] == 0).all()]
+        fo = detrend_cells(Config("tas", device="cpu", slab_cells=3, fit_only=True), *args)
+        ok += [fo["cfact"] is None, np.array_equal(fo["params"][:, 0], cells)]
+        q.put((rank, [bool(x) for x in ok]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_cells", [11, 1])
+def test_batched_driver_world_size_2_gloo(n_cells):
+    """``detrend_cells`` under torch.distributed (gloo, two ranks) with the solver stubbed out: the reference's
+    partition of the cells, local series, per-cell results gathered over uneven (or empty) shards, and the trace /
+    report-variables / fit-only modes."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() + n_cells) % 2000
+    procs = [ctx.Process(target=_driver_worker, args=(r, 2, port, n_cells, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    got = dict(q.get(timeout=5) for _ in range(2))
+    assert all(got[0]) and all(got[1]), got
