@@ -117,6 +117,29 @@ class ModelCuda:
         return self._distribution_class(**out)
 
     def fit_cached(self, defining_data_inputs=None, cache_dir=None, timeout=None, **kwargs):
-        """The reference wraps ``fit`` in a joblib cache and a wall-clock timeout (model.py:118-188); a
-        fit takes milliseconds here, so this simply fits."""
-        return self.fit(**kwargs)
+        """``Model.fit_cached`` (attrici/estimation/model.py:118-188), which is what ``fit_and_detrend_cell`` calls
+        (attrici/detrend.py:335-350): with a ``cache_dir`` the trace is stored in / taken from a joblib cache keyed
+        by ``defining_data_inputs``; with a ``timeout`` (seconds) ``None`` is returned if the fit takes longer (the
+        reference then skips the cell).  A fit takes milliseconds here, so both matter for interface parity only."""
+        def cached_fit():
+            if cache_dir is None:
+                return self.fit(**kwargs)
+            from joblib import Memory
+
+            def _fit(inputs):  # `inputs` only defines for which data the cached trace is valid
+                return self.fit(**kwargs)
+
+            return Memory(cache_dir, verbose=0).cache(_fit)(defining_data_inputs)
+
+        if timeout is None:
+            return cached_fit()
+        from concurrent.futures import ThreadPoolExecutor
+        from concurrent.futures import TimeoutError as FutureTimeout
+
+        pool = ThreadPoolExecutor(max_workers=1)
+        try:
+            return pool.submit(cached_fit).result(timeout=timeout)
+        except FutureTimeout:
+            return None
+        finally:
+            pool.shutdown(wait=False)

@@ -120,3 +120,39 @@ def test_fit_and_estimate_flow_with_stubbed_solver(monkeypatch):
     assert isinstance(d, BernoulliGamma) and d.nu[0] == 30.0
     with pytest.raises(ValueError, match="1-D and aligned"):
         ModelCuda(Normal, NORMAL_PARS, Arr(y[:40], TIME[:40]), pred, modes=4)
+
+
+def test_fit_cached_cache_and_timeout(monkeypatch, tmp_path):
+    """attrici/estimation/model.py:118-188: joblib cache keyed by the defining inputs, ``None`` on timeout."""
+    import time
+
+    fits = []
+
+    class Counting(_Stub):
+        def fit(self, ys):
+            fits.append(1)
+            return super().fit(ys)
+
+    monkeypatch.setattr(estimation, "CellBatchSolver", Counting)
+    obs, pred = Arr(np.zeros(50), TIME), Arr(np.linspace(0, 1, 50), TIME)
+    m = ModelCuda(Normal, NORMAL_PARS, obs, pred, modes=4)
+    key = {"data": np.arange(5), "modes": 4, "seed": 0, "solver": "cuda"}
+    a = m.fit_cached(key, cache_dir=str(tmp_path), timeout=30)
+    b = m.fit_cached(key, cache_dir=str(tmp_path), timeout=30)                        # served from the cache
+    assert len(fits) == 1 and a["logp"] == b["logp"] and np.array_equal(a["params"], b["params"])
+    m.fit_cached({**key, "seed": 1}, cache_dir=str(tmp_path))                         # other inputs: a new fit
+    assert len(fits) == 2
+    m.fit_cached(key)                                                                  # no cache directory: always fits
+    assert len(fits) == 3
+
+    class Slow(_Stub):
+        def fit(self, ys):
+            time.sleep(1.0)
+            return super().fit(ys)
+
+    monkeypatch.setattr(estimation, "CellBatchSolver", Slow)
+    m = ModelCuda(Normal, NORMAL_PARS, obs, pred, modes=4)
+    t0 = time.perf_counter()
+    assert m.fit_cached(key, timeout=0.1) is None                                     # model.py:185-187
+    assert time.perf_counter() - t0 < 0.9
+    assert m.fit_cached(key, timeout=10)["logp"] == -12.5
