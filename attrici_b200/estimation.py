@@ -133,13 +133,22 @@ class ModelCuda:
 
         if timeout is None:
             return cached_fit()
-        from concurrent.futures import ThreadPoolExecutor
-        from concurrent.futures import TimeoutError as FutureTimeout
+        import threading
 
-        pool = ThreadPoolExecutor(max_workers=1)
-        try:
-            return pool.submit(cached_fit).result(timeout=timeout)
-        except FutureTimeout:
+        # a daemon thread (like func_timeout's): a fit that never returns must not keep the process alive at exit
+        box = {}
+
+        def run():
+            try:
+                box["result"] = cached_fit()
+            except BaseException as e:  # noqa: BLE001 - re-raised in the caller's thread
+                box["error"] = e
+
+        worker = threading.Thread(target=run, daemon=True)
+        worker.start()
+        worker.join(timeout)
+        if worker.is_alive():
             return None
-        finally:
-            pool.shutdown(wait=False)
+        if "error" in box:
+            raise box["error"]
+        return box["result"]

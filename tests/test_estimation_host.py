@@ -156,3 +156,16 @@ def test_fit_cached_cache_and_timeout(monkeypatch, tmp_path):
     assert m.fit_cached(key, timeout=0.1) is None                                     # model.py:185-187
     assert time.perf_counter() - t0 < 0.9
     assert m.fit_cached(key, timeout=10)["logp"] == -12.5
+
+
+def test_fit_cached_passes_errors_through(monkeypatch):
+    class Failing(_Stub):
+        def fit(self, ys):
+            raise RuntimeError("boom")
+
+    monkeypatch.setattr(estimation, "CellBatchSolver", Failing)
+    m = ModelCuda(Normal, NORMAL_PARS, Arr(np.zeros(50), TIME), Arr(np.linspace(0, 1, 50), TIME), modes=4)
+    with pytest.raises(RuntimeError, match="boom"):
+        m.fit_cached({"data": 1}, timeout=5)
+    with pytest.raises(RuntimeError, match="boom"):
+        m.fit_cached({"data": 1})
