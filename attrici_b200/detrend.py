@@ -243,6 +243,19 @@ def report_series(spec, report_variables):
     return [k for k in ["y_scaled", "cfact_scaled"] + fields if k in report_variables]
 
 
+def passthrough_series(report_variables, y_local, gmt_scaled):
+    """The inputs a ``report_variables`` list names (``y``, ``gmt_scaled``: attrici/detrend.py:449-451) as they go into
+    ``res["series"]`` next to the computed ones: ``y`` [T, n_local] (the caller's array, not a copy), ``gmt_scaled`` [T].
+    ``logp`` is the per-cell ``res["logp"]`` whatever the list says."""
+    out = {}
+    want_all = "all" in report_variables
+    if want_all or "y" in report_variables:
+        out["y"] = y_local.numpy() if hasattr(y_local, "numpy") else np.asarray(y_local)
+    if want_all or "gmt_scaled" in report_variables:
+        out["gmt_scaled"] = np.asarray(gmt_scaled, dtype=np.float64)
+    return out
+
+
 def _slabs_on_device(solver, config, y_local, days, gmt, fit_window, seeds, trace_local, want_map, extras=()):
     """The two modes of the reference's cell function that are not the whole path: ``fit_only`` (scale and fit,
     attrici/detrend.py:353-354) and a given trace (no fit; the quantile map runs on the stored coefficients and
@@ -315,7 +328,8 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
     these coefficients.  ``config.fit_only`` stops after the fit (``cfact`` / ``replaced`` are None).
     ``fit_window``: ``[i0, i1)`` on the time axis (``fit_window_indices`` for start / stop dates).
     ``config.report_variables`` beyond ``cfact`` / ``replaced`` adds ``res["series"]``: name -> [T, n_local]
-    (``y_scaled`` float32, ``cfact_scaled``, distribution fields and ``<field>_cfact`` float64; detrend.py:447-467).
+    (``y_scaled`` float32, ``cfact_scaled``, distribution fields and ``<field>_cfact`` float64; detrend.py:447-467;
+    ``y`` as given and ``gmt_scaled`` [T] are passed through; ``logp`` is always ``res["logp"]``).
     """
     import os
 
@@ -347,6 +361,10 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
     if lat.shape != (C,) or lon.shape != (C,):
         raise ValueError("lat / lon must have one entry per cell")
     dist, rank, world = _dist_info()
+    if world > 1 and config.task_count > 1:
+        # ranks of one process group already are the tasks; a SLURM array on top needs one group per array task
+        raise ValueError("task_id / task_count cannot be combined with an initialised torch.distributed process group "
+                         f"(world size {world}): the ranks take the reference's task ranges themselves")
     task_id, task_count = (rank, world) if world > 1 else (config.task_id, config.task_count)
     idx = get_task_indices(C, task_id, task_count)
     device = config.device or f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
@@ -378,6 +396,9 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
         else:
             o = solver.detrend_host(y_local, days, gmt_scaled, fit_window, seeds, config.slab_cells, out=out)
         local = {k: (o[k].numpy() if o[k] is not None else None) for k in o}
+        passed = {} if config.fit_only else passthrough_series(config.report_variables, y_local, gmt_scaled)
+        if passed:
+            res.setdefault("series", {}).update(passed)
         if config.validate and local["cfact"] is not None:
             validate_bounds(spec, local["cfact"])
     else:

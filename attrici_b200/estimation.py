@@ -34,6 +34,25 @@ _DEPENDENT = {
 }
 
 
+def _family_of(distribution):
+    """Family of a distribution class.  ``ModelScipy`` compares the class with the classes of
+    ``attrici.distributions`` by identity (model_scipy.py:423, 448, 461, 474, 487); so does this for a class that
+    comes from that module (a subclass or a same-named class of another module of the reference is rejected like
+    there).  Classes from elsewhere - the dataclasses of a host application that mirrors the reference - are matched
+    by name."""
+    import sys
+
+    name = getattr(distribution, "__name__", None)
+    if name not in _FAMILY_OF_DISTRIBUTION:
+        raise ValueError(f"Distribution {distribution} not supported")
+    module = getattr(distribution, "__module__", "")
+    if module.startswith("attrici."):
+        ref = sys.modules.get("attrici.distributions")
+        if module != "attrici.distributions" or ref is None or getattr(ref, name, None) is not distribution:
+            raise ValueError(f"Distribution {distribution} not supported")
+    return _FAMILY_OF_DISTRIBUTION[name]
+
+
 def _values(x):
     return np.asarray(getattr(x, "values", x))
 
@@ -65,10 +84,8 @@ class ModelCuda:
             raise NotImplementedError("Rolling window not implemented for the CUDA solver")
         if modes is None:
             raise ValueError("modes must be given")
-        name = getattr(distribution, "__name__", str(distribution))
-        if name not in _FAMILY_OF_DISTRIBUTION:
-            raise ValueError(f"Distribution {distribution} not supported")
-        family = _FAMILY_OF_DISTRIBUTION[name]
+        family = _family_of(distribution)
+        name = distribution.__name__
         expect = FAMILY_PARAMETERS[family]
         if tuple(parameters) != expect:
             raise ValueError(f"{name} expects parameters {expect} in this order, got {tuple(parameters)}")

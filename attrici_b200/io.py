@@ -144,7 +144,8 @@ class MergedOutputWriter:
         self._fill = {}
         for name, dt in (series or {}).items():
             code, cast = _nc_type(dt)
-            self._fill[name] = cast(0 if code in ("i1", "i4") else np.nan)
+            # `replaced` has _FillValue 0 whatever its type (attrici/detrend.py:471-476)
+            self._fill[name] = cast(0 if (code in ("i1", "i4") or name == "replaced") else np.nan)
             records.append((name, ("time", "lat", "lon"), code, {"_FillValue": self._fill[name]}, n_grid))
         self._casts = {name: np.dtype(_BE[code]).newbyteorder("=").type for name, _, code, _, _ in records}
         self._series = tuple(series or {})
@@ -238,9 +239,31 @@ class MergedOutputWriter:
         self.close()
 
 
+class ReplacedFlagsView:
+    """[T, C] view of the library's uint8 ``replaced`` codes that yields the reference's float64 flags
+    (0 / NaN / +Inf / -Inf, attrici/detrend.py:397-410) a block of days at a time, so that a merged file holds what
+    the reference's files hold without a second [T, C] float64 array in memory."""
+
+    dtype = np.dtype(np.float64)
+
+    def __init__(self, codes):
+        self.codes = codes
+        self.shape = tuple(codes.shape)
+
+    def __getitem__(self, key):
+        return replaced_flags(np.asarray(self.codes[key]))
+
+    def __array__(self, dtype=None, copy=None):
+        return replaced_flags(np.asarray(self.codes))
+
+
 def write_merged_output(path, series, lat, lon, time, time_units="days since 1901-01-01 00:00:00",
-                        calendar="proleptic_gregorian", scalars=None, shared=None, attrs=None):
+                        calendar="proleptic_gregorian", scalars=None, shared=None, attrs=None, replaced_as_flags=True):
     """One ``(time, lat, lon)`` file for a batch of cells.
+
+    An integer ``replaced`` series (the library's codes 0..3) is stored as the reference's float64 flags
+    0 / NaN / +Inf / -Inf (attrici/detrend.py:397-410, ``replaced_as_flags``; ``False`` keeps the one-byte codes, with
+    the code table in the variable's ``flag_meanings`` attribute).
 
     ``series``: dict name -> [T, C] array (e.g. ``{"y": y, "cfact": res["cfact"], "replaced": res["replaced"]}``, the
     ``report_variables`` of detrend.py:462-467); ``scalars``: dict name -> [C] (e.g. ``logp``); ``shared``: dict
@@ -248,6 +271,8 @@ def write_merged_output(path, series, lat, lon, time, time_units="days since 190
     time = np.asarray(time)
     T = time.size
     series = {k: (v.numpy() if hasattr(v, "numpy") else np.asarray(v)) for k, v in (series or {}).items()}
+    if replaced_as_flags and "replaced" in series and series["replaced"].dtype.kind in "iub":
+        series["replaced"] = ReplacedFlagsView(series["replaced"])
     shared = {k: np.asarray(v) for k, v in (shared or {}).items()}
     n_cells = np.asarray(lat).size
     for name, arr in series.items():
@@ -266,7 +291,7 @@ def write_merged_output(path, series, lat, lon, time, time_units="days since 190
 
 
 def write_merged_output_sharded(path, series_local, counts, lat, lon, time, dist, group=None, dst=0,
-                                block_bytes=64 << 20, **kwargs):
+                                block_bytes=64 << 20, replaced_as_flags=True, **kwargs):
     """The final host gather of a multi-rank run, straight into the merged file: every rank holds the series of its
     contiguous cell range (``series_local``: name -> [T, counts[rank]], the ``cfact`` / ``replaced`` of
     ``detrend_cells``); block of days by block of days the ranks' slices are gathered to rank ``dst`` over ``group``
@@ -275,7 +300,8 @@ def write_merged_output_sharded(path, series_local, counts, lat, lon, time, dist
 
     ``lat`` / ``lon`` / ``time`` and the keyword arguments (``scalars``, ``shared``, ``attrs``, ...: full-size, as for
     ``write_merged_output``) are only read on ``dst``.  Collective: all ranks of ``group`` must call it with the same
-    variable names.  Returns the number of days written (on ``dst``) or None."""
+    variable names.  Integer ``replaced`` codes are stored as the reference's float64 flags unless
+    ``replaced_as_flags=False``.  Returns the number of days written (on ``dst``) or None."""
     import torch
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -304,7 +330,9 @@ def write_merged_output_sharded(path, series_local, counts, lat, lon, time, dist
     if rank == dst:
         shared = {k: np.asarray(v) for k, v in (kwargs.pop("shared", None) or {}).items()}
         time = np.asarray(time)
-        writer = MergedOutputWriter(path, lat, lon, {k: local[k].numpy().dtype for k in names},
+        as_flags = {k for k in names if k == "replaced" and replaced_as_flags and local[k].numpy().dtype.kind in "iub"}
+        writer = MergedOutputWriter(path, lat, lon, {k: np.dtype(np.float64) if k in as_flags else local[k].numpy().dtype
+                                                     for k in names},
                                     shared={k: v.dtype for k, v in shared.items()}, time_dtype=time.dtype,
                                     block_bytes=block_bytes, **kwargs)
     try:
@@ -322,6 +350,8 @@ def write_merged_output_sharded(path, series_local, counts, lat, lon, time, dist
                 dist.gather(part, bucket, dst=dst if group is None else dist.get_global_rank(group, dst), group=group)
                 if rank == dst:
                     block[k] = torch.cat([t[:, :c] for t, c in zip(bucket, counts)], dim=1).numpy()
+                    if k in as_flags:                        # the reference's float flags (detrend.py:397-410)
+                        block[k] = replaced_flags(block[k])
             if rank == dst:
                 writer.append(time[a:b], block, {k: v[a:b] for k, v in shared.items()})
     finally:

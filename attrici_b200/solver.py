@@ -278,6 +278,9 @@ class CellBatchSolver:
             return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
         with torch.cuda.device(self.device):
+            # the library works on its own streams: whatever the torch stream still has queued on memory the caching
+            # allocator may hand out again (the scratch above, outputs of an earlier call) must have finished
+            torch.cuda.current_stream(self.device).synchronize()
             _lib.check(self.lib.attrici_detrend_host(
                 C.byref(self.var), C.byref(self.options), hp(yt), yt.stride(0), T, C_, i0, i1,
                 C.c_void_p(days.ctypes.data), C.c_void_p(gmt.ctypes.data),

@@ -25,6 +25,36 @@ def smoothed_gmt(n_days=DAYS_1901_2019):
     return (g - g.min()) / (g.max() - g.min())
 
 
+def raw_gmt(n_days=DAYS_1901_2019, seed=7):
+    """Daily raw global-mean temperature in K: 14 degC + a 1.2 K sigmoid-like ramp + ENSO-like
+    AR(1) noise + a small annual cycle - the kind of series ``attrici ssa`` reads (attrici/ssa.py:12-59)."""
+    rng = np.random.default_rng(seed)
+    x = np.arange(n_days, dtype=np.float64) / max(n_days - 1, 1)
+    ramp = 1.2 / (1.0 + np.exp(-(x - 0.72) / 0.10))
+    eps = rng.standard_normal(n_days) * 0.02
+    ar = np.empty(n_days)
+    acc = 0.0
+    for i in range(n_days):                      # AR(1), e-folding time ~ 200 days
+        acc = 0.995 * acc + eps[i]
+        ar[i] = acc
+    return 287.15 + ramp + ar + 0.1 * np.cos(2 * np.pi * np.arange(n_days) / 365.25)
+
+
+def ssa_gmt(n_days=DAYS_1901_2019, seed=7, window_size=365, subset=10, calc_gmt_by_ssa=None):
+    """The predictor of BASELINE configs[1]: ``raw_gmt`` smoothed by SSA (``calc_gmt_by_ssa``, window 365 on every
+    10th day: attrici/preprocessing.py:13-40), stretched to the daily axis and scaled to [0, 1]
+    (attrici/detrend.py:698-707).  ``calc_gmt_by_ssa``: the smoother, default the library's SSA kernels
+    (``attrici_b200.preprocessing``); the CPU arm of bench.py and the tests pass the oracle's restatement."""
+    from .detrend import scale_predictor
+
+    if calc_gmt_by_ssa is None:
+        from .preprocessing import calc_gmt_by_ssa
+    raw = raw_gmt(n_days, seed)
+    w = min(window_size, len(raw[::subset]))
+    smooth, _ = calc_gmt_by_ssa(raw, np.arange(n_days), window_size=w, subset=subset)
+    return scale_predictor(np.asarray(smooth), n_time=n_days)
+
+
 def _tau(n_days):
     return np.arange(n_days, dtype=np.float64) / 365.25
 

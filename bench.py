@@ -41,6 +41,16 @@ METRIC = "gridcell-fits/sec (43k-day series, modes=4)"
 UNIT = "cells/s"
 
 
+def bench_config(cells=TILE_CELLS):
+    """``config`` of the JSON line: identical for the CUDA arm and the reference arm (what was sampled / measured
+    per arm is in ``cpu_baseline.sample``, ``e2e`` and ``fit_stats``)."""
+    return {"workload": "tas Gaussian 100x100-cell tile, T=43464, modes=4, SSA-smoothed GMT predictor (BASELINE configs[1])",
+            "cells_per_gpu": cells, "days": T_DAYS, "modes": MODES,
+            "l2": "inputs larger than L2 (1.74 GB float32 series per tile; streamed twice per step: scale + sums, "
+                  "quantile map)",
+            "report_variables": ["cfact", "replaced"]}
+
+
 def ncu_traffic(kernel_prefix):
     """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/r1_traffic.json, same tile)."""
     p = os.path.join(ROOT, "profiles", "r1_traffic.json")
@@ -141,21 +151,56 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port), one cell per process
 # ------------------------------------------------------------------------------------------------
+_CPU_GMT = {}
+
+
+def cpu_kind():
+    """"reference": the unmodified reference from baseline/_ref (or /root/reference) through oracle/reference_runner;
+    "port": the oracle's restatement of the same algorithm, when the reference is not installed."""
+    from oracle import reference_runner
+
+    return "reference" if reference_runner.available() else "port"
+
+
+CPU_KIND_TEXT = {
+    "reference": "the UNMODIFIED reference (baseline/_ref: create_variable -> ModelScipy.fit = SciPy L-BFGS-B with "
+                 "finite differences -> estimate_distribution x2 -> quantile_mapping -> rescale), xarray replaced by a "
+                 "1-D container stand-in",
+    "port": "oracle port of the reference algorithm (SciPy L-BFGS-B + finite differences on the reference objective, "
+            "scipy.stats quantile map); the reference itself is not installed here",
+}
+
+
 def _cpu_cell(args):
     cell, n_days = args
     from attrici_b200 import synthetic
-    from oracle import attrici_oracle as oracle
 
     y = synthetic.tas_cells(1, n_days, seed=1234, first_cell=cell)[:, 0]
-    gmt, days = synthetic.smoothed_gmt(n_days), synthetic.time_axis(n_days)
+    if n_days not in _CPU_GMT:
+        from oracle.ssa_oracle import calc_gmt_by_ssa
+
+        _CPU_GMT[n_days] = synthetic.ssa_gmt(n_days, calc_gmt_by_ssa=calc_gmt_by_ssa)
+    gmt, days = _CPU_GMT[n_days], synthetic.time_axis(n_days)
     t0 = time.perf_counter()
-    out = oracle.detrend_cell("tas", y, gmt, days, MODES, solver="lbfgsb")
-    return time.perf_counter() - t0, int(out["trace"]["nfev"])
+    if cpu_kind() == "reference":
+        from oracle import reference_runner
+
+        out = reference_runner.detrend_cell("tas", y, gmt, days, MODES)
+        nfev = out["nfev"]
+    else:
+        from oracle import attrici_oracle as oracle
+
+        out = oracle.detrend_cell("tas", y, gmt, days, MODES, solver="lbfgsb")
+        nfev = out["trace"]["nfev"]
+    return time.perf_counter() - t0, int(nfev)
 
 
 def _cpu_init():
     from attrici_b200 import synthetic  # noqa: F401
-    from oracle import attrici_oracle  # noqa: F401
+    from oracle import attrici_oracle, reference_runner  # noqa: F401
+
+    if reference_runner.available():
+        reference_runner._modules()
 
 
 def cpu_pool(cores):
@@ -209,6 +254,7 @@ def run_reference(args):
     # to the pool back to back (no barrier between steps: a step smaller than the pool would leave cores idle), so
     # that the K steps are timed as one region and all cores stay busy.
     n_cells = reference_cells_per_step(args.steps, cores)
+    kind = cpu_kind()
     with cpu_pool(cores) as pool:  # worker start-up and imports are the warm-up; the CPU path has no other
         total, _ = cpu_sample(pool, n_cells * args.steps)
     value = n_cells * args.steps / total
@@ -216,12 +262,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "tas Gaussian 100x100-cell tile, T=43464, modes=4 (BASELINE configs[1])",
-                   "cells_per_step": n_cells},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": bench_config(args.cells),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{n_cells} cells of the tile per step ({n_cells * args.steps} in all, fed to the pool "
-                                   "back to back), one process per core, "
-                                   "SciPy L-BFGS-B + finite differences on the reference objective, scipy.stats quantile map"},
+                                   f"back to back), one process per core; {CPU_KIND_TEXT[kind]}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -258,7 +302,7 @@ def run_cuda(args):
 
     C, T = args.cells, T_DAYS
     y = synthetic.tas_tile_torch(C, T, seed=1234 + rank, device=device, nan_fraction=0.001)
-    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    gmt, days = synthetic.ssa_gmt(T), synthetic.time_axis(T)   # SSA-smoothed GMT (library kernels), configs[1]
     solver = CellBatchSolver("tas", modes=MODES, device=device, profile=True)
     solver.set_predictor(days, gmt, C)
     P = solver.n_params
@@ -369,9 +413,10 @@ def run_cuda(args):
             cores = min(host_cores(), 64)
             with cpu_pool(cores) as pool:
                 wall, r = cpu_sample(pool, cores)
-            cpu = {"value": cores / wall, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{cores} cells of the same tile, one process per core (SciPy L-BFGS-B with finite "
-                             f"differences, {int(np.mean([x[1] for x in r]))} objective evaluations per cell on average)"}
+            kind = cpu_kind()
+            cpu = {"value": cores / wall, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": f"{cores} cells of the same tile, one process per core; {CPU_KIND_TEXT[kind]}; "
+                             f"{int(np.mean([x[1] for x in r]))} objective evaluations per cell on average"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,

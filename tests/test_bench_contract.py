@@ -18,9 +18,15 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["unit"] == "cells/s" and d["value"] > 0 and d["metric"].startswith("gridcell-fits/sec")
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import reference_runner
+
+    # the unmodified reference when it is installed (baseline/_ref travels to the GPU box), else the oracle port
+    assert d["cpu_baseline"]["kind"] == ("reference" if reference_runner.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert d["config"] == bench.bench_config()            # identical to the CUDA arm's config (driver: same_config)
 
 
 def test_reference_arm_sample_is_bounded():

@@ -345,7 +345,8 @@ def _writer_worker(rank, world, port, n_cells, path, q):
             full = np.array(nc.variables["cfact"][:]).reshape(T, -1)
             rep = np.array(nc.variables["replaced"][:]).reshape(T, -1)
             ok = (n == T and np.array_equal(full[:, :n_cells], cfact) and np.isnan(full[:, n_cells:]).all()
-                  and np.array_equal(rep[:, :n_cells], replaced.astype(np.int8)) and (rep[:, n_cells:] == 0).all()
+                  and np.array_equal(rep[:, :n_cells], aio.replaced_flags(replaced), equal_nan=True)   # float flags
+                  and (rep[:, n_cells:] == 0).all()
                   and np.array_equal(np.array(nc.variables["logp"][:]).ravel()[:n_cells], np.arange(n_cells))
                   and np.array_equal(np.array(nc.variables["gmt_scaled"][:]), np.linspace(0, 1, T)))
             nc.close()
