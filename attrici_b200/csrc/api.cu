@@ -155,6 +155,12 @@ bool fold_enabled() {
     return on;
 }
 
+// ATTRICI_NO_FUSED=1 keeps the folded Normal fit on the per-pass kernels of fold.cu / step.cu (A/B measurements only)
+bool fused_enabled() {
+    static const bool on = [] { const char* e = getenv("ATTRICI_NO_FUSED"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 // does the phase-folded pass apply?  Normal term on a gap-free daily axis (flag left by attrici_build_basis)
 // whose per-phase sums were gathered by attrici_prep_scale_mask on this workspace.  Synchronises `s`.
 // how a term's likelihood passes run: FOLD_SUMS = Normal term from the per-phase sums of prep (fold.cu),
@@ -228,6 +234,10 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
     ATTRICI_TRY(launch_fit_init(ws, sp, ws.list[cur], ws.counters + cur, s));
     ATTRICI_TRY(fold_applies(ws, sp.term, i0, i1, s, &fold));
     if (fold != FOLD_SUMS && !y_scaled) { set_error("y_scaled is needed: the phase-folded pass does not apply"); return ATTRICI_EINVAL; }
+    if (fold == FOLD_SUMS && ws.T >= NPHASE && fused_enabled() && !o.profile) {
+        // the whole iteration of the term in one persistent kernel (fit_fused.cu): no host round trip
+        return launch_fit_fused(ws, sp, FISHER_PASSES, CHORD_PASSES, s);
+    }
     ATTRICI_TRY(read_counter(ws.counters + cur, &running, s));
     const bool profile = o.profile != 0;
     std::vector<cudaEvent_t> ev;

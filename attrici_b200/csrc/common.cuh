@@ -88,6 +88,12 @@ struct Workspace {
     double* ystat;     // [NPHASE][3][Cp] per-phase sums {y, y^2, y gmt} over the cell's valid window days (Normal only)
     double* gstat;     // [NPHASE][3][Cp] per-phase {n, sum gmt, sum gmt^2} of cells with missing days (Normal only)
     float* psums;      // [NPHASE][11][Cp] per-phase sums of the day terms (two-stage pass of the other families)
+    // fused fit (fit_fused.cu): cell-major per-phase sums, per-cell affine map of the sums, pair tables
+    double* ysumT;     // [Cp][3][FUSED_SP] {u, u^2, u gmt} per phase, u = y_scaled or y - pivot (Normal only)
+    double* gsumT;     // [Cp][3][FUSED_SP] {n, sum gmt, sum gmt^2} per phase of cells with missing days (Normal only)
+    double* aff;       // [Cp][2] {m, s}: y_scaled = (u - m) / s
+    double* ftab_d;    // [FUSED_ND][FUSED_TP]
+    float* ftab_f;     // [16][FUSED_FP]
     void* h_tab;       // [NTRI] moment indices of the information-matrix entries of the term being fitted (step.cu)
 
     static size_t align(size_t x) { return (x + 255) & ~size_t(255); }
@@ -146,6 +152,11 @@ struct Workspace {
         ystat = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)NPHASE * c) : nullptr;
         gstat = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)NPHASE * c) : nullptr;
         psums = (family != ATTRICI_NORMAL) ? (float*)take(4 * 11 * (size_t)NPHASE * c) : nullptr;
+        ysumT = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)FUSED_SP * c) : nullptr;
+        gsumT = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)FUSED_SP * c) : nullptr;
+        aff = (double*)take(8 * 2 * c);
+        ftab_d = (double*)take(8 * (size_t)FUSED_ND * FUSED_TP);
+        ftab_f = (float*)take(4 * 16 * (size_t)FUSED_FP);
         h_tab = take(16 * (size_t)NTRI);
         bytes = off;
         return off;
@@ -224,6 +235,11 @@ int launch_fold_pass_generic(Workspace& ws, const PassShape& ps, int term, bool 
 int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, int mode, cudaStream_t s,
                   const int* status = nullptr);
 
+// fused fit of the folded Normal term (fit_fused.cu): pair tables of the fit window, the cell-major copy of sums
+// gathered in the phase-major layout, and the whole iteration of a term in one persistent kernel
+int launch_fused_tables(Workspace& ws, cudaStream_t s);
+int launch_fused_from_phase_major(Workspace& ws, cudaStream_t s);
+
 struct StepParams {
     int term;
     int modes;
@@ -240,6 +256,7 @@ int launch_fit_init(Workspace& ws, const StepParams& sp, int* list_out, int* cou
 // point is reused
 int launch_fit_step(Workspace& ws, const StepParams& sp, const int* list_in, int n_in, int* list_out, int* counter,
                     cudaStream_t s, bool fresh_fisher = true);
+int launch_fit_fused(Workspace& ws, const StepParams& sp, int fisher_passes, int chord_passes, cudaStream_t s);
 // th_trial := th_acc, rotated into th_pass (before the final FP64 evaluation)
 int launch_fit_final_point(Workspace& ws, const StepParams& sp, cudaStream_t s);
 // after an FP64 pass without moments at th_acc (+ reduce): store coefficients / logp / status of this term slot

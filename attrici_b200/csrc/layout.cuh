@@ -33,6 +33,11 @@ constexpr int PASS_TILE = 64;                // days per shared-memory basis til
 constexpr int MAX_CHUNKS = 32;
 constexpr int ZM_COLS = 51;                  // moment-matrix columns gmt^p x trig17 (tensor-core pass)
 constexpr int NPHASE = 1461;                // days after which every Fourier column repeats (4 x 365.25)
+constexpr int FUSED_NPAIR = NPHASE / 2 + 1;  // 731 items of the fused fit: phase 0 alone, then the pairs (d, 1461 - d)
+constexpr int FUSED_TP = 736;                // pairs padded to 23 sweeps of 32 lanes (pitch of the FP64 pair tables)
+constexpr int FUSED_FP = 740;                // pitch of the TF32 pair table (= 4 mod 32: conflict-free B fragments)
+constexpr int FUSED_SP = 1464;               // phases per row of the cell-major per-phase sums (1461 padded)
+constexpr int FUSED_ND = 14;                 // rows of the FP64 pair table: cos 1..4, sin 1..4, {n, sum g, sum g^2} of d and of 1461 - d
 constexpr int ZM_STRIDE = 100;               // floats per day of the moment matrix: 56 hi + 24 lo + pad; = 4 (mod 32)
 
 // likelihood term kinds (a Bernoulli-Gamma fit is a Bernoulli term plus a Gamma term that share

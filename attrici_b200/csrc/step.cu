@@ -3,6 +3,7 @@
 // between the reference's theta layout and the canonical per-term layout.
 #include "common.cuh"
 #include "step_impl.cuh"
+#include "step_warp.cuh"
 
 namespace attrici {
 
@@ -12,85 +13,6 @@ constexpr int STEP_WARPS = 4;
 constexpr int STEP_THREADS = 32 * STEP_WARPS;
 constexpr int RED_THREADS = 128;
 constexpr int RED_GROUP = 2;    // accumulators per thread of the reduction kernel
-
-struct WarpCtx {
-    static constexpr int W = 32;
-    static constexpr bool kRegisterSolve = true;
-    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
-    __device__ bool solve(CellScratch& S, double lam) const;
-    __device__ __forceinline__ void sync() const { __syncwarp(); }
-    __device__ __forceinline__ double sum(double v) const {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        return v;
-    }
-    __device__ __forceinline__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
-};
-
-// (H + lam D) delta = -g with lane = row: the lane's row of H (then of the Cholesky factor L) lives in registers,
-// the factorisation is right-looking: column j is scaled and published through shared memory (S.y), then every
-// later column k takes its rank-1 update with L[k][j] read back as a warp-wide broadcast.  The forward
-// substitution is column-oriented in registers; for the backward one the rows of L are parked in S.L so that
-// lane k can read L[i][k] while delta[i] is broadcast.  Same mathematics as lm_solve() (step_impl.cuh) in about a
-// quarter of the instructions; returns false if a pivot is not positive.  Every loop is fully unrolled so that
-// the row stays in registers.
-__device__ bool WarpCtx::solve(CellScratch& S, double lam) const {
-    constexpr unsigned FULL = 0xffffffffu;
-    const int l = lane();
-    const bool row = l < NP;
-    double a[NP];
-#pragma unroll
-    for (int k = 0; k < NP; ++k) {
-        double v = (row && k <= l) ? S.H[l * (l + 1) / 2 + k] : 0.0;
-        if (k == l) v += lam * fmax(fabs(v), 1e-12);
-        a[k] = v;
-    }
-    double inv_diag = 1.0;   // 1 / L[l][l]
-    bool ok = true;
-    double* col = S.y;       // column j of L, indexed by row (free until the substitutions)
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-        const double d = __shfl_sync(FULL, a[j], j);
-        if (!(d > 0.0) || !isfinite(d)) { ok = false; break; }   // uniform: d is the same in every lane
-        const double inv = rsqrt(d), ljj = d * inv;   // 1 ulp-level: the factor only shapes a damped step
-        if (l == j) { a[j] = ljj; inv_diag = inv; }
-        else a[j] *= inv;                                  // L[l][j] for l > j (rows l < j hold zeros)
-        if (j + 1 < NP) {
-            if (row) col[l] = a[j];
-            __syncwarp();
-#pragma unroll
-            for (int k = j + 1; k < NP; ++k) a[k] = fma(-a[j], col[k], a[k]);   // only entries k <= l are ever read
-            __syncwarp();
-        }
-    }
-    if (!ok) return false;
-    // rows of L for the backward substitution
-    if (row) {
-#pragma unroll
-        for (int k = 0; k < NP; ++k)
-            if (k <= l) S.L[l * (l + 1) / 2 + k] = a[k];
-    }
-    // L y = -g, column-oriented: once y[i] is known every later row subtracts L[.][i] y[i]
-    double r = row ? -S.g[l] : 0.0, y = 0.0;
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const double yi = __shfl_sync(FULL, r * inv_diag, i);
-        if (l == i) y = yi;
-        if (l > i) r = fma(-a[i], yi, r);
-    }
-    __syncwarp();
-    // L^T delta = y, column-oriented from the last row: delta[i] = r[i] / L[i][i], then r[k] -= L[i][k] delta[i], k < i
-    double rb = y, delta = 0.0;
-#pragma unroll
-    for (int i = NP - 1; i >= 0; --i) {
-        const double di = __shfl_sync(FULL, rb * inv_diag, i);
-        if (l == i) delta = di;
-        if (l < i) rb = fma(-S.L[i * (i + 1) / 2 + l], di, rb);
-    }
-    if (row) S.delta[l] = delta;
-    __syncwarp();
-    return true;
-}
 
 // table of the information-matrix entries for this launch's (term, modes), built once per CTA
 __device__ __forceinline__ void build_h_table(const StepArgs& a, HEntry* tab) {
@@ -302,7 +224,12 @@ __global__ void scatter_kat_kernel(int C, int family, int modes, int slot, const
     }
 }
 
-StepArgs make_args(Workspace& ws, const StepParams& sp) {
+inline int warp_blocks(int n) { return (n + STEP_WARPS - 1) / STEP_WARPS; }
+inline int thread_blocks(int n) { return (n + 127) / 128; }
+
+}  // namespace
+
+StepArgs make_step_args(Workspace& ws, const StepParams& sp) {
     StepArgs a;
     a.C = ws.C; a.Cp = ws.Cp;
     a.term = sp.term; a.modes = sp.modes; a.slot = sp.slot;
@@ -317,16 +244,11 @@ StepArgs make_args(Workspace& ws, const StepParams& sp) {
     return a;
 }
 
-inline int warp_blocks(int n) { return (n + STEP_WARPS - 1) / STEP_WARPS; }
-inline int thread_blocks(int n) { return (n + 127) / 128; }
-
-}  // namespace
-
 int launch_fit_init(Workspace& ws, const StepParams& sp, int* list_out, int* counter, cudaStream_t s) {
     ATTRICI_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), s));
-    fit_init_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp), list_out, counter);
+    fit_init_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_step_args(ws, sp), list_out, counter);
     ATTRICI_LAUNCH_CHECK();
-    h_table_kernel<<<3, 128, 0, s>>>(make_args(ws, sp), reinterpret_cast<HEntry*>(ws.h_tab));
+    h_table_kernel<<<3, 128, 0, s>>>(make_step_args(ws, sp), reinterpret_cast<HEntry*>(ws.h_tab));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
@@ -335,7 +257,7 @@ int launch_fit_step(Workspace& ws, const StepParams& sp, const int* list_in, int
                     cudaStream_t s, bool fresh_fisher) {
     ATTRICI_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int), s));
     if (n_in <= 0) return 0;
-    fit_step_kernel<<<warp_blocks(n_in), STEP_THREADS, 0, s>>>(make_args(ws, sp), list_in, n_in, list_out, counter,
+    fit_step_kernel<<<warp_blocks(n_in), STEP_THREADS, 0, s>>>(make_step_args(ws, sp), list_in, n_in, list_out, counter,
                                                                fresh_fisher ? 1 : 0,
                                                                reinterpret_cast<const HEntry*>(ws.h_tab));
     ATTRICI_LAUNCH_CHECK();
@@ -343,13 +265,13 @@ int launch_fit_step(Workspace& ws, const StepParams& sp, const int* list_in, int
 }
 
 int launch_fit_final_point(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    fit_final_point_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    fit_final_point_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_step_args(ws, sp));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_fit_store(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    fit_store_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    fit_store_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_step_args(ws, sp));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
@@ -372,19 +294,19 @@ int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, int mode, cudaS
 }
 
 int launch_assemble(Workspace& ws, const StepParams& sp, double* nll, double* grad, double* fisher, cudaStream_t s) {
-    assemble_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp), nll, grad, fisher);
+    assemble_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_step_args(ws, sp), nll, grad, fisher);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_phase_only(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    phase_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    phase_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_step_args(ws, sp));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_rotate(Workspace& ws, const StepParams& sp, cudaStream_t s) {
-    rotate_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_args(ws, sp));
+    rotate_kernel<<<warp_blocks(ws.C), STEP_THREADS, 0, s>>>(make_step_args(ws, sp));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }

@@ -303,7 +303,7 @@ def run_cuda(args):
     C, T = args.cells, T_DAYS
     y = synthetic.tas_tile_torch(C, T, seed=1234 + rank, device=device, nan_fraction=0.001)
     gmt, days = synthetic.ssa_gmt(T), synthetic.time_axis(T)   # SSA-smoothed GMT (library kernels), configs[1]
-    solver = CellBatchSolver("tas", modes=MODES, device=device, profile=True)
+    solver = CellBatchSolver("tas", modes=MODES, device=device, profile=os.environ.get("ATTRICI_NO_FUSED") == "1")
     solver.set_predictor(days, gmt, C)
     P = solver.n_params
     gathered = torch.empty((world * C, P), dtype=torch.float64, device=device) if world > 1 else None

@@ -510,7 +510,9 @@ def test_batched_driver_report_variables():
     np.testing.assert_allclose(res["cfact"], lean["cfact"], rtol=1e-9, equal_nan=True)
     assert np.array_equal(res["replaced"], lean["replaced"])
     ser = res["series"]
-    assert set(ser) == {"y_scaled", "cfact_scaled", "mu", "sigma", "mu_cfact", "sigma_cfact"}
+    # the inputs named by the reference's dataset (detrend.py:449-451) are passed through next to the computed series
+    assert set(ser) == {"y", "gmt_scaled", "y_scaled", "cfact_scaled", "mu", "sigma", "mu_cfact", "sigma_cfact"}
+    assert np.array_equal(ser["y"], y, equal_nan=True) and np.array_equal(ser["gmt_scaled"], gmt)
     s = CellBatchSolver("tas", device=DEV)
     out = s.detrend_device(dev(y), days, gmt)
     assert np.array_equal(ser["y_scaled"], host(out["y_scaled"]), equal_nan=True)
