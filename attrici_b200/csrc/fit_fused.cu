@@ -35,7 +35,7 @@ namespace attrici {
 
 namespace {
 
-constexpr int FF_WARPS = 4;
+constexpr int FF_WARPS = 12;          // one CTA per SM: the pair tables (127 KB) live in shared memory once
 constexpr int FF_THREADS = 32 * FF_WARPS;
 constexpr int FF_WPITCH = 36;          // floats per row of the weight transposition buffer (36 = 4 mod 32: conflict-free fragments)
 constexpr int FF_SWEEPS = FUSED_TP / 32;   // 23
@@ -77,7 +77,8 @@ __device__ __forceinline__ double ff_wsum(double v) {
 // cell's momd rows (global, read back by the step code of this warp).
 //   mode PASS_NLL: row NACC only; PASS_GRAD: + gradient moments; PASS_FULL / PASS_FLAT: + Fisher moments
 //   (PASS_FLAT: only the two intercepts are non-zero - no predictor chain, one exp)
-__device__ __forceinline__ void fused_pass(const FusedArgs& a, int cell, int mode, const double* th, uint32_t* W) {
+__device__ __forceinline__ void fused_pass(const FusedArgs& a, const double* tab_d, const float* tab_f, int cell, int mode,
+                                           const double* th, uint32_t* W, double* mom) {
     const int lane = threadIdx.x & 31;
     const int gid = lane >> 2, tig = lane & 3;
     const bool flat = mode == PASS_FLAT;
@@ -99,39 +100,41 @@ __device__ __forceinline__ void fused_pass(const FusedArgs& a, int cell, int mod
     double nll = 0.0;
     const double e2_flat = flat ? exp(-2.0 * th[NA]) : 0.0;
 
-    // the cell's sums of the next sweep are requested before the current one is evaluated
+    // the cell's sums of the next sweep are requested before the current one is evaluated.  Lanes beyond the last
+    // pair, and the mirror of pair 0, read the zero padding of the rows (phases 1461 .. FUSED_SP - 1): no selects
     double nx[6];
     auto request = [&](int sweep, double (&v)[6]) {
         const int q = sweep * 32 + lane;
-        const bool valid = q < FUSED_NPAIR;
-        const int qm = (valid && q > 0) ? NPHASE - q : 0;
+        const int qi = q < FUSED_NPAIR ? q : NPHASE;
+        const int qm = (q < FUSED_NPAIR && q > 0) ? NPHASE - q : NPHASE;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            v[k] = valid ? __ldg(ys + k * FUSED_SP + q) : 0.0;
-            v[3 + k] = qm ? __ldg(ys + k * FUSED_SP + qm) : 0.0;
+            v[k] = __ldg(ys + k * FUSED_SP + qi);
+            v[3 + k] = __ldg(ys + k * FUSED_SP + qm);
         }
     };
     request(0, nx);
+#pragma unroll 1
     for (int sweep = 0; sweep < FF_SWEEPS; ++sweep) {
         const int q = sweep * 32 + lane;
-        const bool valid = q < FUSED_NPAIR;
         const double sy = nx[0], syy = nx[1], syg = nx[2], sym = nx[3], syym = nx[4], sygm = nx[5];
         if (sweep + 1 < FF_SWEEPS) request(sweep + 1, nx);
         double n, sg, sgg, nm, sgm, sggm;
         if (own) {
-            const int qm = (valid && q > 0) ? NPHASE - q : 0;
-            n = valid ? gs[q] : 0.0; sg = valid ? gs[FUSED_SP + q] : 0.0; sgg = valid ? gs[2 * FUSED_SP + q] : 0.0;
-            nm = qm ? gs[qm] : 0.0; sgm = qm ? gs[FUSED_SP + qm] : 0.0; sggm = qm ? gs[2 * FUSED_SP + qm] : 0.0;
+            const int qi = q < FUSED_NPAIR ? q : NPHASE;
+            const int qm = (q < FUSED_NPAIR && q > 0) ? NPHASE - q : NPHASE;
+            n = gs[qi]; sg = gs[FUSED_SP + qi]; sgg = gs[2 * FUSED_SP + qi];
+            nm = gs[qm]; sgm = gs[FUSED_SP + qm]; sggm = gs[2 * FUSED_SP + qm];
         } else {
-            const double* t = a.tab_d + q;
-            n = __ldg(t + 8 * FUSED_TP); sg = __ldg(t + 9 * FUSED_TP); sgg = __ldg(t + 10 * FUSED_TP);
-            nm = __ldg(t + 11 * FUSED_TP); sgm = __ldg(t + 12 * FUSED_TP); sggm = __ldg(t + 13 * FUSED_TP);
+            const double* t = tab_d + q;
+            n = t[8 * FUSED_TP]; sg = t[9 * FUSED_TP]; sgg = t[10 * FUSED_TP];
+            nm = t[11 * FUSED_TP]; sgm = t[12 * FUSED_TP]; sggm = t[13 * FUSED_TP];
         }
         double ck[MAXM], sk[MAXM];
 #pragma unroll
         for (int k = 0; k < MAXM; ++k) {
-            ck[k] = __ldg(a.tab_d + k * FUSED_TP + q);
-            sk[k] = __ldg(a.tab_d + (MAXM + k) * FUSED_TP + q);
+            ck[k] = tab_d[k * FUSED_TP + q];
+            sk[k] = tab_d[(MAXM + k) * FUSED_TP + q];
         }
         double av, bv, cv, amv, bmv, cmv, e2, e2m;
         if (flat) {
@@ -189,15 +192,15 @@ __device__ __forceinline__ void fused_pass(const FusedArgs& a, int cell, int mod
                 W[(8 + i) * FF_WPITCH + lane] = lo;
             }
             __syncwarp();
-            const float* tf = a.tab_f + sweep * 32 + tig;
+            const float* tf = tab_f + sweep * 32 + tig;
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const uint32_t a0 = W[gid * FF_WPITCH + 8 * s + tig], a1 = W[(gid + 8) * FF_WPITCH + 8 * s + tig];
                 const uint32_t a2 = W[gid * FF_WPITCH + 8 * s + tig + 4], a3 = W[(gid + 8) * FF_WPITCH + 8 * s + tig + 4];
-                const uint32_t bc0 = __float_as_uint(__ldg(tf + gid * FUSED_FP + 8 * s));
-                const uint32_t bc1 = __float_as_uint(__ldg(tf + gid * FUSED_FP + 8 * s + 4));
-                const uint32_t bs0 = __float_as_uint(__ldg(tf + (8 + gid) * FUSED_FP + 8 * s));
-                const uint32_t bs1 = __float_as_uint(__ldg(tf + (8 + gid) * FUSED_FP + 8 * s + 4));
+                const uint32_t bc0 = __float_as_uint(tf[gid * FUSED_FP + 8 * s]);
+                const uint32_t bc1 = __float_as_uint(tf[gid * FUSED_FP + 8 * s + 4]);
+                const uint32_t bs0 = __float_as_uint(tf[(8 + gid) * FUSED_FP + 8 * s]);
+                const uint32_t bs1 = __float_as_uint(tf[(8 + gid) * FUSED_FP + 8 * s + 4]);
                 ff_mma(cc, a0, a1, a2, a3, bc0, bc1);
                 ff_mma(cs, a0, a1, a2, a3, bs0, bs1);
             }
@@ -205,11 +208,9 @@ __device__ __forceinline__ void fused_pass(const FusedArgs& a, int cell, int mod
         }
     }
 
-    // ---- results -> momd rows of the cell (layout of pass.cu: ACC_AA / ACC_AB / ACC_BB / ACC_GA / ACC_GB, row NACC = nll)
-    const size_t cp = a.st.Cp;
-    double* mo = const_cast<double*>(a.st.momd) + cell;
+    // ---- results -> the warp's moment scratch (layout of pass.cu: ACC_AA / ACC_AB / ACC_BB / ACC_GA / ACC_GB, [NACC] = nll)
     nll = ff_wsum(nll);
-    if (lane == 0) mo[(size_t)NACC * cp] = nll;
+    if (lane == 0) mom[NACC] = nll;
     if (grad) {
 #pragma unroll
         for (int i = 0; i < 2 * NB; ++i) GA[i] = ff_wsum(GA[i]);
@@ -218,10 +219,10 @@ __device__ __forceinline__ void fused_pass(const FusedArgs& a, int cell, int mod
         // every lane holds the totals: lane i stores entry i (static indexing keeps the arrays in registers)
 #pragma unroll
         for (int i = 0; i < 2 * NB; ++i)
-            if (lane == i) mo[(size_t)(ACC_GA + i) * cp] = GA[i];
+            if (lane == i) mom[ACC_GA + i] = GA[i];
 #pragma unroll
         for (int i = 0; i < NB; ++i)
-            if (lane == 2 * NB + i) mo[(size_t)(ACC_GB + i) * cp] = GB[i];
+            if (lane == 2 * NB + i) mom[ACC_GB + i] = GB[i];
     }
     if (fisher) {
 #pragma unroll
@@ -235,34 +236,49 @@ __device__ __forceinline__ void fused_pass(const FusedArgs& a, int cell, int mod
         const int p = gid & 3;
         const int base = p < 3 ? ACC_AA + p * NTRIG : ACC_BB;
         if (gid < 4) {   // rows 0..3 (+ low parts in rows 8..11) of the cos tile: cos moments 2 tig + 1, 2 tig + 2
-            mo[(size_t)(base + 1 + 2 * tig) * cp] = (double)cc[0] + (double)cc[2];
-            mo[(size_t)(base + 2 + 2 * tig) * cp] = (double)cc[1] + (double)cc[3];
+            mom[base + 1 + 2 * tig] = (double)cc[0] + (double)cc[2];
+            mom[base + 2 + 2 * tig] = (double)cc[1] + (double)cc[3];
         } else {         // rows 4..7 (+ 12..15) of the sin tile
-            mo[(size_t)(base + NH + 1 + 2 * tig) * cp] = (double)cs[0] + (double)cs[2];
-            mo[(size_t)(base + NH + 2 + 2 * tig) * cp] = (double)cs[1] + (double)cs[3];
+            mom[base + NH + 1 + 2 * tig] = (double)cs[0] + (double)cs[2];
+            mom[base + NH + 2 + 2 * tig] = (double)cs[1] + (double)cs[3];
         }
         if (lane < 4) {
             const int b0 = lane < 3 ? ACC_AA + lane * NTRIG : ACC_BB;
-            mo[(size_t)b0 * cp] = (double)(lane == 0 ? fc[0] : (lane == 1 ? fc[1] : (lane == 2 ? fc[2] : fc[3])));
+            mom[b0] = (double)(lane == 0 ? fc[0] : (lane == 1 ? fc[1] : (lane == 2 ? fc[2] : fc[3])));
         }
         // the mu x sigma block of the Normal information matrix is zero
-        for (int i = lane; i < 2 * NTRIG; i += 32) mo[(size_t)(ACC_AB + i) * cp] = 0.0;
+        for (int i = lane; i < 2 * NTRIG; i += 32) mom[ACC_AB + i] = 0.0;
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(FF_THREADS, 3) fit_fused_kernel(FusedArgs a) {
-    __shared__ CellScratch S[FF_WARPS];
-    __shared__ HEntry tab[NTRI];
-    __shared__ uint32_t Wbuf[FF_WARPS][16 * FF_WPITCH];
-    __shared__ double th_s[FF_WARPS][32];
+using FusedScratch = CellScratchT<true>;
+
+// dynamic shared memory of one CTA: the pair tables, then per warp {scratch, weight buffer, coefficients}
+constexpr size_t FF_TABD_BYTES = sizeof(double) * FUSED_ND * FUSED_TP;
+constexpr size_t FF_TABF_BYTES = sizeof(float) * 16 * FUSED_FP;
+constexpr size_t FF_HTAB_BYTES = (sizeof(HEntry) * NTRI + 15) / 16 * 16;
+constexpr size_t FF_WARP_BYTES = (sizeof(FusedScratch) + sizeof(uint32_t) * 16 * FF_WPITCH + sizeof(double) * 32 + 15) / 16 * 16;
+constexpr size_t FF_SMEM_BYTES = FF_TABD_BYTES + FF_TABF_BYTES + FF_HTAB_BYTES + FF_WARPS * FF_WARP_BYTES;
+static_assert(FF_SMEM_BYTES <= 227 * 1024, "fused fit: shared memory of one CTA");
+
+__global__ void __launch_bounds__(FF_THREADS, 1) fit_fused_kernel(FusedArgs a) {
+    extern __shared__ __align__(16) unsigned char ff_smem[];
+    double* tab_d = reinterpret_cast<double*>(ff_smem);
+    float* tab_f = reinterpret_cast<float*>(ff_smem + FF_TABD_BYTES);
+    HEntry* tab = reinterpret_cast<HEntry*>(ff_smem + FF_TABD_BYTES + FF_TABF_BYTES);
+    for (int i = threadIdx.x; i < FUSED_ND * FUSED_TP; i += FF_THREADS) tab_d[i] = __ldg(a.tab_d + i);
+    for (int i = threadIdx.x; i < 16 * FUSED_FP; i += FF_THREADS) tab_f[i] = __ldg(a.tab_f + i);
+    static_assert(sizeof(HEntry) == 12, "HEntry is copied as three words");
     for (int i = threadIdx.x; i < NTRI * 3; i += FF_THREADS)
         reinterpret_cast<int*>(tab)[i] = __ldg(reinterpret_cast<const int*>(a.tab_g) + i);
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpCtx ctx;
-    CellScratch& Sw = S[w];
-    double* th = th_s[w];
+    unsigned char* mine = ff_smem + FF_TABD_BYTES + FF_TABF_BYTES + FF_HTAB_BYTES + (size_t)w * FF_WARP_BYTES;
+    FusedScratch& Sw = *reinterpret_cast<FusedScratch*>(mine);
+    uint32_t* Wb = reinterpret_cast<uint32_t*>(mine + sizeof(FusedScratch));
+    double* th = reinterpret_cast<double*>(mine + sizeof(FusedScratch) + sizeof(uint32_t) * 16 * FF_WPITCH);
+    WarpCtxT<true> ctx;   // the Normal information matrix has no mu x sigma block
     const size_t cp = a.st.Cp;
     for (;;) {
         int cell = 0;
@@ -270,23 +286,33 @@ __global__ void __launch_bounds__(FF_THREADS, 3) fit_fused_kernel(FusedArgs a) {
         cell = __shfl_sync(0xffffffffu, cell, 0);
         if (cell >= a.st.C) break;
         bool run = a.st.status[cell] == ATTRICI_STATUS_RUNNING;
-        for (int it = 0; run; ++it) {
+        bool final_pass = false, evaluated = false;
+        for (int it = 0;; ++it) {
             // pass 0 evaluates the point fit_init leaves (flat); passes fisher_passes .. + chord_passes - 1 reuse the
-            // information matrix of the accepted point (see api.cu)
+            // information matrix of the accepted point (see api.cu).  Cells that did not converge get one more pass
+            // without moments for the log posterior of the returned point (model_scipy.py:525: trace["logp"] =
+            // -res.fun); converged cells have it from the last evaluated point (cell_store, use_f_acc).
             const bool fresh = it < a.fisher_passes || it >= a.fisher_passes + a.chord_passes;
-            const int mode = it == 0 ? PASS_FLAT : (fresh ? PASS_FULL : PASS_GRAD);
+            int mode = it == 0 ? PASS_FLAT : (fresh ? PASS_FULL : PASS_GRAD);
+            if (!run) {
+                evaluated = it > 0 && a.st.status[cell] == ATTRICI_STATUS_CONVERGED;
+                if (evaluated) break;
+                cell_final_point(a.st, cell, Sw, ctx);
+                mode = PASS_NLL;
+                final_pass = true;
+            }
             if (lane < NP) th[lane] = a.st.th_pass[(size_t)lane * cp + cell];
             __syncwarp();
-            fused_pass(a, cell, mode, th, Wbuf[w]);
-            run = cell_step(a.st, cell, Sw, ctx, tab, fresh);
+            fused_pass(a, tab_d, tab_f, cell, mode, th, Wb, Sw.mom);
+            if (final_pass) {   // cell_store takes the sum of the day terms from the momd row
+                if (lane == 0) const_cast<double*>(a.st.momd)[(size_t)NACC * cp + cell] = Sw.mom[NACC];
+                __syncwarp();
+                break;
+            }
+            run = cell_step(a.st, cell, Sw, ctx, tab, fresh, true);
             __syncwarp();
         }
-        // log posterior of the accepted point (model_scipy.py:525: trace["logp"] = -res.fun)
-        cell_final_point(a.st, cell, Sw, ctx);
-        if (lane < NP) th[lane] = a.st.th_pass[(size_t)lane * cp + cell];
-        __syncwarp();
-        fused_pass(a, cell, PASS_NLL, th, Wbuf[w]);
-        cell_store(a.st, cell, Sw, ctx);
+        cell_store(a.st, cell, Sw, ctx, evaluated);
         __syncwarp();
     }
 }
@@ -374,10 +400,11 @@ int launch_fit_fused(Workspace& ws, const StepParams& sp, int fisher_passes, int
     a.work = ws.counters + 8;
     a.fisher_passes = fisher_passes; a.chord_passes = chord_passes;
     ATTRICI_CUDA_CHECK(cudaMemsetAsync(a.work, 0, sizeof(int), s));
-    int ctas = 148 * 3;
+    int ctas = 148;   // persistent: one CTA per SM, cells handed out through a.work
     const int need = (ws.C + FF_WARPS - 1) / FF_WARPS;
     if (ctas > need) ctas = need;
-    fit_fused_kernel<<<ctas, FF_THREADS, 0, s>>>(a);
+    ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(fit_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM_BYTES));
+    fit_fused_kernel<<<ctas, FF_THREADS, FF_SMEM_BYTES, s>>>(a);
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }

@@ -63,9 +63,15 @@ __global__ void __launch_bounds__(STEP_THREADS, 5) fit_step_kernel(StepArgs a, c
     __syncthreads();
     int cell = warp_cell(list_in, n_in);
     if (cell < 0) return;
-    WarpCtx ctx;
-    bool run = cell_step(a, cell, S[threadIdx.x >> 5], ctx, tab, fresh_fisher != 0);
-    if (run && ctx.lane() == 0) list_out[atomicAdd(counter, 1)] = cell;
+    bool run;
+    if (!term_has_ab(a.term)) {   // no cross block: both diagonal blocks are factorised side by side (step_warp.cuh)
+        WarpCtxT<true> ctx;
+        run = cell_step(a, cell, S[threadIdx.x >> 5], ctx, tab, fresh_fisher != 0);
+    } else {
+        WarpCtxT<false> ctx;
+        run = cell_step(a, cell, S[threadIdx.x >> 5], ctx, tab, fresh_fisher != 0);
+    }
+    if (run && (threadIdx.x & 31) == 0) list_out[atomicAdd(counter, 1)] = cell;
 }
 
 __global__ void __launch_bounds__(STEP_THREADS) fit_final_point_kernel(StepArgs a) {

@@ -44,13 +44,18 @@ struct StepArgs {
 
 constexpr int H_ZERO = NACC + 1;   // CellScratch::mom slot that holds 0
 
-// per-cell scratch (shared memory on the device)
-struct CellScratch {
+// per-cell scratch (shared memory on the device).  SHARE_L: the Cholesky factor overwrites the packed information
+// matrix (the register-resident solves of step_warp.cuh read their rows of H before they store rows of L; the
+// diagonal of H the predicted decrease needs is kept in hd) - 5.2 KB per cell instead of 8.2 KB.
+template <bool SHARE_L> struct CellScratchT {
     double mom[NACC + 2];   // [NACC] = sum of the day terms of the nll, [NACC + 1] = 0 (the "no moment" slot of HEntry)
     double H[NTRI];
-    double L[NTRI];
+    double Lbuf[SHARE_L ? 1 : NTRI];
     double g[NP], th[NP], delta[NP], y[NP];
+    double hd[NP];          // diagonal of H as assembled (before damping), filled by the solve
+    ATTRICI_HD double* L() { return SHARE_L ? H : Lbuf; }
 };
+using CellScratch = CellScratchT<false>;
 
 // serial "group" of one lane (CPU unit tests)
 struct SerialCtx {
@@ -106,9 +111,12 @@ ATTRICI_HD void rotate_to_shared(const StepArgs& a, int cell, const double* th_c
 
 // chunk-reduced moments of one cell -> S.mom, every trig moment rotated into the cell frame
 // (cos kx = ck cos kX + sk sin kX ; sin kx = ck sin kX - sk cos kX).  mom layout = pass.cu's.
-template <class Ctx> ATTRICI_HD void load_moments(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
+// in_scratch: the pass of this group left the moments in S.mom already (fit_fused.cu)
+template <class Ctx, class Scr>
+ATTRICI_HD void load_moments(const StepArgs& a, int cell, Scr& S, const Ctx& ctx, bool in_scratch = false) {
     const size_t cp = a.Cp;
-    for (int i = ctx.lane(); i <= NACC; i += Ctx::W) S.mom[i] = a.momd[(size_t)i * cp + cell];
+    if (!in_scratch)
+        for (int i = ctx.lane(); i <= NACC; i += Ctx::W) S.mom[i] = a.momd[(size_t)i * cp + cell];
     if (ctx.lane() == 0) S.mom[H_ZERO] = 0.0;
     ctx.sync();
     const double* rot = a.rot + (size_t)cell * 2 * NH;
@@ -176,8 +184,8 @@ ATTRICI_HD HEntry h_entry(int term, int modes, int i, int j) {
 
 // objective, gradient (S.g) and Fisher information + prior (S.H, packed lower triangle) of one cell in
 // the cell frame, canonical layout, at S.th.  Needs S.mom (load_moments).  Returns the objective.
-template <class Ctx>
-ATTRICI_HD double assemble(const StepArgs& a, CellScratch& S, bool want_H, const Ctx& ctx, const HEntry* tab = nullptr) {
+template <class Ctx, class Scr>
+ATTRICI_HD double assemble(const StepArgs& a, Scr& S, bool want_H, const Ctx& ctx, const HEntry* tab = nullptr) {
     double fp = 0.0;
     for (int i = ctx.lane(); i < NP; i += Ctx::W) {
         Col ci = col_of(i);
@@ -225,10 +233,12 @@ ATTRICI_HD double assemble(const StepArgs& a, CellScratch& S, bool want_H, const
 }
 
 // solve (H + lam D) delta = -g by Cholesky (S.L), rows in parallel; returns false if not SPD
-template <class Ctx> ATTRICI_HD bool lm_solve(CellScratch& S, double lam, const Ctx& ctx) {
+template <class Ctx, class Scr> ATTRICI_HD bool lm_solve(Scr& S, double lam, const Ctx& ctx) {
+    for (int i = ctx.lane(); i < NP; i += Ctx::W) S.hd[i] = S.H[tri(i, i)];
+    ctx.sync();
     for (int j = 0; j < NP; ++j) {
         double part = 0.0;
-        for (int k = ctx.lane(); k < j; k += Ctx::W) { double l = S.L[tri(j, k)]; part += l * l; }
+        for (int k = ctx.lane(); k < j; k += Ctx::W) { double l = S.L()[tri(j, k)]; part += l * l; }
         double hjj = S.H[tri(j, j)];
         double s = hjj + lam * fmax(fabs(hjj), 1e-12) - ctx.sum(part);
         if (!(s > 0.0) || !isfinite(s)) return false;   // uniform: s is the same in every lane
@@ -236,23 +246,23 @@ template <class Ctx> ATTRICI_HD bool lm_solve(CellScratch& S, double lam, const 
         double inv = 1.0 / ljj;
         for (int i = j + 1 + ctx.lane(); i < NP; i += Ctx::W) {
             double t = S.H[tri(i, j)];
-            for (int k = 0; k < j; ++k) t -= S.L[tri(i, k)] * S.L[tri(j, k)];
-            S.L[tri(i, j)] = t * inv;
+            for (int k = 0; k < j; ++k) t -= S.L()[tri(i, k)] * S.L()[tri(j, k)];
+            S.L()[tri(i, j)] = t * inv;
         }
-        if (ctx.lane() == 0) S.L[tri(j, j)] = ljj;
+        if (ctx.lane() == 0) S.L()[tri(j, j)] = ljj;
         ctx.sync();
     }
     for (int i = 0; i < NP; ++i) {   // L y = -g
         double part = 0.0;
-        for (int k = ctx.lane(); k < i; k += Ctx::W) part += S.L[tri(i, k)] * S.y[k];
-        double t = (-S.g[i] - ctx.sum(part)) / S.L[tri(i, i)];
+        for (int k = ctx.lane(); k < i; k += Ctx::W) part += S.L()[tri(i, k)] * S.y[k];
+        double t = (-S.g[i] - ctx.sum(part)) / S.L()[tri(i, i)];
         if (ctx.lane() == 0) S.y[i] = t;
         ctx.sync();
     }
     for (int i = NP - 1; i >= 0; --i) {   // L^T delta = y
         double part = 0.0;
-        for (int k = i + 1 + ctx.lane(); k < NP; k += Ctx::W) part += S.L[tri(k, i)] * S.delta[k];
-        double t = (S.y[i] - ctx.sum(part)) / S.L[tri(i, i)];
+        for (int k = i + 1 + ctx.lane(); k < NP; k += Ctx::W) part += S.L()[tri(k, i)] * S.delta[k];
+        double t = (S.y[i] - ctx.sum(part)) / S.L()[tri(i, i)];
         if (ctx.lane() == 0) S.delta[i] = t;
         ctx.sync();
     }
@@ -278,8 +288,8 @@ struct FirstStep {
 
 // from the accepted state in S (th, g, H) and lam: next trial point, or termination.
 // Every lane returns the same status.
-template <class Ctx>
-ATTRICI_HD int propose(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx, FirstStep first = FirstStep{false, 0.0, 0.0}) {
+template <class Ctx, class Scr>
+ATTRICI_HD int propose(const StepArgs& a, int cell, Scr& S, const Ctx& ctx, FirstStep first = FirstStep{false, 0.0, 0.0}) {
     double lam = a.lam[cell];
     bool ok = false;
     for (int tries = 0; tries < 40 && !ok; ++tries) {
@@ -301,7 +311,7 @@ ATTRICI_HD int propose(const StepArgs& a, int cell, CellScratch& S, const Ctx& c
         // -0.5 g.d + 0.5 lam d.D.d
         double part = 0.0;
         for (int i = ctx.lane(); i < NP; i += Ctx::W) {
-            const double di = S.delta[i], hii = S.H[tri(i, i)];
+            const double di = S.delta[i], hii = S.hd[i];
             part += -0.5 * S.g[i] * di + 0.5 * lam * fmax(fabs(hii), 1e-12) * di * di;
         }
         pred = ctx.sum(part);
@@ -357,7 +367,7 @@ template <class Ctx> ATTRICI_HD void cell_phase(const StepArgs& a, int cell, con
 }
 
 // returns true if the cell takes part in the iteration
-template <class Ctx> ATTRICI_HD bool cell_init(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
+template <class Ctx, class Scr> ATTRICI_HD bool cell_init(const StepArgs& a, int cell, Scr& S, const Ctx& ctx) {
     const size_t so = (size_t)a.slot * a.Cp + cell;
     double n = a.st_cnt[so];
     int first = a.st_first[so];
@@ -423,12 +433,12 @@ template <class Ctx> ATTRICI_HD bool cell_init(const StepArgs& a, int cell, Cell
 
 // after a pass at th_trial (moments reduced into momd): accept / reject, update damping, propose the
 // next trial.  Returns true if the cell needs another pass.
-template <class Ctx>
-ATTRICI_HD bool cell_step(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx, const HEntry* tab = nullptr,
-                          bool fresh_fisher = true) {
+template <class Ctx, class Scr>
+ATTRICI_HD bool cell_step(const StepArgs& a, int cell, Scr& S, const Ctx& ctx, const HEntry* tab = nullptr,
+                          bool fresh_fisher = true, bool moments_in_scratch = false) {
     if (a.status[cell] != ATTRICI_STATUS_RUNNING) return false;
     for (int i = ctx.lane(); i < NP; i += Ctx::W) S.th[i] = a.th_trial[(size_t)cell * NP + i];
-    load_moments(a, cell, S, ctx);
+    load_moments(a, cell, S, ctx, moments_in_scratch);
     // without fresh Fisher moments the information matrix of the accepted point stays in use (the matrix only
     // steers the step; near the optimum it changes by less than the damping does)
     double f_t = assemble(a, S, fresh_fisher, ctx, tab);
@@ -503,7 +513,7 @@ ATTRICI_HD bool cell_step(const StepArgs& a, int cell, CellScratch& S, const Ctx
 }
 
 // th_trial := th_acc and its shared-frame image (before the final FP64 evaluation)
-template <class Ctx> ATTRICI_HD void cell_final_point(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
+template <class Ctx, class Scr> ATTRICI_HD void cell_final_point(const StepArgs& a, int cell, Scr& S, const Ctx& ctx) {
     for (int i = ctx.lane(); i < NP; i += Ctx::W) {
         double v = a.th_acc[(size_t)cell * NP + i];
         S.th[i] = v;
@@ -516,7 +526,11 @@ template <class Ctx> ATTRICI_HD void cell_final_point(const StepArgs& a, int cel
 
 // after the FP64 pass at th_acc (day terms reduced into momd row NACC): log posterior
 // (model_scipy.py:525 "logp"), coefficients, status
-template <class Ctx> ATTRICI_HD void cell_store(const StepArgs& a, int cell, CellScratch& S, const Ctx& ctx) {
+// use_f_acc (converged cells): no pass at the returned point.  Either it is the accepted point the last pass evaluated
+// in FP64 (objective a.f_acc), or that point plus the final step propose() applied without evaluation because its
+// predicted decrease was <= TOL_FINAL_STEP |f|: the objective there is f_acc - pred up to the error of the quadratic
+// model on a step of that size (observed < 1e-2 pred, i.e. < 1e-10 |f|).
+template <class Ctx, class Scr> ATTRICI_HD void cell_store(const StepArgs& a, int cell, Scr& S, const Ctx& ctx, bool use_f_acc = false) {
     const size_t cp = a.Cp;
     double fp = 0.0;
     for (int i = ctx.lane(); i < NP; i += Ctx::W) {
@@ -526,6 +540,10 @@ template <class Ctx> ATTRICI_HD void cell_store(const StepArgs& a, int cell, Cel
         if (col_active(c, a.term, a.modes)) fp += 0.5 * prior_prec(c) * v * v;
     }
     double f = a.momd[(size_t)NACC * cp + cell] + ctx.sum(fp) - prior_const(a.term, a.modes);
+    if (use_f_acc) {
+        const double fa = a.f_acc[cell], pred = a.pred[cell];
+        f = (pred <= a.tol_pred * fmax(fabs(fa), 1.0)) ? fa : fa - pred;
+    }
     int st = a.status[cell];
     bool bad = (st == ATTRICI_STATUS_NO_DATA || st == ATTRICI_STATUS_NONFINITE);
     ctx.sync();
