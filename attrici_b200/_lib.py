@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libattrici_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_MODES = 4
 
 # enums of include/attrici_b200.h
@@ -49,6 +49,18 @@ class FitOptions(C.Structure):
     ]
 
 
+class HostOptions(C.Structure):
+    """``attrici_host_options_t``"""
+
+    _fields_ = [
+        ("prep_flags", C.c_int32),
+        ("cfact_dtype", C.c_int32),
+        ("replaced_mode", C.c_int32),
+        ("slab_major", C.c_int32),
+        ("sparse_capacity", C.c_int64),
+    ]
+
+
 class AttriciCudaError(RuntimeError):
     pass
 
@@ -64,6 +76,7 @@ _SIGNATURES = {
     "attrici_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "attrici_build_basis": (_i, [_vp, _sz, _i, _vp, _vp, _i, _i, _vp]),
     "attrici_prep_scale_mask": (_i, [_vp, _sz, C.POINTER(Variable), _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "attrici_prep_scale_mask_ex": (_i, [_vp, _sz, C.POINTER(Variable), _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp]),
     "attrici_nll_grad": (_i, [_vp, _sz, C.POINTER(Variable), _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "attrici_fit_batch": (_i, [_vp, _sz, C.POINTER(Variable), _vp, _i64, _i, _i, _i, _i, C.POINTER(FitOptions),
                                 _vp, _vp, _vp, _vp, _vp]),
@@ -82,7 +95,15 @@ _SIGNATURES = {
     "attrici_detrend_host_scratch_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
     "attrici_detrend_host": (_i, [C.POINTER(Variable), C.POINTER(FitOptions), _vp, _i64, _i, _i, _i, _i, _vp, _vp,
                                    _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i]),
+    "attrici_default_host_options": (_i, [C.POINTER(HostOptions)]),
+    "attrici_host_slab_range": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "attrici_detrend_host_ex": (_i, [C.POINTER(Variable), C.POINTER(FitOptions), C.POINTER(HostOptions), _vp, _i64, _i, _i,
+                                      _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i]),
+    "attrici_quantile_map_f32": (_i, [_vp, _sz, C.POINTER(Variable), _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
 }
+F64, F32 = 0, 1
+FLAGS_DENSE, FLAGS_SPARSE, FLAGS_OFF = 0, 1, 2
+PREP_EXACT_SUMS = 1      # attrici_prep_scale_mask_ex: two-pass sums of the float32 y_scaled
 WHICH_EXPECTATION = -1   # attrici_eval_parameter: Distribution.expectation() instead of a parameter
 EXPORTS = tuple(_SIGNATURES)
 

@@ -1,12 +1,14 @@
 // C ABI of libattrici_b200.so (declared in include/attrici_b200.h): argument checking, workspace
-// carving, the batched fit loop and the host-buffer pipeline.  No torch types, no global mutable
-// state; every call is asynchronous on the caller's stream except where stated.
+// carving, the batched fit loop and the host-buffer pipeline.  No torch types; process-wide state is limited to
+// diagnostics and plumbing (launch counter, last-error text, fit profile, the read-back mailbox, environment
+// switches read once); every call is asynchronous on the caller's stream except where stated.
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <atomic>
+#include <mutex>
 #include <vector>
 #include "common.cuh"
 
@@ -109,9 +111,12 @@ StepParams step_params(const attrici_variable_t& var, const attrici_fit_options_
 // Small device -> host read-backs (numbers of running cells, the fold flags) go through a pinned, mapped host
 // mailbox written by a one-warp kernel, not through cudaMemcpyAsync: a copy would queue on the D2H copy engine
 // behind the bulk download of the previous slab of attrici_detrend_host (tens of ms) and stall the fit.
+// One mailbox per process (not per thread: ModelCuda.fit_cached runs every fit with a timeout on a fresh thread, a
+// per-thread mailbox would leak one pinned page per cell), used under a mutex from the launch to the read.
 struct Mailbox { int* host = nullptr; int* dev = nullptr; bool tried = false; };
+std::mutex g_mailbox_mutex;
 Mailbox& mailbox() {
-    static thread_local Mailbox m;
+    static Mailbox m;
     if (!m.tried) {
         m.tried = true;
         void* h = nullptr;
@@ -133,7 +138,47 @@ __global__ void post_ints_kernel(const int* __restrict__ src, int n, volatile in
     __threadfence_system();
 }
 
+// FP64 counterfactual of one slab -> float32 (families whose quantile-map kernels store FP64 only)
+__global__ void narrow_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
+}
+
+// `replaced` plane of one slab -> list of (day, cell, code) of its non-zero entries, appended to a pinned, mapped host
+// buffer through the device counter `count` (entries beyond `capacity` are counted, not stored).  The plane is
+// non-zero on << 1 % of the days, so the list replaces a byte per cell-day of download by a few KB.
+__global__ void replaced_sparse_kernel(const uint8_t* __restrict__ plane, int T, int nc, int cell0, int32_t* __restrict__ entries,
+                                       unsigned long long capacity, unsigned long long* __restrict__ count) {
+    const size_t n = (size_t)T * nc;
+    const size_t n16 = n / 16;
+    const uint4* p16 = reinterpret_cast<const uint4*>(plane);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n16; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        size_t e0 = i * 16;
+        int nb = 16;
+        if (i < n16) {
+            const uint4 v = __ldg(p16 + i);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            if (!(w[0] | w[1] | w[2] | w[3])) continue;
+        } else {
+            nb = (int)(n - e0);   // tail of fewer than 16 bytes
+        }
+        for (int b = 0; b < nb; ++b) {
+            const uint32_t code = (i < n16) ? ((w[b >> 2] >> (8 * (b & 3))) & 0xffu) : (uint32_t)plane[e0 + b];
+            if (code) {
+                const size_t e = e0 + b;
+                const unsigned long long k = atomicAdd(count, 1ull);
+                if (k < capacity) {
+                    entries[3 * k + 0] = (int32_t)(e / nc);
+                    entries[3 * k + 1] = cell0 + (int32_t)(e % nc);
+                    entries[3 * k + 2] = (int32_t)code;
+                }
+            }
+        }
+    }
+}
 int read_ints(const int* dev, int* host, int n, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_mailbox_mutex);
     Mailbox& m = mailbox();
     if (m.host && n <= 32) {
         post_ints_kernel<<<1, 32, 0, s>>>(dev, n, m.dev);
@@ -166,12 +211,15 @@ bool fused_enabled() {
 // how a term's likelihood passes run: FOLD_SUMS = Normal term from the per-phase sums of prep (fold.cu),
 // FOLD_STREAM = the other terms streamed in phase order, FOLD_NONE = day-by-day kernels
 enum { FOLD_NONE = 0, FOLD_SUMS = 1, FOLD_STREAM = 2 };
-int fold_applies(Workspace& ws, int term, int i0, int i1, cudaStream_t s, int* fold) {
+int fold_applies(Workspace& ws, int term, int i0, int i1, cudaStream_t s, int* fold, bool* phase_major = nullptr) {
     *fold = FOLD_NONE;
+    if (phase_major) *phase_major = true;
     if (!fold_enabled()) return 0;
     if (term == T_NORMAL && !ws.ystat) return 0;
-    int h[3] = {1, -1, -1};   // {days off the gap-free axis, fit window the phase rows / sums were gathered for}
-    ATTRICI_TRY(read_ints(ws.fold_bad, h, 3, s));
+    // {days off the gap-free axis, fit window the phase rows / sums were gathered for, sums also in fold.cu's layout}
+    int h[4] = {1, -1, -1, 1};
+    ATTRICI_TRY(read_ints(ws.fold_bad, h, 4, s));
+    if (phase_major) *phase_major = h[3] != 0;
     if (h[0] == 0 && h[1] == i0 && h[2] == i1) {
         // measured (scripts/bench_families.py): the phase-ordered stream wins for the Gamma and Bernoulli terms
         // (tasrange fit 2.1x, pr 1.5x); the Beta and Weibull terms spend their time in per-day special functions and
@@ -232,9 +280,10 @@ int fit_term(Workspace& ws, const attrici_variable_t& var, const attrici_fit_opt
     int cur = 0, running = 0;
     int fold = FOLD_NONE;
     ATTRICI_TRY(launch_fit_init(ws, sp, ws.list[cur], ws.counters + cur, s));
-    ATTRICI_TRY(fold_applies(ws, sp.term, i0, i1, s, &fold));
+    bool phase_major = true;
+    ATTRICI_TRY(fold_applies(ws, sp.term, i0, i1, s, &fold, &phase_major));
     if (fold != FOLD_SUMS && !y_scaled) { set_error("y_scaled is needed: the phase-folded pass does not apply"); return ATTRICI_EINVAL; }
-    if (fold == FOLD_SUMS && ws.T >= NPHASE && fused_enabled() && !o.profile) {
+    if (fold == FOLD_SUMS && ws.T >= NPHASE && ((fused_enabled() && !o.profile) || !phase_major)) {
         // the whole iteration of the term in one persistent kernel (fit_fused.cu): no host round trip
         return launch_fit_fused(ws, sp, FISHER_PASSES, CHORD_PASSES, s);
     }
@@ -346,6 +395,12 @@ int attrici_build_basis(void* workspace, size_t workspace_bytes, int family, con
 int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
                             const float* y, float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
                             double* scaling, void* stream) {
+    return attrici_prep_scale_mask_ex(workspace, workspace_bytes, var, y, y_scaled, ld, T, C, i0, i1, scaling, 0, stream);
+}
+
+int attrici_prep_scale_mask_ex(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                               const float* y, float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
+                               double* scaling, int flags, void* stream) {
     ATTRICI_TRY(check_var(var));
     ATTRICI_TRY(check_shape(T, C, ld));
     ATTRICI_TRY(check_window(T, i0, i1));
@@ -356,7 +411,8 @@ int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes, const attri
     }
     Workspace ws;
     ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, var->family));
-    return launch_prep(ws, *var, y, y_scaled, ld, i0, i1, scaling, (cudaStream_t)stream);
+    if (flags & ~ATTRICI_PREP_EXACT_SUMS) { set_error("unknown prep flags 0x%x", flags); return ATTRICI_EINVAL; }
+    return launch_prep(ws, *var, y, y_scaled, ld, i0, i1, scaling, flags, (cudaStream_t)stream);
 }
 
 int attrici_nll_grad(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
@@ -468,7 +524,7 @@ bool contiguous_host(const int32_t* days, int T) {
 }
 
 struct SlabBuffers {
-    float* y; float* ys; double* cfact; uint8_t* replaced; double* params; double* logp; double* scaling;
+    float* y; float* ys; double* cfact; float* cfact32; uint8_t* replaced; double* params; double* logp; double* scaling;
     int32_t* status; int32_t* npass; uint32_t* seeds; void* ws; size_t ws_bytes;
 };
 
@@ -482,7 +538,8 @@ size_t slab_layout(int family, int T, int slab, int P, char* base, SlabBuffers* 
     size_t ts = (size_t)T * slab;
     SlabBuffers tmp;
     tmp.y = (float*)take(4 * ts);
-    tmp.ys = (float*)take(4 * ts);
+    tmp.ys = (float*)take(4 * ts);     // y_scaled, or the float32 counterfactual of families that do not keep it
+    tmp.cfact32 = tmp.ys;
     tmp.cfact = (double*)take(8 * ts);
     tmp.replaced = (uint8_t*)take(ts);
     tmp.params = (double*)take(8 * (size_t)slab * P);
@@ -497,6 +554,21 @@ size_t slab_layout(int family, int T, int slab, int P, char* base, SlabBuffers* 
     if (b) *b = tmp;
     return off;
 }
+
+// cell ranges of the slabs.  The pipeline is bound by the D2H copies, which can only start once the first slab has
+// been uploaded and detrended: a short first slab shortens that fill time.
+std::vector<int> slab_starts(int C, int slab_cells) {
+    std::vector<int> start;
+    if (slab_cells > C) slab_cells = C;
+    int first = slab_cells / 4;
+    if (first < 256) first = slab_cells;
+    int c = 0;
+    if (first < slab_cells && C > slab_cells) { start.push_back(0); c = first; }
+    for (; c < C; c += slab_cells) start.push_back(c);
+    start.push_back(C);
+    return start;
+}
+
 }  // namespace
 
 int attrici_detrend_host_scratch_bytes(int family, int T, int slab_cells, size_t* bytes) {
@@ -504,10 +576,31 @@ int attrici_detrend_host_scratch_bytes(int family, int T, int slab_cells, size_t
     if (!valid_family(family)) { set_error("unknown family %d", family); return ATTRICI_EINVAL; }
     ATTRICI_TRY(check_shape(T, slab_cells, slab_cells));
     const int P = family_num_params(family, ATTRICI_MAX_MODES);
-    // two slab buffer sets (double buffering) + the day / gmt vectors
+    // two slab buffer sets (double buffering) + the day / gmt vectors + the counter of the sparse `replaced` list
     *bytes = 2 * slab_layout(family, T, slab_cells, P, nullptr, nullptr) + Workspace::align(4 * (size_t)T) +
-             Workspace::align(8 * (size_t)T);
+             Workspace::align(8 * (size_t)T) + 256;
     return 0;
+}
+
+int attrici_default_host_options(attrici_host_options_t* o) {
+    if (!o) { set_error("options is null"); return ATTRICI_EINVAL; }
+    o->prep_flags = 0;
+    o->cfact_dtype = ATTRICI_F64;
+    o->replaced_mode = ATTRICI_FLAGS_DENSE;
+    o->slab_major = 0;
+    o->sparse_capacity = 0;
+    return 0;
+}
+
+int attrici_host_slab_range(int C, int slab_cells, int k, int* cell0, int* n_cells) {
+    if (C < 1 || slab_cells < 1) { set_error("need C >= 1 and slab_cells >= 1"); return ATTRICI_EINVAL; }
+    const std::vector<int> start = slab_starts(C, slab_cells);
+    const int n = (int)start.size() - 1;
+    if (k >= 0 && k < n) {
+        if (cell0) *cell0 = start[k];
+        if (n_cells) *n_cells = start[k + 1] - start[k];
+    }
+    return n;
 }
 
 int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_options_t* opts,
@@ -517,6 +610,23 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
                          double* params_host, double* logp_host, double* scaling_host,
                          int32_t* status_host, int32_t* n_pass_host,
                          void* device_scratch, size_t device_scratch_bytes, int slab_cells) {
+    attrici_host_options_t ho;
+    attrici_default_host_options(&ho);
+    if (!replaced_host) ho.replaced_mode = ATTRICI_FLAGS_OFF;
+    return attrici_detrend_host_ex(var, opts, &ho, y_host, ld_host, T, C, i0, i1, days_host, gmt_host, seeds_host, cfact_host,
+                                   ld_out_host, replaced_host, nullptr, nullptr, params_host, logp_host, scaling_host,
+                                   status_host, n_pass_host, device_scratch, device_scratch_bytes, slab_cells);
+}
+
+int attrici_detrend_host_ex(const attrici_variable_t* var, const attrici_fit_options_t* opts,
+                            const attrici_host_options_t* hopts,
+                            const float* y_host, int64_t ld_host, int T, int C, int i0, int i1,
+                            const int32_t* days_host, const double* gmt_host, const uint32_t* seeds_host,
+                            void* cfact_host, int64_t ld_out_host, uint8_t* replaced_host,
+                            int32_t* replaced_sparse_host, int64_t* n_sparse_host,
+                            double* params_host, double* logp_host, double* scaling_host,
+                            int32_t* status_host, int32_t* n_pass_host,
+                            void* device_scratch, size_t device_scratch_bytes, int slab_cells) {
     ATTRICI_TRY(check_var(var));
     ATTRICI_TRY(check_shape(T, C, ld_host));
     ATTRICI_TRY(check_window(T, i0, i1));
@@ -525,7 +635,31 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
         set_error("y / days / gmt / cfact / params host pointer is null");
         return ATTRICI_EINVAL;
     }
-    if (ld_out_host < C) { set_error("ld_out_host %lld < C=%d", (long long)ld_out_host, C); return ATTRICI_EINVAL; }
+    attrici_host_options_t ho;
+    attrici_default_host_options(&ho);
+    if (hopts) ho = *hopts;
+    if (ho.cfact_dtype != ATTRICI_F64 && ho.cfact_dtype != ATTRICI_F32) { set_error("unknown cfact_dtype %d", ho.cfact_dtype); return ATTRICI_EINVAL; }
+    if (ho.replaced_mode < ATTRICI_FLAGS_DENSE || ho.replaced_mode > ATTRICI_FLAGS_OFF) {
+        set_error("unknown replaced_mode %d", ho.replaced_mode);
+        return ATTRICI_EINVAL;
+    }
+    if (ho.prep_flags & ~ATTRICI_PREP_EXACT_SUMS) { set_error("unknown prep flags 0x%x", ho.prep_flags); return ATTRICI_EINVAL; }
+    if (!ho.slab_major && ld_out_host < C) { set_error("ld_out_host %lld < C=%d", (long long)ld_out_host, C); return ATTRICI_EINVAL; }
+    if (ho.replaced_mode == ATTRICI_FLAGS_DENSE && !replaced_host) { set_error("replaced_host is null"); return ATTRICI_EINVAL; }
+    int32_t* sparse_dev = nullptr;
+    if (ho.replaced_mode == ATTRICI_FLAGS_SPARSE) {
+        if (!replaced_sparse_host || !n_sparse_host || ho.sparse_capacity < 1) {
+            set_error("the sparse `replaced` list needs replaced_sparse_host, n_sparse_host and sparse_capacity >= 1");
+            return ATTRICI_EINVAL;
+        }
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, replaced_sparse_host, 0) != cudaSuccess || !d) {
+            cudaGetLastError();
+            set_error("replaced_sparse_host must be pinned (page-locked) host memory: the kernel appends to it directly");
+            return ATTRICI_EINVAL;
+        }
+        sparse_dev = (int32_t*)d;
+    }
     if (var->family == ATTRICI_BERNOULLI_GAMMA && !seeds_host) {
         set_error("pr needs per-cell seeds (detrend.py:285)");
         return ATTRICI_EINVAL;
@@ -546,6 +680,9 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
     slab_layout(var->family, T, slab_cells, Pmax, base + one, &buf[1]);
     int32_t* d_days = (int32_t*)(base + 2 * one);
     double* d_gmt = (double*)(base + 2 * one + Workspace::align(4 * (size_t)T));
+    unsigned long long* d_count = (unsigned long long*)(base + 2 * one + Workspace::align(4 * (size_t)T) + Workspace::align(8 * (size_t)T));
+    const bool f32 = ho.cfact_dtype == ATTRICI_F32;
+    const size_t csize = f32 ? 4 : 8;
 
     cudaStream_t st[2];
     ATTRICI_CUDA_CHECK(cudaStreamCreateWithFlags(&st[0], cudaStreamNonBlocking));
@@ -554,18 +691,9 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
     auto run = [&]() -> int {
         ATTRICI_CUDA_CHECK(cudaMemcpyAsync(d_days, days_host, 4 * (size_t)T, cudaMemcpyHostToDevice, st[0]));
         ATTRICI_CUDA_CHECK(cudaMemcpyAsync(d_gmt, gmt_host, 8 * (size_t)T, cudaMemcpyHostToDevice, st[0]));
+        ATTRICI_CUDA_CHECK(cudaMemsetAsync(d_count, 0, 8, st[0]));
         ATTRICI_CUDA_CHECK(cudaStreamSynchronize(st[0]));
-        // cell ranges of the slabs.  The pipeline is bound by the D2H copies, which can only start once the first
-        // slab has been uploaded and detrended: a short first slab shortens that fill time.
-        std::vector<int> start;
-        {
-            int first = slab_cells / 4;
-            if (first < 256) first = slab_cells;
-            int c = 0;
-            if (first < slab_cells && C > slab_cells) { start.push_back(0); c = first; }
-            for (; c < C; c += slab_cells) start.push_back(c);
-            start.push_back(C);
-        }
+        const std::vector<int> start = slab_starts(C, slab_cells);
         const int n_slabs = (int)start.size() - 1;
         // upload of slab k is issued before the (host-synchronising) fit of slab k-1 starts, on the
         // stream that owns its buffer set: stream order serialises the reuse of that set, and the copy
@@ -582,7 +710,8 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
             return 0;
         };
         ATTRICI_TRY(upload(0));
-        const bool skip_scaled = var->family == ATTRICI_NORMAL && fold_enabled() && contiguous_host(days_host, T);
+        const bool gap_free = contiguous_host(days_host, T);
+        const bool skip_scaled = var->family == ATTRICI_NORMAL && fold_enabled() && gap_free;
         for (int is = 0; is < n_slabs; ++is) {
             const int b = is & 1;
             cudaStream_t s = st[b];
@@ -594,17 +723,51 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
             // Normal family on a gap-free daily axis: the fit runs on the per-phase sums and the quantile map
             // recomputes y_scaled from y, so the scaled series is never materialised
             float* ys = skip_scaled ? nullptr : B.ys;
-            ATTRICI_TRY(attrici_prep_scale_mask(B.ws, B.ws_bytes, var, B.y, ys, nc, T, nc, i0, i1, B.scaling, s));
+            ATTRICI_TRY(attrici_prep_scale_mask_ex(B.ws, B.ws_bytes, var, B.y, ys, nc, T, nc, i0, i1, B.scaling, ho.prep_flags, s));
             ATTRICI_TRY(attrici_fit_batch(B.ws, B.ws_bytes, var, ys, nc, T, nc, i0, i1, opts, B.params, B.logp,
                                           B.status, B.npass, s));
-            ATTRICI_TRY(attrici_quantile_map(B.ws, B.ws_bytes, var, B.y, ys, nc, T, nc, B.params, B.scaling,
-                                             seeds_host ? B.seeds : nullptr, B.cfact, replaced_host ? B.replaced : nullptr,
-                                             nullptr, nc, s));
-            ATTRICI_CUDA_CHECK(cudaMemcpy2DAsync(cfact_host + c0, 8 * (size_t)ld_out_host, B.cfact, 8 * (size_t)nc,
-                                                 8 * (size_t)nc, T, cudaMemcpyDeviceToHost, s));
-            if (replaced_host)
-                ATTRICI_CUDA_CHECK(cudaMemcpy2DAsync(replaced_host + c0, (size_t)ld_out_host, B.replaced, (size_t)nc,
-                                                     (size_t)nc, T, cudaMemcpyDeviceToHost, s));
+            const bool want_plane = ho.replaced_mode != ATTRICI_FLAGS_OFF;
+            // float32 counterfactual: stored directly by the lean Normal kernel (which needs the plane), narrowed from
+            // the FP64 result for every other case
+            const bool direct32 = f32 && skip_scaled && qmap_fold_lean_applies(*var, nullptr, B.replaced);
+            const void* cfact_dev = B.cfact;
+            if (direct32) {
+                Workspace w;
+                ATTRICI_TRY(bind_workspace(w, B.ws, B.ws_bytes, T, nc, var->family));
+                ATTRICI_TRY(launch_qmap(w, *var, B.y, nullptr, nc, B.params, B.scaling, nullptr, nullptr, B.replaced, nullptr, nc, s,
+                                        B.cfact32));
+                cfact_dev = B.cfact32;
+            } else {
+                ATTRICI_TRY(attrici_quantile_map(B.ws, B.ws_bytes, var, B.y, ys, nc, T, nc, B.params, B.scaling,
+                                                 seeds_host ? B.seeds : nullptr, B.cfact, want_plane ? B.replaced : nullptr,
+                                                 nullptr, nc, s));
+                if (f32) {
+                    // y_scaled is dead after the quantile map: its buffer takes the narrowed counterfactual
+                    narrow_f64_f32_kernel<<<148 * 8, 256, 0, s>>>(B.cfact, B.cfact32, (size_t)T * nc);
+                    ATTRICI_LAUNCH_CHECK();
+                    cfact_dev = B.cfact32;
+                }
+            }
+            if (ho.slab_major) {
+                // the host array holds the slabs one after the other, each [T x nc] contiguous: one linear copy
+                ATTRICI_CUDA_CHECK(cudaMemcpyAsync((char*)cfact_host + csize * (size_t)T * c0, cfact_dev, csize * (size_t)T * nc,
+                                                   cudaMemcpyDeviceToHost, s));
+            } else {
+                ATTRICI_CUDA_CHECK(cudaMemcpy2DAsync((char*)cfact_host + csize * c0, csize * (size_t)ld_out_host, cfact_dev,
+                                                     csize * (size_t)nc, csize * (size_t)nc, T, cudaMemcpyDeviceToHost, s));
+            }
+            if (ho.replaced_mode == ATTRICI_FLAGS_DENSE) {
+                if (ho.slab_major)
+                    ATTRICI_CUDA_CHECK(cudaMemcpyAsync(replaced_host + (size_t)T * c0, B.replaced, (size_t)T * nc,
+                                                       cudaMemcpyDeviceToHost, s));
+                else
+                    ATTRICI_CUDA_CHECK(cudaMemcpy2DAsync(replaced_host + c0, (size_t)ld_out_host, B.replaced, (size_t)nc,
+                                                         (size_t)nc, T, cudaMemcpyDeviceToHost, s));
+            } else if (ho.replaced_mode == ATTRICI_FLAGS_SPARSE) {
+                replaced_sparse_kernel<<<148 * 8, 256, 0, s>>>(B.replaced, T, nc, c0, sparse_dev,
+                                                              (unsigned long long)ho.sparse_capacity, d_count);
+                ATTRICI_LAUNCH_CHECK();
+            }
             ATTRICI_CUDA_CHECK(cudaMemcpyAsync(params_host + (size_t)c0 * P, B.params, 8 * (size_t)nc * P,
                                                cudaMemcpyDeviceToHost, s));
             if (logp_host)
@@ -619,6 +782,15 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
         }
         ATTRICI_CUDA_CHECK(cudaStreamSynchronize(st[0]));
         ATTRICI_CUDA_CHECK(cudaStreamSynchronize(st[1]));
+        if (ho.replaced_mode == ATTRICI_FLAGS_SPARSE) {
+            unsigned long long n = 0;
+            ATTRICI_CUDA_CHECK(cudaMemcpy(&n, d_count, 8, cudaMemcpyDeviceToHost));
+            *n_sparse_host = (int64_t)n;
+            if ((int64_t)n > ho.sparse_capacity) {
+                set_error("the sparse `replaced` list holds %lld of %llu entries: raise sparse_capacity", (long long)ho.sparse_capacity, n);
+                return ATTRICI_EWORKSPACE;
+            }
+        }
         return 0;
     };
     rc = run();
@@ -626,6 +798,30 @@ int attrici_detrend_host(const attrici_variable_t* var, const attrici_fit_option
     cudaStreamDestroy(st[0]);
     cudaStreamDestroy(st[1]);
     return rc;
+}
+
+int attrici_quantile_map_f32(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                             const float* y, const float* y_scaled, int64_t ld, int T, int C,
+                             const double* params, const double* scaling, float* cfact, uint8_t* replaced,
+                             int64_t ld_out, void* stream) {
+    ATTRICI_TRY(check_var(var));
+    ATTRICI_TRY(check_shape(T, C, ld));
+    if (ld_out < C) { set_error("ld_out %lld < C=%d", (long long)ld_out, C); return ATTRICI_EINVAL; }
+    if (!y || !params || !scaling || !cfact || !replaced) { set_error("y / params / scaling / cfact / replaced is null"); return ATTRICI_EINVAL; }
+    if (!qmap_fold_lean_applies(*var, nullptr, replaced)) {
+        set_error("a float32 counterfactual is available for Normal variables without a post rule (tas, ps, rlds, ...)");
+        return ATTRICI_EUNSUPPORTED;
+    }
+    Workspace ws;
+    ATTRICI_TRY(bind_workspace(ws, workspace, workspace_bytes, T, C, var->family));
+    int h[1] = {1};
+    ATTRICI_TRY(read_ints(ws.fold_bad, h, 1, (cudaStream_t)stream));
+    if (h[0] != 0 || !fold_enabled()) {
+        set_error("a float32 counterfactual needs a gap-free daily time axis (the phase-ordered kernel)");
+        return ATTRICI_EUNSUPPORTED;
+    }
+    return launch_qmap(ws, *var, y, y_scaled, ld, params, scaling, nullptr, nullptr, replaced, nullptr, ld_out,
+                       (cudaStream_t)stream, cfact);
 }
 
 }  // extern "C"

@@ -91,6 +91,8 @@ struct Workspace {
     // fused fit (fit_fused.cu): cell-major per-phase sums, per-cell affine map of the sums, pair tables
     double* ysumT;     // [Cp][3][FUSED_SP] {u, u^2, u gmt} per phase, u = y_scaled or y - pivot (Normal only)
     double* gsumT;     // [Cp][3][FUSED_SP] {n, sum gmt, sum gmt^2} per phase of cells with missing days (Normal only)
+    uint8_t* cntT;     // [Cp][FUSED_SP] valid window days per phase (read for cells with missing days)
+    float* pivot;      // [Cp] u = y - pivot (one-pass prep)
     double* aff;       // [Cp][2] {m, s}: y_scaled = (u - m) / s
     double* ftab_d;    // [FUSED_ND][FUSED_TP]
     float* ftab_f;     // [16][FUSED_FP]
@@ -154,6 +156,8 @@ struct Workspace {
         psums = (family != ATTRICI_NORMAL) ? (float*)take(4 * 11 * (size_t)NPHASE * c) : nullptr;
         ysumT = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)FUSED_SP * c) : nullptr;
         gsumT = (family == ATTRICI_NORMAL) ? (double*)take(8 * 3 * (size_t)FUSED_SP * c) : nullptr;
+        cntT = (family == ATTRICI_NORMAL) ? (uint8_t*)take((size_t)FUSED_SP * c) : nullptr;
+        pivot = (float*)take(4 * c);
         aff = (double*)take(8 * 2 * c);
         ftab_d = (double*)take(8 * (size_t)FUSED_ND * FUSED_TP);
         ftab_f = (float*)take(4 * 16 * (size_t)FUSED_FP);
@@ -207,7 +211,7 @@ void count_launch();
 int launch_build_basis(Workspace& ws, const int32_t* days, const double* gmt, cudaStream_t s);
 
 int launch_prep(Workspace& ws, const attrici_variable_t& var, const float* y, float* y_scaled, int64_t ld,
-                int i0, int i1, double* scaling, cudaStream_t s);
+                int i0, int i1, double* scaling, int flags, cudaStream_t s);
 
 // one likelihood pass over the fit window [i0, i1) at ws.th_pass for the cells of `ps`; fills ws.part_nll /
 // ws.part_acc.  status != nullptr (only without a list): only cells whose status is RUNNING are evaluated.
@@ -239,6 +243,12 @@ int launch_reduce(Workspace& ws, const PassShape& ps, bool fp64, int mode, cudaS
 // gathered in the phase-major layout, and the whole iteration of a term in one persistent kernel
 int launch_fused_tables(Workspace& ws, cudaStream_t s);
 int launch_fused_from_phase_major(Workspace& ws, cudaStream_t s);
+// one pass over the series: min / max and the per-phase sums of y - pivot, cell-major (prep_onepass.cu); Normal family
+// on a gap-free daily axis when the caller does not ask for y_scaled.  flags: ATTRICI_PREP_* of the C ABI
+bool prep_onepass_applies(const Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled, int64_t ld,
+                          int flags);
+int launch_prep_onepass(Workspace& ws, const attrici_variable_t& var, const float* y, int64_t ld, int i0, int i1,
+                        double* scaling, cudaStream_t s);
 
 struct StepParams {
     int term;
@@ -278,11 +288,13 @@ int launch_scatter_kat(Workspace& ws, int family, int modes, int slot, const dou
 
 int launch_qmap(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled,
                 int64_t ld, const double* params, const double* scaling, const uint32_t* seeds, double* cfact,
-                uint8_t* replaced, double* cfact_scaled, int64_t ld_out, cudaStream_t s);
+                uint8_t* replaced, double* cfact_scaled, int64_t ld_out, cudaStream_t s, float* cfact32 = nullptr);
+// does the lean Normal kernel (the one that can store a float32 counterfactual) serve this request?
+bool qmap_fold_lean_applies(const attrici_variable_t& var, const double* cfact_scaled, const uint8_t* replaced);
 // Normal family in phase order (qmap_fold.cu); runs only if ws.fold_bad[0] == 0 (checked on the device)
 int launch_qmap_fold(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled, int64_t ld,
                      const double* params, const double* scaling, double* cfact, uint8_t* replaced,
-                     double* cfact_scaled, int64_t ld_out, cudaStream_t s);
+                     double* cfact_scaled, int64_t ld_out, cudaStream_t s, float* cfact32 = nullptr);
 // Gamma / Weibull families in phase order (scale shortcut), same device-side dispatch; needs y_scaled
 int launch_qmap_fold_scale(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled, int64_t ld,
                            const double* params, const double* scaling, double* cfact, uint8_t* replaced,

@@ -47,6 +47,7 @@ struct FusedArgs {
     const double* gsumT;     // [Cp][3][FUSED_SP] per-phase {n, sum g, sum g^2} of cells with missing days
     const double* aff;       // [Cp][2] {m, s}: y_scaled = (u - m) / s
     const int* miss;         // [Cp]
+    const uint8_t* cntT;     // [Cp][FUSED_SP] valid window days per phase
     const double* tab_d;     // [FUSED_ND][FUSED_TP]
     const float* tab_f;      // [16][FUSED_FP] TF32-rounded cos 1..8, sin 1..8 per pair
     int* work;               // next cell to hand out
@@ -121,10 +122,15 @@ __device__ __forceinline__ void fused_pass(const FusedArgs& a, const double* tab
         if (sweep + 1 < FF_SWEEPS) request(sweep + 1, nx);
         double n, sg, sgg, nm, sgm, sggm;
         if (own) {
+            // a cell with missing days: its own day count per phase, and its own gmt sums where days are missing
             const int qi = q < FUSED_NPAIR ? q : NPHASE;
             const int qm = (q < FUSED_NPAIR && q > 0) ? NPHASE - q : NPHASE;
-            n = gs[qi]; sg = gs[FUSED_SP + qi]; sgg = gs[2 * FUSED_SP + qi];
-            nm = gs[qm]; sgm = gs[FUSED_SP + qm]; sggm = gs[2 * FUSED_SP + qm];
+            const uint8_t* cn = a.cntT + (size_t)cell * FUSED_SP;
+            const double* t = tab_d + q;
+            n = (double)cn[qi]; nm = (double)cn[qm];
+            const bool lost = n != t[8 * FUSED_TP], lostm = nm != t[11 * FUSED_TP];
+            sg = lost ? gs[FUSED_SP + qi] : t[9 * FUSED_TP]; sgg = lost ? gs[2 * FUSED_SP + qi] : t[10 * FUSED_TP];
+            sgm = lostm ? gs[FUSED_SP + qm] : t[12 * FUSED_TP]; sggm = lostm ? gs[2 * FUSED_SP + qm] : t[13 * FUSED_TP];
         } else {
             const double* t = tab_d + q;
             n = t[8 * FUSED_TP]; sg = t[9 * FUSED_TP]; sgg = t[10 * FUSED_TP];
@@ -367,6 +373,14 @@ __global__ void fused_unit_affine_kernel(double* aff, int C) {
     if (c < C) { aff[2 * (size_t)c] = 0.0; aff[2 * (size_t)c + 1] = 1.0; }
 }
 
+// day counts of the cells with missing days from the n row of their (transposed) own sums; one warp per cell
+__global__ void fused_counts_kernel(const double* __restrict__ gsumT, const int* __restrict__ miss, uint8_t* __restrict__ cntT, int C) {
+    const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (cell >= C || miss[cell] == 0) return;
+    for (int d = threadIdx.x & 31; d < FUSED_SP; d += 32)
+        cntT[(size_t)cell * FUSED_SP + d] = d < NPHASE ? (uint8_t)gsumT[(size_t)cell * 3 * FUSED_SP + d] : 0;
+}
+
 }  // namespace
 
 // pair tables of the fit window; after fold_phase_basis_kernel (prep.cu)
@@ -386,6 +400,8 @@ int launch_fused_from_phase_major(Workspace& ws, cudaStream_t s) {
     ATTRICI_LAUNCH_CHECK();
     fused_unit_affine_kernel<<<(ws.C + 127) / 128, 128, 0, s>>>(ws.aff, ws.C);
     ATTRICI_LAUNCH_CHECK();
+    fused_counts_kernel<<<(ws.C + 3) / 4, 128, 0, s>>>(ws.gsumT, ws.miss, ws.cntT, ws.C);
+    ATTRICI_LAUNCH_CHECK();
     return 0;
 }
 
@@ -395,7 +411,7 @@ int launch_fit_fused(Workspace& ws, const StepParams& sp, int fisher_passes, int
     FusedArgs a;
     a.st = make_step_args(ws, sp);
     a.tab_g = reinterpret_cast<const HEntry*>(ws.h_tab);
-    a.ysumT = ws.ysumT; a.gsumT = ws.gsumT; a.aff = ws.aff; a.miss = ws.miss;
+    a.ysumT = ws.ysumT; a.gsumT = ws.gsumT; a.aff = ws.aff; a.miss = ws.miss; a.cntT = ws.cntT;
     a.tab_d = ws.ftab_d; a.tab_f = ws.ftab_f;
     a.work = ws.counters + 8;
     a.fisher_passes = fisher_passes; a.chord_passes = chord_passes;

@@ -343,7 +343,12 @@ int launch_mt19937(const uint32_t* seeds, int C, int n, double* out, int64_t ld,
 
 int launch_qmap(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled,
                 int64_t ld, const double* params, const double* scaling, const uint32_t* seeds, double* cfact,
-                uint8_t* replaced, double* cfact_scaled, int64_t ld_out, cudaStream_t s) {
+                uint8_t* replaced, double* cfact_scaled, int64_t ld_out, cudaStream_t s, float* cfact32) {
+    if (cfact32) {
+        // float32 counterfactual: written by the lean phase-ordered Normal kernel only (the caller has checked that
+        // the axis is gap-free daily: attrici_quantile_map_ex / attrici_detrend_host_ex)
+        return launch_qmap_fold(ws, var, y, y_scaled, ld, params, scaling, nullptr, replaced, cfact_scaled, ld_out, s, cfact32);
+    }
     QmapArgs a;
     a.y = y; a.ys = y_scaled; a.ld = ld;
     a.T = ws.T; a.C = ws.C; a.Cp = ws.Cp;

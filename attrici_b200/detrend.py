@@ -395,7 +395,7 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
             res["series"] = {k: v.numpy() for k, v in o.pop("series").items()}
         else:
             o = solver.detrend_host(y_local, days, gmt_scaled, fit_window, seeds, config.slab_cells, out=out)
-        local = {k: (o[k].numpy() if o[k] is not None else None) for k in o}
+        local = {k: (o[k].numpy() if o[k] is not None else None) for k in o if not k.startswith("_")}
         passed = {} if config.fit_only else passthrough_series(config.report_variables, y_local, gmt_scaled)
         if passed:
             res.setdefault("series", {}).update(passed)

@@ -447,6 +447,16 @@ def provenance_attrs(config=None, **other_metadata):
     return res
 
 
+def dense_replaced(entries, n_time, n_cells):
+    """[T, C] uint8 plane of replacement codes from the sparse ``(day, cell, code)`` rows of
+    ``CellBatchSolver.detrend_host(replaced="sparse")``."""
+    plane = np.zeros((n_time, n_cells), dtype=np.uint8)
+    e = np.asarray(entries)
+    if e.size:
+        plane[e[:, 0], e[:, 1]] = e[:, 2].astype(np.uint8)
+    return plane
+
+
 def replaced_flags(codes):
     """The library's ``replaced`` codes (``ATTRICI_REPLACED_*``: 0 none, 1 NaN, 2 +Inf, 3 -Inf) as the float64 flags
     the reference stores (attrici/detrend.py:396-409: 0, NaN, +Inf, -Inf; ``_FillValue`` 0)."""

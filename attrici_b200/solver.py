@@ -48,7 +48,7 @@ class CellBatchSolver:
     """Scale -> fit -> quantile-map for a batch of cells of one variable on one GPU."""
 
     def __init__(self, variable, modes=4, device="cuda:0", use_fp64=False, zero_init=False, max_pass=60,
-                 tol_pred=1e-11, profile=False):
+                 tol_pred=1e-11, profile=False, exact_scaled_sums=False):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.AttriciCudaError("attrici_b200 needs a CUDA device (no CPU fallback)")
@@ -63,6 +63,10 @@ class CellBatchSolver:
         self.options.max_pass = int(max_pass)
         self.options.tol_pred = float(tol_pred)
         self.options.profile = int(profile)
+        # Normal family without a materialised y_scaled: True keeps the two-pass sums of the float32-rounded scaled
+        # values the reference fits; the default gathers sums of the unrounded ones in one pass over the series
+        # (logp differs by ~2e-9 relative; attrici_prep_scale_mask_ex)
+        self.prep_flags = _lib.PREP_EXACT_SUMS if exact_scaled_sums else 0
         self._ws = None
         self._ws_key = None
         self.T = self.C = None
@@ -126,8 +130,9 @@ class CellBatchSolver:
         scaling = torch.empty((C_, 2), dtype=torch.float64, device=self.device)
         ws = self._ws
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.attrici_prep_scale_mask(_ptr(ws), ws.numel(), C.byref(self.var), _ptr(y), _ptr(ys),
-                                                        ld, T, C_, i0, i1, _ptr(scaling), self._stream()))
+            _lib.check(self.lib.attrici_prep_scale_mask_ex(_ptr(ws), ws.numel(), C.byref(self.var), _ptr(y), _ptr(ys),
+                                                           ld, T, C_, i0, i1, _ptr(scaling), self.prep_flags,
+                                                           self._stream()))
         self._fit_window = (i0, i1)
         return ys, scaling
 
@@ -185,6 +190,17 @@ class CellBatchSolver:
         self._need_basis(T, C_)
         cfact = out if out is not None else torch.empty((T, C_), dtype=torch.float64, device=self.device)
         replaced = torch.empty((T, C_), dtype=torch.uint8, device=self.device) if want_replaced else None
+        if cfact.dtype == torch.float32:
+            # opt-in output type (``out=`` a float32 tensor): the FP64 result rounded once; Normal variables without a
+            # post rule on a gap-free daily axis (attrici_quantile_map_f32)
+            if not want_replaced or want_scaled:
+                raise ValueError("a float32 counterfactual comes with `replaced` and without cfact_scaled")
+            ws = self._ws
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.attrici_quantile_map_f32(_ptr(ws), ws.numel(), C.byref(self.var), _ptr(y), _ptr(y_scaled),
+                                                             ld, T, C_, _ptr(params), _ptr(scaling), _ptr(cfact),
+                                                             _ptr(replaced), cfact.stride(0), self._stream()))
+            return cfact, replaced, None
         cs = torch.empty((T, C_), dtype=torch.float64, device=self.device) if want_scaled else None
         if seeds is not None:
             seeds = torch.as_tensor(np.ascontiguousarray(seeds, dtype=np.uint32).view(np.int32)).to(self.device)
@@ -239,17 +255,45 @@ class CellBatchSolver:
         cfact, replaced, _ = self.quantile_map(y, ys, fit.params, scaling, seeds, want_replaced)
         return {"y_scaled": ys, "scaling": scaling, "fit": fit, "cfact": cfact, "replaced": replaced}
 
-    def detrend_host(self, y_host, days, gmt, fit_window=None, seeds=None, slab_cells=2048, out=None,
-                     want_replaced=True):
-        """Whole hot path with HOST buffers (pinned recommended): slabs of cells, copies and kernels
-        overlapped on the library's two internal streams (``attrici_detrend_host``).
+    def host_slabs(self, n_cells, slab_cells=2048):
+        """Cell ranges ``[(cell0, n_cells), ...]`` of the slabs ``detrend_host`` cuts a batch into
+        (``attrici_host_slab_range``; a short first slab shortens the fill of the copy / compute pipeline)."""
+        slab = int(min(slab_cells, n_cells))
+        c0, nc = C.c_int(0), C.c_int(0)
+        n = self.lib.attrici_host_slab_range(n_cells, slab, -1, None, None)
+        if n < 0:
+            _lib.check(n)
+        out = []
+        for k in range(n):
+            self.lib.attrici_host_slab_range(n_cells, slab, k, C.byref(c0), C.byref(nc))
+            out.append((c0.value, nc.value))
+        return out
 
-        ``y_host``: [T, C] float32 numpy array or CPU tensor.  Returns a dict of numpy arrays
-        (views of pinned tensors): cfact [T, C] f64, replaced [T, C] u8, params [C, P], logp [C],
-        scaling [C, 2], status [C], n_pass [C]."""
+    def detrend_host(self, y_host, days, gmt, fit_window=None, seeds=None, slab_cells=2048, out=None,
+                     want_replaced=True, cfact_dtype=torch.float64, replaced="dense", slab_major=False,
+                     sparse_capacity=None):
+        """Whole hot path with HOST buffers (pinned recommended): slabs of cells, copies and kernels
+        overlapped on the library's two internal streams (``attrici_detrend_host_ex``).
+
+        ``y_host``: [T, C] float32 numpy array or CPU tensor.  Returns a dict of CPU tensors (pinned):
+        cfact [T, C] (``cfact_dtype``: float64 like the reference's output, or float32 = the FP64 result rounded once
+        to the dtype of the input files), replaced, params [C, P], logp [C], scaling [C, 2], status [C], n_pass [C].
+
+        What crosses PCIe bounds this call, so the result layout is selectable:
+        ``replaced="dense"``: [T, C] uint8 codes; ``"sparse"``: ``replaced_sparse`` [n, 3] int32 rows (day, cell, code)
+        of the non-zero entries (unordered; ``io.dense_replaced`` rebuilds the plane); ``None`` / want_replaced=False: none.
+        ``slab_major=True``: ``cfact`` (and a dense ``replaced``) come back as one flat pinned tensor holding the cell
+        slabs one after the other, each [T, n_k] contiguous (one linear copy per slab instead of a T-row pitched one);
+        ``cfact_slabs`` / ``replaced_slabs`` are the per-slab [T, n_k] views and ``slabs`` their (cell0, n_k)."""
         yt = y_host if isinstance(y_host, torch.Tensor) else torch.from_numpy(np.asarray(y_host))
         if yt.dtype != torch.float32 or yt.dim() != 2 or yt.stride(1) != 1 or yt.is_cuda:
             raise TypeError("y_host must be a 2-D float32 host array [T, C] with unit stride along cells")
+        if cfact_dtype not in (torch.float64, torch.float32):
+            raise TypeError("cfact_dtype must be torch.float64 or torch.float32")
+        if not want_replaced:
+            replaced = None
+        if replaced not in ("dense", "sparse", None):
+            raise ValueError("replaced must be 'dense', 'sparse' or None")
         T, C_ = yt.shape
         i0, i1 = (0, T) if fit_window is None else fit_window
         slab = int(min(slab_cells, C_))
@@ -258,16 +302,30 @@ class CellBatchSolver:
             self._scratch = None
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
         pin = torch.cuda.is_available()
-        if out is None:
+        if sparse_capacity is None:
+            sparse_capacity = max(4096, (T * C_) // 16)
+        key = (T, C_, cfact_dtype, replaced, bool(slab_major))
+        if out is not None and "_key" not in out:
+            out["_key"] = key      # buffers allocated by the caller (time-major, dense): used as they are
+        if out is None or out.get("_key") != key:
+            shape = (T * C_,) if slab_major else (T, C_)
             out = {
-                "cfact": torch.empty((T, C_), dtype=torch.float64, pin_memory=pin),
-                "replaced": torch.empty((T, C_), dtype=torch.uint8, pin_memory=pin) if want_replaced else None,
+                "_key": key,
+                "cfact": torch.empty(shape, dtype=cfact_dtype, pin_memory=pin),
+                "replaced": torch.empty(shape, dtype=torch.uint8, pin_memory=pin) if replaced == "dense" else None,
                 "params": torch.empty((C_, self.n_params), dtype=torch.float64, pin_memory=pin),
                 "logp": torch.empty(C_, dtype=torch.float64, pin_memory=pin),
                 "scaling": torch.empty((C_, 2), dtype=torch.float64, pin_memory=pin),
                 "status": torch.empty(C_, dtype=torch.int32, pin_memory=pin),
                 "n_pass": torch.empty(C_, dtype=torch.int32, pin_memory=pin),
             }
+            if replaced == "sparse":
+                out["_sparse_buf"] = torch.empty((int(sparse_capacity), 3), dtype=torch.int32, pin_memory=pin)
+            if slab_major:
+                out["slabs"] = self.host_slabs(C_, slab)
+                out["cfact_slabs"] = [out["cfact"][T * c0:T * (c0 + n)].view(T, n) for c0, n in out["slabs"]]
+                if replaced == "dense":
+                    out["replaced_slabs"] = [out["replaced"][T * c0:T * (c0 + n)].view(T, n) for c0, n in out["slabs"]]
         days = np.ascontiguousarray(days, dtype=np.int32)
         gmt = np.ascontiguousarray(gmt, dtype=np.float64)
         if len(days) != T or len(gmt) != T:
@@ -277,15 +335,27 @@ class CellBatchSolver:
         def hp(t):
             return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
+        ho = _lib.HostOptions()
+        _lib.check(self.lib.attrici_default_host_options(C.byref(ho)))
+        ho.prep_flags = self.prep_flags
+        ho.cfact_dtype = _lib.F32 if cfact_dtype == torch.float32 else _lib.F64
+        ho.replaced_mode = {"dense": _lib.FLAGS_DENSE, "sparse": _lib.FLAGS_SPARSE, None: _lib.FLAGS_OFF}[replaced]
+        ho.slab_major = int(bool(slab_major))
+        sparse_buf = out.get("_sparse_buf")
+        ho.sparse_capacity = 0 if sparse_buf is None else sparse_buf.shape[0]
+        n_sparse = C.c_int64(0)
         with torch.cuda.device(self.device):
             # the library works on its own streams: whatever the torch stream still has queued on memory the caching
             # allocator may hand out again (the scratch above, outputs of an earlier call) must have finished
             torch.cuda.current_stream(self.device).synchronize()
-            _lib.check(self.lib.attrici_detrend_host(
-                C.byref(self.var), C.byref(self.options), hp(yt), yt.stride(0), T, C_, i0, i1,
+            _lib.check(self.lib.attrici_detrend_host_ex(
+                C.byref(self.var), C.byref(self.options), C.byref(ho), hp(yt), yt.stride(0), T, C_, i0, i1,
                 C.c_void_p(days.ctypes.data), C.c_void_p(gmt.ctypes.data),
                 C.c_void_p(seeds_np.ctypes.data) if seeds_np is not None else C.c_void_p(0),
-                hp(out["cfact"]), out["cfact"].stride(0), hp(out["replaced"]), hp(out["params"]), hp(out["logp"]),
+                hp(out["cfact"]), 0 if slab_major else out["cfact"].stride(0), hp(out["replaced"]), hp(sparse_buf),
+                C.byref(n_sparse), hp(out["params"]), hp(out["logp"]),
                 hp(out["scaling"]), hp(out["status"]), hp(out["n_pass"]), _ptr(self._scratch),
                 self._scratch.numel(), slab))
+        if sparse_buf is not None:
+            out["replaced_sparse"] = sparse_buf[:n_sparse.value]
         return out

@@ -387,7 +387,10 @@ def run_cuda(args):
         e2e_s = float(t.item())
     e2e_value = world * C * e2e_steps / e2e_s
     h2d = y_host.numel() * 4 + T * 12
-    d2h = sum(int(v.numel() * v.element_size()) for v in res.values() if v is not None)
+    d2h = sum(int(v.numel() * v.element_size()) for k, v in res.items()
+              if isinstance(v, torch.Tensor) and not k.startswith("_") and k != "replaced_sparse")
+    if res.get("replaced_sparse") is not None:
+        d2h += int(res["replaced_sparse"].numel() * 4)
 
     if rank == 0:
         peak, peak_src = measured_peaks()

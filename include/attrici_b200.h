@@ -9,8 +9,10 @@
  *
  * Conventions
  *   - every array pointer is a DEVICE pointer unless the parameter name ends in _host;
- *     the caller (torch / cudaMalloc) owns every buffer, the library never allocates device
- *     memory except inside attrici_detrend_host (streams/events only, see there);
+ *     the caller (torch / cudaMalloc) owns every buffer and the library never allocates device
+ *     memory.  What it does create: attrici_detrend_host makes and destroys two CUDA streams per
+ *     call, and one 256-byte pinned, mapped host mailbox per process (cudaHostAlloc on first use,
+ *     kept) carries the small device -> host read-backs of the fit;
  *   - cell series are TIME-MAJOR: element (day t, cell c) of a [T x C] array lives at
  *     t*ld + c, ld >= C (the layout a (time, lat, lon) NetCDF variable already has after
  *     the reference's obs_data.stack(latlon=("lat","lon")), attrici/detrend.py:672);
@@ -20,7 +22,10 @@
  *     success, a negative ATTRICI_E* code for invalid arguments, or a positive cudaError_t;
  *     attrici_last_error() gives a thread-local message;  numerical trouble in one cell is
  *     reported in status[c], never as a call failure;
- *   - the library is re-entrant per stream and keeps no global mutable state.
+ *   - the library is re-entrant per stream.  Process-wide state is limited to diagnostics and plumbing that
+ *     do not influence results: the launch counter (atomic), the thread-local last-error text and fit
+ *     profile, the mailbox above (mutex-guarded), and the ATTRICI_* tuning variables read once from the
+ *     environment.
  */
 #ifndef ATTRICI_B200_H
 #define ATTRICI_B200_H
@@ -32,7 +37,7 @@
 extern "C" {
 #endif
 
-#define ATTRICI_ABI_VERSION 1
+#define ATTRICI_ABI_VERSION 2
 #if defined(__GNUC__)
 #define ATTRICI_API __attribute__((visibility("default")))
 #else
@@ -141,6 +146,16 @@ ATTRICI_API int attrici_prep_scale_mask(void* workspace, size_t workspace_bytes,
                             const float* y, float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
                             double* scaling, void* stream);
 
+/* The same with flags.  With y_scaled == NULL (Normal family, gap-free daily axis, T >= 1461) the default gathers the
+ * per-phase sums in ONE pass over the series, together with the min / max of variables.py:108-110: sums of
+ * y - pivot, mapped to the scaled values by a per-cell affine map inside the fit.  Those are the sums of the
+ * UNROUNDED scaled values, where the reference fits y_scaled rounded to float32: logp moves by ~2e-9 relative.
+ * ATTRICI_PREP_EXACT_SUMS keeps the two-pass form (min / max, then the sums of the float32 y_scaled). */
+#define ATTRICI_PREP_EXACT_SUMS 1
+ATTRICI_API int attrici_prep_scale_mask_ex(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                               const float* y, float* y_scaled, int64_t ld, int T, int C, int i0, int i1,
+                               double* scaling, int flags, void* stream);
+
 /* log-posterior, gradient and Fisher information at given coefficients (known-answer entry).
  * replaces DistributionScipy.log_likelihood (model_scipy.py:311-331) summed as in :520; the
  * reference has no gradient (finite differences inside scipy's L-BFGS-B).
@@ -153,7 +168,10 @@ ATTRICI_API int attrici_nll_grad(void* workspace, size_t workspace_bytes, const 
 /* batched MAP fit: Fisher-scoring Levenberg-Marquardt with per-cell convergence masks.
  * replaces ModelScipy.fit (model_scipy.py:505-527: scipy L-BFGS-B with finite differences).
  *   params[C x P] out, logp[C] out (log posterior, FP64 evaluation at the returned point),
- *   status[C] out, n_pass[C] out (nullable).  Synchronises `stream` internally (once per block of passes).
+ *   status[C] out, n_pass[C] out (nullable).  Synchronises `stream` internally: once for the Normal family on a
+ *   gap-free daily axis (the whole iteration of a term is one persistent kernel), once per block of passes
+ *   otherwise.  logp of a converged cell of that fused path is the objective of the last evaluated point, minus the
+ *   predicted decrease of the final step when that step was applied unevaluated (<= 1e-8 |logp|, see step_impl.cuh).
  *   y_scaled may be NULL for the Normal family on a gap-free daily axis when attrici_prep_scale_mask ran on
  *   this workspace with the same window (the passes then read the per-phase sums); otherwise ATTRICI_EINVAL. */
 ATTRICI_API int attrici_fit_batch(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
@@ -202,7 +220,7 @@ ATTRICI_API int attrici_ssa_first_component(const double* x, int n, int window, 
                                 size_t workspace_bytes, int max_iter, double tol, int32_t* info, double* eigenvalue,
                                 void* stream);
 
-/* ---- block bootstrap of the fitted trend (attrici/detrend.py:479-612; Normal family in this version) ----
+/* ---- block bootstrap of the fitted trend (attrici/detrend.py:479-612; all five families) ----
  * The samples of a batch of cells are refitted as extra cells of a [T x R C] series (column r C + c) through
  * attrici_prep_scale_mask / attrici_fit_batch / attrici_eval_parameter; these four entries provide the rest.
  *
@@ -249,6 +267,49 @@ ATTRICI_API int attrici_detrend_host(const attrici_variable_t* var, const attric
                          double* params_host, double* logp_host, double* scaling_host,
                          int32_t* status_host, int32_t* n_pass_host,
                          void* device_scratch, size_t device_scratch_bytes, int slab_cells);
+
+/* The same with options for what is carried across PCIe - the pipeline is bound by the download of the results:
+ *   cfact_dtype    ATTRICI_F64 (the reference's output type) or ATTRICI_F32 (the FP64 result rounded once to the dtype
+ *                  of the input files, 6e-8 relative; cfact_host is then float*): halves the download;
+ *   replaced_mode  ATTRICI_FLAGS_DENSE: the [T x C] uint8 plane; ATTRICI_FLAGS_SPARSE: the non-zero entries as
+ *                  (day, cell, code) int32 triples appended (in no particular order) to replaced_sparse_host, which
+ *                  must be PINNED host memory of sparse_capacity triples; *n_sparse_host receives their number
+ *                  (ATTRICI_EWORKSPACE if it exceeds the capacity); ATTRICI_FLAGS_OFF: not returned;
+ *   slab_major     1: cfact_host (and the dense replaced_host) hold the cell slabs one after the other, slab k =
+ *                  [T x n_cells_k] contiguous at element offset T * cell0_k (attrici_host_slab_range), so that each slab
+ *                  comes down as one linear copy instead of a T-row pitched one; ld_out_host is ignored;
+ *   prep_flags     ATTRICI_PREP_* of attrici_prep_scale_mask_ex. */
+#define ATTRICI_F64 0
+#define ATTRICI_F32 1
+#define ATTRICI_FLAGS_DENSE 0
+#define ATTRICI_FLAGS_SPARSE 1
+#define ATTRICI_FLAGS_OFF 2
+typedef struct {
+    int32_t prep_flags;
+    int32_t cfact_dtype;
+    int32_t replaced_mode;
+    int32_t slab_major;
+    int64_t sparse_capacity;
+} attrici_host_options_t;
+ATTRICI_API int attrici_default_host_options(attrici_host_options_t* options);
+/* slab k of the pipeline for (C, slab_cells): *cell0, *n_cells (k outside the range: untouched); returns the number of slabs */
+ATTRICI_API int attrici_host_slab_range(int C, int slab_cells, int k, int* cell0, int* n_cells);
+ATTRICI_API int attrici_detrend_host_ex(const attrici_variable_t* var, const attrici_fit_options_t* opts,
+                            const attrici_host_options_t* host_options,
+                            const float* y_host, int64_t ld_host, int T, int C, int i0, int i1,
+                            const int32_t* days_host, const double* gmt_host, const uint32_t* seeds_host,
+                            void* cfact_host, int64_t ld_out_host, uint8_t* replaced_host,
+                            int32_t* replaced_sparse_host, int64_t* n_sparse_host,
+                            double* params_host, double* logp_host, double* scaling_host,
+                            int32_t* status_host, int32_t* n_pass_host,
+                            void* device_scratch, size_t device_scratch_bytes, int slab_cells);
+
+/* quantile map with a float32 counterfactual (device buffers): Normal variables without a post rule on a gap-free
+ * daily axis, `replaced` required; anything else returns ATTRICI_EUNSUPPORTED.  Synchronises `stream` once. */
+ATTRICI_API int attrici_quantile_map_f32(void* workspace, size_t workspace_bytes, const attrici_variable_t* var,
+                             const float* y, const float* y_scaled, int64_t ld, int T, int C,
+                             const double* params, const double* scaling, float* cfact, uint8_t* replaced,
+                             int64_t ld_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -84,10 +84,12 @@ def test_workspace_query_and_argument_errors():
     lib = _lib.load()
     n = _lib.workspace_bytes(_lib.NORMAL, 43464, 10000)
     assert 50e6 < n < 2.0e9
-    # per-phase buffers of the folded passes: Normal 2 x [1461][3][C] float64, other families [1461][11][C] float32
+    # per-phase buffers of the folded passes: Normal 2 x [1461][3][C] float64 (phase-major, fold.cu) + 2 x [C][3][1464]
+    # float64 and [C][1464] uint8 (cell-major, fit_fused.cu); other families [1461][11][C] float32
     n_gamma = _lib.workspace_bytes(_lib.GAMMA, 43464, 10000)
-    assert n - 2 * 3 * 8 * 1461 * 10000 > 50e6 and n_gamma - 4 * 11 * 1461 * 10000 > 50e6
-    assert abs((n - 2 * 3 * 8 * 1461 * 10016) - (n_gamma - 4 * 11 * 1461 * 10016)) < 4096
+    normal_only = (2 * 3 * 8 * 1461 + 2 * 3 * 8 * 1464 + 1464) * 10016
+    assert n - normal_only > 50e6 and n_gamma - 4 * 11 * 1461 * 10000 > 50e6
+    assert abs((n - normal_only) - (n_gamma - 4 * 11 * 1461 * 10016)) < 8192
     # the Bernoulli-Gamma family also holds the [T x C] MT19937 uniforms
     assert _lib.workspace_bytes(_lib.BERNOULLI_GAMMA, 43464, 10000) > n_gamma + 8 * 43464 * 10000 - 1
     with pytest.raises(_lib.AttriciCudaError, match="T >= 2"):
