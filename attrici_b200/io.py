@@ -251,7 +251,8 @@ class ReplacedFlagsView:
         self.shape = tuple(codes.shape)
 
     def __getitem__(self, key):
-        return replaced_flags(np.asarray(self.codes[key]))
+        part = self.codes[key]
+        return replaced_flags(part.numpy() if hasattr(part, "numpy") else np.asarray(part))
 
     def __array__(self, dtype=None, copy=None):
         return replaced_flags(np.asarray(self.codes))
@@ -270,9 +271,13 @@ def write_merged_output(path, series, lat, lon, time, time_units="days since 190
     name -> [T] (``gmt_scaled``).  Streams through ``MergedOutputWriter``."""
     time = np.asarray(time)
     T = time.size
-    series = {k: (v.numpy() if hasattr(v, "numpy") else np.asarray(v)) for k, v in (series or {}).items()}
-    if replaced_as_flags and "replaced" in series and series["replaced"].dtype.kind in "iub":
+    lazy = (ColumnBlocks, SparseReplaced)   # sliced by days on demand
+    series = {k: (v if isinstance(v, lazy) else (v.numpy() if hasattr(v, "numpy") else np.asarray(v)))
+              for k, v in (series or {}).items()}
+    np_dtype = {k: (v.numpy_dtype() if isinstance(v, lazy) else v.dtype) for k, v in series.items()}
+    if replaced_as_flags and "replaced" in series and np_dtype["replaced"].kind in "iub":
         series["replaced"] = ReplacedFlagsView(series["replaced"])
+        np_dtype["replaced"] = np.dtype(np.float64)
     shared = {k: np.asarray(v) for k, v in (shared or {}).items()}
     n_cells = np.asarray(lat).size
     for name, arr in series.items():
@@ -281,13 +286,91 @@ def write_merged_output(path, series, lat, lon, time, time_units="days since 190
     for name, arr in shared.items():
         if arr.shape != (T,):
             raise ValueError(f"shared variable {name} must have shape [T]")
-    with MergedOutputWriter(path, lat, lon, {k: v.dtype for k, v in series.items()},
+    def days_of(v, a, b):
+        part = v[a:b]
+        return part.numpy() if hasattr(part, "numpy") else part
+
+    with MergedOutputWriter(path, lat, lon, np_dtype,
                             shared={k: v.dtype for k, v in shared.items()}, scalars=scalars, time_dtype=time.dtype,
                             time_units=time_units, calendar=calendar, attrs=attrs) as w:
         step = max(1, w.block_bytes // w._rec_size)
         for a in range(0, T, step):
             b = min(T, a + step)
-            w.append(time[a:b], {k: v[a:b] for k, v in series.items()}, {k: v[a:b] for k, v in shared.items()})
+            w.append(time[a:b], {k: days_of(v, a, b) for k, v in series.items()}, {k: v[a:b] for k, v in shared.items()})
+
+
+class ColumnBlocks:
+    """[T, n] series held as column blocks (the per-slab ``cfact_slabs`` of ``CellBatchSolver.detrend_host(slab_major=
+    True)``): slicing a range of days concatenates the blocks' rows, so the writers can consume the slab-major result
+    without a [T, n] copy."""
+
+    def __init__(self, blocks, dtype=None):
+        """``dtype``: torch dtype the rows are cast to when they are sliced (e.g. float32 for a file of the inputs' dtype)."""
+        import torch
+
+        self.blocks = [b if isinstance(b, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(b)) for b in blocks]
+        self.shape = (int(self.blocks[0].shape[0]), int(sum(b.shape[1] for b in self.blocks)))
+        self.dtype = dtype or self.blocks[0].dtype
+        self.is_cuda = False
+
+    def dim(self):
+        return 2
+
+    def element_size(self):
+        return self.blocks[0][:0].to(self.dtype).element_size()
+
+    def numpy_dtype(self):
+        return self.blocks[0][:0].to(self.dtype).numpy().dtype
+
+    def __getitem__(self, key):
+        import torch
+
+        return torch.cat([b[key].to(self.dtype) for b in self.blocks], dim=1)
+
+    def columns(self, cols):
+        """[T, len(cols)] copy of the given columns."""
+        import torch
+
+        edges = np.cumsum([0] + [b.shape[1] for b in self.blocks])
+        out = []
+        for c in cols:
+            k = int(np.searchsorted(edges, c, side="right") - 1)
+            out.append(self.blocks[k][:, int(c - edges[k])])
+        return torch.stack(out, dim=1)
+
+
+class SparseReplaced:
+    """[T, n] uint8 plane of replacement codes given as the sparse ``(day, cell, code)`` rows of
+    ``detrend_host(replaced="sparse")``; a range of days is materialised on demand."""
+
+    def __init__(self, entries, n_time, n_cells):
+        import torch
+
+        e = np.asarray(entries).reshape(-1, 3)
+        order = np.argsort(e[:, 0], kind="stable")
+        self._e = e[order]
+        self.shape = (int(n_time), int(n_cells))
+        self.dtype = torch.uint8
+        self.is_cuda = False
+
+    def dim(self):
+        return 2
+
+    def element_size(self):
+        return 1
+
+    def numpy_dtype(self):
+        return np.dtype(np.uint8)
+
+    def __getitem__(self, key):
+        import torch
+
+        a, b, _ = key.indices(self.shape[0])
+        out = np.zeros((b - a, self.shape[1]), dtype=np.uint8)
+        lo, hi = np.searchsorted(self._e[:, 0], [a, b])
+        rows = self._e[lo:hi]
+        out[rows[:, 0] - a, rows[:, 1]] = rows[:, 2].astype(np.uint8)
+        return torch.from_numpy(out)
 
 
 def write_merged_output_sharded(path, series_local, counts, lat, lon, time, dist, group=None, dst=0,
@@ -312,7 +395,8 @@ def write_merged_output_sharded(path, series_local, counts, lat, lon, time, dist
     local = {}
     for k in names:
         t = series_local[k]
-        t = t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t))
+        if not isinstance(t, (torch.Tensor, ColumnBlocks, SparseReplaced)):
+            t = torch.from_numpy(np.ascontiguousarray(t))
         if t.dim() != 2 or t.shape[1] != counts[rank] or t.is_cuda:
             raise ValueError(f"series {k} must be a host array [T, {counts[rank]}] on rank {rank}")
         local[k] = t
@@ -330,8 +414,10 @@ def write_merged_output_sharded(path, series_local, counts, lat, lon, time, dist
     if rank == dst:
         shared = {k: np.asarray(v) for k, v in (kwargs.pop("shared", None) or {}).items()}
         time = np.asarray(time)
-        as_flags = {k for k in names if k == "replaced" and replaced_as_flags and local[k].numpy().dtype.kind in "iub"}
-        writer = MergedOutputWriter(path, lat, lon, {k: np.dtype(np.float64) if k in as_flags else local[k].numpy().dtype
+        np_dtype = {k: (local[k].numpy_dtype() if hasattr(local[k], "numpy_dtype") else local[k][:0].numpy().dtype)
+                    for k in names}
+        as_flags = {k for k in names if k == "replaced" and replaced_as_flags and np_dtype[k].kind in "iub"}
+        writer = MergedOutputWriter(path, lat, lon, {k: np.dtype(np.float64) if k in as_flags else np_dtype[k]
                                                      for k in names},
                                     shared={k: v.dtype for k, v in shared.items()}, time_dtype=time.dtype,
                                     block_bytes=block_bytes, **kwargs)

@@ -44,26 +44,11 @@ UNIT = "cells/s"
 def bench_config(cells=TILE_CELLS):
     """``config`` of the JSON line: identical for the CUDA arm and the reference arm (what was sampled / measured
     per arm is in ``cpu_baseline.sample``, ``e2e`` and ``fit_stats``)."""
-    return {"workload": "tas Gaussian 100x100-cell tile, T=43464, modes=4, SSA-smoothed GMT predictor (BASELINE configs[1])",
+    return {"workload": WORKLOADS["tas"],
             "cells_per_gpu": cells, "days": T_DAYS, "modes": MODES,
-            "l2": "inputs larger than L2 (1.74 GB float32 series per tile; streamed twice per step: scale + sums, "
-                  "quantile map)",
+            "l2": "inputs larger than L2 (1.74 GB float32 series per tile; streamed twice per step: min/max + per-phase "
+                  "sums in one pass, then the quantile map)",
             "report_variables": ["cfact", "replaced"]}
-
-
-def ncu_traffic(kernel_prefix):
-    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/r1_traffic.json, same tile)."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
-        return None
-    with open(p) as f:
-        d = json.load(f)
-    if d.get("cells") != TILE_CELLS or d.get("days") != T_DAYS:
-        return None
-    for name, v in d["kernels"].items():
-        if name.startswith(kernel_prefix):
-            return v["dram_bytes"]
-    return None
 
 
 def measured_peaks():
@@ -275,12 +260,169 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
+# measured FP64 FMA peak of this pool's B200 (scripts/micro/fp64_peak.cu / dmma_peak.cu, profiles/r2_dmma_peak.txt:
+# 57.4 DFMA / clk / SM scalar, 63.6 through DMMA - the same pipe): the roofline of the fit kernel
+FP64_PEAK_GFMAS = 16700.0
+# FP64 operations of one (cell, phase pair) of one likelihood pass of the fused fit, counted on the mathematics
+# (DESIGN.md section 5): predictors 27, two exp 2 x 14, residual sums 2 x 8, nll 2 x 3, gradient weights 2 x 6 + 6,
+# gradient moments 27, u-space map 8
+FIT_FP64_PER_PAIR = 124.0
+WORKLOADS = {
+    "tas": "tas Gaussian 100x100-cell tile, T=43464, modes=4, SSA-smoothed GMT predictor (BASELINE configs[1])",
+    "pr": "pr Bernoulli-Gamma (wet/dry mask + gamma fit) on the same tile (BASELINE configs[2])",
+    "sfcWind": "sfcWind Weibull on the same tile (BASELINE configs[3])",
+    "hurs": "hurs Beta on the same tile (BASELINE configs[3])",
+    "tasrange": "tasrange Gamma on the same tile",
+    "rsds": "rsds Gaussian with the <= 0 rule on the same tile (BASELINE configs[3])",
+}
+
+
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/r2_traffic.json, same tile)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(p):
+            continue
+        with open(p) as f:
+            d = json.load(f)
+        if d.get("cells") != TILE_CELLS or d.get("days") != T_DAYS:
+            continue
+        for k, v in d["kernels"].items():
+            if k.startswith(kernel_prefix):
+                return v["dram_bytes"], name
+    return None, None
+
+
+def family_tile(variable, C, T, device, seed):
+    """Synthetic tile of a non-tas variable in HBM: distinct cells generated on the host (the generators are NumPy
+    loops), tiled to C columns."""
+    import torch
+
+    from attrici_b200 import synthetic
+
+    base = synthetic.GENERATORS[variable](min(C, 64), T, seed=seed)
+    reps = (C + base.shape[1] - 1) // base.shape[1]
+    return torch.from_numpy(np.tile(base, (1, reps))[:, :C].copy()).to(device)
+
+
+def measure_device(solver, y, seeds, steps, warmup, keep_scaled, barrier, after_step=None):
+    """W warm-up + K timed steps of scale -> fit -> quantile map with everything resident in HBM.
+    Returns (ms total, per-segment ms per step, last fit)."""
+    import torch
+
+    T, C = y.shape
+    cfact = torch.empty((T, C), dtype=torch.float64, device=y.device)
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        ys, scaling = solver.scale(y, None, keep_scaled=keep_scaled)
+        if ev:
+            ev[1].record()
+        fit = solver.fit(ys)
+        if ev:
+            ev[2].record()
+        solver.quantile_map(y, ys, fit.params, scaling, seeds, out=cfact)
+        if ev:
+            ev[3].record()
+        if after_step:
+            after_step(fit)
+        return fit
+
+    for _ in range(warmup):
+        fit = step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    seg_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    barrier()
+    t_begin = time.time()
+    ev0.record()
+    for k in range(steps):
+        fit = step(seg_ev[k])
+    ev1.record()
+    barrier()
+    t_end = time.time()
+    ms = ev0.elapsed_time(ev1)
+    seg_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in seg_ev) / steps for i in range(3)]
+    del cfact
+    return ms, seg_ms, fit, (t_begin, t_end)
+
+
+def segment_rooflines(variable, seg_ms, n_pass_mean, T, C, peak_hbm):
+    """Per-segment roofline statements.  Algorithmic bytes per cell-day: Normal family on the
+    one-pass path - scale 4 B (the series once), quantile map 13 B (4 in, 8 + 1 out); families that keep y_scaled -
+    scale 12 B (read twice, y_scaled written), every likelihood pass 4 B, quantile map 17 B.  The Normal fit runs on
+    35 KB of per-phase sums per cell and is FP64-bound: FIT_FP64_PER_PAIR operations per (cell, pair, pass)."""
+    normal = variable == "tas"
+    cd = float(T) * C
+    out = {}
+    sb = (4.0 if normal else 12.0) * cd
+    qb = (13.0 if normal else 17.0) * cd
+    out["scale"] = {"ms": seg_ms[0], "bound": "hbm", "algorithmic_bytes": sb, "achieved": sb / 1e9 / (seg_ms[0] / 1e3),
+                    "peak": peak_hbm, "unit": "GB/s"}
+    out["quantile_map"] = {"ms": seg_ms[2], "bound": "hbm", "algorithmic_bytes": qb,
+                           "achieved": qb / 1e9 / (seg_ms[2] / 1e3), "peak": peak_hbm, "unit": "GB/s"}
+    if normal:
+        ops = FIT_FP64_PER_PAIR * 731 * (n_pass_mean + 1.0) * C   # + the evaluation of the returned point
+        out["fit"] = {"ms": seg_ms[1], "bound": "fp64", "algorithmic_fma": ops, "achieved": ops / 1e9 / (seg_ms[1] / 1e3),
+                      "peak": FP64_PEAK_GFMAS, "unit": "GFMA/s (FP64)"}
+    else:
+        fb = 4.0 * cd * (n_pass_mean + 1.0)
+        out["fit"] = {"ms": seg_ms[1], "bound": "hbm", "algorithmic_bytes": fb, "achieved": fb / 1e9 / (seg_ms[1] / 1e3),
+                      "peak": peak_hbm, "unit": "GB/s"}
+    for v in out.values():
+        v["frac"] = v["achieved"] / v["peak"]
+    return out
+
+
+SEG_KERNEL = {
+    ("tas", "scale"): "prep_onepass_kernel", ("tas", "fit"): "fit_fused_kernel", ("tas", "quantile_map"): "qmap_fold_lean_kernel",
+}
+LIMITER = {
+    "pr": "quantile map: incomplete-gamma inverses on wet days only - 9.8 of 32 lanes active per instruction (warp = 32 cells "
+          "of one day), FP64 pipe 29 % (profiles/r2_qmap_pr_hurs_ncu.txt); not memory-bound",
+    "hurs": "quantile map: incomplete-beta inverses (Halley iterations of continued fractions), FP64 pipe ~30 % at 17 % "
+            "occupancy (profiles/r2_qmap_pr_hurs_ncu.txt); not memory-bound",
+}
+
+
+def run_workload(variable, device, C, T, days, gmt, steps, warmup, barrier):
+    """Device-resident throughput of one of the other workloads (configs[2], [3]) on the same tile shape."""
+    import torch
+
+    from attrici_b200 import synthetic
+    from attrici_b200.solver import CellBatchSolver, cell_seeds
+
+    y = family_tile(variable, C, T, device, seed=4321)
+    solver = CellBatchSolver(variable, modes=MODES, device=device)
+    solver.set_predictor(days, gmt, C)
+    seeds = None
+    if variable == "pr":
+        lat, lon = synthetic.tile_coordinates(100, (C + 99) // 100)
+        seeds = cell_seeds(0, lat[:C], lon[:C])
+    ms, seg_ms, fit, _ = measure_device(solver, y, seeds, steps, warmup, keep_scaled=True, barrier=barrier)
+    n_pass = fit.n_pass.float().mean().item()
+    peak, _ = measured_peaks()
+    segs = segment_rooflines(variable, seg_ms, n_pass, T, C, peak)
+    dom = max(segs, key=lambda k: segs[k]["ms"])
+    res = {"workload": WORKLOADS[variable], "value": C * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps,
+           "steps": steps, "warmup": warmup, "cells": C, "passes_per_cell_mean": n_pass,
+           "converged_fraction": float((fit.status == 0).float().mean().item()),
+           "segments": {k: {"ms": v["ms"], "frac": v["frac"], "bound": v["bound"]} for k, v in segs.items()},
+           "roofline": dict(segs[dom], segment=dom)}
+    if variable in LIMITER:
+        res["limiter"] = LIMITER[variable]
+    del y, solver
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
 
     from attrici_b200 import _lib, synthetic
-    from attrici_b200.solver import CellBatchSolver
+    from attrici_b200.solver import CellBatchSolver, cell_seeds
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -300,119 +442,119 @@ def run_cuda(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # whatever level is asked for: not on stdout
         dist.init_process_group("nccl", device_id=torch.device(device))
 
+    variable = args.workload
     C, T = args.cells, T_DAYS
-    y = synthetic.tas_tile_torch(C, T, seed=1234 + rank, device=device, nan_fraction=0.001)
     gmt, days = synthetic.ssa_gmt(T), synthetic.time_axis(T)   # SSA-smoothed GMT (library kernels), configs[1]
-    solver = CellBatchSolver("tas", modes=MODES, device=device, profile=os.environ.get("ATTRICI_NO_FUSED") == "1")
+    normal = variable == "tas"
+    if normal:
+        y = synthetic.tas_tile_torch(C, T, seed=1234 + rank, device=device, nan_fraction=0.001)
+        seeds = None
+    else:
+        y = family_tile(variable, C, T, device, seed=4321 + rank)
+        lat, lon = synthetic.tile_coordinates(100, (C + 99) // 100)
+        seeds = cell_seeds(0, lat[:C], lon[:C]) if variable == "pr" else None
+    solver = CellBatchSolver(variable, modes=MODES, device=device, profile=os.environ.get("ATTRICI_NO_FUSED") == "1")
     solver.set_predictor(days, gmt, C)
     P = solver.n_params
     gathered = torch.empty((world * C, P), dtype=torch.float64, device=device) if world > 1 else None
-
-    # pre-allocated outputs: nothing but the library's kernels runs between the events of a step
-    cfact = torch.empty((T, C), dtype=torch.float64, device=device)
-    seg_names = ("scale", "fit", "quantile_map")
-
-    def step(ev=None):
-        """scale -> fit -> quantile map, outputs left in HBM.  The scaled series is an intermediate the
-        Normal family does not materialise (report_variables = cfact, replaced)."""
-        if ev:
-            ev[0].record()
-        ys, scaling = solver.scale(y, None, keep_scaled=False)
-        if ev:
-            ev[1].record()
-        fit = solver.fit(ys)
-        if ev:
-            ev[2].record()
-        _, replaced, _ = solver.quantile_map(y, ys, fit.params, scaling, out=cfact)
-        if ev:
-            ev[3].record()
-        if world > 1:  # the path's one collective: final gather of the per-cell coefficients
-            dist.all_gather_into_tensor(gathered, fit.params)
-        return fit
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def after_step(fit):
+        if world > 1:  # the path's one collective: final gather of the per-cell coefficients
+            dist.all_gather_into_tensor(gathered, fit.params)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        fit = step()
-    barrier()
+    launches0 = [0]
+
+    def counted_barrier():
+        barrier()
+        launches0.append(_lib.launch_count())
+
+    # the scaled series is an intermediate the Normal family does not materialise (report_variables = cfact, replaced)
+    ms, seg_ms, fit, (t_begin, t_end) = measure_device(solver, y, seeds, args.steps, max(args.warmup, 3), keep_scaled=not normal,
+                                                       barrier=counted_barrier, after_step=after_step)
+    sampler.t_begin, sampler.t_end = t_begin, t_end
+    clocks = sampler.stop()
+    # launches between the barrier before the timed steps and the one after them (the second and third barrier)
+    launches = launches0[3] - launches0[2]
     n_pass = fit.n_pass.cpu().numpy()
     status = fit.status.cpu().numpy()
-    _lib.fit_profile(reset=True)
-    launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    seg_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    barrier()
-    sampler.begin_region()
-    ev0.record()
-    for k in range(args.steps):
-        step(seg_ev[k])
-    ev1.record()
-    barrier()
-    sampler.end_region()
-    clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    seg_ms = [sum(e[i].elapsed_time(e[i + 1]) for e in seg_ev) / args.steps for i in range(3)]
-    launches = _lib.launch_count() - launches0
-    pass_ms, pass_launches, cell_days = _lib.fit_profile(reset=True)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * C * args.steps / (ms / 1e3)
 
-    # end to end through the host API: pinned host buffers, copies inside the timed region
-    del cfact, fit
+    # ---- end to end through the host API: pinned host buffers, copies inside the timed region ----
+    del fit
     y_host = torch.empty((T, C), dtype=torch.float32, pin_memory=True)
     y_host.copy_(y)
     del y
     torch.cuda.empty_cache()
-    solver_h = CellBatchSolver("tas", modes=MODES, device=device)
-    res = solver_h.detrend_host(y_host, days, gmt, slab_cells=args.slab)  # warm-up, allocates pinned outputs
+    solver_h = CellBatchSolver(variable, modes=MODES, device=device)
     e2e_steps = max(1, min(args.steps, 3))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res = solver_h.detrend_host(y_host, days, gmt, slab_cells=args.slab, out=res)
-        _ = float(res["logp"][0])  # result read on the host
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * C * e2e_steps / e2e_s
-    h2d = y_host.numel() * 4 + T * 12
-    d2h = sum(int(v.numel() * v.element_size()) for k, v in res.items()
-              if isinstance(v, torch.Tensor) and not k.startswith("_") and k != "replaced_sparse")
-    if res.get("replaced_sparse") is not None:
-        d2h += int(res["replaced_sparse"].numel() * 4)
+
+    def e2e_run(**kw):
+        res = solver_h.detrend_host(y_host, days, gmt, seeds=seeds, slab_cells=args.slab, **kw)  # warm-up, allocates pinned outputs
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res = solver_h.detrend_host(y_host, days, gmt, seeds=seeds, slab_cells=args.slab, out=res, **kw)
+            _ = float(res["logp"][0])  # result read on the host
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        d2h = sum(int(v.numel() * v.element_size()) for k, v in res.items()
+                  if isinstance(v, torch.Tensor) and not k.startswith("_") and k != "replaced_sparse")
+        if res.get("replaced_sparse") is not None:
+            d2h += int(res["replaced_sparse"].numel() * 4)
+        return world * C * e2e_steps / dt, d2h
+
+    h2d = y_host.numel() * 4 + T * 12 + (4 * C if seeds is not None else 0)
+    # the reference's outputs: float64 counterfactual + the replacement flags (as the list of their non-zero entries),
+    # slabs of cells contiguous in host memory
+    e2e_value, d2h = e2e_run(replaced="sparse", slab_major=True)
+    variants = {}
+    if rank == 0 or world > 1:
+        v, b = e2e_run(cfact_dtype=torch.float32, replaced="sparse", slab_major=True)
+        variants["float32_cfact"] = {"value": v, "unit": UNIT, "d2h_bytes_per_step": b,
+                                     "note": "opt-in: the FP64 result rounded once to the dtype of the input files"}
+        v, b = e2e_run(replaced="dense", slab_major=False)
+        variants["dense_time_major"] = {"value": v, "unit": UNIT, "d2h_bytes_per_step": b,
+                                        "note": "round-1 layout: [T x C] float64 + uint8 plane, pitched copies"}
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        # algorithmic bytes per cell-day of each segment (DESIGN.md "Kernels and rooflines"):
-        #   scale: the series is read twice (min/max, then scaling + per-phase sums)          8 B
-        #   quantile map: float32 observation in, float64 counterfactual + uint8 flag out     13 B
-        #   fit: per pass 3 float64 sums per phase instead of the series (1461 x 24 B per cell and pass)
-        seg_bytes = {"scale": 8.0 * T * C, "quantile_map": 13.0 * T * C,
-                     "fit": 24.0 * min(T, 1461) * C * float(n_pass.mean() + 1)}
-        segments = {n: {"ms": seg_ms[i], "share_of_step": seg_ms[i] / (ms / args.steps),
-                        "algorithmic_gbs": seg_bytes[n] / 1e9 / (seg_ms[i] / 1e3)}
-                    for i, n in enumerate(seg_names)}
-        dom = max(("scale", "quantile_map"), key=lambda n: segments[n]["ms"])
-        dom_kernel = {"scale": "prep_minmax_kernel + prep_scale_fold_kernel (2 launches)",
-                      "quantile_map": "qmap_fold_lean_kernel"}[dom]
-        achieved = segments[dom]["algorithmic_gbs"]
-        traffic = None
-        if C == TILE_CELLS:
-            traffic = (ncu_traffic("qmap_fold_lean_kernel") if dom == "quantile_map" else
-                       sum(filter(None, [ncu_traffic("prep_minmax_kernel"), ncu_traffic("prep_scale_fold_kernel")])) or None)
+        segs = segment_rooflines(variable, seg_ms, float(n_pass.mean()), T, C, peak)
+        step_ms = ms / args.steps
+        for v in segs.values():
+            v["share_of_step"] = v["ms"] / step_ms
+        dom = max(segs, key=lambda k: segs[k]["ms"])
+        roof = dict(segs[dom])
+        roof["segment"] = dom
+        roof["kernel"] = SEG_KERNEL.get((variable, dom), dom)
+        roof["launches"] = args.steps
+        roof["avg_launch_ms"] = segs[dom]["ms"]
+        roof["peak_source"] = (peak_src if roof["bound"] == "hbm" else
+                               "measured FP64 FMA rate of this pool's B200 (scripts/micro/fp64_peak.cu, profiles/r2_dmma_peak.txt)")
+        traffic, traffic_src = (ncu_traffic(roof["kernel"]) if C == TILE_CELLS and normal else (None, None))
+        roof["traffic"] = traffic
+        roof["traffic_unit"] = f"bytes per launch (ncu dram__bytes_read + write, profiles/{traffic_src})" if traffic_src else None
+        # the step as a whole against the HBM roofline: bytes that must move (series in once, counterfactual + flags out)
+        must = 13.0 * T * C
+        moved = sum(v.get("algorithmic_bytes", 0.0) for v in segs.values()) + (24.0 * 1464 * C * 2 if normal else 0.0)
+        whole = {"must_move_bytes": must, "frac_of_hbm_peak_must_move": must / 1e9 / (step_ms / 1e3) / peak,
+                 "moved_bytes_model": moved, "frac_of_hbm_peak_moved": moved / 1e9 / (step_ms / 1e3) / peak}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and normal:
             cores = min(host_cores(), 64)
             with cpu_pool(cores) as pool:
                 wall, r = cpu_sample(pool, cores)
@@ -420,29 +562,34 @@ def run_cuda(args):
             cpu = {"value": cores / wall, "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": f"{cores} cells of the same tile, one process per core; {CPU_KIND_TEXT[kind]}; "
                              f"{int(np.mean([x[1] for x in r]))} objective evaluations per cell on average"}
+        workloads = None
+        if world == 1 and normal and not args.no_workloads:
+            del solver
+            torch.cuda.empty_cache()
+            workloads = {}
+            for wv in ("pr", "sfcWind", "hurs", "rsds"):
+                workloads[wv] = run_workload(wv, device, C, T, days, gmt, steps=3, warmup=3, barrier=barrier)
+        cfg = bench_config(C)   # identical for both arms; per-arm measurements live outside of it
+        cfg["workload"] = WORKLOADS[variable]
+        fit_stats = {"passes_per_cell_mean": float(n_pass.mean()), "passes_per_cell_max": int(n_pass.max()),
+                     "converged_fraction": float((status == 0).mean())}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 scaling (bit-exact), f64 sums/likelihood/solve/quantile map",
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 (sums, likelihood, solve, quantile map; f32 bit-exact scaling, TF32 tensor-core Fisher moments)",
             "data": "synthetic",
-            "config": {"workload": "tas Gaussian 100x100-cell tile, T=43464, modes=4 (BASELINE configs[1])",
-                       "cells_per_gpu": C, "days": T, "modes": MODES,
-                       "l2": "inputs larger than L2 (1.74 GB float32 series per tile, streamed three times per step)",
-                       "report_variables": ["cfact", "replaced"],
-                       "passes_per_cell_mean": float(n_pass.mean()), "passes_per_cell_max": int(n_pass.max()),
-                       "converged_fraction": float((status == 0).mean())},
+            "config": cfg,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "slab_cells": args.slab, "cpus_bound_per_rank": bound_cpus},
+                    "steps": e2e_steps, "slab_cells": args.slab, "cpus_bound_per_rank": bound_cpus,
+                    "outputs": "float64 cfact, replaced as sparse (day, cell, code) list, slab-major host layout",
+                    "variants": variants},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read + write, profiles/r1_traffic.json)",
-                         "algorithmic_bytes": seg_bytes[dom], "peak_source": peak_src,
-                         "launches": args.steps, "avg_launch_ms": segments[dom]["ms"],
-                         "share_of_step": segments[dom]["share_of_step"]},
-            "segments": segments,
-            "fit_passes": {"launches": int(pass_launches), "avg_launch_ms": pass_ms / max(pass_launches, 1),
-                           "share_of_step": pass_ms / ms},
+            "roofline": roof,
+            "segments": segs,
+            "whole_step": whole,
+            "fit_stats": fit_stats,
+            "workloads": workloads,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
@@ -460,6 +607,10 @@ def main():
     ap.add_argument("--cells", type=int, default=TILE_CELLS, help="cells per GPU (default: the 100x100 tile)")
     ap.add_argument("--slab", type=int, default=2048, help="cells per device slab of the host pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="tas", choices=sorted(WORKLOADS),
+                    help="variable of the tile (default tas = BASELINE configs[1]; the default single-GPU tas run also "
+                         "reports pr / sfcWind / hurs / rsds under \"workloads\")")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the other workloads in the default run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -15,7 +15,7 @@ run() {  # name, env assignments...
 import json
 try:
     d = json.load(open("gpurun_out/bench_${TAG}_$name.json"))
-    print("$name", "value", round(d["value"]), "ms", round(d["ms_per_step"], 3), {k: round(v["ms"], 3) for k, v in d["segments"].items()}, "e2e", round(d["e2e"]["value"]), d["config"].get("passes_per_cell_mean"))
+    print("$name", "value", round(d["value"]), "ms", round(d["ms_per_step"], 3), {k: round(v["ms"], 3) for k, v in d["segments"].items()}, "e2e", round(d["e2e"]["value"]), d.get("fit_stats",{}).get("passes_per_cell_mean"))
 except Exception as e:
     print("$name", "failed", e)
 PY

@@ -224,3 +224,36 @@ def test_provenance_attributes(tmp_path):
     nc = netcdf_file(path, "r", mmap=False)
     assert tomllib.loads(nc.attrici_config.decode())["variable"] == "tas" and nc.note == b"synthetic"
     nc.close()
+
+
+def test_writer_takes_slab_major_and_sparse_results(tmp_path):
+    """``ColumnBlocks`` (per-slab [T, n_k] blocks of ``detrend_host(slab_major=True)``) and ``SparseReplaced`` (the
+    (day, cell, code) list of ``replaced="sparse"``) are written like the dense [T, C] arrays they stand for."""
+    import torch
+    from scipy.io import netcdf_file
+
+    from attrici_b200 import io as aio
+
+    rng = np.random.default_rng(3)
+    T, C = 37, 11
+    lat, lon = np.repeat([10.25, 10.75], 6)[:C], np.tile(np.arange(6) * 0.5 + 3.25, 2)[:C]
+    cfact = rng.normal(size=(T, C))
+    rep = (rng.random((T, C)) < 0.05).astype(np.uint8) * rng.integers(1, 4, size=(T, C)).astype(np.uint8)
+    entries = np.array([(t, c, rep[t, c]) for t in range(T) for c in range(C) if rep[t, c]], dtype=np.int32).reshape(-1, 3)
+    entries = entries[rng.permutation(len(entries))]                      # the kernel appends in no particular order
+    assert np.array_equal(aio.dense_replaced(entries, T, C), rep)
+    blocks = aio.ColumnBlocks([torch.from_numpy(cfact[:, :4].copy()), torch.from_numpy(cfact[:, 4:9].copy()),
+                               torch.from_numpy(cfact[:, 9:].copy())])
+    assert blocks.shape == (T, C) and np.array_equal(blocks[5:9].numpy(), cfact[5:9])
+    assert np.array_equal(blocks.columns([0, 4, 10]).numpy(), cfact[:, [0, 4, 10]])
+    sparse = aio.SparseReplaced(entries, T, C)
+    assert np.array_equal(sparse[3:20].numpy(), rep[3:20])
+    a, b = str(tmp_path / "a.nc"), str(tmp_path / "b.nc")
+    aio.write_merged_output(a, {"cfact": cfact, "replaced": rep}, lat, lon, np.arange(T, dtype=np.int32), replaced_as_flags=False)
+    aio.write_merged_output(b, {"cfact": blocks, "replaced": sparse}, lat, lon, np.arange(T, dtype=np.int32),
+                            replaced_as_flags=False)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    aio.write_merged_output(b, {"cfact": blocks, "replaced": sparse}, lat, lon, np.arange(T, dtype=np.int32))
+    with netcdf_file(b, mmap=False) as f:
+        flags = f.variables["replaced"][:].reshape(T, -1)
+    assert np.isnan(flags).sum() == (rep == 1).sum() and np.isposinf(flags).sum() == (rep == 2).sum()
