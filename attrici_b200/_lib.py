@@ -83,6 +83,11 @@ _SIGNATURES = {
     "attrici_quantile_map": (_i, [_vp, _sz, C.POINTER(Variable), _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _i64, _vp]),
     "attrici_eval_parameter": (_i, [_vp, _sz, C.POINTER(Variable), _i, _i, _vp, _i, _i, _vp, _i64, _vp]),
+    "attrici_window_workspace_bytes": (_i, [_i, C.POINTER(_sz)]),
+    "attrici_window_fit": (_i, [_vp, _sz, C.POINTER(Variable), _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
+                                 _vp, _vp, _vp]),
+    "attrici_window_quantile_map": (_i, [C.POINTER(Variable), _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                                          _vp]),
     "attrici_mt19937_uniform": (_i, [_vp, _i, _i, _vp, _i64, _vp]),
     "attrici_ssa_workspace_bytes": (_i, [_i, _i, C.POINTER(_sz)]),
     "attrici_ssa_first_component": (_i, [_vp, _i, _i, _vp, _vp, _sz, _i, C.c_double, _vp, _vp, _vp]),

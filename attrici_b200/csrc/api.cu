@@ -507,6 +507,57 @@ int attrici_eval_parameter(void* workspace, size_t workspace_bytes, const attric
     return launch_eval_parameter(ws, *var, params, which, counterfactual, out, ld_out, (cudaStream_t)stream);
 }
 
+int attrici_window_workspace_bytes(int C, size_t* bytes) {
+    if (!bytes || C < 1) { set_error("bytes is null or C < 1"); return ATTRICI_EINVAL; }
+    *bytes = window_workspace_bytes(C);
+    return 0;
+}
+
+int attrici_window_fit(void* workspace, size_t workspace_bytes, const attrici_variable_t* var, const float* y_scaled,
+                       int64_t ld, int T, int C, int i0, int i1, const double* gmt, const int32_t* run_start,
+                       const int32_t* run_first_doy, const int32_t* run_len, int n_runs, int window_size, double* params,
+                       double* logp, int32_t* status, int32_t* n_iter, void* stream) {
+    ATTRICI_TRY(check_var(var));
+    ATTRICI_TRY(check_shape(T, C, ld));
+    ATTRICI_TRY(check_window(T, i0, i1));
+    if (var->family != ATTRICI_NORMAL) {
+        set_error("the rolling-window model is implemented for the Normal family (tas, ps, rlds, rsds, tasskew)");
+        return ATTRICI_EUNSUPPORTED;
+    }
+    if (window_size < 1 || window_size % 2 == 0 || window_size / 2 + 2 > i1 - i0) {
+        set_error("window_size must be odd and shorter than the fit series, got %d", window_size);
+        return ATTRICI_EINVAL;
+    }
+    if (!y_scaled || !gmt || !run_start || !run_first_doy || !run_len || n_runs < 1 || !params || !logp) {
+        set_error("y_scaled / gmt / runs / params / logp is null");
+        return ATTRICI_EINVAL;
+    }
+    if (!workspace || ((uintptr_t)workspace & 255) != 0 || workspace_bytes < window_workspace_bytes(C)) {
+        set_error("window workspace: %zu bytes given, %zu needed (256-byte aligned)", workspace_bytes, window_workspace_bytes(C));
+        return ATTRICI_EWORKSPACE;
+    }
+    return launch_window_fit(workspace, y_scaled, ld, T, C, i0, i1, gmt, run_start, run_first_doy, run_len, n_runs, window_size,
+                             params, logp, status, n_iter, (cudaStream_t)stream);
+}
+
+int attrici_window_quantile_map(const attrici_variable_t* var, const float* y, const float* y_scaled, int64_t ld, int T, int C,
+                                const double* gmt, const int16_t* dayofyear, const double* params, const double* scaling,
+                                double* cfact, uint8_t* replaced, double* cfact_scaled, int64_t ld_out, void* stream) {
+    ATTRICI_TRY(check_var(var));
+    ATTRICI_TRY(check_shape(T, C, ld));
+    if (var->family != ATTRICI_NORMAL) {
+        set_error("the rolling-window model is implemented for the Normal family (tas, ps, rlds, rsds, tasskew)");
+        return ATTRICI_EUNSUPPORTED;
+    }
+    if (ld_out < C) { set_error("ld_out %lld < C=%d", (long long)ld_out, C); return ATTRICI_EINVAL; }
+    if (!y || !y_scaled || !gmt || !dayofyear || !params || !scaling || !cfact) {
+        set_error("y / y_scaled / gmt / dayofyear / params / scaling / cfact is null");
+        return ATTRICI_EINVAL;
+    }
+    return launch_window_qmap(*var, y, y_scaled, ld, T, C, gmt, dayofyear, params, scaling, cfact, replaced, cfact_scaled, ld_out,
+                              (cudaStream_t)stream);
+}
+
 int attrici_mt19937_uniform(const uint32_t* seeds, int C, int n, double* out, int64_t ld, void* stream) {
     if (!seeds || !out) { set_error("seeds / out is null"); return ATTRICI_EINVAL; }
     if (C < 1 || n < 1 || ld < C) { set_error("bad shape C=%d n=%d ld=%lld", C, n, (long long)ld); return ATTRICI_EINVAL; }

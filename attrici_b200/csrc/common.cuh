@@ -301,6 +301,14 @@ int launch_qmap_fold_scale(Workspace& ws, const attrici_variable_t& var, const f
                            double* cfact_scaled, int64_t ld_out, cudaStream_t s);
 int launch_eval_parameter(Workspace& ws, const attrici_variable_t& var, const double* params, int which,
                           int counterfactual, double* out, int64_t ld_out, cudaStream_t s);
+// rolling-window model of the Normal family (window.cu)
+size_t window_workspace_bytes(int C);
+int launch_window_fit(void* workspace, const float* ys, int64_t ld, int T, int C, int i0, int i1, const double* gmt,
+                      const int* run_start, const int* run_first, const int* run_len, int n_runs, int window_size,
+                      double* params, double* logp, int32_t* status, int32_t* n_iter, cudaStream_t s);
+int launch_window_qmap(const attrici_variable_t& var, const float* y, const float* ys, int64_t ld, int T, int C,
+                       const double* gmt, const int16_t* doy, const double* params, const double* scaling, double* cfact,
+                       uint8_t* replaced, double* cfact_scaled, int64_t ld_out, cudaStream_t s);
 int launch_mt19937(const uint32_t* seeds, int C, int n, double* out, int64_t ld, cudaStream_t s);
 
 }  // namespace attrici

@@ -220,6 +220,29 @@ ATTRICI_API int attrici_ssa_first_component(const double* x, int n, int window, 
                                 size_t workspace_bytes, int max_iter, double tol, int32_t* info, double* eigenvalue,
                                 void* stream);
 
+/* ---- rolling-window model (`--window-size`; attrici/util.py:107-172 collect_windows, attrici/estimation/
+ * model_pymc5.py:366-547; attrici/detrend.py:646-649 modes XOR window_size) - Normal family ----
+ * Every day of the year k = 1..366 has its own weights: mu(t) = a_k + b_k gmt(t), sigma(t) = exp(c_k), k = dayofyear(t),
+ * each with a N(0, 1) prior, fitted on the window_size days around every day t of the fit series [i0, i1) whose day of
+ * the year is k (series mirrored at both ends; day 366 = the windows around the day after each day 365).
+ *   run_start / run_first_doy / run_len [n_runs] (device int32): the fit series as runs of consecutive days with
+ *     consecutive days of the year (calendar years): first day relative to i0, its day of the year (1-based), length.
+ *     The integers come from the host (numpy / pandas `time.dt.dayofyear`), never from floating point on the device.
+ *   params [C x 3 x 366] out: weights_mu_longterm_intercept, weights_mu_longterm_trend, weights_sigma_longterm_intercept
+ *     (the reference's trace entries for the Normal family); logp [C] out: log posterior at the MAP;
+ *   status [C] out, n_iter [C] out (largest Newton iteration count of the cell's 366 problems), both nullable.
+ * Missing days are skipped inside the windows (the reference drops them before it windows by index).
+ * attrici_window_quantile_map: estimate_distribution (:435-447, :524-538) by day of the year + quantile map, rescale and
+ *   replacement as attrici_quantile_map; dayofyear [T] device int16 for the WHOLE axis. */
+ATTRICI_API int attrici_window_workspace_bytes(int C, size_t* bytes);
+ATTRICI_API int attrici_window_fit(void* workspace, size_t workspace_bytes, const attrici_variable_t* var, const float* y_scaled,
+                       int64_t ld, int T, int C, int i0, int i1, const double* gmt, const int32_t* run_start,
+                       const int32_t* run_first_doy, const int32_t* run_len, int n_runs, int window_size, double* params,
+                       double* logp, int32_t* status, int32_t* n_iter, void* stream);
+ATTRICI_API int attrici_window_quantile_map(const attrici_variable_t* var, const float* y, const float* y_scaled, int64_t ld, int T, int C,
+                                const double* gmt, const int16_t* dayofyear, const double* params, const double* scaling,
+                                double* cfact, uint8_t* replaced, double* cfact_scaled, int64_t ld_out, void* stream);
+
 /* ---- block bootstrap of the fitted trend (attrici/detrend.py:479-612; all five families) ----
  * The samples of a batch of cells are refitted as extra cells of a [T x R C] series (column r C + c) through
  * attrici_prep_scale_mask / attrici_fit_batch / attrici_eval_parameter; these four entries provide the rest.
