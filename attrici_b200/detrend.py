@@ -35,7 +35,7 @@ class Config:
     # ("all",)): beyond cfact / replaced, "y_scaled", "cfact_scaled", the distribution fields ("mu", "sigma", ...)
     # and their counterfactual twins ("mu_cfact", ...) come back in res["series"]
     report_variables: tuple = ("cfact", "replaced")
-    window_size: int = None      # rolling-window model: not implemented (like ModelScipy, model_scipy.py:58-59)
+    window_size: int = None      # rolling-window model (Normal family): detrend_cells(..., time=...) with datetime64 days
 
 
 def get_task_indices(indices_len, task_id, task_count):
@@ -309,8 +309,60 @@ def _slabs_on_device(solver, config, y_local, days, gmt, fit_window, seeds, trac
     return res
 
 
+def _detrend_cells_window(config, y, gmt_scaled, time, lat, lon, fit_window, gather, units):
+    """``detrend_cells`` for the rolling-window model (``config.window_size``; Normal family): slabs of cells through
+    ``window.WindowBatchSolver`` with everything of a slab resident on the device.  ``params`` is [C, 3, 366] in the order
+    of ``window.TRACE_KEYS``; ``time``: datetime64 days of the axis (the model is indexed by day of the year)."""
+    import os
+
+    import torch
+
+    from .window import WindowBatchSolver
+
+    if time is None or not np.issubdtype(np.asarray(time).dtype, np.datetime64):
+        raise TypeError("the rolling-window model needs time= as datetime64 days")
+    g = np.asarray(gmt_scaled, dtype=np.float64)
+    spec = create_variable(config.variable)
+    check_units(spec, units)
+    y = y if isinstance(y, torch.Tensor) else torch.from_numpy(np.asarray(y))
+    T, C = y.shape
+    dist, rank, world = _dist_info()
+    task_id, task_count = (rank, world) if world > 1 else (config.task_id, config.task_count)
+    idx = get_task_indices(C, task_id, task_count)
+    device = config.device or f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+    res = {"indices": idx}
+    n_local = len(idx)
+    keys = ("params", "logp", "status", "n_pass", "scaling")
+    local = {"params": np.zeros((n_local, 3, 366)), "logp": np.zeros(n_local), "status": np.zeros(n_local, np.int32),
+             "n_pass": np.zeros(n_local, np.int32), "scaling": np.zeros((n_local, 2))}
+    cfact = np.empty((T, n_local), dtype=np.float64)
+    replaced = np.empty((T, n_local), dtype=np.uint8)
+    if n_local:
+        solver = WindowBatchSolver(spec, config.window_size, device=device)
+        c0 = int(idx[0])
+        for a in range(0, n_local, config.slab_cells):
+            b = min(n_local, a + config.slab_cells)
+            out = solver.detrend_device(y[:, c0 + a:c0 + b].to(device), time, g, fit_window)
+            local["params"][a:b] = out["params"].cpu().numpy()
+            local["logp"][a:b] = out["logp"].cpu().numpy()
+            local["status"][a:b] = out["status"].cpu().numpy()
+            local["n_pass"][a:b] = out["n_iter"].cpu().numpy()
+            local["scaling"][a:b] = out["scaling"].cpu().numpy()
+            cfact[:, a:b] = out["cfact"].cpu().numpy()
+            replaced[:, a:b] = out["replaced"].cpu().numpy()
+    res["cfact"], res["replaced"] = cfact, replaced
+    if gather and world > 1:
+        counts = [len(get_task_indices(C, r, world)) for r in range(world)]
+        flat = dict(local, params=local["params"].reshape(n_local, -1))
+        got = gather_cells(flat, counts, dist, device)
+        got["params"] = got["params"].reshape(-1, 3, 366)
+        local = got
+    res.update({k: local[k] for k in keys})
+    return res
+
+
 def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather=True, out=None, units=None,
-                  trace=None):
+                  trace=None, time=None):
     """Detrend the cells of ``y`` ([T, C] float32 host array, time-major, cells stacked lat-major as
     attrici/detrend.py:672 does) that the reference's partition assigns to this rank.
 
@@ -344,7 +396,7 @@ def detrend_cells(config, y, gmt_scaled, days, lat, lon, fit_window=None, gather
     if config.window_size is not None and config.window_size % 2 == 0:
         raise ValueError("Window size must be an odd number")                          # detrend.py:648-649
     if config.window_size is not None:
-        raise NotImplementedError("Rolling window not implemented for the CUDA solver")
+        return _detrend_cells_window(config, y, gmt_scaled, time, lat, lon, fit_window, gather, units)
     g = np.asarray(gmt_scaled, dtype=np.float64)
     if g.ndim != 1:
         raise ValueError("GMT data must have dimension 'time'")                         # detrend.py:654-655

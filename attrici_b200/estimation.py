@@ -79,12 +79,18 @@ class ModelCuda:
 
     def __init__(self, distribution, parameters, observed, predictor, modes=None, window_size=None,
                  device="cuda:0", use_fp64=False, zero_init=False):
-        if window_size is not None:
-            # same restriction and exception as ModelScipy (model_scipy.py:58-59)
-            raise NotImplementedError("Rolling window not implemented for the CUDA solver")
-        if modes is None:
-            raise ValueError("modes must be given")
+        if (modes is None) == (window_size is None):
+            raise ValueError("Exactly one of `modes` and `window_size` must be set")   # detrend.py:646-647
         family = _family_of(distribution)
+        self._window_size = None
+        if window_size is not None:
+            # the reference's second model family (model_pymc5.py:366-547); built for the Normal family, the others
+            # raise like ModelScipy does for every family (model_scipy.py:58-59)
+            if family != _lib.NORMAL:
+                raise NotImplementedError("Rolling window is implemented for the Normal family only in the CUDA solver")
+            if int(window_size) % 2 == 0:
+                raise ValueError("Window size must be an odd number")                  # detrend.py:648-649
+            self._window_size = int(window_size)
         name = distribution.__name__
         expect = FAMILY_PARAMETERS[family]
         if tuple(parameters) != expect:
@@ -94,7 +100,8 @@ class ModelCuda:
                 raise ValueError(f"parameter {pname} of {name}: dependent={not dep} is not a model of the reference")
         self._distribution_class = distribution
         self._family = family
-        self._modes = int(modes)
+        self._modes = int(modes) if modes is not None else 1
+        self._time = _values(getattr(predictor, "time", np.zeros(0)))
         y = _values(observed).astype(np.float32)
         gmt = _values(predictor).astype(np.float64)
         if y.shape != gmt.shape or y.ndim != 1:
@@ -106,8 +113,25 @@ class ModelCuda:
         spec = VariableSpec("cell", family, _lib.SCALE_NONE)
         self._solver = CellBatchSolver(spec, modes=self._modes, device=device, use_fp64=use_fp64, zero_init=zero_init)
 
+    def _window_solver(self):
+        from .window import WindowBatchSolver
+
+        if not np.issubdtype(self._time.dtype, np.datetime64):
+            raise TypeError("the rolling-window model needs a datetime64 time coordinate (day of the year)")
+        return WindowBatchSolver(self._solver.spec, self._window_size, device=self._solver.device)
+
     def fit(self, **kwargs):
-        """Returns the SciPy trace schema ``{"logp": float, "params": ndarray[P]}`` (model_scipy.py:524-527)."""
+        """Returns the SciPy trace schema ``{"logp": float, "params": ndarray[P]}`` (model_scipy.py:524-527); with
+        ``window_size`` the PyMC5 trace schema of the rolling-window model (``weights_<par>_longterm_intercept`` /
+        ``_trend`` of length 366 and ``logp``, model_pymc5.py:403-414, 686-689)."""
+        if self._window_size is not None:
+            from .window import trace_of
+
+            w = self._window_solver()
+            ys = torch.from_numpy(np.ascontiguousarray(self._y.reshape(-1, 1))).to(w.device)
+            params, logp, status, n_iter = w.fit(ys, self._time, self._gmt)
+            self._status, self._n_pass = int(status.item()), int(n_iter.item())
+            return trace_of(params[0].cpu().numpy(), logp.item())
         s = self._solver
         s.set_predictor(self._days, self._gmt, 1)
         y = torch.from_numpy(np.ascontiguousarray(self._y.reshape(-1, 1))).to(s.device)
@@ -124,6 +148,14 @@ class ModelCuda:
         """Per-day distribution parameters on ``predictor``'s time axis (phase origin = its first day, as
         model_scipy.py:565-567 re-sets the predictor data) wrapped in the distribution class given to the
         constructor."""
+        if self._window_size is not None:
+            # estimate() of the rolling-window parameter classes (model_pymc5.py:435-447, 524-538): weights by day of year
+            from .window import TRACE_KEYS, dayofyear
+
+            k = dayofyear(_values(predictor.time)).astype(np.int64) - 1
+            g = _values(predictor).astype(np.float64)
+            a, b, c = (np.asarray(trace[key], dtype=np.float64) for key in TRACE_KEYS)
+            return self._distribution_class(mu=a[k] + b[k] * g, sigma=np.exp(c[k]))
         s = self._solver
         gmt = _values(predictor).astype(np.float64)
         s.set_predictor(_day_offsets(predictor), gmt, 1)

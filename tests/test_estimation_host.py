@@ -56,10 +56,12 @@ def test_day_offsets():
 
 def test_constructor_rejects_what_the_reference_rejects():
     obs, pred = Arr(np.zeros(50, np.float32), TIME), Arr(np.linspace(0, 1, 50), TIME)
-    with pytest.raises(NotImplementedError):                                          # model_scipy.py:58-59
+    with pytest.raises(ValueError, match="Exactly one of"):                           # detrend.py:646-647
         ModelCuda(Normal, NORMAL_PARS, obs, pred, modes=4, window_size=31)
-    with pytest.raises(ValueError, match="modes must be given"):
+    with pytest.raises(ValueError, match="Exactly one of"):
         ModelCuda(Normal, NORMAL_PARS, obs, pred)
+    with pytest.raises(ValueError, match="odd"):                                      # detrend.py:648-649
+        ModelCuda(Normal, NORMAL_PARS, obs, pred, window_size=30)
     with pytest.raises(ValueError, match="not supported"):                            # unknown distribution class
         ModelCuda(dict, NORMAL_PARS, obs, pred, modes=4)
     with pytest.raises(ValueError, match="in this order"):                            # theta layout = dict order
