@@ -35,8 +35,10 @@ namespace attrici {
 
 namespace {
 
-constexpr int FF_WARPS = 12;          // one CTA per SM: the pair tables (127 KB) live in shared memory once
-constexpr int FF_THREADS = 32 * FF_WARPS;
+// one CTA per SM (the pair tables, 127 KB, live in shared memory once).  12 warps leave 168 registers per thread, with
+// which the sweep spills a few loop-invariant values; registers are allocated for multiples of four warps, so the
+// alternative without spills is 8 warps (255 registers) - ATTRICI_FUSED_WARPS=8 selects it (A/B measurements)
+constexpr int FF_WARPS_MAX = 12;
 constexpr int FF_WPITCH = 36;          // floats per row of the weight transposition buffer (36 = 4 mod 32: conflict-free fragments)
 constexpr int FF_SWEEPS = FUSED_TP / 32;   // 23
 
@@ -78,6 +80,15 @@ __device__ __forceinline__ double ff_wsum(double v) {
 // cell's momd rows (global, read back by the step code of this warp).
 //   mode PASS_NLL: row NACC only; PASS_GRAD: + gradient moments; PASS_FULL / PASS_FLAT: + Fisher moments
 //   (PASS_FLAT: only the two intercepts are non-zero - no predictor chain, one exp)
+// shared-memory load the compiler may not merge with an earlier one of the same address (RELOAD: the trig values of the
+// pair are read again for the gradient moments instead of staying in 16 registers across the exp / residual section)
+__device__ __forceinline__ double ff_lds(const double* p) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+
+template <bool RELOAD, bool PREFETCH>
 __device__ __forceinline__ void fused_pass(const FusedArgs& a, const double* tab_d, const float* tab_f, int cell, int mode,
                                            const double* th, uint32_t* W, double* mom) {
     const int lane = threadIdx.x & 31;
@@ -103,23 +114,42 @@ __device__ __forceinline__ void fused_pass(const FusedArgs& a, const double* tab
 
     // the cell's sums of the next sweep are requested before the current one is evaluated.  Lanes beyond the last
     // pair, and the mirror of pair 0, read the zero padding of the rows (phases 1461 .. FUSED_SP - 1): no selects
+    // PREFETCH: the next sweep's six segments are requested with prefetch.global.L1 (no registers held across the
+    // sweep); otherwise they are loaded one sweep ahead into registers
     double nx[6];
-    auto request = [&](int sweep, double (&v)[6]) {
+    auto index_of = [&](int sweep, int& qi, int& qm) {
         const int q = sweep * 32 + lane;
-        const int qi = q < FUSED_NPAIR ? q : NPHASE;
-        const int qm = (q < FUSED_NPAIR && q > 0) ? NPHASE - q : NPHASE;
+        qi = q < FUSED_NPAIR ? q : NPHASE;
+        qm = (q < FUSED_NPAIR && q > 0) ? NPHASE - q : NPHASE;
+    };
+    auto request = [&](int sweep, double (&v)[6]) {
+        int qi, qm;
+        index_of(sweep, qi, qm);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             v[k] = __ldg(ys + k * FUSED_SP + qi);
             v[3 + k] = __ldg(ys + k * FUSED_SP + qm);
         }
     };
-    request(0, nx);
+    auto prefetch = [&](int sweep) {
+        int qi, qm;
+        index_of(sweep, qi, qm);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ys + k * FUSED_SP + qi));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(ys + k * FUSED_SP + qm));
+        }
+    };
+    if (PREFETCH) prefetch(0); else request(0, nx);
 #pragma unroll 1
     for (int sweep = 0; sweep < FF_SWEEPS; ++sweep) {
         const int q = sweep * 32 + lane;
+        if (PREFETCH) {
+            if (sweep + 1 < FF_SWEEPS) prefetch(sweep + 1);
+            request(sweep, nx);
+        }
         const double sy = nx[0], syy = nx[1], syg = nx[2], sym = nx[3], syym = nx[4], sygm = nx[5];
-        if (sweep + 1 < FF_SWEEPS) request(sweep + 1, nx);
+        if (!PREFETCH && sweep + 1 < FF_SWEEPS) request(sweep + 1, nx);
         double n, sg, sgg, nm, sgm, sggm;
         if (own) {
             // a cell with missing days: its own day count per phase, and its own gmt sums where days are missing
@@ -175,12 +205,14 @@ __device__ __forceinline__ void fused_pass(const FusedArgs& a, const double* tab
             GA[0] += w0c; GA[NB] += w1c; GB[0] += wbc;
 #pragma unroll
             for (int k = 0; k < MAXM; ++k) {
-                GA[1 + k] = fma(w0c, ck[k], GA[1 + k]);
-                GA[1 + MAXM + k] = fma(w0s, sk[k], GA[1 + MAXM + k]);
-                GA[NB + 1 + k] = fma(w1c, ck[k], GA[NB + 1 + k]);
-                GA[NB + 1 + MAXM + k] = fma(w1s, sk[k], GA[NB + 1 + MAXM + k]);
-                GB[1 + k] = fma(wbc, ck[k], GB[1 + k]);
-                GB[1 + MAXM + k] = fma(wbs, sk[k], GB[1 + MAXM + k]);
+                const double c_k = RELOAD ? ff_lds(tab_d + k * FUSED_TP + q) : ck[k];
+                const double s_k = RELOAD ? ff_lds(tab_d + (MAXM + k) * FUSED_TP + q) : sk[k];
+                GA[1 + k] = fma(w0c, c_k, GA[1 + k]);
+                GA[1 + MAXM + k] = fma(w0s, s_k, GA[1 + MAXM + k]);
+                GA[NB + 1 + k] = fma(w1c, c_k, GA[NB + 1 + k]);
+                GA[NB + 1 + MAXM + k] = fma(w1s, s_k, GA[NB + 1 + MAXM + k]);
+                GB[1 + k] = fma(wbc, c_k, GB[1 + k]);
+                GB[1 + MAXM + k] = fma(wbs, s_k, GB[1 + MAXM + k]);
             }
         }
         if (fisher) {
@@ -265,10 +297,12 @@ constexpr size_t FF_TABD_BYTES = sizeof(double) * FUSED_ND * FUSED_TP;
 constexpr size_t FF_TABF_BYTES = sizeof(float) * 16 * FUSED_FP;
 constexpr size_t FF_HTAB_BYTES = (sizeof(HEntry) * NTRI + 15) / 16 * 16;
 constexpr size_t FF_WARP_BYTES = (sizeof(FusedScratch) + sizeof(uint32_t) * 16 * FF_WPITCH + sizeof(double) * 32 + 15) / 16 * 16;
-constexpr size_t FF_SMEM_BYTES = FF_TABD_BYTES + FF_TABF_BYTES + FF_HTAB_BYTES + FF_WARPS * FF_WARP_BYTES;
-static_assert(FF_SMEM_BYTES <= 227 * 1024, "fused fit: shared memory of one CTA");
+constexpr size_t ff_smem_bytes(int warps) { return FF_TABD_BYTES + FF_TABF_BYTES + FF_HTAB_BYTES + warps * FF_WARP_BYTES; }
+static_assert(ff_smem_bytes(FF_WARPS_MAX) <= 227 * 1024, "fused fit: shared memory of one CTA");
 
-__global__ void __launch_bounds__(FF_THREADS, 1) fit_fused_kernel(FusedArgs a) {
+template <int FF_WARPS, bool RELOAD, bool PREFETCH>
+__global__ void __launch_bounds__(32 * FF_WARPS, 1) fit_fused_kernel(FusedArgs a) {
+    constexpr int FF_THREADS = 32 * FF_WARPS;
     extern __shared__ __align__(16) unsigned char ff_smem[];
     double* tab_d = reinterpret_cast<double*>(ff_smem);
     float* tab_f = reinterpret_cast<float*>(ff_smem + FF_TABD_BYTES);
@@ -309,7 +343,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) fit_fused_kernel(FusedArgs a) {
             }
             if (lane < NP) th[lane] = a.st.th_pass[(size_t)lane * cp + cell];
             __syncwarp();
-            fused_pass(a, tab_d, tab_f, cell, mode, th, Wb, Sw.mom);
+            fused_pass<RELOAD, PREFETCH>(a, tab_d, tab_f, cell, mode, th, Wb, Sw.mom);
             if (final_pass) {   // cell_store takes the sum of the day terms from the momd row
                 if (lane == 0) const_cast<double*>(a.st.momd)[(size_t)NACC * cp + cell] = Sw.mom[NACC];
                 __syncwarp();
@@ -416,11 +450,27 @@ int launch_fit_fused(Workspace& ws, const StepParams& sp, int fisher_passes, int
     a.work = ws.counters + 8;
     a.fisher_passes = fisher_passes; a.chord_passes = chord_passes;
     ATTRICI_CUDA_CHECK(cudaMemsetAsync(a.work, 0, sizeof(int), s));
+    static const int warps = [] {
+        const char* e = getenv("ATTRICI_FUSED_WARPS");
+        const int w = e ? atoi(e) : 12;
+        return w == 8 ? 8 : 12;   // (variant 3 below runs 8 warps by itself)
+    }();
     int ctas = 148;   // persistent: one CTA per SM, cells handed out through a.work
-    const int need = (ws.C + FF_WARPS - 1) / FF_WARPS;
+    const int need = (ws.C + warps - 1) / warps;
     if (ctas > need) ctas = need;
-    ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(fit_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM_BYTES));
-    fit_fused_kernel<<<ctas, FF_THREADS, FF_SMEM_BYTES, s>>>(a);
+    auto launch = [&](auto kernel, int w) -> int {
+        ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ff_smem_bytes(w)));
+        kernel<<<ctas, 32 * w, ff_smem_bytes(w), s>>>(a);
+        return 0;
+    };
+    // measured (10 000 cells): trig values re-read for the gradient moments 1.70 -> 1.52 ms (fewer spills at 168 registers)
+    static const int variant = [] { const char* e = getenv("ATTRICI_FUSED_VARIANT"); return e ? atoi(e) : 0; }();
+    // and the next sweep's sums requested by prefetch.global.L1 instead of held in registers 1.52 -> 1.39 ms; 8 warps
+    // (no spills at all, a third fewer warps) 1.59 ms
+    if (warps == 8) ATTRICI_TRY(launch(fit_fused_kernel<8, true, true>, 8));
+    else if (variant == 1) ATTRICI_TRY(launch(fit_fused_kernel<12, false, false>, 12));
+    else if (variant == 2) ATTRICI_TRY(launch(fit_fused_kernel<12, true, false>, 12));
+    else ATTRICI_TRY(launch(fit_fused_kernel<12, true, true>, 12));
     ATTRICI_LAUNCH_CHECK();
     return 0;
 }

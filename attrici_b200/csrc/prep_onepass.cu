@@ -21,6 +21,7 @@
 // every (cell, phase) is stored (one byte); a phase that lost days also gets its own {n, sum g, sum g^2}.
 #include <stdlib.h>
 #include "common.cuh"
+#include "bulk.cuh"
 
 namespace attrici {
 
@@ -54,6 +55,12 @@ struct OnePassArgs {
 
 __device__ __forceinline__ float op_nan() { return __int_as_float(0x7fc00000); }
 
+// ---- bulk asynchronous copies (TMA engine, cp.async.bulk) completing on an mbarrier ----------------------------
+constexpr int OP_NS = 3;       // stages of the input ring of the TMA variant (each one batch of OP_U days)
+
+// barrier of the OP_THREADS consumer threads only (the producer warp of the TMA variant has left by then)
+__device__ __forceinline__ void op_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(OP_THREADS) : "memory"); }
+
 template <int V> __device__ __forceinline__ void op_load(const float* p, float (&v)[V]);
 template <> __device__ __forceinline__ void op_load<1>(const float* p, float (&v)[1]) { v[0] = __ldg(p); }
 template <> __device__ __forceinline__ void op_load<2>(const float* p, float (&v)[2]) {
@@ -61,13 +68,22 @@ template <> __device__ __forceinline__ void op_load<2>(const float* p, float (&v
     v[0] = t.x; v[1] = t.y;
 }
 
-template <int V>
-__global__ void __launch_bounds__(OP_THREADS) prep_onepass_kernel(OnePassArgs a, int nj_max) {
+// MASKS: the variable has threshold masks (in place: hurs / tasrange / wind; fit only: tasskew); without them the only
+// invalid values are NaN and +-Inf, one comparison per value
+// TMA: the CTA's rows are brought into a shared-memory ring by bulk asynchronous copies (cp.async.bulk, one 1 KB row
+// segment per day, issued by one thread and completing on an mbarrier per stage) instead of per-thread loads into a
+// register double buffer: OP_NS batches of OP_U days ahead of the arithmetic, no load / address instruction and no
+// register copy in the issue stream.  Needs 16-byte aligned row segments (leading dimension and C multiples of 4).
+template <int V, bool MASKS, bool TMA>
+__global__ void __launch_bounds__(OP_THREADS + 32) prep_onepass_kernel(OnePassArgs a, int nj_max) {
     constexpr int CW = OP_THREADS * V;
     extern __shared__ __align__(16) unsigned char op_smem[];
     double* g_s = reinterpret_cast<double*>(op_smem);                       // [ph_len][nj_max]
     double* stage = g_s + a.ph_len * nj_max;                                // [OP_STAGE][3][CW]
     int* stage_n = reinterpret_cast<int*>(stage + OP_STAGE * 3 * CW);       // [OP_STAGE][CW]
+    float* ring = reinterpret_cast<float*>(stage_n + OP_STAGE * CW);        // [OP_NS][OP_U][CW]   (TMA)
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (TMA ? OP_NS * OP_U * CW : 0));   // [OP_NS]
+    unsigned long long* empty = full + OP_NS;                                                                  // [OP_NS]
 
     const int tid = threadIdx.x;
     const int cta_cell0 = blockIdx.x * CW;
@@ -77,7 +93,7 @@ __global__ void __launch_bounds__(OP_THREADS) prep_onepass_kernel(OnePassArgs a,
     const int n_ph = NPHASE;
     const int d0 = chunk * a.ph_len, d1 = min(n_ph, d0 + a.ph_len);
     const int nph = d1 - d0;
-    for (int i = tid; i < nph * nj_max; i += OP_THREADS) {
+    for (int i = tid; i < nph * nj_max; i += (int)blockDim.x) {
         const int p = i / nj_max, j = i - p * nj_max;
         const int t = d0 + p + j * NPHASE;
         g_s[i] = (t < a.T) ? a.basis64[(size_t)t * B_STRIDE] : 0.0;
@@ -113,19 +129,64 @@ __global__ void __launch_bounds__(OP_THREADS) prep_onepass_kernel(OnePassArgs a,
 #pragma unroll
         for (int u = 0; u < OP_U; ++u) op_load<V>(a.y + row0 + (size_t)min(u, last) * jstride, vv[u]);
     };
+    // TMA variant: warp 4 is the producer.  Its lane 0 walks the CTA's batches, waits until the consumer warps have
+    // released the stage (empty barrier, one arrival per consumer warp), arms the full barrier with the byte count and
+    // issues one bulk copy per day; the four consumer warps never synchronise with each other for the input.
+    if (TMA) {
+        if (tid == 0) {
+            for (int st = 0; st < OP_NS; ++st) { bulk::mbar_init(full + st, 1); bulk::mbar_init(empty + st, OP_THREADS / 32); }
+            bulk::mbar_init_fence();
+        }
+        __syncthreads();
+        if (tid >= OP_THREADS) {
+            if (tid == OP_THREADS) {
+                const unsigned row_bytes = 4u * (unsigned)min(CW, a.C - cta_cell0);
+                int b = 0;
+                for (int pp = 0; pp < nph; ++pp) {
+                    const int njp = days_of(pp);
+                    for (int pj = 0; pj < njp; pj += OP_U, ++b) {
+                        const int st = b % OP_NS;
+                        if (b >= OP_NS) bulk::mbar_wait(empty + st, (unsigned)(((b / OP_NS) - 1) & 1));
+                        const int nu = min(OP_U, njp - pj);
+                        bulk::mbar_expect_tx(full + st, row_bytes * (unsigned)nu);
+                        const float* src = a.y + (size_t)(d0 + pp + pj * NPHASE) * a.ld + cta_cell0;
+                        for (int u = 0; u < nu; ++u)
+                            bulk::g2s(ring + ((size_t)st * OP_U + u) * CW, src + (size_t)u * jstride, row_bytes, full + st);
+                    }
+                }
+            }
+            return;
+        }
+    }
 
     double su[V], suu[V], sug[V];
     int cnt[V];
     float va[OP_U][V], vb[OP_U][V];
-    int p = 0, j0 = 0, ja = 0, jb = 0;
-    load_batch(0, 0, va);
+    int p = 0, j0 = 0, ja = 0, jb = 0, batch = 0;
+    if (!TMA) load_batch(0, 0, va);
     while (true) {
         const int d = d0 + p;
         const int nj = days_of(p);
         int pn = p, jn = j0 + OP_U;
         if (jn >= nj) { pn = p + 1; jn = 0; }
         const bool has_next = pn < nph;
-        if (has_next) load_batch(pn, jn, vb);
+        if (TMA) {
+            // this batch's rows have landed in stage batch % OP_NS; each thread takes its V columns of the OP_U days
+            const int st = batch % OP_NS;
+            bulk::mbar_wait(full + st, (unsigned)((batch / OP_NS) & 1));
+            const float* rp = ring + (size_t)st * OP_U * CW + tid * V;
+#pragma unroll
+            for (int u = 0; u < OP_U; ++u) {
+                if (V == 2) {
+                    const float2 t2 = *reinterpret_cast<const float2*>(rp + u * CW);
+                    va[u][0] = t2.x; va[u][V - 1] = t2.y;
+                } else {
+                    va[u][0] = rp[u * CW];
+                }
+            }
+        } else if (has_next) {
+            load_batch(pn, jn, vb);
+        }
         if (j0 == 0) {
             ja = a.i0 > d ? (a.i0 - d + NPHASE - 1) / NPHASE : 0;
             jb = a.i1 > d ? min(nj, (a.i1 - d + NPHASE - 1) / NPHASE) : 0;
@@ -135,22 +196,54 @@ __global__ void __launch_bounds__(OP_THREADS) prep_onepass_kernel(OnePassArgs a,
         const double* gp = g_s + p * nj_max + j0;
         const int last = nj - 1 - j0;
         const bool whole = last >= OP_U - 1 && j0 >= ja && j0 + OP_U <= jb;   // batch inside the phase and the window
+        if (whole) {
 #pragma unroll
-        for (int u = 0; u < OP_U; ++u) {
-            const bool in_phase = whole || u <= last;
-            const bool in_win = whole || (in_phase && j0 + u >= ja && j0 + u < jb);
-            const double g = gp[whole ? u : min(u, last)];
+            for (int u = 0; u < OP_U; ++u) {
+                const double g = gp[u];
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                float x = va[u][v];
-                if (x <= in_lo || x >= in_hi) x = op_nan();     // detrend.py:311, mask_thresholded (in place)
-                if (in_phase) { mn[v] = fminf(mn[v], x); mx[v] = fmaxf(mx[v], x); }   // NaN-skipping (variables.py:108-110)
-                const bool used = in_win && (x == x) && !(x <= fit_lo || x >= fit_hi);
-                const float xs = used ? x : pivf[v];            // unused days contribute u = 0
-                const double uu = (double)xs - piv[v];
-                su[v] += uu; suu[v] = fma(uu, uu, suu[v]); sug[v] = fma(uu, g, sug[v]);
-                cnt[v] += used ? 1 : 0;
+                for (int v = 0; v < V; ++v) {
+                    const float x = va[u][v];
+                    bool in_range, used;
+                    if (MASKS) {
+                        in_range = !(x <= in_lo || x >= in_hi) && (x == x);
+                        used = in_range && !(x <= fit_lo || x >= fit_hi);
+                    } else {
+                        in_range = used = fabsf(x) < INFINITY;          // false for NaN and +-Inf (detrend.py:311)
+                    }
+                    const float xm = in_range ? x : op_nan();
+                    mn[v] = fminf(mn[v], xm); mx[v] = fmaxf(mx[v], xm);    // NaN-skipping (variables.py:108-110)
+                    const float xs = used ? x : pivf[v];                   // unused days contribute u = 0
+                    const double uu = (double)xs - piv[v];
+                    su[v] += uu; suu[v] = fma(uu, uu, suu[v]); sug[v] = fma(uu, g, sug[v]);
+                    cnt[v] += used ? 1 : 0;
+                }
             }
+        } else {
+#pragma unroll
+            for (int u = 0; u < OP_U; ++u) {
+                const bool in_phase = u <= last;
+                const bool in_win = in_phase && j0 + u >= ja && j0 + u < jb;
+                const double g = gp[min(u, last)];
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    float x = va[u][v];
+                    if (x <= in_lo || x >= in_hi) x = op_nan();     // detrend.py:311, mask_thresholded (in place)
+                    if (in_phase) { mn[v] = fminf(mn[v], x); mx[v] = fmaxf(mx[v], x); }
+                    const bool used = in_win && (x == x) && !(x <= fit_lo || x >= fit_hi);
+                    const float xs = used ? x : pivf[v];
+                    const double uu = (double)xs - piv[v];
+                    su[v] += uu; suu[v] = fma(uu, uu, suu[v]); sug[v] = fma(uu, g, sug[v]);
+                    cnt[v] += used ? 1 : 0;
+                }
+            }
+        }
+        if (TMA) {
+            // The stage is released only here, after the arithmetic has consumed every value read from it.  Releasing
+            // it right after the shared-memory loads were ISSUED is a race: mbarrier.arrive does not wait for the
+            // warp's loads in flight, and the refill (three batches ahead, often an L2 hit) can land first - measured
+            // as a few hundred cells per 10 000 whose sums changed from run to run (scripts/check_race.py).
+            __syncwarp();
+            if ((tid & 31) == 0) bulk::mbar_arrive(empty + (batch % OP_NS));
         }
         if (pn != p) {
             // phase complete
@@ -160,7 +253,7 @@ __global__ void __launch_bounds__(OP_THREADS) prep_onepass_kernel(OnePassArgs a,
                 tot_u[v] += su[v]; tot_uu[v] += suu[v]; tot_n[v] += cnt[v];
                 if (cnt[v] == expected) {
                     if (expected > 0) first_day[v] = min(first_day[v], d + ja * NPHASE);
-                } else {
+                } else if (cell0 + v < a.C) {
                     // days are missing in this phase: its own {n, sum g, sum g^2} and first used day (rare)
                     double n = 0.0, sg = 0.0, sgg = 0.0;
                     const float* yp = a.y + (size_t)d * a.ld + min(col0 + v, a.C - 1);
@@ -192,7 +285,7 @@ __global__ void __launch_bounds__(OP_THREADS) prep_onepass_kernel(OnePassArgs a,
                 const int g0 = p & ~(OP_STAGE - 1);
                 const int ng = p - g0 + 1;
                 const int dg = d0 + g0;
-                __syncthreads();
+                if (TMA) op_consumer_sync(); else __syncthreads();
                 for (int i = tid; i < 3 * CW; i += OP_THREADS) {
                     const int k = i / CW, c = i - k * CW;
                     if (cta_cell0 + c < a.C) {
@@ -224,15 +317,17 @@ __global__ void __launch_bounds__(OP_THREADS) prep_onepass_kernel(OnePassArgs a,
                             for (int s = NPHASE; s < FUSED_SP; ++s) dst[s - dg] = 0;
                     }
                 }
-                __syncthreads();
+                if (TMA) op_consumer_sync(); else __syncthreads();
             }
         }
         if (!has_next) break;
+        if (!TMA) {
 #pragma unroll
-        for (int u = 0; u < OP_U; ++u)
+            for (int u = 0; u < OP_U; ++u)
 #pragma unroll
-            for (int v = 0; v < V; ++v) va[u][v] = vb[u][v];
-        p = pn; j0 = jn;
+                for (int v = 0; v < V; ++v) va[u][v] = vb[u][v];
+        }
+        p = pn; j0 = jn; ++batch;
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -316,7 +411,8 @@ int launch_prep_onepass(Workspace& ws, const attrici_variable_t& var, const floa
     a.fit_lo = (only_fit && has_lo) ? var.lower_threshold : -INFINITY;
     a.fit_hi = (only_fit && has_hi) ? var.upper_threshold : INFINITY;
     a.basis64 = ws.basis64;
-    const bool vec2 = (ld % 2 == 0) && ((uintptr_t)y % 8 == 0) && ws.C >= 2;
+    static const bool force_v1 = [] { const char* e = getenv("ATTRICI_ONEPASS_V"); return e && e[0] == '1'; }();   // tuning only
+    const bool vec2 = (ld % 2 == 0) && ((uintptr_t)y % 8 == 0) && ws.C >= 2 && !force_v1;
     const int V = vec2 ? 2 : 1;
     const int n_cb = (ws.C + OP_THREADS * V - 1) / (OP_THREADS * V);
     // partials live in the (otherwise idle) moment-partial buffer: 6 arrays of [chunk][Cp] 8-byte slots
@@ -348,17 +444,29 @@ int launch_prep_onepass(Workspace& ws, const attrici_variable_t& var, const floa
     a.st_cnt = ws.st_cnt; a.st_sum = ws.st_sum; a.st_sq = ws.st_sq; a.st_ln = ws.st_ln; a.st_first = ws.st_first;
     a.scaling_out = scaling;
     const int nj_max = (ws.T + NPHASE - 1) / NPHASE;
+    // bulk asynchronous copies need 16-byte aligned row segments
+    // measured (10 000 cells): 0.75 ms against 0.72 ms for the per-thread loads once the stage is released after use (the
+    // early release that made it 0.66 ms is a race, see the kernel) - the variant is opt-in: ATTRICI_TMA_PREP=1
+    static const bool tma_off = [] {
+        const char* e = getenv("ATTRICI_NO_TMA"); const char* f = getenv("ATTRICI_TMA_PREP");
+        return (e && e[0] == '1') || !(f && f[0] == '1');
+    }();
+    const bool tma = !tma_off && V == 2 && (ld % 4 == 0) && ((uintptr_t)y % 16 == 0) && (ws.C % 4 == 0);
     const size_t smem = sizeof(double) * ((size_t)a.ph_len * nj_max + (size_t)OP_STAGE * 3 * OP_THREADS * V) +
-                        sizeof(int) * (size_t)OP_STAGE * OP_THREADS * V;
+                        sizeof(int) * (size_t)OP_STAGE * OP_THREADS * V +
+                        (tma ? sizeof(float) * (size_t)OP_NS * OP_U * OP_THREADS * V + 16 * OP_NS : 0);
     if (smem > 200 * 1024) { set_error("series too long for the one-pass scaling kernel (T=%d)", ws.T); return ATTRICI_EUNSUPPORTED; }
     dim3 grid(n_cb, a.n_chunks);
-    if (V == 2) {
-        ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(prep_onepass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prep_onepass_kernel<2><<<grid, OP_THREADS, smem, s>>>(a, nj_max);
-    } else {
-        ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(prep_onepass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prep_onepass_kernel<1><<<grid, OP_THREADS, smem, s>>>(a, nj_max);
-    }
+    const bool masks = (in_place || only_fit) && (has_lo || has_hi);
+    const int threads = tma ? OP_THREADS + 32 : OP_THREADS;   // the TMA variant adds its producer warp
+    auto launch = [&](auto kernel) -> int {
+        ATTRICI_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, threads, smem, s>>>(a, nj_max);
+        return 0;
+    };
+    if (tma) ATTRICI_TRY(masks ? launch(prep_onepass_kernel<2, true, true>) : launch(prep_onepass_kernel<2, false, true>));
+    else if (V == 2) ATTRICI_TRY(masks ? launch(prep_onepass_kernel<2, true, false>) : launch(prep_onepass_kernel<2, false, false>));
+    else ATTRICI_TRY(masks ? launch(prep_onepass_kernel<1, true, false>) : launch(prep_onepass_kernel<1, false, false>));
     ATTRICI_LAUNCH_CHECK();
     prep_onepass_finalize_kernel<<<(ws.C + OP_THREADS - 1) / OP_THREADS, OP_THREADS, 0, s>>>(a);
     ATTRICI_LAUNCH_CHECK();

@@ -1,15 +1,16 @@
 #!/bin/bash
-# A/B on the GPU box: parity tests, then the bench with the default path and with env-selected variants
+# A/B on the GPU box: parity tests, then the bench with the default path and with env-selected variants.
+# Every step runs under its own short timeout (a handshake bug must cost minutes, not the call's whole limit).
 mkdir -p gpurun_out
 TAG=${TAG:-ab}
 if [ "${SKIP_TESTS:-0}" != "1" ]; then
-timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu_$TAG.log 2>&1
+timeout ${TEST_TIMEOUT:-420} python -m pytest tests -m gpu -q -x -p no:cacheprovider ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu_$TAG.log 2>&1
 echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu_$TAG.log
 tail -8 gpurun_out/pytest_gpu_$TAG.log
 fi
 run() {  # name, env assignments...
     name=$1; shift
-    env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}_$name.json 2> gpurun_out/bench_${TAG}_$name.err
+    env "$@" timeout ${BENCH_TIMEOUT:-200} python bench.py --steps 10 --warmup 3 --no-cpu-baseline ${BENCH_ARGS:---no-workloads} > gpurun_out/bench_${TAG}_$name.json 2> gpurun_out/bench_${TAG}_$name.err
     tail -2 gpurun_out/bench_${TAG}_$name.err
     python - <<PY
 import json

@@ -7,7 +7,7 @@ KREGEX=${KREGEX:-pass_kernel}
 SKIP=${SKIP:-0}
 COUNT=${COUNT:-3}
 TAG=${TAG:-r1}
-CMD="python bench.py --cells $CELLS --steps 1 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --cells $CELLS --steps 1 --warmup 3 --no-cpu-baseline ${BENCH_ARGS:---no-workloads}"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "ncu list exit $?"

@@ -9,15 +9,21 @@ import sys
 csv.field_size_limit(10**9)
 
 
+def fresh():
+    return ({"hot": dict(ex=0, samples=0, static=0, stalls=collections.Counter(), ops=collections.Counter(), ops_s=collections.Counter()),
+             "rest": dict(ex=0, samples=0, static=0, stalls=collections.Counter(), ops=collections.Counter(), ops_s=collections.Counter())}, [])
+
+
 def main():
     path = sys.argv[1]
     split = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
     hdr = None
-    regions = {"hot": dict(ex=0, samples=0, static=0, stalls=collections.Counter(), ops=collections.Counter(), ops_s=collections.Counter()),
-               "rest": dict(ex=0, samples=0, static=0, stalls=collections.Counter(), ops=collections.Counter(), ops_s=collections.Counter())}
-    lines = []
+    regions, lines = fresh()
     for row in csv.reader(open(path, errors="ignore")):
         if row and row[0] == "Kernel Name":
+            report(regions, lines, top)
+            regions, lines = fresh()
             print("kernel:", row[1][:120])
             continue
         if row and row[0] == "Address":
@@ -45,6 +51,12 @@ def main():
                     r["stalls"][h[6:]] += int(row[i])
                 except ValueError:
                     pass
+    report(regions, lines, top)
+
+
+def report(regions, lines, top):
+    if not lines:
+        return
     for name, r in regions.items():
         if not r["ex"]:
             continue
@@ -55,7 +67,7 @@ def main():
         print("   by samples :", ", ".join(f"{a}={100 * b / max(1, r['samples']):.1f}%" for a, b in r["ops_s"].most_common(14)))
     lines.sort(reverse=True)
     print("== hottest instructions (samples, executed, SASS)")
-    for s, ex, t in lines[:30]:
+    for s, ex, t in lines[:top]:
         print(f"   {s:6d} {ex:9d}  {t}")
 
 

@@ -609,13 +609,15 @@ def test_strided_unaligned_input_matches_contiguous(offset, width):
     assert np.array_equal(host(c["cfact"]), host(e["cfact"]), equal_nan=True)
 
 
-@pytest.mark.parametrize("keep_scaled", [False, True])
-def test_lean_quantile_map_matches_generic_kernel(keep_scaled):
-    """The streamlined Normal quantile-map kernel (no post rule, no cfact_scaled output; hoisted reciprocal in the
+@pytest.mark.parametrize("keep_scaled,C", [(False, 70), (True, 70), (False, 80), (False, 272)])
+def test_lean_quantile_map_matches_generic_kernel(keep_scaled, C):
+    """The streamlined Normal quantile-map kernels (no post rule, no cfact_scaled output; hoisted reciprocal in the
     float32 scaling) must give the bits of the generic kernel, which is selected by asking for cfact_scaled -
     including for NaN / Inf days, the cell's own minimum (numerator 0), tail days and cells whose scale lies
-    outside the range the hoisted reciprocal is used for."""
-    T, C = 6000, 70
+    outside the range the hoisted reciprocal is used for.  C = 70: per-thread loads and stores; C = 80 / 272 (row
+    segments of 16-byte multiples; 272 = two full 128-cell CTAs and a 16-cell one): the bulk-copy kernel with its
+    shared-memory stages, whose rare days are mapped again out of line after the batch."""
+    T = 6000
     y = synthetic.tas_cells(C, T, seed=31, nan_fraction=0.02)
     y[17, 4] = np.inf
     y[18, 4] = -np.inf
@@ -644,6 +646,52 @@ def test_lean_quantile_map_matches_generic_kernel(keep_scaled):
     assert np.array_equal(host(lean_c), host(gen_c), equal_nan=True)
     assert torch.equal(lean_r, gen_r)
     assert host(lean_r)[17, 4] == 1 and host(lean_r)[100, 9] != 1
+    if not keep_scaled:   # the float32 counterfactual (opt-in output type) is the rounding of the same FP64 values
+        f32_c, f32_r, _ = s.quantile_map(yd2, None, params, sc2, out=torch.empty(lean_c.shape, dtype=torch.float32, device=DEV))
+        assert np.array_equal(host(f32_c), host(gen_c).astype(np.float32), equal_nan=True)
+        assert torch.equal(f32_r, gen_r)
+
+
+_BITS_SCRIPT = """
+import json, sys, torch
+from attrici_b200 import synthetic
+from attrici_b200.solver import CellBatchSolver
+C, T = int(sys.argv[1]), synthetic.DAYS_1901_2019
+y = synthetic.tas_tile_torch(C, T, device="cuda:0", nan_fraction=0.001)
+gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+s = CellBatchSolver("tas", device="cuda:0")
+sums = []
+for r in range(int(sys.argv[2])):
+    out = s.detrend_device(y, days, gmt, keep_scaled=False)
+    sums.append([int(out["fit"].params.view(torch.int64).sum().item()), int(out["cfact"].view(torch.int64).sum().item()),
+                 int(out["replaced"].sum().item())])
+    del out
+print(json.dumps(sums))
+"""
+
+
+def test_bulk_copy_kernels_give_the_bits_of_the_per_thread_kernels():
+    """The streaming kernels on bulk asynchronous copies (prep_onepass TMA variant, qmap_fold_bulk_kernel) run the
+    arithmetic of the kernels with per-thread loads; only the data movement differs.  Coefficients, counterfactual and
+    flags of the BASELINE tile must therefore be bit-identical between the two builds of the path (ATTRICI_NO_TMA=1
+    selects the per-thread kernels; it is read once per process, hence the subprocesses) and from run to run - a
+    handshake race shows up as a few cells whose sums change between runs (this is how the early release of an
+    input stage was found: mbarrier.arrive does not wait for shared-memory loads in flight)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("bulk", {}), ("per_thread", {"ATTRICI_NO_TMA": "1"})):
+        e = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), **env)
+        out = subprocess.run([sys.executable, "-c", _BITS_SCRIPT, "10000", "4" if tag == "bulk" else "1"], env=e, cwd=root,
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[tag] = json.loads(out.stdout.strip().splitlines()[-1])
+    assert all(r == res["bulk"][0] for r in res["bulk"]), res["bulk"]
+    assert res["bulk"][0] == res["per_thread"][0], res
 
 
 @pytest.mark.parametrize("T", [400, 1461, 1462])
@@ -724,7 +772,7 @@ def test_model_cuda_plugin_interface():
     want = oracle.estimate_params("normal", trace["params"], c.gmt, c.days, 4)
     np.testing.assert_allclose(d.mu, want["mu"], rtol=1e-12)
     np.testing.assert_allclose(d.sigma, want["sigma"], rtol=1e-12)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="Exactly one"):                     # detrend.py:646-647
         ModelCuda(Normal, {"mu": Par(None, True), "sigma": Par(np.exp, False)}, obs, pred, modes=4, window_size=31)
     with pytest.raises(ValueError):
         ModelCuda(dict, {"mu": Par(None, True)}, obs, pred, modes=4)

@@ -170,15 +170,15 @@ def test_fit_window_from_dates():
 
 
 def test_driver_rejects_what_the_reference_rejects():
-    """attrici/detrend.py:646-647 (modes xor window_size) and the window model's NotImplementedError
-    (model_scipy.py:58-59) are raised before anything touches the GPU."""
+    """attrici/detrend.py:646-647 (modes xor window_size), the window-size rule and the window model's need of a
+    calendar axis are raised before anything touches the GPU."""
     y = np.zeros((10, 2), dtype=np.float32)
     args = (y, np.linspace(0, 1, 10), np.arange(10), [0.25, 0.25], [0.25, 0.75])
     with pytest.raises(ValueError, match="Exactly one of `modes` and `window_size` must be set"):
         detrend_cells(Config("tas", modes=4, window_size=31), *args)
     with pytest.raises(ValueError, match="Exactly one of `modes` and `window_size` must be set"):
         detrend_cells(Config("tas", modes=None), *args)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError, match="datetime64"):      # day of the year needs calendar days (util.py:126-133)
         detrend_cells(Config("tas", modes=None, window_size=31), *args)
     with pytest.raises(ValueError, match="Window size must be an odd number"):
         detrend_cells(Config("tas", modes=None, window_size=30), *args)
