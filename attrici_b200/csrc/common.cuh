@@ -296,6 +296,9 @@ int launch_qmap_fold(Workspace& ws, const attrici_variable_t& var, const float* 
                      const double* params, const double* scaling, double* cfact, uint8_t* replaced,
                      double* cfact_scaled, int64_t ld_out, cudaStream_t s, float* cfact32 = nullptr);
 // Gamma / Weibull families in phase order (scale shortcut), same device-side dispatch; needs y_scaled
+int launch_qmap_fold_pr(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled, int64_t ld,
+                        const double* params, const double* scaling, const double* uniforms, double* cfact,
+                        uint8_t* replaced, double* cfact_scaled, int64_t ld_out, cudaStream_t s);
 int launch_qmap_fold_scale(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled, int64_t ld,
                            const double* params, const double* scaling, double* cfact, uint8_t* replaced,
                            double* cfact_scaled, int64_t ld_out, cudaStream_t s);

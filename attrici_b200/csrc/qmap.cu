@@ -292,32 +292,58 @@ __global__ void __launch_bounds__(QMAP_THREADS) eval_parameter_fold_kernel(EvalA
     }
 }
 
-// one MT19937 stream per cell; the state lives in (L1-cached, cell-interleaved) local memory
-struct LocalState {
-    uint32_t* p;
-    __device__ uint32_t& operator()(int i) const { return p[i]; }
-};
+// One MT19937 stream per cell (np.random.seed(seed); np.random.rand(n): detrend.py:285, variables.py:458), one WARP
+// per stream: the state (624 words) lives in shared memory, the twist runs 32 words at a time - word k of the new
+// state needs the old words k, k + 1 and either the old word k + 397 (k < 227) or the NEW word k - 227, which an
+// earlier 32-word step has already written - and the lanes temper and convert 32 doubles at a time.  (A thread per
+// stream with the state in local memory, the first version, ran at 3 % occupancy: 17.9 ms per 10 000 cells x 43 464
+// doubles, as long as a fifth of the whole precipitation step.)
+constexpr int MT_WARPS = 8;
 
-__global__ void __launch_bounds__(64) mt19937_kernel(const uint32_t* __restrict__ seeds, int C, int n,
-                                                     double* __restrict__ out, int64_t ld) {
-    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= C) return;
-    uint32_t mt[Mt19937::N];
-    LocalState st{mt};
-    Mt19937::seed(st, seeds[cell]);
-    int pos = Mt19937::N;
-    uint32_t pending = 0;
-    bool have = false;
-    int produced = 0;
-    while (produced < n) {
-        if (pos >= Mt19937::N) { Mt19937::twist(st); pos = 0; }
-        uint32_t v = Mt19937::temper(mt[pos++]);
-        if (!have) { pending = v; have = true; }
-        else {
-            out[(size_t)produced * ld + cell] = Mt19937::to_double(pending, v);
-            ++produced;
-            have = false;
+__global__ void __launch_bounds__(32 * MT_WARPS) mt19937_kernel(const uint32_t* __restrict__ seeds, int C, int n,
+                                                                double* __restrict__ out, int64_t ld) {
+    __shared__ __align__(8) uint32_t state[MT_WARPS][Mt19937::N];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell = blockIdx.x * MT_WARPS + w;
+    if (cell >= C) return;   // whole warps
+    uint32_t* mt = state[w];
+    if (lane == 0) {   // init_genrand: a serial recurrence
+        uint32_t p = seeds[cell];
+        mt[0] = p;
+        for (int i = 1; i < Mt19937::N; ++i) {
+            p = 1812433253u * (p ^ (p >> 30)) + (uint32_t)i;
+            mt[i] = p;
         }
+    }
+    __syncwarp();
+    constexpr int N = Mt19937::N, M = Mt19937::M;
+    for (int produced = 0; produced < n; produced += N / 2) {
+        for (int k0 = 0; k0 < N; k0 += 32) {
+            const int k = k0 + lane;
+            const bool act = k < N - 1;
+            uint32_t v = 0;
+            if (act) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[k + 1] & 0x7fffffffu);
+                v = mt[k < N - M ? k + M : k + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            __syncwarp();   // every lane has read the old words of this step (lane 31's k + 1 belongs to the next)
+            if (act) mt[k] = v;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const uint32_t y = (mt[N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+            mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        __syncwarp();
+        // random_sample: consecutive word pairs (624 is even: no pair straddles two states)
+        for (int i0 = 0; i0 < N / 2; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < N / 2 && produced + i < n) {
+                const uint2 ab = *reinterpret_cast<const uint2*>(mt + 2 * i);
+                out[(size_t)(produced + i) * ld + cell] = Mt19937::to_double(Mt19937::temper(ab.x), Mt19937::temper(ab.y));
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -336,9 +362,15 @@ int qmap_chunks(int T, int C, int* chunk_len) {
 
 int launch_mt19937(const uint32_t* seeds, int C, int n, double* out, int64_t ld, cudaStream_t s) {
     if (C <= 0 || n <= 0) return 0;
-    mt19937_kernel<<<(C + 63) / 64, 64, 0, s>>>(seeds, C, n, out, ld);
+    mt19937_kernel<<<(C + MT_WARPS - 1) / MT_WARPS, 32 * MT_WARPS, 0, s>>>(seeds, C, n, out, ld);
     ATTRICI_LAUNCH_CHECK();
     return 0;
+}
+
+// ATTRICI_NO_PR_FOLD=1: precipitation keeps the day-ordered kernel (A/B measurements)
+static bool pr_fold_off() {
+    static const bool off = [] { const char* e = getenv("ATTRICI_NO_PR_FOLD"); return e && e[0] == '1'; }();
+    return off;
 }
 
 int launch_qmap(Workspace& ws, const attrici_variable_t& var, const float* y, const float* y_scaled,
@@ -379,6 +411,9 @@ int launch_qmap(Workspace& ws, const attrici_variable_t& var, const float* y, co
         a.want_fold = 0;
     } else if (fold_on && y_scaled && (var.family == ATTRICI_GAMMA || var.family == ATTRICI_WEIBULL)) {
         ATTRICI_TRY(launch_qmap_fold_scale(ws, var, y, y_scaled, ld, params, scaling, cfact, replaced, cfact_scaled, ld_out, s));
+        a.want_fold = 0;
+    } else if (fold_on && y_scaled && var.family == ATTRICI_BERNOULLI_GAMMA && !pr_fold_off()) {
+        ATTRICI_TRY(launch_qmap_fold_pr(ws, var, y, y_scaled, ld, params, scaling, a.uniforms, cfact, replaced, cfact_scaled, ld_out, s));
         a.want_fold = 0;
     }
     int n_chunks = qmap_chunks(ws.T, ws.C, &a.chunk_len);

@@ -57,9 +57,10 @@ ATTRICI_HD double gamma_cdf(double y, double a, double scale) {
     return gamma_p(a, x);
 }
 // x0: optional starting value for the standardised quantile (<= 0: none)
-ATTRICI_HD double gamma_ppf(double q, double a, double scale, double x0 = -1.0) {
+// p0 / q0: P(a, x0) and Q(a, x0) when the caller has them (see gamma_p_inv)
+ATTRICI_HD double gamma_ppf(double q, double a, double scale, double x0 = -1.0, double p0 = -1.0, double q0 = -1.0) {
     if (isnan(q) || isnan(a) || isnan(scale) || !(a > 0.0) || !(scale > 0.0) || q < 0.0 || q > 1.0) return NAN;
-    return gamma_p_inv(a, q, x0) * scale;
+    return gamma_p_inv(a, q, x0, p0, q0) * scale;
 }
 
 // distribution parameters of the family (the values `report_variables` would store)
@@ -250,13 +251,29 @@ ATTRICI_HD QmapOut qmap_day(int family, int scaling, int post_rule, float y, flo
         // Pr.quantile_mapping, variables.py:422-480
         const bool dry = (ys != ys);
         const double y0 = dry ? 0.0 : (double)ys;
-        const double q = dist_cdf(family, ref, y0);
+        // factual quantile as dist_cdf forms it, keeping P and Q of the gamma part: the shape nu^2 does not depend
+        // on the predictor, so x = y0 / scale_ref is also where the counterfactual inverse starts (for equal dry-day
+        // probabilities it is the root), with P(a, x) already known
+        const double a = ref.p2 * ref.p2, sc_ref = ref.p1 / a;
+        double x = -1.0, P = -1.0, Q = -1.0, q;
+        if (isnan(a) || isnan(sc_ref) || !(a > 0.0) || !(sc_ref > 0.0)) {
+            q = NAN;
+        } else {
+            x = y0 / sc_ref;
+            if (x <= 0.0) { q = ref.p0; x = -1.0; }
+            else { gamma_pq_l(a, x, lgamma(a), &P, &Q); q = ref.p0 + (1.0 - ref.p0) * P; }
+        }
         const bool drier_cf = cf.p0 > ref.p0;
         const bool qm0 = drier_cf && (q > cf.p0);
         const bool qm1 = !drier_cf && !dry;
         const bool to_wet = !qm1 && (u * ref.p0 > cf.p0);
         cs = 0.0;
-        if (qm0 || qm1 || to_wet) cs = dist_invcdf(family, cf, q, dry ? -1.0 : y0);
+        if (qm0 || qm1 || to_wet) {
+            const double acf = cf.p2 * cf.p2;
+            const bool known = !dry && acf == a && isfinite(x) && x > 0.0;
+            cs = gamma_ppf((q - cf.p0) / (1.0 - cf.p0), acf, cf.p1 / acf, known ? x : (dry ? -1.0 : y0 * acf / cf.p1),
+                           known ? P : -1.0, known ? Q : -1.0);
+        }
     }
     return qmap_finish(scaling, post_rule, cs, y, datamin, scale);
 }

@@ -207,7 +207,9 @@ ATTRICI_HD double gamma_q(double a, double x) { return gamma_q_l(a, x, lgamma(a)
 
 // x with P(a, x) = p   (scipy.special.gammaincinv); safeguarded Halley iteration
 // x0 > 0: starting value supplied by the caller (the quantile map knows a point whose quantile is close)
-ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p, double x0 = -1.0) {
+// p0 >= 0: P(a, x0) and q0 = Q(a, x0), already known to the caller - the first iteration then costs no evaluation of
+// the incomplete gamma function (pr: the factual quantile was just computed at that very point)
+ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p, double x0 = -1.0, double p0 = -1.0, double q0 = -1.0) {
     if (isnan(a) || isnan(p) || a <= 0.0 || p < 0.0 || p > 1.0) return NAN;
     if (p == 0.0) return 0.0;
     if (p == 1.0) return INFINITY;
@@ -239,7 +241,8 @@ ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p, double x0 = -1.0) {
         if (x <= 0.0) x = 0.5 * (lo + (isinf(hi) ? lo + 1e-300 : hi));
         // error in the better-conditioned tail
         double pv, qv;
-        gamma_pq_l(a, x, gln, &pv, &qv);
+        if (it == 0 && p0 >= 0.0 && x == x0) { pv = p0; qv = q0; }
+        else gamma_pq_l(a, x, gln, &pv, &qv);
         double err = (p < 0.5) ? pv - p : (1.0 - p) - qv;
         if (err > 0.0) hi = x; else lo = x;
         double dens;  // dP/dx
@@ -257,9 +260,11 @@ ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p, double x0 = -1.0) {
         if (corr > 1.0) corr = 1.0;
         double dx = u / (1.0 - 0.5 * corr);
         double xn = x - dx;
-        // Halley converges cubically: a step below 1e-10 x leaves an error far below one ulp, while waiting for a
-        // step below 4 ulp just iterates on the rounding noise of err / dens
-        if (fabs(xn - x) <= 1e-10 * x) { x = xn; break; }
+        // Halley converges cubically (error after the step ~ (a1 / x - 1)^2 / 12 ... times the cube of the step, in
+        // relative terms a small multiple of (dx / x)^3): a step below 2e-5 x leaves an error below 1e-13 x, the
+        // level of the series itself, so the point after the step is taken without evaluating there again.  Only a
+        // plain Halley step from inside the bracket qualifies.
+        if (fabs(xn - x) <= 2e-5 * x && xn >= lo && xn <= hi && corr <= 0.5 && corr >= -0.5) { x = xn; break; }
         if (!(xn >= lo) || !(xn <= hi)) xn = isinf(hi) ? 2.0 * x : 0.5 * (lo + hi);
         x = xn;
     }
