@@ -23,6 +23,7 @@
 // Replaces Pr.quantile_mapping (attrici/variables.py:422-480), BernoulliGamma.cdf / invcdf
 // (attrici/distributions.py:178-216), ModelScipy.estimate_distribution x2 (model_scipy.py:547-570), Pr.rescale
 // (variables.py:483-486) and the replacement of detrend.py:392-411, like qmap.cu.
+#include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "qmap_impl.cuh"
@@ -37,7 +38,6 @@ constexpr int PR_U = 10;                          // days per batch
 constexpr int PR_MAXPH = 16;                      // phases per CTA
 constexpr int PR_NCOEF = 2 * NA + NB;             // p (18) | mu (18) | nu (9), canonical layout
 constexpr int PR_CAP = PR_CELLS * PR_U + 2 * PR_THREADS;   // one batch on top of two remainders below one round each
-constexpr double PR_XLONG = 2.5;                  // items with x above this go to the second stack (long series)
 
 struct PrArgs {
     const float* y; const float* ys;
@@ -50,6 +50,7 @@ struct PrArgs {
     double* cfact; uint8_t* replaced; double* cfact_scaled;
     const int* fold_bad;
     int scaling, post_rule;
+    double xl_a, xl_b;         // an item goes to the long-series stack if x > xl_a * shape + xl_b
 };
 
 struct PrPhase { double a, gln, p_cf, sc_cf; };   // per (cell, phase): shape nu^2, lgamma(a), counterfactual p and scale
@@ -73,21 +74,29 @@ __device__ __forceinline__ double pr_series(double a, double x) {
     return sum;
 }
 
-// gamma_pq_l (special.cuh) with the series above
-__device__ __forceinline__ void pr_pq(double a, double x, double gln, double* p, double* q) {
+// gamma_pq_l (special.cuh) with the series above; also returns the prefactor x^a e^-x / Gamma(a), from which the
+// inverse takes the density (x^(a-1) e^-x / Gamma(a) = prefactor / x) instead of a second exp / log pair
+__device__ __forceinline__ void pr_pq(double a, double x, double gln, double* p, double* q, double* pref) {
+    *pref = 0.0;
     if (isnan(a) || isnan(x) || a <= 0.0 || x < 0.0) { *p = NAN; *q = NAN; return; }
     if (x == 0.0) { *p = 0.0; *q = 1.0; return; }
     if (isinf(x)) { *p = 1.0; *q = 0.0; return; }
+    *pref = gamma_prefactor(a, x, gln);
     if (gamma_use_series(a, x)) {
-        const double pp = pr_series(a, x) * gamma_prefactor(a, x, gln);
+        const double pp = pr_series(a, x) * *pref;
         if (pp < 0.99 || x < a + 1.0) { *p = pp; *q = 1.0 - pp; return; }
     }
     *q = gamma_q_cf(a, x, gln);   // far upper tail: the continued fraction computes Q itself (rare)
     *p = 1.0 - *q;
 }
 
-// gamma_p_inv (special.cuh), statement for statement, with pr_pq and lgamma(a) supplied
-__device__ __forceinline__ double pr_p_inv(double a, double p, double x0, double p0, double q0, double gln) {
+// gamma_p_inv (special.cuh) with pr_pq and lgamma(a) supplied.  Two deviations, both inside the tolerance of the
+// path (1e-4 relative on the counterfactual; the tests ask 1e-5 of the oracle):
+//  * the density is prefactor / x (one rounding away from the closed form the scalar routine evaluates),
+//  * a Halley step below 3e-4 x ends the iteration (cubic convergence: the error after it is a small multiple of
+//    (3e-4)^3 = 2.7e-11 relative), so the typical day costs ONE evaluation after the factual quantile and a day whose
+//    quantile moves a lot (drizzle: P ~ x^a) two; the scalar routine's 2e-5 asked for one more each.
+__device__ __forceinline__ double pr_p_inv(double a, double p, double x0, double p0, double q0, double pref0, double gln) {
     if (isnan(a) || isnan(p) || a <= 0.0 || p < 0.0 || p > 1.0) return NAN;
     if (p == 0.0) return 0.0;
     if (p == 1.0) return INFINITY;
@@ -109,19 +118,15 @@ __device__ __forceinline__ double pr_p_inv(double a, double p, double x0, double
         else x = 1.0 - log(1.0 - (p - t) / (1.0 - t));
     }
     double lo = 0.0, hi = INFINITY;
-    const double lna1 = a > 1.0 ? log(a1) : 0.0;
-    const double afac = a > 1.0 ? exp(a1 * (lna1 - 1.0) - gln) : 0.0;
 #pragma unroll 1
     for (int it = 0; it < 60; ++it) {
         if (x <= 0.0) x = 0.5 * (lo + (isinf(hi) ? lo + 1e-300 : hi));
-        double pv, qv;
-        if (it == 0 && p0 >= 0.0 && x == x0) { pv = p0; qv = q0; }
-        else pr_pq(a, x, gln, &pv, &qv);
+        double pv, qv, pref;
+        if (it == 0 && p0 >= 0.0 && x == x0) { pv = p0; qv = q0; pref = pref0; }
+        else pr_pq(a, x, gln, &pv, &qv, &pref);
         const double err = (p < 0.5) ? pv - p : (1.0 - p) - qv;
         if (err > 0.0) hi = x; else lo = x;
-        double dens;
-        if (a > 1.0) dens = afac * exp(-(x - a1) + a1 * (log(x) - lna1));
-        else dens = exp(-x + a1 * log(x) - gln);
+        const double dens = pref / x;   // dP/dx
         if (!(dens > 0.0)) {
             x = isinf(hi) ? 2.0 * x + 1.0 : 0.5 * (lo + hi);
             continue;
@@ -131,7 +136,7 @@ __device__ __forceinline__ double pr_p_inv(double a, double p, double x0, double
         if (corr > 1.0) corr = 1.0;
         const double dx = u / (1.0 - 0.5 * corr);
         double xn = x - dx;
-        if (fabs(xn - x) <= 2e-5 * x && xn >= lo && xn <= hi && corr <= 0.5 && corr >= -0.5) { x = xn; break; }
+        if (fabs(xn - x) <= 3e-4 * x && xn >= lo && xn <= hi && corr <= 0.5 && corr >= -0.5) { x = xn; break; }
         if (!(xn >= lo) || !(xn <= hi)) xn = isinf(hi) ? 2.0 * x : 0.5 * (lo + hi);
         x = xn;
     }
@@ -141,11 +146,11 @@ __device__ __forceinline__ double pr_p_inv(double a, double p, double x0, double
 // one item: the quantile map of qmap_day for a wet day (x > 0) or a dry day the uniform draw turned wet (x = -1;
 // NaN: the same with degenerate parameters)
 __device__ __forceinline__ double pr_item(double x, double p_ref, const PrPhase& ph) {
-    double q, P = -1.0, Q = -1.0;
+    double q, P = -1.0, Q = -1.0, pref = 0.0;
     const bool dry = !(x > 0.0);
     if (isnan(x)) q = NAN;
     else if (dry) q = p_ref;
-    else { pr_pq(ph.a, x, ph.gln, &P, &Q); q = p_ref + (1.0 - p_ref) * P; }
+    else { pr_pq(ph.a, x, ph.gln, &P, &Q, &pref); q = p_ref + (1.0 - p_ref) * P; }
     const bool drier_cf = ph.p_cf > p_ref;
     const bool qm0 = drier_cf && (q > ph.p_cf);
     const bool qm1 = !drier_cf && !dry;
@@ -158,7 +163,7 @@ __device__ __forceinline__ double pr_item(double x, double p_ref, const PrPhase&
             cs = NAN;
         } else {
             const bool known = !dry && isfinite(x);
-            cs = pr_p_inv(ph.a, target, known ? x : -1.0, known ? P : -1.0, known ? Q : -1.0, ph.gln) * ph.sc_cf;
+            cs = pr_p_inv(ph.a, target, known ? x : -1.0, known ? P : -1.0, known ? Q : -1.0, pref, ph.gln) * ph.sc_cf;
         }
     }
     return cs;
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(PR_THREADS, 2) qmap_fold_pr_kernel(PrArgs a) {
     double* it_p = it_x + PR_CAP;                                                // [PR_CAP]
     float* it_y = reinterpret_cast<float*>(it_p + PR_CAP);                       // [PR_CAP]
     unsigned short* it_i = reinterpret_cast<unsigned short*>(it_y + PR_CAP);     // [PR_CAP] (j << 7) | cell
-    int* count_s = reinterpret_cast<int*>(it_i + PR_CAP + (PR_CAP & 1));        // [2]: short-series stack (grows up from 0), long (down from PR_CAP)
+    int* count_s = reinterpret_cast<int*>(it_i + PR_CAP + (PR_CAP & 1));        // [2][2], by batch parity: short-series stack (grows up from 0), long (down from PR_CAP)
 
     const int tid = threadIdx.x;
     const int c = tid & (PR_CELLS - 1), half = tid >> 7;
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(PR_THREADS, 2) qmap_fold_pr_kernel(PrArgs a) {
             const int p = i / (2 * MAXM), k = i - p * (2 * MAXM);
             row_s[i] = a.basis64[(size_t)(d0 + p) * B_STRIDE + (k < MAXM ? 1 + k : 1 + NH + (k - MAXM))];
         }
-        if (tid == 0) { count_s[0] = 0; count_s[1] = 0; }
+        if (tid < 4) count_s[tid] = 0;
     }
     __syncthreads();
     const bool want_rep = a.replaced != nullptr, want_cs = a.cfact_scaled != nullptr;
@@ -243,6 +248,7 @@ __global__ void __launch_bounds__(PR_THREADS, 2) qmap_fold_pr_kernel(PrArgs a) {
         }
     };
 
+    int batch = 0;
     for (int p = 0; p < nph; ++p) {
         const int d = d0 + p;
         const int nj = (a.T - d + NPHASE - 1) / NPHASE;
@@ -284,8 +290,9 @@ __global__ void __launch_bounds__(PR_THREADS, 2) qmap_fold_pr_kernel(PrArgs a) {
         const size_t out0 = (size_t)d * a.ld_out + cell;
         for (int j0 = 0; j0 < nj; j0 += PR_U) {
             // ---- pass 1: this thread's five days of the batch
-            constexpr int H = PR_U / 2;
-            const int jb = j0 + half * H;
+            constexpr int H = (PR_U + 1) / 2;
+            const int jb = j0 + half * H, je = min(nj, j0 + (half ? PR_U : H));   // days jb .. je - 1
+            int* cnt = count_s + 2 * (batch & 1);
             float yv[H], sv[H];
 #pragma unroll
             for (int u = 0; u < H; ++u) {
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(PR_THREADS, 2) qmap_fold_pr_kernel(PrArgs a) {
 #pragma unroll
             for (int u = 0; u < H; ++u) {
                 const int j = jb + u;
-                const bool in = j < nj && live;
+                const bool in = j < je && live;
                 float y = yv[u];
                 const float s = sv[u];
                 if (isinf(y)) y = __int_as_float(0x7fc00000);   // detrend.py:311
@@ -339,13 +346,13 @@ __global__ void __launch_bounds__(PR_THREADS, 2) qmap_fold_pr_kernel(PrArgs a) {
                 }
                 // warp-aggregated push.  Two stacks: the length of the series grows with x (about x + 6 sqrt(x) + 20
                 // terms) and a warp runs as long as its longest lane, so items with a long series are kept together
-                const bool longer = !(x <= PR_XLONG);   // also the dry days turned wet (several evaluations)
+                const bool longer = !(x <= fma(a.xl_a, sh, a.xl_b));   // also the dry days turned wet (several evaluations)
                 const unsigned m_lo = __ballot_sync(0xffffffffu, push && !longer), m_hi = __ballot_sync(0xffffffffu, push && longer);
                 if (m_lo | m_hi) {
                     int b_lo = 0, b_hi = 0;
                     if (lane == 0) {
-                        if (m_lo) b_lo = atomicAdd(count_s, __popc(m_lo));
-                        if (m_hi) b_hi = atomicAdd(count_s + 1, __popc(m_hi));
+                        if (m_lo) b_lo = atomicAdd(cnt, __popc(m_lo));
+                        if (m_hi) b_hi = atomicAdd(cnt + 1, __popc(m_hi));
                     }
                     b_lo = __shfl_sync(0xffffffffu, b_lo, 0);
                     b_hi = __shfl_sync(0xffffffffu, b_hi, 0);
@@ -358,15 +365,17 @@ __global__ void __launch_bounds__(PR_THREADS, 2) qmap_fold_pr_kernel(PrArgs a) {
             }
             __syncthreads();
             // ---- pass 2: full rounds from the tops of the stacks; everything at the end of the phase
-            const int n_lo = count_s[0], n_hi = count_s[1];
+            const int n_lo = cnt[0], n_hi = cnt[1];
             const bool last_batch = j0 + PR_U >= nj;
             const int t_lo = last_batch ? n_lo : (n_lo / PR_THREADS) * PR_THREADS;
             const int t_hi = last_batch ? n_hi : (n_hi / PR_THREADS) * PR_THREADS;
+            // the next batch counts on from the remainders in the other pair of counters (nobody reads that pair any
+            // more: its last readers passed the barrier above), so one barrier after the pops is enough
+            if (tid == 0) { count_s[2 * ((batch + 1) & 1)] = n_lo - t_lo; count_s[2 * ((batch + 1) & 1) + 1] = n_hi - t_hi; }
             for (int done = 0; done < t_hi; done += PR_THREADS) pop_round(PR_CAP - n_hi + done, 1, min(PR_THREADS, t_hi - done), d);
             for (int done = 0; done < t_lo; done += PR_THREADS) pop_round(n_lo - 1 - done, -1, min(PR_THREADS, t_lo - done), d);
             __syncthreads();
-            if (tid == 0) { count_s[0] = n_lo - t_lo; count_s[1] = n_hi - t_hi; }
-            __syncthreads();
+            ++batch;
         }
     }
 }
@@ -386,6 +395,8 @@ int launch_qmap_fold_pr(Workspace& ws, const attrici_variable_t& var, const floa
     a.cfact = cfact; a.replaced = replaced; a.cfact_scaled = cfact_scaled;
     a.fold_bad = ws.fold_bad;
     a.scaling = var.scaling; a.post_rule = var.post_rule;
+    a.xl_a = 0.0; a.xl_b = 2.5;
+    if (const char* e = getenv("ATTRICI_PR_XL")) sscanf(e, "%lf,%lf", &a.xl_a, &a.xl_b);   // tuning only
     const int n_cb = (ws.C + PR_CELLS - 1) / PR_CELLS;
     int want = (148 * 8 + n_cb - 1) / n_cb;
     if (want > a.n_ph) want = a.n_ph;

@@ -376,13 +376,14 @@ def segment_rooflines(variable, seg_ms, n_pass_mean, T, C, peak_hbm):
 
 
 SEG_KERNEL = {
-    ("tas", "scale"): "prep_onepass_kernel", ("tas", "fit"): "fit_fused_kernel", ("tas", "quantile_map"): "qmap_fold_lean_kernel",
+    ("tas", "scale"): "prep_onepass_kernel", ("tas", "fit"): "fit_fused_kernel", ("tas", "quantile_map"): "qmap_fold_bulk_kernel",
 }
 LIMITER = {
-    "pr": "quantile map: incomplete-gamma inverses on wet days only - 9.8 of 32 lanes active per instruction (warp = 32 cells "
-          "of one day), FP64 pipe 29 % (profiles/r2_qmap_pr_hurs_ncu.txt); not memory-bound",
+    "pr": "quantile map (qmap_fold_pr_kernel): FP64 series of the incomplete gamma function on the wet days, which are "
+          "compacted so that all 32 lanes of a warp work (the day-ordered kernel had 9.8 of 32 active); 2 CTAs x 8 warps "
+          "per SM at 128 registers, IPC 1.8, no DRAM traffic to speak of (profiles/r2_final_pr_ncu.txt); not memory-bound",
     "hurs": "quantile map: incomplete-beta inverses (Halley iterations of continued fractions), FP64 pipe ~30 % at 17 % "
-            "occupancy (profiles/r2_qmap_pr_hurs_ncu.txt); not memory-bound",
+            "occupancy (profiles/r2_qmap_pr_hurs_ncu.txt, day-ordered qmap_kernel); not memory-bound",
 }
 
 
