@@ -56,7 +56,6 @@ struct OnePassArgs {
 __device__ __forceinline__ float op_nan() { return __int_as_float(0x7fc00000); }
 
 // ---- bulk asynchronous copies (TMA engine, cp.async.bulk) completing on an mbarrier ----------------------------
-constexpr int OP_NS = 3;       // stages of the input ring of the TMA variant (each one batch of OP_U days)
 
 // barrier of the OP_THREADS consumer threads only (the producer warp of the TMA variant has left by then)
 __device__ __forceinline__ void op_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(OP_THREADS) : "memory"); }
@@ -74,9 +73,10 @@ template <> __device__ __forceinline__ void op_load<2>(const float* p, float (&v
 // segment per day, issued by one thread and completing on an mbarrier per stage) instead of per-thread loads into a
 // register double buffer: OP_NS batches of OP_U days ahead of the arithmetic, no load / address instruction and no
 // register copy in the issue stream.  Needs 16-byte aligned row segments (leading dimension and C multiples of 4).
-template <int V, bool MASKS, bool TMA>
+template <int V, bool MASKS, int TMA>
 __global__ void __launch_bounds__(OP_THREADS + 32) prep_onepass_kernel(OnePassArgs a, int nj_max) {
     constexpr int CW = OP_THREADS * V;
+    constexpr int OP_NS = TMA > 0 ? TMA : 1;   // stages of the input ring of the TMA variant (each one batch of OP_U days)
     extern __shared__ __align__(16) unsigned char op_smem[];
     double* g_s = reinterpret_cast<double*>(op_smem);                       // [ph_len][nj_max]
     double* stage = g_s + a.ph_len * nj_max;                                // [OP_STAGE][3][CW]
@@ -445,13 +445,18 @@ int launch_prep_onepass(Workspace& ws, const attrici_variable_t& var, const floa
     a.scaling_out = scaling;
     const int nj_max = (ws.T + NPHASE - 1) / NPHASE;
     // bulk asynchronous copies need 16-byte aligned row segments
-    // measured (10 000 cells): 0.75 ms against 0.72 ms for the per-thread loads once the stage is released after use (the
-    // early release that made it 0.66 ms is a race, see the kernel) - the variant is opt-in: ATTRICI_TMA_PREP=1
-    static const bool tma_off = [] {
+    // measured (10 000 cells): 0.752 / 0.748 / 0.798 ms with 3 / 4 / 5 stages against 0.719 ms for the per-thread loads
+    // once a stage is released after use (the early release that made it 0.66 ms is a race, see the kernel): more bytes
+    // in flight do not help, the kernel is bound by the latency of its FP64 accumulation chains at 12 - 16 warps per SM.
+    // The variant is opt-in: ATTRICI_TMA_PREP = number of stages of the ring (3 or 4; 1 = 3)
+    static const int tma_ns = [] {
         const char* e = getenv("ATTRICI_NO_TMA"); const char* f = getenv("ATTRICI_TMA_PREP");
-        return (e && e[0] == '1') || !(f && f[0] == '1');
+        if ((e && e[0] == '1') || !f) return 0;
+        const int n = atoi(f);
+        return n == 1 ? 3 : (n == 3 || n == 4 ? n : 0);
     }();
-    const bool tma = !tma_off && V == 2 && (ld % 4 == 0) && ((uintptr_t)y % 16 == 0) && (ws.C % 4 == 0);
+    const int OP_NS = tma_ns;
+    const bool tma = tma_ns > 0 && V == 2 && (ld % 4 == 0) && ((uintptr_t)y % 16 == 0) && (ws.C % 4 == 0);
     const size_t smem = sizeof(double) * ((size_t)a.ph_len * nj_max + (size_t)OP_STAGE * 3 * OP_THREADS * V) +
                         sizeof(int) * (size_t)OP_STAGE * OP_THREADS * V +
                         (tma ? sizeof(float) * (size_t)OP_NS * OP_U * OP_THREADS * V + 16 * OP_NS : 0);
@@ -464,9 +469,10 @@ int launch_prep_onepass(Workspace& ws, const attrici_variable_t& var, const floa
         kernel<<<grid, threads, smem, s>>>(a, nj_max);
         return 0;
     };
-    if (tma) ATTRICI_TRY(masks ? launch(prep_onepass_kernel<2, true, true>) : launch(prep_onepass_kernel<2, false, true>));
-    else if (V == 2) ATTRICI_TRY(masks ? launch(prep_onepass_kernel<2, true, false>) : launch(prep_onepass_kernel<2, false, false>));
-    else ATTRICI_TRY(masks ? launch(prep_onepass_kernel<1, true, false>) : launch(prep_onepass_kernel<1, false, false>));
+    if (tma && OP_NS == 3) ATTRICI_TRY(masks ? launch(prep_onepass_kernel<2, true, 3>) : launch(prep_onepass_kernel<2, false, 3>));
+    else if (tma) ATTRICI_TRY(masks ? launch(prep_onepass_kernel<2, true, 4>) : launch(prep_onepass_kernel<2, false, 4>));
+    else if (V == 2) ATTRICI_TRY(masks ? launch(prep_onepass_kernel<2, true, 0>) : launch(prep_onepass_kernel<2, false, 0>));
+    else ATTRICI_TRY(masks ? launch(prep_onepass_kernel<1, true, 0>) : launch(prep_onepass_kernel<1, false, 0>));
     ATTRICI_LAUNCH_CHECK();
     prep_onepass_finalize_kernel<<<(ws.C + OP_THREADS - 1) / OP_THREADS, OP_THREADS, 0, s>>>(a);
     ATTRICI_LAUNCH_CHECK();

@@ -23,11 +23,17 @@ def main():
     hdr = rows[0]
     ki, vi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
     seq = [(short_name(r[ki]), r[gi], float(r[vi].replace(",", "")) / 1000.0) for r in rows[1:]]
-    want_x = ((cells + 127) // 128 + 3) // 4
-    starts = [i for i, (k, g, _) in enumerate(seq) if k.startswith("prep_minmax") and g.startswith(f"({want_x},")]
+    # a step starts with the first pass over the series: the one-pass scaling kernel (Normal family on a gap-free axis;
+    # 256 cells per CTA) or the min / max pass (512 cells per CTA)
+    first = {"prep_onepass_kernel": (cells + 255) // 256, "prep_minmax": ((cells + 127) // 128 + 3) // 4}
+
+    def is_start(k, g):
+        return any(k.startswith(n) and g.startswith(f"({x},") for n, x in first.items())
+
+    starts = [i for i, (k, g, _) in enumerate(seq) if is_start(k, g)]
     i0 = starts[-1]
     i1 = i0 + 1
-    while i1 < len(seq) and not (seq[i1][0].startswith("prep_minmax") or seq[i1][0].startswith("build_basis")):
+    while i1 < len(seq) and not (is_start(seq[i1][0], seq[i1][1]) or seq[i1][0].startswith("build_basis")):
         i1 += 1
     tot = collections.OrderedDict()
     for k, _, v in seq[i0:i1]:
