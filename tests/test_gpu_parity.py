@@ -549,6 +549,66 @@ def test_batched_driver_report_variables():
         detrend_cells(Config("tas", report_variables=("cfact", "nu")), y, gmt, days, lat, lon)
 
 
+@pytest.mark.parametrize("modes", [1, 2, 3])
+def test_pr_modes_sweep(modes):
+    """pr (Bernoulli-Gamma, two likelihood terms) at modes 1-3 through the phase-ordered kernels: dry / wet mask
+    bit-exact, same days made wet (<= 2 flips per cell at the solver's own optimum), counterfactual within 2e-4."""
+    T, C = 5000, 3
+    y = synthetic.pr_cells(C, T)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    lat, lon = synthetic.tile_coordinates(1, 3)
+    seeds = cell_seeds(0, lat, lon)
+    s = CellBatchSolver("pr", modes=modes, device=DEV)
+    out = s.detrend_device(dev(y), days, gmt, seeds=seeds)
+    ys, cfact = host(out["y_scaled"]), host(out["cfact"])
+    assert (host(out["fit"].status) == 0).all()
+    for j in (0, C - 1):
+        ref = oracle.detrend_cell("pr", y[:, j], gmt, days, modes, lat=lat[j], lon=lon[j])
+        assert np.array_equal(np.isnan(ys[:, j]), np.isnan(ref["y_scaled"]))
+        differ = (cfact[:, j] == 0) != (ref["cfact"] == 0)
+        assert differ.sum() <= 2
+        m = ~differ & (ref["cfact"] > 0)
+        np.testing.assert_allclose(cfact[m, j], ref["cfact"][m], rtol=2e-4)
+        np.testing.assert_allclose(host(out["fit"].logp)[j], ref["logp"], rtol=3e-7)
+
+
+@pytest.mark.parametrize("variable", ["hurs", "pr"])
+def test_rank_preservation_beta_and_bernoulli_gamma(variable):
+    """north_star: the quantile map preserves the rank, F_cf(cfact_scaled) == F_ref(y_scaled), for every family.  The
+    Normal case is checked at full length above; here the families whose inverses are iterations (incomplete beta /
+    gamma, Halley steps stopped on cubic convergence): SciPy's cdf of the mapped value under the counterfactual
+    parameters against SciPy's cdf of the observation under the factual ones, at the coefficients the solver returned,
+    1e-10 on every day that was mapped (pr: wet days that stay wet)."""
+    T, C = 6000, 4
+    family = {"hurs": "beta", "pr": "bernoulli_gamma"}[variable]
+    y = synthetic.GENERATORS[variable](C, T) if variable != "pr" else synthetic.pr_cells(C, T)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    seeds = None
+    if variable == "pr":
+        lat, lon = synthetic.tile_coordinates(2, 2)
+        seeds = cell_seeds(0, lat, lon)
+    s = CellBatchSolver(variable, device=DEV)
+    s.set_predictor(days, gmt, C)
+    yd = dev(y)
+    ys, scaling = s.scale(yd)
+    fit = s.fit(ys)
+    assert (fit.status == 0).all()
+    _, replaced, cs = s.quantile_map(yd, ys, fit.params, scaling, seeds=seeds, want_scaled=True)
+    ys_h, cs_h, rep = host(ys).astype(np.float64), host(cs), host(replaced)
+    zero = np.zeros(len(gmt))
+    for j in range(C):
+        theta = host(fit.params)[j]
+        ref = oracle.estimate_params(family, theta, gmt, days, helpers.MODES)
+        cf = oracle.estimate_params(family, theta, zero, days, helpers.MODES)
+        ok = ~np.isnan(ys_h[:, j]) & (rep[:, j] == 0)
+        if variable == "pr":
+            ok &= cs_h[:, j] > 0
+        assert ok.sum() > 1000
+        q_ref = oracle.cdf(family, {k: v[ok] for k, v in ref.items()}, ys_h[ok, j])
+        q_cf = oracle.cdf(family, {k: v[ok] for k, v in cf.items()}, cs_h[ok, j])
+        assert np.abs(q_ref - q_cf).max() < 1e-10
+
+
 def test_full_length_series_properties():
     """BASELINE size in time (43 464 days), 1 024 cells: size-independent properties of the map."""
     T, C = synthetic.DAYS_1901_2019, 1024
