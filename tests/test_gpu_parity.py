@@ -569,7 +569,10 @@ def test_pr_modes_sweep(modes):
         assert differ.sum() <= 2
         m = ~differ & (ref["cfact"] > 0)
         np.testing.assert_allclose(cfact[m, j], ref["cfact"][m], rtol=2e-4)
-        np.testing.assert_allclose(host(out["fit"].logp)[j], ref["logp"], rtol=3e-7)
+        # logp carries n_wet * ln(scale) (Jacobian of Pr.scale), and the gamma-fit scale agrees with scipy's float32
+        # brentq to ~1e-6 relative only (the fit itself is checked at 1e-9 on the golden fixtures)
+        n_wet = int((~np.isnan(ref["y_scaled"])).sum())
+        np.testing.assert_allclose(host(out["fit"].logp)[j], ref["logp"], rtol=1e-9, atol=5e-6 * n_wet)
 
 
 @pytest.mark.parametrize("variable", ["hurs", "pr"])
