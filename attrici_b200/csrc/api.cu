@@ -221,9 +221,8 @@ int fold_applies(Workspace& ws, int term, int i0, int i1, cudaStream_t s, int* f
     ATTRICI_TRY(read_ints(ws.fold_bad, h, 4, s));
     if (phase_major) *phase_major = h[3] != 0;
     if (h[0] == 0 && h[1] == i0 && h[2] == i1) {
-        // measured (scripts/bench_families.py): the phase-ordered stream wins for the Gamma and Bernoulli terms
-        // (tasrange fit 2.1x, pr 1.5x); the Beta and Weibull terms spend their time in per-day special functions and
-        // run faster in the day-ordered kernel, which keeps more warps resident
+        // measured (scripts/bench_families.py, two-stage form of fold.cu): the phase-ordered stream wins for every other
+        // term - hurs fit 29.6 -> 13.9 ms, pr 12.6 -> 5.0 ms, tasrange 11.0 -> 3.1 ms, sfcWind 3.4 -> 2.2 ms per 1 024 cells
         if (term == T_NORMAL) *fold = FOLD_SUMS;
         else *fold = FOLD_STREAM;
     }

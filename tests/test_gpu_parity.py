@@ -639,11 +639,12 @@ def test_full_length_series_properties():
     q_ref = torch.special.ndtr(z)
     q_cf = torch.special.ndtr((cs - mu_cf) / sigma)
     assert (q_ref - q_cf).abs()[inner].max().item() < 1e-12
-    # one cell against the oracle at full length
-    yh = y[:, 5].cpu().numpy()
-    ref = oracle.detrend_cell("tas", yh, gmt, days, helpers.MODES)
-    np.testing.assert_allclose(fit.logp[5].item(), ref["logp"], rtol=1e-9)
-    np.testing.assert_allclose(cfact[:, 5].cpu().numpy(), ref["cfact"], rtol=1e-5, equal_nan=True)
+    # cells at the start, inside and at the end of the batch against the oracle at full length
+    for j in (0, 5, 517, C - 1):
+        yh = y[:, j].cpu().numpy()
+        ref = oracle.detrend_cell("tas", yh, gmt, days, helpers.MODES)
+        np.testing.assert_allclose(fit.logp[j].item(), ref["logp"], rtol=1e-9)
+        np.testing.assert_allclose(cfact[:, j].cpu().numpy(), ref["cfact"], rtol=1e-5, equal_nan=True)
 
 
 @pytest.mark.parametrize("offset,width", [(3, 41), (4, 64), (1, 130)])
@@ -797,6 +798,12 @@ def test_global_land_size_batch():
     np.testing.assert_allclose(host(big["cfact"][:, pick]), host(small["cfact"]), rtol=1e-9, equal_nan=True)
     assert torch.equal(big["replaced"][:, pick], small["replaced"])
     assert torch.equal(torch.isnan(big["cfact"]), torch.isnan(y))
+    # the probed cells of the global batch against the oracle (one-pass sums of the unrounded scaled values: 2e-9 on
+    # logp at this length; the bulk-copy quantile map for the big batch, per-thread stores for the small one)
+    for k in range(len(pick)):
+        ref = oracle.detrend_cell("tas", host(ysub[:, k]), gmt, days, helpers.MODES)
+        np.testing.assert_allclose(host(big["fit"].logp[pick[k]]), ref["logp"], rtol=1e-8)
+        np.testing.assert_allclose(host(big["cfact"][:, pick[k]]), ref["cfact"], rtol=1e-5, equal_nan=True)
 
 
 def test_model_cuda_plugin_interface():
