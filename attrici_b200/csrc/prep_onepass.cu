@@ -38,6 +38,7 @@ struct OnePassArgs {
     int T, C, Cp, i0, i1;
     int ph_len, n_chunks;
     int scaling;
+    int prefetch;            // request the batch after next into L2 (ATTRICI_PREP_PREFETCH=0 turns it off)
     float in_lo, in_hi;      // in-place input masks (hurs / tasrange / wind), -Inf / +Inf = none (Inf -> NaN, detrend.py:311)
     float fit_lo, fit_hi;    // values excluded from the fit only (tasskew)
     const double* basis64;
@@ -129,6 +130,16 @@ __global__ void __launch_bounds__(OP_THREADS + 32) prep_onepass_kernel(OnePassAr
 #pragma unroll
         for (int u = 0; u < OP_U; ++u) op_load<V>(a.y + row0 + (size_t)min(u, last) * jstride, vv[u]);
     };
+    // the batch after the next one is requested into L2 while the next one is on its way into registers: its loads then
+    // find their lines in L2 (the kernel waits on its loads - long scoreboard 3 per issued instruction - and has no
+    // registers left for a second batch in flight)
+    auto prefetch_batch = [&](int p, int j0) {
+        const size_t row0 = (size_t)(d0 + p + j0 * NPHASE) * a.ld + col0;
+        const int last = days_of(p) - 1 - j0;
+#pragma unroll
+        for (int u = 0; u < OP_U; ++u)
+            if (u <= last) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.y + row0 + (size_t)u * jstride));
+    };
     // TMA variant: warp 4 is the producer.  Its lane 0 walks the CTA's batches, waits until the consumer warps have
     // released the stage (empty barrier, one arrival per consumer warp), arms the full barrier with the byte count and
     // issues one bulk copy per day; the four consumer warps never synchronise with each other for the input.
@@ -186,6 +197,11 @@ __global__ void __launch_bounds__(OP_THREADS + 32) prep_onepass_kernel(OnePassAr
             }
         } else if (has_next) {
             load_batch(pn, jn, vb);
+            if (a.prefetch) {
+                int p2 = pn, j2 = jn + OP_U;
+                if (j2 >= days_of(pn)) { p2 = pn + 1; j2 = 0; }
+                if (p2 < nph) prefetch_batch(p2, j2);
+            }
         }
         if (j0 == 0) {
             ja = a.i0 > d ? (a.i0 - d + NPHASE - 1) / NPHASE : 0;
@@ -402,6 +418,8 @@ int launch_prep_onepass(Workspace& ws, const attrici_variable_t& var, const floa
     OnePassArgs a;
     a.y = y; a.ld = ld; a.T = ws.T; a.C = ws.C; a.Cp = ws.Cp; a.i0 = i0; a.i1 = i1;
     a.scaling = var.scaling;
+    static const bool prefetch_on = [] { const char* e = getenv("ATTRICI_PREP_PREFETCH"); return !(e && e[0] == '0'); }();
+    a.prefetch = prefetch_on ? 1 : 0;
     const bool has_lo = !(var.lower_threshold != var.lower_threshold);
     const bool has_hi = !(var.upper_threshold != var.upper_threshold);
     const bool in_place = (var.scaling == ATTRICI_SCALE_PERCENT || var.scaling == ATTRICI_SCALE_RANGE);

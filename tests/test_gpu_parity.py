@@ -673,6 +673,25 @@ def test_strided_unaligned_input_matches_contiguous(offset, width):
     assert np.array_equal(host(c["cfact"]), host(e["cfact"]), equal_nan=True)
 
 
+def test_bulk_copy_kernels_with_a_leading_dimension():
+    """An aligned column window of a wider array (64 cells at column 16 of 96: rows 16-byte aligned, leading dimension
+    larger than the cell count): the bulk-copy kernels take strided row segments and must give the bits of the
+    contiguous copy; the path that keeps y_scaled (per-thread kernels) agrees to the one-pass tolerance."""
+    T = 3000
+    wide = dev(synthetic.tas_cells(96, T, seed=29, nan_fraction=0.05))
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    window = wide[:, 16:80]
+    assert window.stride(0) == 96 and window.data_ptr() % 16 == 0
+    a = CellBatchSolver("tas", device=DEV).detrend_device(window, days, gmt, keep_scaled=False)
+    b = CellBatchSolver("tas", device=DEV).detrend_device(window.contiguous(), days, gmt, keep_scaled=False)
+    assert torch.equal(a["fit"].params, b["fit"].params)
+    assert np.array_equal(host(a["cfact"]), host(b["cfact"]), equal_nan=True)
+    assert torch.equal(a["replaced"], b["replaced"])
+    c = CellBatchSolver("tas", device=DEV).detrend_device(window, days, gmt)
+    np.testing.assert_allclose(host(c["cfact"]), host(a["cfact"]), rtol=1e-6, equal_nan=True)
+    assert torch.equal(c["replaced"], a["replaced"])
+
+
 @pytest.mark.parametrize("keep_scaled,C", [(False, 70), (True, 70), (False, 80), (False, 272)])
 def test_lean_quantile_map_matches_generic_kernel(keep_scaled, C):
     """The streamlined Normal quantile-map kernels (no post rule, no cfact_scaled output; hoisted reciprocal in the
@@ -758,11 +777,10 @@ def test_bulk_copy_kernels_give_the_bits_of_the_per_thread_kernels():
     assert res["bulk"][0] == res["per_thread"][0], res
 
 
-@pytest.mark.parametrize("T", [400, 1461, 1462])
-def test_series_shorter_than_one_phase_cycle(T):
+@pytest.mark.parametrize("T,C", [(400, 12), (1461, 12), (1462, 12), (400, 16), (1462, 16)])
+def test_series_shorter_than_one_phase_cycle(T, C):
     """Phase folding with fewer days than phases (every phase holds at most one day) and right at the 1461-day
-    boundary."""
-    C = 12
+    boundary; 16 cells: the bulk-copy quantile map with one-day batches."""
     y = synthetic.tas_cells(C, T, seed=17)
     y[5:40, 3] = np.nan
     gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
