@@ -274,40 +274,41 @@ ATTRICI_HD_NOINLINE double gamma_p_inv(double a, double p, double x0 = -1.0, dou
 // ---------------------------------------------------------------------------------------
 // regularised incomplete beta I_x(a, b) and its inverse
 // ---------------------------------------------------------------------------------------
+// Continued fraction of the incomplete beta function (the h of Numerical Recipes' betacf), evaluated by the forward
+// recurrence of its convergents A_n / B_n (A_n = A_{n-1} + d_n A_{n-2}, the same for B) instead of the modified Lentz
+// form: one reciprocal per double step - both partial numerators share 1 / ((a + 2m - 1)(a + 2m)(a + 2m + 1)) - where
+// Lentz needs five, and the convergence test |A_n B_{n-2} - A_{n-2} B_n| < eps |A_n B_{n-2}| needs none.  The
+// convergents are rescaled when they leave [2^-200, 2^200].  The quantile map of hurs spends its time here.
 ATTRICI_HD_NOINLINE double beta_cf(double a, double b, double x) {
-    const double tiny = 1e-300;
-    double qab = a + b, qap = a + 1.0, qam = a - 1.0;
-    double c = 1.0, d = 1.0 - qab * x / qap;
-    if (fabs(d) < tiny) d = tiny;
-    d = 1.0 / d;
-    double h = d;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    // convergents after the first partial numerator d_1 = -(a + b) x / (a + 1):  1 / (1 + d_1)
+    double am = 1.0, bm = 1.0, az = 1.0, bz = 1.0 - qab * x / qap;
     for (int m = 1; m < 3000; ++m) {
-        int m2 = 2 * m;
-        // both coefficients of this double step share the factor 1 / (a + 2m)
-        const double r0 = rcp(a + m2);
-        double aa = m * (b - m) * x * rcp(qam + m2) * r0;
-        d = 1.0 + aa * d;
-        if (fabs(d) < tiny) d = tiny;
-        c = 1.0 + aa * rcp(c);
-        if (fabs(c) < tiny) c = tiny;
-        d = rcp(d);
-        h *= d * c;
-        aa = -(a + m) * (qab + m) * x * r0 * rcp(qap + m2);
-        d = 1.0 + aa * d;
-        if (fabs(d) < tiny) d = tiny;
-        c = 1.0 + aa * rcp(c);
-        if (fabs(c) < tiny) c = tiny;
-        d = rcp(d);
-        double del = d * c;
-        h *= del;
-        if (fabs(del - 1.0) < 1e-16) break;
+        const double em = (double)m, t2 = em + em;
+        const double p1 = qam + t2, p2 = a + t2, p3 = qap + t2;
+        const double r = rcp(p1 * p2 * p3);
+        const double de = em * (b - em) * x * (p3 * r);               // m (b - m) x / ((a + 2m - 1)(a + 2m))
+        const double dd = -(a + em) * (qab + em) * x * (p1 * r);      // -(a + m)(a + b + m) x / ((a + 2m)(a + 2m + 1))
+        const double ap = az + de * am, bp = bz + de * bm;
+        const double app = ap + dd * az, bpp = bp + dd * bz;
+        const double cross = app * bz;
+        const bool done = fabs(az * bpp - cross) < 1e-16 * fabs(cross);
+        am = ap; bm = bp; az = app; bz = bpp;
+        if (done) break;
+        const double mag = fabs(bz);
+        if (mag > 1.6e60 || mag < 6.2e-61) {   // 2^+-200
+            const double sc = mag > 1.0 ? 6.223015277861142e-61 : 1.6069380442589903e60;
+            am *= sc; bm *= sc; az *= sc; bz *= sc;
+        }
     }
-    return h;
+    return az / bz;
 }
 
 // returns I_x(a,b); if comp != nullptr also 1 - I_x(a,b) computed without cancellation.
 // lnb = lgamma(a + b) - lgamma(a) - lgamma(b), hoisted by callers that evaluate several times at the same (a, b)
-ATTRICI_HD_NOINLINE double beta_i2_l(double a, double b, double x, double lnb, double* comp) {
+// pref (optional): x^a (1 - x)^b / B(a, b), from which the inverse takes the density (pref / (x (1 - x)))
+ATTRICI_HD_NOINLINE double beta_i2_l(double a, double b, double x, double lnb, double* comp, double* pref = nullptr) {
+    if (pref) *pref = 0.0;
     if (isnan(a) || isnan(b) || isnan(x) || a <= 0.0 || b <= 0.0 || x < 0.0 || x > 1.0) {
         if (comp) *comp = NAN;
         return NAN;
@@ -315,6 +316,7 @@ ATTRICI_HD_NOINLINE double beta_i2_l(double a, double b, double x, double lnb, d
     if (x == 0.0) { if (comp) *comp = 1.0; return 0.0; }
     if (x == 1.0) { if (comp) *comp = 0.0; return 1.0; }
     double bt = exp(lnb + a * log(x) + b * log1p(-x));
+    if (pref) *pref = bt;
     // one continued-fraction call with the arguments swapped where needed: lanes on either side of the switch
     // then run the same code instead of two divergent calls
     const bool flip = !(x < (a + 1.0) / (a + b + 2.0));
@@ -362,11 +364,12 @@ ATTRICI_HD_NOINLINE double beta_i_inv(double a, double b, double p, double x0 = 
     double lo = 0.0, hi = 1.0;
     for (int it = 0; it < 80; ++it) {
         if (!(x > 0.0) || !(x < 1.0)) x = 0.5 * (lo + hi);
-        double q;
-        double pv = beta_i2_l(a, b, x, afac, &q);
+        double q, pref;
+        double pv = beta_i2_l(a, b, x, afac, &q, &pref);
         double err = (p < 0.5) ? pv - p : (1.0 - p) - q;
         if (err > 0.0) hi = x; else lo = x;
-        double dens = exp(a1 * log(x) + b1 * log1p(-x) + afac);
+        // dI/dx = x^(a-1) (1 - x)^(b-1) / B(a, b): the prefactor of the evaluation just made, over x (1 - x)
+        double dens = pref / (x * (1.0 - x));
         double xn;
         if (!(dens > 0.0) || isinf(dens)) {
             xn = 0.5 * (lo + hi);
@@ -375,9 +378,12 @@ ATTRICI_HD_NOINLINE double beta_i_inv(double a, double b, double p, double x0 = 
             double corr = u * (a1 / x - b1 / (1.0 - x));
             if (corr > 1.0) corr = 1.0;
             xn = x - u / (1.0 - 0.5 * corr);
-            // Halley converges cubically: a step below 1e-10 x leaves an error far below one ulp, while waiting for a
-        // step below 4 ulp just iterates on the rounding noise of err / dens
-        if (fabs(xn - x) <= 1e-10 * x) { x = xn; break; }
+            // Halley converges cubically, in units of the distance to the nearer end of (0, 1): a plain step from inside
+            // the bracket below 1e-6 of that distance leaves an error far below one ulp, so the point after the step is
+            // taken without evaluating there again (waiting for a step below 1e-10 asked for one evaluation more)
+            const double edge = fmin(x, 1.0 - x);
+            if (fabs(xn - x) <= 1e-6 * edge && xn >= lo && xn <= hi && corr <= 0.5 && corr >= -0.5) { x = xn; break; }
+            if (fabs(xn - x) <= 1e-10 * x) { x = xn; break; }
             if (!(xn >= lo) || !(xn <= hi)) xn = 0.5 * (lo + hi);
         }
         x = xn;
