@@ -206,7 +206,9 @@ def gather_cells(local, counts, dist=None, device=None):
 
     ``local``: dict name -> array whose first axis is this rank's cells;
     ``counts``: cells per rank.  Uses ``all_gather`` on tensors padded to the largest shard (shards are
-    uneven under the reference's partition rule)."""
+    uneven under the reference's partition rule).  Meant for the per-cell results (coefficients, logp, scaling,
+    status: MBs); a per-day series does not belong here - ``io.write_merged_output_sharded`` gathers those a block of
+    days at a time - and an array above 256 MB per rank is refused."""
     import torch
 
     if dist is None:
@@ -220,6 +222,9 @@ def gather_cells(local, counts, dist=None, device=None):
     out = {}
     for name, arr in local.items():
         a = np.ascontiguousarray(arr)
+        if a.nbytes > (1 << 28):
+            raise ValueError(f"gather_cells is for per-cell results; {name!r} holds {a.nbytes >> 20} MB on this rank "
+                             "(per-day series go through io.write_merged_output_sharded)")
         pad = np.zeros((cmax,) + a.shape[1:], dtype=a.dtype)
         pad[: a.shape[0]] = a
         t = torch.from_numpy(pad).to(dev)
