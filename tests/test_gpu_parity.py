@@ -692,6 +692,35 @@ def test_bulk_copy_kernels_with_a_leading_dimension():
     assert torch.equal(c["replaced"], a["replaced"])
 
 
+@pytest.mark.parametrize("variable", ["rsds", "tasskew"])
+def test_bulk_quantile_map_with_post_rule_matches_generic_kernel(variable):
+    """Normal variables with a post rule (rsds: cfact_scaled <= 0 -> NaN, tasskew: outside (0, 1) -> NaN; variables.py:
+    645-653, 691-698): the bulk-copy kernel hands such a day its observation back, flagged NaN, inline - the bits of
+    the generic kernel (selected by asking for cfact_scaled), incl. missing / infinite days and tail days, on two full
+    128-cell CTAs' worth of columns plus a 16-cell one."""
+    T, C = 5000, 144
+    if variable == "tasskew":
+        rng = np.random.default_rng(5)
+        y = np.clip(rng.normal(0.5, 0.2, size=(T, C)), -0.2, 1.2).astype(np.float32)
+    else:
+        y = synthetic.rsds_cells(C, T, seed=31)
+    y[np.random.default_rng(6).random((T, C)) < 0.02] = np.nan
+    y[17, 4] = np.inf
+    y[100:103, 9] += (60.0 if variable == "rsds" else 0.0)
+    gmt, days = synthetic.smoothed_gmt(T), synthetic.time_axis(T)
+    s = CellBatchSolver(variable, device=DEV)
+    s.set_predictor(days, gmt, C)
+    yd = dev(y)
+    ys, scaling = s.scale(yd)
+    fit = s.fit(ys)
+    bulk_c, bulk_r, _ = s.quantile_map(yd, None, fit.params, scaling)
+    gen_c, gen_r, gen_s = s.quantile_map(yd, None, fit.params, scaling, want_scaled=True)
+    assert np.array_equal(host(bulk_c), host(gen_c), equal_nan=True)
+    assert torch.equal(bulk_r, gen_r)
+    # the rule fires on days that are present: more NaN flags than missing inputs
+    assert int((gen_r == 1).sum()) > int(torch.isnan(ys).sum())
+
+
 @pytest.mark.parametrize("keep_scaled,C", [(False, 70), (True, 70), (False, 80), (False, 272)])
 def test_lean_quantile_map_matches_generic_kernel(keep_scaled, C):
     """The streamlined Normal quantile-map kernels (no post rule, no cfact_scaled output; hoisted reciprocal in the
