@@ -19,8 +19,8 @@
 //    of a cell live in one slot per cell).
 //
 // The decisions and formulas per day are those of qmap_impl.cuh::qmap_day; the incomplete gamma function is evaluated
-// by this file's own copies of the series / Halley iteration of special.cuh (four series terms per reciprocal, the
-// density from the prefactor, a cubic stopping rule at 3e-4 x - rounding-level and 3e-11-level differences, inside
+// by this file's own copy of the Halley iteration of special.cuh (the density from the prefactor, a cubic stopping rule
+// at 3e-4 x - rounding-level and 3e-11-level differences, inside
 // the 1e-5 the tests ask of the counterfactual); the trig columns are those of the phase's first day, as in every
 // phase-ordered kernel.  Measured (10 000 cells x 43 464 days): 253 ms for the day-ordered kernel and its MT19937
 // stream at the start of round 2, 41 ms now.
@@ -60,28 +60,7 @@ struct PrArgs {
 
 struct PrPhase { double a, gln, p_cf, sc_cf; };   // per (cell, phase): shape nu^2, lgamma(a), counterfactual p and scale
 
-// series for P(a, x) without its prefactor: gamma_p_series (special.cuh) with FOUR terms per reciprocal -
-//   t_{n+k} = t_n x^k / ((a + n + 1) .. (a + n + k)),  all four over the common R = 1 / ((a+n+1)(a+n+2)(a+n+3)(a+n+4))
-// - and the stopping rule checked every fourth term (the rule asks for terms below 1e-17 of the sum, beyond the
-// precision of the sum, so the extra terms change nothing).  ~8 instructions per term instead of ~20 with a reciprocal
-// per term; inlined: an item's cost is this loop.
-__device__ __forceinline__ double pr_series(double a, double x) {
-    double ap = a, del = 1.0 / a, sum = del;
-    const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
-    for (int n = 0; n < 500; ++n) {
-        const double d1 = ap + 1.0, d2 = ap + 2.0, d3 = ap + 3.0, d4 = ap + 4.0;
-        const double p12 = d1 * d2, p34 = d3 * d4;
-        const double dr = del * rcp(p12 * p34);
-        const double t1 = dr * x * (d2 * p34), t2 = dr * x2 * p34, t3 = dr * x3 * d4, t4 = dr * x4;
-        sum += (t1 + t2) + (t3 + t4);
-        del = t4;
-        ap = d4;
-        if (fabs(t4) < fabs(sum) * 1e-17) break;
-    }
-    return sum;
-}
-
-// gamma_pq_l (special.cuh) with the series above; also returns the prefactor x^a e^-x / Gamma(a), from which the
+// gamma_pq_l (special.cuh) with the series inlined (an item's cost is that loop); also returns the prefactor x^a e^-x / Gamma(a), from which the
 // inverse takes the density (x^(a-1) e^-x / Gamma(a) = prefactor / x) instead of a second exp / log pair
 __device__ __forceinline__ void pr_pq(double a, double x, double gln, double* p, double* q, double* pref) {
     *pref = 0.0;
@@ -90,7 +69,7 @@ __device__ __forceinline__ void pr_pq(double a, double x, double gln, double* p,
     if (isinf(x)) { *p = 1.0; *q = 0.0; return; }
     *pref = gamma_prefactor(a, x, gln);
     if (gamma_use_series(a, x)) {
-        const double pp = pr_series(a, x) * *pref;
+        const double pp = gamma_p_series_sum(a, x) * *pref;
         if (pp < 0.99 || x < a + 1.0) { *p = pp; *q = 1.0 - pp; return; }
     }
     *q = gamma_q_cf(a, x, gln);   // far upper tail: the continued fraction computes Q itself (rare)

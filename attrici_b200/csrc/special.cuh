@@ -129,16 +129,29 @@ ATTRICI_HD_NOINLINE double ndtri(double p) {
 // gln = lgamma(a), hoisted by callers that evaluate several times at the same shape
 ATTRICI_HD double gamma_prefactor(double a, double x, double gln) { return exp(a * log(x) - x - gln); }
 
-// series for P, converges quickly for x < a + 1
-ATTRICI_HD_NOINLINE double gamma_p_series(double a, double x, double gln) {
+// series for P without its prefactor: sum_n x^n / (a (a + 1) .. (a + n)), converges quickly for x < a + 1.
+// Four terms per reciprocal - t_{n+k} = t_n x^k / ((a + n + 1) .. (a + n + k)), all four over the common
+// R = 1 / ((a+n+1)(a+n+2)(a+n+3)(a+n+4)) - and the stopping rule checked every fourth term (it asks for terms below
+// 1e-17 of the sum, beyond the precision of the sum, so the extra terms change nothing): ~8 instructions per term
+// instead of ~20 with a reciprocal per term.
+ATTRICI_HD double gamma_p_series_sum(double a, double x) {
     double ap = a, del = 1.0 / a, sum = del;
-    for (int n = 0; n < 2000; ++n) {
-        ap += 1.0;
-        del *= x * rcp(ap);
-        sum += del;
-        if (fabs(del) < fabs(sum) * 1e-17) break;
+    const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
+    for (int n = 0; n < 500; ++n) {
+        const double d1 = ap + 1.0, d2 = ap + 2.0, d3 = ap + 3.0, d4 = ap + 4.0;
+        const double p12 = d1 * d2, p34 = d3 * d4;
+        const double dr = del * rcp(p12 * p34);
+        const double t1 = dr * x * (d2 * p34), t2 = dr * x2 * p34, t3 = dr * x3 * d4, t4 = dr * x4;
+        sum += (t1 + t2) + (t3 + t4);
+        del = t4;
+        ap = d4;
+        if (fabs(t4) < fabs(sum) * 1e-17) break;
     }
-    return sum * gamma_prefactor(a, x, gln);
+    return sum;
+}
+
+ATTRICI_HD_NOINLINE double gamma_p_series(double a, double x, double gln) {
+    return gamma_p_series_sum(a, x) * gamma_prefactor(a, x, gln);
 }
 
 // modified Lentz continued fraction for Q, converges quickly for x > a + 1
