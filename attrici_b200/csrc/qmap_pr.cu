@@ -60,75 +60,6 @@ struct PrArgs {
 
 struct PrPhase { double a, gln, p_cf, sc_cf; };   // per (cell, phase): shape nu^2, lgamma(a), counterfactual p and scale
 
-// gamma_pq_l (special.cuh) with the series inlined (an item's cost is that loop); also returns the prefactor x^a e^-x / Gamma(a), from which the
-// inverse takes the density (x^(a-1) e^-x / Gamma(a) = prefactor / x) instead of a second exp / log pair
-__device__ __forceinline__ void pr_pq(double a, double x, double gln, double* p, double* q, double* pref) {
-    *pref = 0.0;
-    if (isnan(a) || isnan(x) || a <= 0.0 || x < 0.0) { *p = NAN; *q = NAN; return; }
-    if (x == 0.0) { *p = 0.0; *q = 1.0; return; }
-    if (isinf(x)) { *p = 1.0; *q = 0.0; return; }
-    *pref = gamma_prefactor(a, x, gln);
-    if (gamma_use_series(a, x)) {
-        const double pp = gamma_p_series_sum(a, x) * *pref;
-        if (pp < 0.99 || x < a + 1.0) { *p = pp; *q = 1.0 - pp; return; }
-    }
-    *q = gamma_q_cf(a, x, gln);   // far upper tail: the continued fraction computes Q itself (rare)
-    *p = 1.0 - *q;
-}
-
-// gamma_p_inv (special.cuh) with pr_pq and lgamma(a) supplied.  Two deviations, both inside the tolerance of the
-// path (1e-4 relative on the counterfactual; the tests ask 1e-5 of the oracle):
-//  * the density is prefactor / x (one rounding away from the closed form the scalar routine evaluates),
-//  * a Halley step below 3e-4 x ends the iteration (cubic convergence: the error after it is a small multiple of
-//    (3e-4)^3 = 2.7e-11 relative), so the typical day costs ONE evaluation after the factual quantile and a day whose
-//    quantile moves a lot (drizzle: P ~ x^a) two; the scalar routine's 2e-5 asked for one more each.
-__device__ __forceinline__ double pr_p_inv(double a, double p, double x0, double p0, double q0, double pref0, double gln) {
-    if (isnan(a) || isnan(p) || a <= 0.0 || p < 0.0 || p > 1.0) return NAN;
-    if (p == 0.0) return 0.0;
-    if (p == 1.0) return INFINITY;
-    const double a1 = a - 1.0;
-    double x;
-    if (x0 > 0.0 && isfinite(x0)) {
-        x = x0;
-    } else if (a > 1.0) {
-        double pp = p < 0.5 ? p : 1.0 - p;
-        double t = sqrt(-2.0 * log(pp));
-        x = (2.30753 + t * 0.27061) / (1.0 + t * (0.99229 + t * 0.04481)) - t;
-        if (p < 0.5) x = -x;
-        double w = 1.0 - 1.0 / (9.0 * a) - x / (3.0 * sqrt(a));
-        x = a * w * w * w;
-        if (x < 1e-3) x = 1e-3;
-    } else {
-        double t = 1.0 - a * (0.253 + a * 0.12);
-        if (p < t) x = pow(p / t, 1.0 / a);
-        else x = 1.0 - log(1.0 - (p - t) / (1.0 - t));
-    }
-    double lo = 0.0, hi = INFINITY;
-#pragma unroll 1
-    for (int it = 0; it < 60; ++it) {
-        if (x <= 0.0) x = 0.5 * (lo + (isinf(hi) ? lo + 1e-300 : hi));
-        double pv, qv, pref;
-        if (it == 0 && p0 >= 0.0 && x == x0) { pv = p0; qv = q0; pref = pref0; }
-        else pr_pq(a, x, gln, &pv, &qv, &pref);
-        const double err = (p < 0.5) ? pv - p : (1.0 - p) - qv;
-        if (err > 0.0) hi = x; else lo = x;
-        const double dens = pref / x;   // dP/dx
-        if (!(dens > 0.0)) {
-            x = isinf(hi) ? 2.0 * x + 1.0 : 0.5 * (lo + hi);
-            continue;
-        }
-        const double u = err / dens;
-        double corr = u * (a1 / x - 1.0);
-        if (corr > 1.0) corr = 1.0;
-        const double dx = u / (1.0 - 0.5 * corr);
-        double xn = x - dx;
-        if (fabs(xn - x) <= 3e-4 * x && xn >= lo && xn <= hi && corr <= 0.5 && corr >= -0.5) { x = xn; break; }
-        if (!(xn >= lo) || !(xn <= hi)) xn = isinf(hi) ? 2.0 * x : 0.5 * (lo + hi);
-        x = xn;
-    }
-    return x;
-}
-
 // one item: the quantile map of qmap_day for a wet day (x > 0) or a dry day the uniform draw turned wet (x = -1;
 // NaN: the same with degenerate parameters)
 __device__ __forceinline__ double pr_item(double x, double p_ref, const PrPhase& ph) {
@@ -136,7 +67,7 @@ __device__ __forceinline__ double pr_item(double x, double p_ref, const PrPhase&
     const bool dry = !(x > 0.0);
     if (isnan(x)) q = NAN;
     else if (dry) q = p_ref;
-    else { pr_pq(ph.a, x, ph.gln, &P, &Q, &pref); q = p_ref + (1.0 - p_ref) * P; }
+    else { gamma_pq_pref_l(ph.a, x, ph.gln, &P, &Q, &pref); q = p_ref + (1.0 - p_ref) * P; }
     const bool drier_cf = ph.p_cf > p_ref;
     const bool qm0 = drier_cf && (q > ph.p_cf);
     const bool qm1 = !drier_cf && !dry;
@@ -149,7 +80,7 @@ __device__ __forceinline__ double pr_item(double x, double p_ref, const PrPhase&
             cs = NAN;
         } else {
             const bool known = !dry && isfinite(x);
-            cs = pr_p_inv(ph.a, target, known ? x : -1.0, known ? P : -1.0, known ? Q : -1.0, pref, ph.gln) * ph.sc_cf;
+            cs = gamma_p_inv_from(ph.a, target, known ? x : -1.0, known ? P : -1.0, known ? Q : -1.0, pref, ph.gln) * ph.sc_cf;
         }
     }
     return cs;

@@ -176,6 +176,17 @@ void hm_binary(int which, const double* a, const double* x, double* out, int n) 
     }
 }
 
+// the inverse as the precipitation quantile map uses it (qmap_pr.cu): P, Q and the prefactor at the starting point x0
+// from one evaluation, then the Halley iteration from x0 to the quantile of p
+void hm_gamma_inv_from(const double* a, const double* x0, const double* p, double* out, int n) {
+    for (int i = 0; i < n; ++i) {
+        const double gln = lgamma(a[i]);
+        double P, Q, pref;
+        gamma_pq_pref_l(a[i], x0[i], gln, &P, &Q, &pref);
+        out[i] = gamma_p_inv_from(a[i], p[i], x0[i], P, Q, pref, gln);
+    }
+}
+
 void hm_ternary(int which, const double* a, const double* b, const double* x, double* out, int n) {
     for (int i = 0; i < n; ++i) {
         switch (which) {

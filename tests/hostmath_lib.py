@@ -62,6 +62,14 @@ def binary(which, a, x):
     return out
 
 
+def gamma_inv_from(a, x0, p):
+    """``gamma_p_inv_from`` started at ``x0`` with P, Q and the prefactor of one evaluation there (qmap_pr.cu)."""
+    a, x0, p = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, x0, p))
+    out = np.empty_like(p)
+    lib().hm_gamma_inv_from(_p(a, C.c_double), _p(x0, C.c_double), _p(p, C.c_double), _p(out, C.c_double), C.c_int(p.size))
+    return out
+
+
 def ternary(which, a, b, x):
     a, b, x = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, b, x))
     out = np.empty_like(x)

@@ -43,6 +43,30 @@ def test_incomplete_gamma():
     assert np.isinf(hm.binary(2, np.array([2.0]), np.array([1.0]))[0])
 
 
+def test_gamma_inverse_from_the_factual_point():
+    """The inverse of the precipitation quantile map (qmap_pr.cu): started at the factual point x0 with P(a, x0),
+    Q(a, x0) known, target quantile Q_cf = beta * Q_ref (the dry-day probabilities of the two distributions differ by a
+    few percent; wider here), Halley steps ended by the cubic rule at 3e-4 x - against SciPy's gammaincinv.  The rule
+    leaves a small multiple of (3e-4)^3 relative; 1e-9 is asked (the path's tolerance on the counterfactual is 1e-4)."""
+    rng = np.random.default_rng(3)
+    n = 20000
+    a = np.exp(rng.uniform(np.log(0.15), np.log(30), n))
+    x0 = rng.gamma(a)
+    x0 = np.maximum(x0, 1e-12)
+    beta = np.exp(rng.uniform(np.log(0.5), np.log(1.5), n))
+    q_ref = special.gammaincc(a, x0)
+    ok = (q_ref > 1e-12) & (beta * q_ref < 1 - 1e-9)
+    a, x0, beta, q_ref = a[ok], x0[ok], beta[ok], q_ref[ok]
+    p = 1.0 - beta * q_ref
+    got = hm.gamma_inv_from(a, x0, p)
+    want = special.gammaincinv(a, p)
+    good = want > 0
+    np.testing.assert_allclose(got[good], want[good], rtol=1e-9)
+    # equal probabilities: the starting point is the root, no iteration moves it beyond rounding
+    same = hm.gamma_inv_from(a, x0, special.gammainc(a, x0))
+    np.testing.assert_allclose(same, x0, rtol=1e-10)
+
+
 def test_incomplete_beta():
     rng = np.random.default_rng(1)
     a = np.exp(rng.uniform(np.log(0.2), np.log(300), 4000))
